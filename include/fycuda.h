@@ -1,0 +1,199 @@
+/* fycuda.h -- C ABI of the B200-native FoamYade coupling engine (libfycuda.so).
+ *
+ * This is the drop-in boundary for ONE hot path of dpkn31/Yade-OpenFOAM-coupling:
+ * the per-timestep particle<->fluid coupling operator Foam::FoamYade
+ * (FoamYade/FoamYade.H:57-161, FoamYade.C) with its k-d-tree mesh search
+ * (FoamYade/meshtree/meshTree.{H,C}), and the PISO/PIMPLE pressure-velocity
+ * solve of icoFoamYade/icoFoamYade.C:65-149 and pimpleFoamYade/.  The host
+ * side (the C++ class Foam::FoamYade in yade-openfoam-coupling_b200/host/, the
+ * solver drivers, the Python ctypes binding used by the tests) sits ABOVE this
+ * header; everything below it is hand-written sm_100a CUDA.
+ *
+ * Conventions
+ *   - plain C: opaque handle, pointers + sizes, int return code
+ *     (0 = FY_OK, < 0 = error; fy_last_error() gives the text). Nothing throws
+ *     across the boundary.  There is NO CPU fallback: without a CUDA device
+ *     every compute entry point fails with FY_ERR_NO_DEVICE.
+ *   - all floating point is IEEE fp64; cell / face indices are int32
+ *     (OpenFOAM `label`, `int` in the reference).
+ *   - vector fields are arrays of [n][3] doubles, tensors [n][9] row-major
+ *     (xx xy xz yx yy yz zx zy zz) -- OpenFOAM's in-memory layout, so a
+ *     volVectorField's internal field can be passed as is.
+ *   - caller owns host buffers; the library owns device buffers.  One CUDA
+ *     stream per handle; a handle is not thread-safe.
+ *   - pointers named h_* are host pointers; d_* device pointers.
+ */
+#ifndef FYCUDA_H
+#define FYCUDA_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fy_ctx* fy_handle;
+
+enum {
+    FY_OK = 0,
+    FY_ERR_INVALID = -1,     /* bad argument / call order */
+    FY_ERR_NO_DEVICE = -2,   /* no usable CUDA device: the engine has no CPU path */
+    FY_ERR_CUDA = -3,        /* CUDA runtime error, see fy_last_error */
+    FY_ERR_ALLOC = -4,
+    FY_ERR_NOT_CONVERGED = -5,
+    FY_ERR_UNSUPPORTED = -6
+};
+
+/* boundary-condition kinds (the subset of OpenFOAM patch fields the synthetic cases use) */
+enum {
+    FY_BC_FIXED_VALUE = 0,    /* fixedValue / noSlip / movingWall: value given per patch */
+    FY_BC_ZERO_GRADIENT = 1
+};
+
+/* A patch: nFaces boundary faces that all belong to one boundary-condition group.
+ * Geometry arrays are per face, in OpenFOAM boundary-face order.                */
+typedef struct {
+    int nFaces;
+    const int* faceCells;        /* [nFaces] owner cell of each boundary face           */
+    const double* Sf;            /* [nFaces][3] outward face-area vectors               */
+    const double* magSf;         /* [nFaces]                                            */
+    const double* deltaCoeffs;   /* [nFaces] 1/|d| (cell centre -> face centre)         */
+    int bcU;                     /* FY_BC_* for U                                       */
+    double valueU[3];            /* patch-uniform value when bcU == FIXED_VALUE         */
+    int bcP;                     /* FY_BC_* for p                                       */
+    double valueP;
+} fy_patch_desc;
+
+/* Mesh in OpenFOAM LDU form (what fvMesh exposes): cells, internal faces in upper-triangular order
+ * (owner < neighbour, sorted by owner then neighbour), face geometry, boundary patches.
+ * Replaces: the `const fvMesh&` argument of Foam::FoamYade::FoamYade (FoamYade.H:106) and the mesh
+ * every fvm:: / fvc:: call of icoFoamYade.C / pimpleFoamYade.C takes implicitly.                    */
+typedef struct {
+    int nCells;
+    const double* C;             /* [nCells][3] cell centres  (mesh.C(), FoamYade.H:121, meshTree.C:13) */
+    const double* V;             /* [nCells]    cell volumes  (mesh.V(), FoamYade.C:69,323)              */
+    /* internal faces -- may be 0/NULL when only the coupling operator is used */
+    int nInternalFaces;
+    const int* owner;            /* [nInternalFaces] */
+    const int* neighbour;        /* [nInternalFaces] */
+    const double* Sf;            /* [nInternalFaces][3] */
+    const double* magSf;         /* [nInternalFaces]    */
+    const double* weights;       /* [nInternalFaces] linear-interpolation weight of the owner */
+    const double* deltaCoeffs;   /* [nInternalFaces] 1/|C_N - C_P| */
+    int nPatches;
+    const fy_patch_desc* patches;
+    /* "containing cell" query (mesh.findCell, FoamYade.C:251) is index arithmetic on an axis-aligned
+     * box of boxN[0] x boxN[1] x boxN[2] hex cells, x fastest; boxN[0] == 0 => point-force mode
+     * unavailable on this mesh.  boxGeom = x0 y0 z0 hx hy hz.                                       */
+    int boxN[3];
+    double boxGeom[6];
+    /* mesh vertex bounding box (min xyz, max xyz) -- what sendMeshBbox ships (FoamYade.C:82-96) */
+    double bbox[6];
+} fy_mesh_desc;
+
+/* ---------------------------------------------------------------------------------------------
+ * life cycle
+ * ------------------------------------------------------------------------------------------- */
+
+/* Library / device probe. Returns the number of CUDA devices (0 on a CPU-only box, never an error). */
+int fy_device_count(void);
+const char* fy_version(void);
+
+/* Creates an engine on CUDA device `device`: uploads the mesh, builds the k-d tree over the cell
+ * centres on the host with the reference's own construction rule (meshTree.C:9-51: axis = depth%3,
+ * std::nth_element at size/2, left = [0,md), right = (md,end)) and uploads it in implicit in-order
+ * layout.  Replaces FoamYade::FoamYade + getRankSize()'s mshTree.build_tree() + initFields()
+ * (FoamYade.C:18-73).                                                                            */
+int fy_create(const fy_mesh_desc* mesh, int device, fy_handle* out);
+int fy_destroy(fy_handle h);
+const char* fy_last_error(fy_handle h);   /* h may be NULL: last create error */
+
+/* FoamYade::setScalarProperties(rhoP, rhoF, nu) (FoamYade.C:9-11) + the `gaussianInterp` ctor flag
+ * (FoamYade.H:117,122).                                                                          */
+int fy_set_properties(fy_handle h, double rhoP, double rhoF, double nu, int gaussianInterp);
+
+/* interpRange, sigmaInterp, interpRangeCu, sigmaPi of initFields() (FoamYade.C:69-72), computed on
+ * the host exactly as written there.                                                              */
+int fy_get_constants(fy_handle h, double out4[4]);
+
+/* Pinned host memory for wire buffers (particle records in, forces out). */
+int fy_host_alloc(void** p, size_t bytes);
+int fy_host_free(void* p);
+
+/* ---------------------------------------------------------------------------------------------
+ * fields the coupling operator binds (FoamYade.H:76-90)
+ *   inputs : U gradP vGrad divT ddtU          outputs: uSourceDrag alpha uSource uParticle
+ * The engine keeps a device copy of each.  With host binding (an OpenFOAM CPU solver owns the
+ * fields) the inputs are uploaded at the start of every fy_set_particle_action and the outputs are
+ * downloaded at its end / at fy_set_source_zero; with the built-in GPU solver (fy_ico_*, fy_pimple_*)
+ * nothing crosses PCIe.
+ * ------------------------------------------------------------------------------------------- */
+typedef enum {
+    FY_F_U = 0, FY_F_GRADP, FY_F_VGRAD, FY_F_DIVT, FY_F_DDTU,
+    FY_F_USOURCEDRAG, FY_F_ALPHA, FY_F_USOURCE, FY_F_UPARTICLE,
+    FY_F_P, FY_F_PHI, FY_F_COUNT
+} fy_field_id;
+
+/* Host pointers of the solver-owned fields (any may be NULL = not host-bound). */
+int fy_bind_host_fields(fy_handle h, const double* U, const double* gradP, const double* vGrad,
+                        const double* divT, const double* ddtU, double* uSourceDrag, double* alpha,
+                        double* uSource, double* uParticle);
+/* Explicit transfers of one field (size is implied by the field id). */
+int fy_upload_field(fy_handle h, int field, const double* h_src);
+int fy_download_field(fy_handle h, int field, double* h_dst);
+/* Device pointer of a field (for callers that already live on the GPU, e.g. torch tensors). */
+int fy_device_field(fy_handle h, int field, double** d_ptr);
+
+/* ---------------------------------------------------------------------------------------------
+ * the coupling operator
+ * ------------------------------------------------------------------------------------------- */
+
+/* meshTree::nnearestCellsRange (meshTree.C:148-179) for n points: h_ids [n][12] nearest-first,
+ * -1 padded; h_counts [n] in 0..12 (the canonical form: the last <= 12 strict improvements of the
+ * nearest-neighbour descent with d^2 < 1.25 range^2).  Parity hook; bit-exact.                     */
+int fy_locate(fy_handle h, const double* h_xyz, int n, int* h_ids, int* h_counts);
+
+/* mesh.findCell (FoamYade.C:251) on the hex box: h_cell [n], -1 outside. */
+int fy_find_cell(fy_handle h, const double* h_xyz, int n, int* h_cell);
+
+/* One fluid step of FoamYade::setParticleAction (FoamYade.C:605-632), split so that several Yade
+ * ranks' buffers can be processed in the reference's order (each YadeProc: locate -> weights ->
+ * per-cell accumulate -> void fraction -> forces; FoamYade.C:612-628):
+ *   fy_coupling_begin : deltaT = dt; uploads host-bound input fields
+ *   fy_coupling_proc  : one particle buffer: h_pdata [n][10] = x y z vx vy vz wx wy wz radius
+ *                       (FoamYade.C:190-219) -> h_found [n] (1 / -1, FoamYade.C:141,222),
+ *                       h_force [n][6] = Fx Fy Fz Tx Ty Tz (FoamYade.C:492-498), zero when not found
+ *   fy_coupling_end   : downloads host-bound output fields
+ * fy_set_particle_action = begin + one proc + end (serial-Yade mode, FoamYade.C:173-184).          */
+int fy_coupling_begin(fy_handle h, double dt);
+int fy_coupling_proc(fy_handle h, const double* h_pdata, int n, int* h_found, double* h_force);
+int fy_coupling_end(fy_handle h);
+int fy_set_particle_action(fy_handle h, double dt, const double* h_pdata, int n, int* h_found, double* h_force);
+
+/* Device-resident variant of fy_coupling_proc: all three buffers are device pointers; no PCIe traffic,
+ * no host synchronisation.                                                                            */
+int fy_coupling_proc_device(fy_handle h, const double* d_pdata, int n, int* d_found, double* d_force);
+
+/* FoamYade::setSourceZero (FoamYade.C:556-566): uSource = 0; Gaussian: alpha = 1, uSourceDrag = 0,
+ * uParticle = 0.  Host-bound output fields are reset too.                                          */
+int fy_set_source_zero(fy_handle h);
+
+/* Cell lists + normalised Gaussian weights of the last fy_coupling_proc (parity hooks):
+ * h_counts [n], h_ids [n][12], h_weights [n][12] (FoamYade.C:293-316). Any pointer may be NULL.     */
+int fy_get_last_lists(fy_handle h, int n, int* h_counts, int* h_ids, double* h_weights);
+
+/* Blocks until all work queued on the handle's stream is complete. */
+int fy_synchronize(fy_handle h);
+
+/* Per-phase device times (ms) of the last coupling_proc, measured with CUDA events on the handle's
+ * stream: [0] h2d [1] locate [2] weights+accumulate [3] void fraction [4] forces [5] d2h.
+ * Only recorded when profiling is on (fy_set_profiling(h, 1)); synchronises.                        */
+int fy_set_profiling(fy_handle h, int on);
+int fy_get_phase_ms(fy_handle h, double out[8]);
+/* Kernel launches issued by this handle since creation (for bench.py's gpu_launches). */
+long long fy_launch_count(fy_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FYCUDA_H */

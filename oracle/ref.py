@@ -1,0 +1,167 @@
+"""oracle/ref.py -- TEST INFRASTRUCTURE ONLY.
+
+ctypes wrapper of oracle/_ref/libfoamyade_ref.so: the UNMODIFIED reference
+coupling operator (/root/reference/FoamYade/FoamYade.C + meshtree/meshTree.C)
+behind the shim + harness of oracle/ref_harness.cpp.  Build with `make -C oracle ref`
+(done by __graft_entry__.build() where /root/reference exists; the built .so
+travels to the GPU box).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libfoamyade_ref.so")
+_lib = None
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+def available():
+    return os.path.exists(LIB_PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(LIB_PATH)
+        L.ref_create.restype = C.c_void_p
+        L.ref_create.argtypes = [C.c_int, _dp, _dp, C.c_int, _dp, _ip, _dp, C.c_int, C.c_int]
+        L.ref_destroy.argtypes = [C.c_void_p]
+        L.ref_set_properties.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+        L.ref_field.restype = _dp
+        L.ref_field.argtypes = [C.c_void_p, C.c_char_p]
+        L.ref_get_constants.argtypes = [C.c_void_p, _dp]
+        L.ref_set_logging.argtypes = [C.c_int]
+        L.ref_get_trace.restype = C.c_int
+        L.ref_get_trace.argtypes = [C.c_char_p, C.c_int]
+        L.ref_get_counts.argtypes = [C.POINTER(C.c_long)]
+        L.ref_get_dt.argtypes = [_dp, C.c_void_p]
+        L.ref_get_bbox.restype = C.c_int
+        L.ref_get_bbox.argtypes = [_dp, C.c_int]
+        L.ref_locate.argtypes = [C.c_void_p, _dp, C.c_int, _ip, _ip, C.c_int]
+        L.ref_find_cell.restype = C.c_int
+        L.ref_find_cell.argtypes = [C.c_void_p, _dp]
+        L.ref_step.argtypes = [C.c_void_p, C.c_double, C.c_double, _dp, C.c_int, _ip, _ip, _dp]
+        L.ref_step_pieces.argtypes = [C.c_void_p, C.c_double, C.c_double, _dp, C.c_int, _ip, C.c_int, C.c_int, _ip, _dp]
+        L.ref_get_lists.argtypes = [C.c_void_p, C.c_int, _ip, _ip]
+        L.ref_get_times.argtypes = [C.c_void_p, _dp]
+        L.ref_set_source_zero.argtypes = [C.c_void_p]
+        L.ref_mt19937_64_uniform.argtypes = [C.c_ulonglong, C.c_long, _dp]
+        _lib = L
+    return _lib
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip)
+
+
+def mt19937_64_uniform(seed, n):
+    out = np.empty(n, dtype=np.float64)
+    lib().ref_mt19937_64_uniform(seed, n, _d(out))
+    return out
+
+
+FIELD_WIDTH = dict(U=3, gradP=3, divT=3, ddtU=3, uSource=3, uParticle=3, vGrad=9, uSourceDrag=1, alpha=1)
+
+
+class RefFoamYade:
+    """The reference Foam::FoamYade object on a mesh given by oracle.meshgen.hex_box()."""
+
+    def __init__(self, mesh, gaussian, n_yade=1):
+        self.L = lib()
+        self.mesh = mesh
+        self.N = mesh["V"].shape[0]
+        self.gaussian = bool(gaussian)
+        self.n_yade = n_yade
+        self.h = self.L.ref_create(self.N, _d(mesh["C"]), _d(mesh["V"]), mesh["points"].shape[0], _d(mesh["points"]),
+                                   _i(mesh["boxN"]), _d(mesh["boxGeom"]), int(gaussian), n_yade)
+
+    def close(self):
+        if self.h:
+            self.L.ref_destroy(self.h)
+            self.h = None
+
+    def set_properties(self, rhoP, rhoF, nu):
+        self.L.ref_set_properties(self.h, rhoP, rhoF, nu)
+
+    def field(self, name):
+        """numpy VIEW of the reference's field storage."""
+        w = FIELD_WIDTH[name]
+        p = self.L.ref_field(self.h, name.encode())
+        a = np.ctypeslib.as_array(p, shape=(self.N * w,))
+        return a.reshape(self.N, w) if w > 1 else a
+
+    def constants(self):
+        out = np.empty(4)
+        self.L.ref_get_constants(self.h, _d(out))
+        return dict(interpRange=out[0], sigmaInterp=out[1], interpRangeCu=out[2], sigmaPi=out[3])
+
+    def locate(self, xyz, stride=16):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+        n = xyz.shape[0]
+        ids = np.empty((n, stride), dtype=np.int32)
+        cnt = np.empty(n, dtype=np.int32)
+        self.L.ref_locate(self.h, _d(xyz), n, _i(ids), _i(cnt), stride)
+        return cnt, ids
+
+    def step(self, dt, pdata, yade_dt=0.0, split=None, pieces=False, truncate12=True, dense=True):
+        pdata = np.ascontiguousarray(pdata, dtype=np.float64)
+        n = pdata.shape[0]
+        found = np.empty(max(n, 1), dtype=np.int32)
+        force = np.empty((max(n, 1), 6), dtype=np.float64)
+        sp = None if split is None else np.ascontiguousarray(split, dtype=np.int32)
+        spp = _i(sp) if sp is not None else None
+        if pieces:
+            self.L.ref_step_pieces(self.h, dt, yade_dt, _d(pdata), n, spp, int(truncate12), int(dense), _i(found), _d(force))
+        else:
+            self.L.ref_step(self.h, dt, yade_dt, _d(pdata), n, spp, _i(found), _d(force))
+        return found[:n], force[:n]
+
+    def lists(self, n):
+        cnt = np.empty(n, dtype=np.int32)
+        ids = np.empty((n, 16), dtype=np.int32)
+        self.L.ref_get_lists(self.h, n, _i(cnt), _i(ids))
+        return cnt, ids
+
+    def times(self):
+        out = np.empty(5)
+        self.L.ref_get_times(self.h, _d(out))
+        return dict(locate=out[0], weights=out[1], accum=out[2], force=out[3], send=out[4])
+
+    def set_source_zero(self):
+        self.L.ref_set_source_zero(self.h)
+
+    def dts(self):
+        out = np.empty(2)
+        self.L.ref_get_dt(_d(out), self.h)
+        return out[0], out[1]
+
+    def counts(self):
+        out = (C.c_long * 5)()
+        self.L.ref_get_counts(out)
+        return dict(bcast=out[0], allreduce=out[1], send=out[2], recv=out[3], isend=out[4])
+
+    def trace(self):
+        n = self.L.ref_get_trace(None, 0)
+        buf = C.create_string_buffer(n + 1)
+        self.L.ref_get_trace(buf, n + 1)
+        return buf.value.decode().splitlines()
+
+
+def fnv1a_lists(cnt, ids):
+    """FNV-1a-64 over the stream of cell ids (u32 each, XOR-then-multiply on the whole word) with 0xffffffff
+    appended after each particle."""
+    h = 0xcbf29ce484222325
+    M = (1 << 64) - 1
+    for i in range(len(cnt)):
+        for j in range(int(cnt[i])):
+            h = ((h ^ (int(ids[i, j]) & 0xffffffff)) * 0x100000001b3) & M
+        h = ((h ^ 0xffffffff) * 0x100000001b3) & M
+    return h

@@ -1,0 +1,263 @@
+"""ctypes binding of libfycuda.so (include/fycuda.h).  No CPU fallback."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+FIELD = dict(U=0, gradP=1, vGrad=2, divT=3, ddtU=4, uSourceDrag=5, alpha=6, uSource=7, uParticle=8, p=9, phi=10)
+_WIDTH = dict(U=3, gradP=3, vGrad=9, divT=3, ddtU=3, uSourceDrag=1, alpha=1, uSource=3, uParticle=3, p=1)
+
+
+class FyError(RuntimeError):
+    pass
+
+
+class _PatchDesc(C.Structure):
+    _fields_ = [("nFaces", C.c_int), ("faceCells", _ip), ("Sf", _dp), ("magSf", _dp), ("deltaCoeffs", _dp),
+                ("bcU", C.c_int), ("valueU", C.c_double * 3), ("bcP", C.c_int), ("valueP", C.c_double)]
+
+
+class _MeshDesc(C.Structure):
+    _fields_ = [("nCells", C.c_int), ("C", _dp), ("V", _dp), ("nInternalFaces", C.c_int), ("owner", _ip),
+                ("neighbour", _ip), ("Sf", _dp), ("magSf", _dp), ("weights", _dp), ("deltaCoeffs", _dp),
+                ("nPatches", C.c_int), ("patches", C.POINTER(_PatchDesc)), ("boxN", C.c_int * 3),
+                ("boxGeom", C.c_double * 6), ("bbox", C.c_double * 6)]
+
+
+def lib_path():
+    return os.path.join(_HERE, "libfycuda.so")
+
+
+_lib = None
+
+
+def lib():
+    """Loads libfycuda.so; raises FyError when it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.exists(p):
+        raise FyError("libfycuda.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'` "
+                      "or `make -C yade-openfoam-coupling_b200`); this engine has no CPU fallback")
+    L = C.CDLL(p)
+    H = C.c_void_p
+    L.fy_device_count.restype = C.c_int
+    L.fy_version.restype = C.c_char_p
+    L.fy_last_error.restype = C.c_char_p
+    L.fy_last_error.argtypes = [H]
+    L.fy_create.argtypes = [C.POINTER(_MeshDesc), C.c_int, C.POINTER(H)]
+    L.fy_destroy.argtypes = [H]
+    L.fy_set_properties.argtypes = [H, C.c_double, C.c_double, C.c_double, C.c_int]
+    L.fy_get_constants.argtypes = [H, _dp]
+    L.fy_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+    L.fy_host_free.argtypes = [C.c_void_p]
+    L.fy_bind_host_fields.argtypes = [H] + [_dp] * 9
+    L.fy_upload_field.argtypes = [H, C.c_int, _dp]
+    L.fy_download_field.argtypes = [H, C.c_int, _dp]
+    L.fy_device_field.argtypes = [H, C.c_int, C.POINTER(C.c_void_p)]
+    L.fy_locate.argtypes = [H, _dp, C.c_int, _ip, _ip]
+    L.fy_find_cell.argtypes = [H, _dp, C.c_int, _ip]
+    L.fy_coupling_begin.argtypes = [H, C.c_double]
+    L.fy_coupling_proc.argtypes = [H, _dp, C.c_int, _ip, _dp]
+    L.fy_coupling_end.argtypes = [H]
+    L.fy_set_particle_action.argtypes = [H, C.c_double, _dp, C.c_int, _ip, _dp]
+    L.fy_coupling_proc_device.argtypes = [H, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.fy_set_source_zero.argtypes = [H]
+    L.fy_get_last_lists.argtypes = [H, C.c_int, _ip, _ip, _dp]
+    L.fy_synchronize.argtypes = [H]
+    L.fy_set_profiling.argtypes = [H, C.c_int]
+    L.fy_get_phase_ms.argtypes = [H, _dp]
+    L.fy_launch_count.restype = C.c_longlong
+    L.fy_launch_count.argtypes = [H]
+    _lib = L
+    return L
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return None if a is None else a.ctypes.data_as(_ip)
+
+
+def _c64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def make_mesh_desc(mesh):
+    """Returns (desc, keepalive) for a dict from mesh.box_mesh()."""
+    keep = []
+
+    def d(a):
+        a = _c64(a)
+        keep.append(a)
+        return _d(a)
+
+    def i(a):
+        a = np.ascontiguousarray(a, dtype=np.int32)
+        keep.append(a)
+        return _i(a)
+
+    md = _MeshDesc()
+    md.nCells = int(mesh["nCells"])
+    md.C = d(mesh["C"])
+    md.V = d(mesh["V"])
+    md.nInternalFaces = int(mesh.get("nInternalFaces", 0))
+    if md.nInternalFaces > 0:
+        md.owner = i(mesh["owner"])
+        md.neighbour = i(mesh["neighbour"])
+        md.Sf = d(mesh["Sf"])
+        md.magSf = d(mesh["magSf"])
+        md.weights = d(mesh["weights"])
+        md.deltaCoeffs = d(mesh["deltaCoeffs"])
+    pl = mesh.get("patches", []) if md.nInternalFaces > 0 else []
+    md.nPatches = len(pl)
+    if pl:
+        arr = (_PatchDesc * len(pl))()
+        for n, p in enumerate(pl):
+            arr[n].nFaces = int(p["faceCells"].shape[0])
+            arr[n].faceCells = i(p["faceCells"])
+            arr[n].Sf = d(p["Sf"])
+            arr[n].magSf = d(p["magSf"])
+            arr[n].deltaCoeffs = d(p["deltaCoeffs"])
+            arr[n].bcU = int(p["bcU"])
+            arr[n].valueU = (C.c_double * 3)(*p["valueU"])
+            arr[n].bcP = int(p["bcP"])
+            arr[n].valueP = float(p["valueP"])
+        keep.append(arr)
+        md.patches = arr
+    md.boxN = (C.c_int * 3)(*[int(v) for v in mesh["boxN"]])
+    md.boxGeom = (C.c_double * 6)(*[float(v) for v in mesh["boxGeom"]])
+    md.bbox = (C.c_double * 6)(*[float(v) for v in mesh["bbox"]])
+    return md, keep
+
+
+class Engine:
+    """One fy_handle.  Mirrors the reference's operator surface (FoamYade.H:106-155):
+    set_properties ~ setScalarProperties, set_particle_action ~ setParticleAction,
+    set_source_zero ~ setSourceZero."""
+
+    def __init__(self, mesh, device=0):
+        self.L = lib()
+        self.mesh = mesh
+        self.N = int(mesh["nCells"])
+        md, self._keep = make_mesh_desc(mesh)
+        h = C.c_void_p()
+        rc = self.L.fy_create(C.byref(md), device, C.byref(h))
+        if rc != 0:
+            raise FyError("fy_create failed (%d): %s" % (rc, self.L.fy_last_error(None).decode()))
+        self.h = h
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise FyError("fycuda error %d: %s" % (rc, self.L.fy_last_error(self.h).decode()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.fy_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_properties(self, rhoP, rhoF, nu, gaussian):
+        self._ck(self.L.fy_set_properties(self.h, rhoP, rhoF, nu, int(gaussian)))
+        self.gaussian = bool(gaussian)
+
+    def constants(self):
+        out = np.empty(4)
+        self._ck(self.L.fy_get_constants(self.h, _d(out)))
+        return dict(interpRange=out[0], sigmaInterp=out[1], interpRangeCu=out[2], sigmaPi=out[3])
+
+    def upload(self, name, arr):
+        a = _c64(arr)
+        self._ck(self.L.fy_upload_field(self.h, FIELD[name], _d(a)))
+
+    def download(self, name, n=None):
+        if name == "phi":
+            out = np.empty(n, dtype=np.float64)
+        else:
+            w = _WIDTH[name]
+            out = np.empty((self.N, w) if w > 1 else (self.N,), dtype=np.float64)
+        self._ck(self.L.fy_download_field(self.h, FIELD[name], _d(out)))
+        return out
+
+    def device_field(self, name):
+        p = C.c_void_p()
+        self._ck(self.L.fy_device_field(self.h, FIELD[name], C.byref(p)))
+        return p.value
+
+    def locate(self, xyz):
+        xyz = _c64(xyz)
+        n = xyz.shape[0]
+        ids = np.empty((n, 12), dtype=np.int32)
+        cnt = np.empty(n, dtype=np.int32)
+        self._ck(self.L.fy_locate(self.h, _d(xyz), n, _i(ids), _i(cnt)))
+        return cnt, ids
+
+    def find_cell(self, xyz):
+        xyz = _c64(xyz)
+        n = xyz.shape[0]
+        cell = np.empty(n, dtype=np.int32)
+        self._ck(self.L.fy_find_cell(self.h, _d(xyz), n, _i(cell)))
+        return cell
+
+    def set_particle_action(self, dt, pdata, found=None, force=None):
+        pdata = _c64(pdata)
+        n = pdata.shape[0]
+        if found is None:
+            found = np.empty(n, dtype=np.int32)
+        if force is None:
+            force = np.empty((n, 6), dtype=np.float64)
+        self._ck(self.L.fy_set_particle_action(self.h, dt, _d(pdata), n, _i(found), _d(force)))
+        return found, force
+
+    def coupling_begin(self, dt):
+        self._ck(self.L.fy_coupling_begin(self.h, dt))
+
+    def coupling_proc(self, pdata):
+        pdata = _c64(pdata)
+        n = pdata.shape[0]
+        found = np.empty(n, dtype=np.int32)
+        force = np.empty((n, 6), dtype=np.float64)
+        self._ck(self.L.fy_coupling_proc(self.h, _d(pdata), n, _i(found), _d(force)))
+        return found, force
+
+    def coupling_end(self):
+        self._ck(self.L.fy_coupling_end(self.h))
+
+    def coupling_proc_device(self, d_pdata, n, d_found, d_force):
+        self._ck(self.L.fy_coupling_proc_device(self.h, d_pdata, n, d_found, d_force))
+
+    def set_source_zero(self):
+        self._ck(self.L.fy_set_source_zero(self.h))
+
+    def last_lists(self, n):
+        cnt = np.empty(n, dtype=np.int32)
+        ids = np.empty((n, 12), dtype=np.int32)
+        w = np.empty((n, 12), dtype=np.float64)
+        self._ck(self.L.fy_get_last_lists(self.h, n, _i(cnt), _i(ids), _d(w)))
+        return cnt, ids, w
+
+    def synchronize(self):
+        self._ck(self.L.fy_synchronize(self.h))
+
+    def set_profiling(self, on):
+        self._ck(self.L.fy_set_profiling(self.h, int(on)))
+
+    def phase_ms(self):
+        out = np.zeros(8)
+        self._ck(self.L.fy_get_phase_ms(self.h, _d(out)))
+        return out
+
+    def launch_count(self):
+        return int(self.L.fy_launch_count(self.h))

@@ -1,0 +1,475 @@
+// coupling.cu -- the particle half of Foam::FoamYade::setParticleAction as sm_100a kernels.
+//
+//   k_locate_gauss   meshTree::nnearestCellsRange / nnearest (meshTree.C:148-238) fused with
+//                    calcInterpWeightGaussian (FoamYade.C:293-316), the wire-record unpack of
+//                    locateAllParticles (FoamYade.C:187-225) and the per-cell accumulate of
+//                    buildCellPartList (FoamYade.C:261-290, here a dense atomic scatter instead of
+//                    the reference's quadratic list scan)
+//   k_void_fraction  setCellVolFraction (FoamYade.C:318-328)
+//   k_force_gauss    hydroDragForce + archimedesForce (FoamYade.C:354-389, 415-435)
+//   k_point_force    locatePt/findCell + stokesDragForce + stokesDragTorque (FoamYade.C:248-253, 437-453)
+//   k_source_zero    setSourceZero (FoamYade.C:556-566)
+//
+// All arithmetic is fp64 and written in the reference's own operation order; the library is built
+// with -fmad=false and the distance test of the tree descent additionally uses explicit
+// round-to-nearest intrinsics, because the strict `<` tests on d^2 decide which cells are returned
+// and the x86-64 reference build has no FMA contraction.
+#include <cmath>
+#include <cstdio>
+
+#include "fy_ctx.h"
+
+namespace {
+
+__device__ __forceinline__ FyKdNode ldNode(const FyKdNode* __restrict__ t, int i)
+{
+    // one 256-bit load (sm_100+): x y z | id pad
+    FyKdNode n;
+    unsigned long long a, b, c, d;
+    asm volatile("ld.global.nc.L1::evict_last.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(a), "=l"(b), "=l"(c), "=l"(d)
+                 : "l"(t + i));
+    n.x = __longlong_as_double((long long)a);
+    n.y = __longlong_as_double((long long)b);
+    n.z = __longlong_as_double((long long)c);
+    n.id = (int)(unsigned)(d & 0xffffffffull);
+    n.pad = 0;
+    return n;
+}
+
+__device__ __forceinline__ double dist2(double px, double py, double pz, const FyKdNode& n)
+{
+    // meshTree.C:54-64: dist = 0; for i: ds = p1[i]-p2[i]; dist += ds*ds   (no contraction)
+    const double dx = __dsub_rn(px, n.x), dy = __dsub_rn(py, n.y), dz = __dsub_rn(pz, n.z);
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+// The nearest-neighbour descent of meshTree.C:182-238 on the implicit tree, iteratively.
+// Every node visit that STRICTLY improves the best squared distance found so far (initially that of
+// the root, so the root itself never qualifies, MT.C:156,192) and lies within maxDist is an
+// "improvement"; the reference's bounded container ends up holding the nearest (= latest) <= 12 of
+// them in ascending distance.  ring/ringD keep the last 12; nImp counts all of them.
+struct Trail {
+    int id[FY_MAXLIST];
+    double d2[FY_MAXLIST];
+    int nImp;
+};
+
+__device__ __forceinline__ void kdDescend(const FyKdNode* __restrict__ tree, int nTree, double px, double py,
+                                          double pz, double maxDist, Trail& tr)
+{
+    tr.nImp = 0;
+    if (nTree <= 0) return;
+    int slo[40], shi[40];
+    double sdf2[40];
+    unsigned char sdep[40];
+    int sp = 0;
+
+    int lo = 0, hi = nTree, depth = 0;
+    double best = dist2(px, py, pz, ldNode(tree, nTree >> 1));     // MT.C:156
+    for (;;) {
+        if (lo < hi) {
+            const int md = lo + ((hi - lo) >> 1);
+            const FyKdNode nd = ldNode(tree, md);
+            const double d = dist2(px, py, pz, nd);
+            if (d < best) {                                         // MT.C:192 (and the re-tests at 217, 229)
+                best = d;
+                if (d < maxDist) {                                  // MT.C:195
+                    const int s = tr.nImp % FY_MAXLIST;
+                    tr.id[s] = nd.id;
+                    tr.d2[s] = d;
+                    tr.nImp++;
+                }
+            }
+            const int axis = depth % 3;
+            const double nc = axis == 0 ? nd.x : (axis == 1 ? nd.y : nd.z);
+            const double pc = axis == 0 ? px : (axis == 1 ? py : pz);
+            const double df = __dsub_rn(nc, pc);                    // MT.C:200
+            const double df2 = __dmul_rn(df, df);
+            int olo, ohi;
+            if (df > 0.0) { olo = md + 1; ohi = hi; hi = md; }      // next = left, other = right (MT.C:206-212)
+            else          { olo = lo; ohi = md; lo = md + 1; }
+            depth++;
+            if (olo < ohi) {
+                slo[sp] = olo; shi[sp] = ohi; sdf2[sp] = df2; sdep[sp] = (unsigned char)depth;
+                sp++;
+            }
+        } else {
+            bool got = false;
+            while (sp > 0) {
+                --sp;
+                if (sdf2[sp] < best) {                              // MT.C:225, tested after the near side returned
+                    lo = slo[sp]; hi = shi[sp]; depth = sdep[sp];
+                    got = true;
+                    break;
+                }
+            }
+            if (!got) break;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// parity hook: cell lists only
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_locate(const FyKdNode* __restrict__ tree, int nTree,
+                                                const double* __restrict__ xyz, int stride, int n, double maxDist,
+                                                int* __restrict__ ids, int* __restrict__ cnt)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const double px = xyz[(size_t)p * stride], py = xyz[(size_t)p * stride + 1], pz = xyz[(size_t)p * stride + 2];
+    Trail tr;
+    kdDescend(tree, nTree, px, py, pz, maxDist, tr);
+    const int k = tr.nImp < FY_MAXLIST ? tr.nImp : FY_MAXLIST;
+    for (int j = 0; j < FY_MAXLIST; ++j)
+        ids[(size_t)p * FY_MAXLIST + j] = j < k ? tr.id[(tr.nImp - 1 - j) % FY_MAXLIST] : -1;
+    cnt[p] = k;
+}
+
+__device__ __forceinline__ int boxCell(double x, double y, double z, int nx, int ny, int nz, double x0, double y0,
+                                       double z0, double hx, double hy, double hz)
+{
+    const double fi = floor((x - x0) / hx), fj = floor((y - y0) / hy), fk = floor((z - z0) / hz);
+    if (!(fi >= 0 && fi < nx && fj >= 0 && fj < ny && fk >= 0 && fk < nz)) return -1;
+    return (int)fi + nx * ((int)fj + ny * (int)fk);
+}
+
+__global__ void k_find_cell(const double* __restrict__ xyz, int stride, int n, int nx, int ny, int nz, double x0,
+                            double y0, double z0, double hx, double hy, double hz, int* __restrict__ cell)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    cell[p] = boxCell(xyz[(size_t)p * stride], xyz[(size_t)p * stride + 1], xyz[(size_t)p * stride + 2], nx, ny, nz,
+                      x0, y0, z0, hx, hy, hz);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gaussian branch, pass 1: locate + weights + per-cell accumulate
+// ---------------------------------------------------------------------------------------------
+struct GaussConst {
+    double maxDist;        // range^2 + 0.25 range^2                      (MT.C:155)
+    double twoSigmaSq;     // 2*pow(sigmaInterp, 2)                       (F.C:308)
+    double interpRangeCu;  // pow(interpRange, 3)                         (F.C:71)
+    double sigmaPi;        // 1/pow(2 pi sigma^2, 1.5)                    (F.C:72)
+};
+
+__global__ void __launch_bounds__(128)
+k_locate_gauss(const FyKdNode* __restrict__ tree, int nTree, const double* __restrict__ pdata, int n, GaussConst gc,
+               int serial, int* __restrict__ ids, int* __restrict__ cnt, double* __restrict__ wts,
+               int* __restrict__ found, double* __restrict__ pvolAcc, double* __restrict__ upAcc,
+               int* __restrict__ stamp)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const double* rec = pdata + (size_t)p * 10;
+    const double px = rec[0], py = rec[1], pz = rec[2];
+    Trail tr;
+    kdDescend(tree, nTree, px, py, pz, gc.maxDist, tr);
+    const int k = tr.nImp < FY_MAXLIST ? tr.nImp : FY_MAXLIST;
+    cnt[p] = k;
+    found[p] = k > 0 ? 1 : -1;                                       // F.C:204,222 / 141
+    if (k == 0) {
+        for (int j = 0; j < FY_MAXLIST; ++j) ids[(size_t)p * FY_MAXLIST + j] = -1;
+        return;
+    }
+    // weights (F.C:301-314): the squared distance is the same number the descent computed
+    // ((C-p)^2 == (p-C)^2 term by term, same summation order), so no cell-centre gather is needed.
+    double w[FY_MAXLIST];
+    int id[FY_MAXLIST];
+    double allwt = 0.0;
+    for (int j = 0; j < k; ++j) {
+        const int s = (tr.nImp - 1 - j) % FY_MAXLIST;
+        id[j] = tr.id[s];
+        const double wj = exp(-tr.d2[s] / gc.twoSigmaSq) * gc.interpRangeCu * gc.sigmaPi;
+        w[j] = wj;
+        allwt += wj;
+    }
+    const double vx = rec[3], vy = rec[4], vz = rec[5];
+    const double dia = 2 * rec[9];                                   // F.C:219
+    const double vol = M_PI * pow(dia, 3.0) / 6.0;                   // F.H:36
+    for (int j = 0; j < FY_MAXLIST; ++j) {
+        if (j < k) {
+            const double wj = w[j] / allwt;                          // F.C:313
+            ids[(size_t)p * FY_MAXLIST + j] = id[j];
+            wts[(size_t)p * FY_MAXLIST + j] = wj;
+            const int c = id[j];
+            // F.C:271-272 / 278-279: pVol*weight ; (linearVelocity*weight)*pVol
+            atomicAdd(&pvolAcc[c], vol * wj);
+            atomicAdd(&upAcc[3 * (size_t)c], vx * wj * vol);
+            atomicAdd(&upAcc[3 * (size_t)c + 1], vy * wj * vol);
+            atomicAdd(&upAcc[3 * (size_t)c + 2], vz * wj * vol);
+            stamp[c] = serial;
+        } else {
+            ids[(size_t)p * FY_MAXLIST + j] = -1;
+            wts[(size_t)p * FY_MAXLIST + j] = 0.0;
+        }
+    }
+}
+
+// pass 2: setCellVolFraction on the cells this proc touched (F.C:318-328); consumes and clears the
+// accumulators so that the next proc starts from zero.
+__global__ void k_void_fraction(int nCells, int serial, const int* __restrict__ stamp, double* __restrict__ pvolAcc,
+                                double* __restrict__ upAcc, const double* __restrict__ V, double* __restrict__ alpha,
+                                double* __restrict__ uParticle)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nCells) return;
+    if (stamp[c] != serial) return;
+    const double v = V[c];
+    const double pvolC = 1.0 - (pvolAcc[c] / v);
+    alpha[c] = (pvolC > 0.10) ? pvolC : 0.10;
+    uParticle[3 * (size_t)c] = upAcc[3 * (size_t)c] / v;
+    uParticle[3 * (size_t)c + 1] = upAcc[3 * (size_t)c + 1] / v;
+    uParticle[3 * (size_t)c + 2] = upAcc[3 * (size_t)c + 2] / v;
+    pvolAcc[c] = 0.0;
+    upAcc[3 * (size_t)c] = 0.0;
+    upAcc[3 * (size_t)c + 1] = 0.0;
+    upAcc[3 * (size_t)c + 2] = 0.0;
+}
+
+// pass 3: hydroDragForce + archimedesForce per particle, reaction scattered to the cells.
+struct ForceConst {
+    double rhoF, nu, small;
+};
+
+__global__ void __launch_bounds__(128)
+k_force_gauss(const double* __restrict__ pdata, int n, const int* __restrict__ ids, const int* __restrict__ cnt,
+              const double* __restrict__ wts, ForceConst fc, const double* __restrict__ U,
+              const double* __restrict__ alpha, const double* __restrict__ uParticle,
+              const double* __restrict__ gradP, const double* __restrict__ divT, const double* __restrict__ V,
+              double* __restrict__ uSourceDrag, double* __restrict__ uSource, double* __restrict__ force)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    double* F = force + (size_t)p * 6;
+    const int k = cnt[p];
+    if (k <= 0) {
+        F[0] = F[1] = F[2] = F[3] = F[4] = F[5] = 0.0;                // F.C:142 zero-initialised buffer
+        return;
+    }
+    const double* rec = pdata + (size_t)p * 10;
+    const double vx = rec[3], vy = rec[4], vz = rec[5];
+    const double dia = 2 * rec[9];
+    const double vol = M_PI * pow(dia, 3.0) / 6.0;
+    const double rhoF = fc.rhoF, nu = fc.nu;
+
+    int id[FY_MAXLIST];
+    double w[FY_MAXLIST];
+    // ---- hydroDragForce gather (F.C:358-365) and archimedesForce gather (F.C:416-424)
+    double ufx = 0, ufy = 0, ufz = 0, alpha_f = 0, pv = 0;
+    double dtx = 0, dty = 0, dtz = 0, pgx = 0, pgy = 0, pgz = 0;
+    const double twoNu = 2.0 * nu;
+    for (int j = 0; j < k; ++j) {
+        const int c = ids[(size_t)p * FY_MAXLIST + j];
+        const double wj = wts[(size_t)p * FY_MAXLIST + j];
+        id[j] = c;
+        w[j] = wj;
+        ufx += U[3 * (size_t)c] * wj;
+        ufy += U[3 * (size_t)c + 1] * wj;
+        ufz += U[3 * (size_t)c + 2] * wj;
+        alpha_f += alpha[c] * wj;
+        pv += vol * wj;
+        dtx = dtx + (twoNu * divT[3 * (size_t)c] * wj * rhoF);
+        dty = dty + (twoNu * divT[3 * (size_t)c + 1] * wj * rhoF);
+        dtz = dtz + (twoNu * divT[3 * (size_t)c + 2] * wj * rhoF);
+        pgx = pgx + (gradP[3 * (size_t)c] * wj);
+        pgy = pgy + (gradP[3 * (size_t)c + 1] * wj);
+        pgz = pgz + (gradP[3 * (size_t)c + 2] * wj);
+    }
+    const double alpha_p = 1 - alpha_f;
+    const double urx = ufx - vx, ury = ufy - vy, urz = ufz - vz;
+    const double magUR = sqrt(urx * urx + ury * ury + urz * urz);
+    const double Re = fc.small + ((magUR * dia) / nu);                                     // F.C:370
+    const double cd = Re < 1000 ? (24 / (Re)) * (1 + (0.15 * pow(Re, 0.687))) : 0.44;      // F.C:371
+    double coeff;
+    if (alpha_f > 0.8) {
+        coeff = 0.75 * cd * alpha_f * alpha_p * rhoF * magUR * pow(alpha_f, -2.65);        // F.C:374
+    } else {
+        const double cf1 = 150 * ((alpha_p * alpha_p) / alpha_f) * ((nu * rhoF) / (dia * dia));
+        const double cf2 = 1.75 * alpha_p * rhoF * (1 / dia) * magUR;
+        coeff = cf1 + cf2;
+    }
+    const double pc = pv * coeff, ooap = 1 / (alpha_p);
+    double Fx = pc * urx * ooap, Fy = pc * ury * ooap, Fz = pc * urz * ooap;               // F.C:381
+    // archimedes (F.C:426): f = pv*(-pg + divt)
+    const double ax = pv * (-pgx + dtx), ay = pv * (-pgy + dty), az = pv * (-pgz + dtz);
+    Fx += ax; Fy += ay; Fz += az;
+    F[0] = Fx; F[1] = Fy; F[2] = Fz;
+    F[3] = 0.0; F[4] = 0.0; F[5] = 0.0;                              // torque disabled on this branch (F.C:618)
+
+    // ---- scatter (F.C:384-387 and 429-434); the two uSource contributions of a pair are summed
+    //      before the atomic so that each cell component sees one RED per pair
+    const double oorho = 1 / rhoF;
+    for (int j = 0; j < k; ++j) {
+        const int c = id[j];
+        const double wj = w[j];
+        const double mcw = -coeff * wj;
+        atomicAdd(&uSourceDrag[c], mcw * oorho);
+        const double ooCellVol = 1. / (V[c] * rhoF);
+        const double sx = (mcw * uParticle[3 * (size_t)c]) / rhoF + (-ax * wj * ooCellVol);
+        const double sy = (mcw * uParticle[3 * (size_t)c + 1]) / rhoF + (-ay * wj * ooCellVol);
+        const double sz = (mcw * uParticle[3 * (size_t)c + 2]) / rhoF + (-az * wj * ooCellVol);
+        atomicAdd(&uSource[3 * (size_t)c], sx);
+        atomicAdd(&uSource[3 * (size_t)c + 1], sy);
+        atomicAdd(&uSource[3 * (size_t)c + 2], sz);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// point-force branch: findCell + Stokes drag + Stokes torque, one cell per particle
+// ---------------------------------------------------------------------------------------------
+struct BoxConst {
+    int nx, ny, nz;
+    double x0, y0, z0, hx, hy, hz;
+};
+
+__global__ void __launch_bounds__(256)
+k_point_force(const double* __restrict__ pdata, int n, BoxConst b, ForceConst fc, const double* __restrict__ U,
+              const double* __restrict__ vGrad, const double* __restrict__ V, double* __restrict__ uSource,
+              int* __restrict__ cellOut, int* __restrict__ found, double* __restrict__ force)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const double* rec = pdata + (size_t)p * 10;
+    double* F = force + (size_t)p * 6;
+    const int c = boxCell(rec[0], rec[1], rec[2], b.nx, b.ny, b.nz, b.x0, b.y0, b.z0, b.hx, b.hy, b.hz);
+    cellOut[p] = c;
+    if (c < 0) {
+        found[p] = -1;
+        F[0] = F[1] = F[2] = F[3] = F[4] = F[5] = 0.0;
+        return;
+    }
+    found[p] = 1;
+    const double dia = 2 * rec[9];
+    const double rhoF = fc.rhoF, nu = fc.nu;
+    // stokesDragForce (F.C:437-444)
+    const double coeff = 3 * M_PI * (dia) * nu * rhoF;
+    const double ooCellVol = 1. / (V[c] * rhoF);
+    const double Fx = coeff * (U[3 * (size_t)c] - rec[3]);
+    const double Fy = coeff * (U[3 * (size_t)c + 1] - rec[4]);
+    const double Fz = coeff * (U[3 * (size_t)c + 2] - rec[5]);
+    const double m = -1 * ooCellVol;
+    atomicAdd(&uSource[3 * (size_t)c], m * Fx);
+    atomicAdd(&uSource[3 * (size_t)c + 1], m * Fy);
+    atomicAdd(&uSource[3 * (size_t)c + 2], m * Fz);
+    // stokesDragTorque (F.C:446-453): tensor row-major xx xy xz yx yy yz zx zy zz
+    const double* g = vGrad + 9 * (size_t)c;
+    const double s1 = g[7] - g[5], s2 = g[6] - g[2], s3 = g[3] - g[1];
+    const double tc = M_PI * (pow(dia, 3.0));
+    F[0] = Fx; F[1] = Fy; F[2] = Fz;
+    F[3] = tc * (s1 - rec[6]) * nu * rhoF;
+    F[4] = tc * (s2 - rec[7]) * nu * rhoF;
+    F[5] = tc * (s3 - rec[8]) * nu * rhoF;
+}
+
+__global__ void k_source_zero(int nCells, int gaussian, double* __restrict__ uSource, double* __restrict__ alpha,
+                              double* __restrict__ uSourceDrag, double* __restrict__ uParticle)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;     // one thread per scalar of the [N][3] fields
+    if (i >= 3 * nCells) return;
+    uSource[i] = 0.0;
+    if (gaussian) {
+        uParticle[i] = 0.0;
+        if (i < nCells) {
+            alpha[i] = 1.0;
+            uSourceDrag[i] = 0.0;
+        }
+    }
+}
+
+__global__ void k_fill(double* __restrict__ a, size_t n, double v)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = v;
+}
+
+}  // namespace
+
+int fyLaunchLocate(fy_ctx* h, const double* d_xyz, int stride, int n, int* d_ids, int* d_cnt)
+{
+    if (n <= 0) return FY_OK;
+    k_locate<<<fyGrid(n, 128), 128, 0, h->stream>>>(h->dTree, h->nTree, d_xyz, stride, n, h->maxDist, d_ids, d_cnt);
+    FY_CHECK_LAUNCH();
+    return FY_OK;
+}
+
+int fyLaunchFindCell(fy_ctx* h, const double* d_xyz, int stride, int n, int* d_cell)
+{
+    if (n <= 0) return FY_OK;
+    k_find_cell<<<fyGrid(n, 256), 256, 0, h->stream>>>(d_xyz, stride, n, h->boxN[0], h->boxN[1], h->boxN[2],
+                                                      h->boxGeom[0], h->boxGeom[1], h->boxGeom[2], h->boxGeom[3],
+                                                      h->boxGeom[4], h->boxGeom[5], d_cell);
+    FY_CHECK_LAUNCH();
+    return FY_OK;
+}
+
+// One YadeProc's worth of FoamYade.C:612-628 on device-resident buffers.
+int fyCouplingProcDevice(fy_ctx* h, const double* d_pdata, int n, int* d_found, double* d_force)
+{
+    if (!h->propsSet) { h->err = "fy_set_properties must be called first"; return FY_ERR_INVALID; }
+    h->lastN = n;
+    if (n <= 0) return FY_OK;
+    const ForceConst fc{h->rhoF, h->nu, 1e-09};                      // F.H:67 `small`
+    const bool prof = h->profiling;
+    if (h->gaussian) {
+        int rc;
+        if ((rc = fyReserve(h, h->dIds, (size_t)n * FY_MAXLIST))) return rc;
+        if ((rc = fyReserve(h, h->dCnt, (size_t)n))) return rc;
+        if ((rc = fyReserve(h, h->dW, (size_t)n * FY_MAXLIST))) return rc;
+        h->procSerial++;
+        const GaussConst gc{h->maxDist, 2 * std::pow(h->sigmaInterp, 2), h->interpRangeCu, h->sigmaPi};
+        if (prof) cudaEventRecord(h->ev[1], h->stream);
+        k_locate_gauss<<<fyGrid(n, 128), 128, 0, h->stream>>>(h->dTree, h->nTree, d_pdata, n, gc, h->procSerial,
+                                                              h->dIds.p, h->dCnt.p, h->dW.p, d_found, h->dPvol,
+                                                              h->dUpAcc, h->dStamp);
+        FY_CHECK_LAUNCH();
+        if (prof) cudaEventRecord(h->ev[2], h->stream);
+        k_void_fraction<<<fyGrid(h->nCells, 256), 256, 0, h->stream>>>(h->nCells, h->procSerial, h->dStamp, h->dPvol,
+                                                                       h->dUpAcc, h->dV, h->dField[FY_F_ALPHA],
+                                                                       h->dField[FY_F_UPARTICLE]);
+        FY_CHECK_LAUNCH();
+        if (prof) cudaEventRecord(h->ev[3], h->stream);
+        k_force_gauss<<<fyGrid(n, 128), 128, 0, h->stream>>>(
+            d_pdata, n, h->dIds.p, h->dCnt.p, h->dW.p, fc, h->dField[FY_F_U], h->dField[FY_F_ALPHA],
+            h->dField[FY_F_UPARTICLE], h->dField[FY_F_GRADP], h->dField[FY_F_DIVT], h->dV,
+            h->dField[FY_F_USOURCEDRAG], h->dField[FY_F_USOURCE], d_force);
+        FY_CHECK_LAUNCH();
+        if (prof) cudaEventRecord(h->ev[4], h->stream);
+    } else {
+        if (h->boxN[0] <= 0) { h->err = "point-force mode needs the hex-box findCell (mesh.boxN)"; return FY_ERR_UNSUPPORTED; }
+        int rc;
+        if ((rc = fyReserve(h, h->dCell, (size_t)n))) return rc;
+        const BoxConst b{h->boxN[0], h->boxN[1], h->boxN[2], h->boxGeom[0], h->boxGeom[1], h->boxGeom[2],
+                         h->boxGeom[3], h->boxGeom[4], h->boxGeom[5]};
+        if (prof) { cudaEventRecord(h->ev[1], h->stream); cudaEventRecord(h->ev[2], h->stream); cudaEventRecord(h->ev[3], h->stream); }
+        k_point_force<<<fyGrid(n, 256), 256, 0, h->stream>>>(d_pdata, n, b, fc, h->dField[FY_F_U],
+                                                            h->dField[FY_F_VGRAD], h->dV, h->dField[FY_F_USOURCE],
+                                                            h->dCell.p, d_found, d_force);
+        FY_CHECK_LAUNCH();
+        if (prof) cudaEventRecord(h->ev[4], h->stream);
+    }
+    return FY_OK;
+}
+
+int fySourceZeroDevice(fy_ctx* h)
+{
+    k_source_zero<<<fyGrid(3LL * h->nCells, 256), 256, 0, h->stream>>>(h->nCells, h->gaussian ? 1 : 0,
+                                                                      h->dField[FY_F_USOURCE], h->dField[FY_F_ALPHA],
+                                                                      h->dField[FY_F_USOURCEDRAG],
+                                                                      h->dField[FY_F_UPARTICLE]);
+    FY_CHECK_LAUNCH();
+    return FY_OK;
+}
+
+// initFields (F.C:56-73): sources zero; alpha = 1 in BOTH modes (F.C:68)
+int fyInitCouplingFields(fy_ctx* h)
+{
+    const size_t N = (size_t)h->nCells;
+    FY_CUDA(cudaMemsetAsync(h->dField[FY_F_USOURCE], 0, 3 * N * sizeof(double), h->stream));
+    FY_CUDA(cudaMemsetAsync(h->dField[FY_F_UPARTICLE], 0, 3 * N * sizeof(double), h->stream));
+    FY_CUDA(cudaMemsetAsync(h->dField[FY_F_USOURCEDRAG], 0, N * sizeof(double), h->stream));
+    k_fill<<<fyGrid((long long)N, 256), 256, 0, h->stream>>>(h->dField[FY_F_ALPHA], N, 1.0);
+    FY_CHECK_LAUNCH();
+    return FY_OK;
+}
