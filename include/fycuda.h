@@ -190,6 +190,10 @@ int fy_synchronize(fy_handle h);
  * Only recorded when profiling is on (fy_set_profiling(h, 1)); synchronises.                        */
 int fy_set_profiling(fy_handle h, int on);
 int fy_get_phase_ms(fy_handle h, double out[8]);
+/* Stopwatch on the handle's own stream (CUDA events): bench.py brackets its timed region with these,
+ * because events recorded on another stream would not see this handle's kernels.  stop synchronises. */
+int fy_timer_start(fy_handle h);
+int fy_timer_stop(fy_handle h, double* ms);
 /* Kernel launches issued by this handle since creation (for bench.py's gpu_launches). */
 long long fy_launch_count(fy_handle h);
 

@@ -253,7 +253,9 @@ void* ref_create(int nCells, const double* C, const double* V, int nPoints, cons
     r->uSource.setSize(nCells); r->uParticle.setSize(nCells); r->vGrad.setSize(nCells);
     r->uSourceDrag.setSize(nCells); r->alpha.setSize(nCells);
 
+    const bool keepLogging = g_peer.logging;     // ref_set_logging(1) before ref_create records the ctor's sends
     g_peer = Peer();
+    g_peer.logging = keepLogging;
     g_peer.nYade = nYade;
     g_peer.clearStep();
     // `bool serialYade` (F.H:91) is only ever set to true (F.C:31): give the object zeroed storage so

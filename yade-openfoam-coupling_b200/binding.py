@@ -72,6 +72,8 @@ def lib():
     L.fy_synchronize.argtypes = [H]
     L.fy_set_profiling.argtypes = [H, C.c_int]
     L.fy_get_phase_ms.argtypes = [H, _dp]
+    L.fy_timer_start.argtypes = [H]
+    L.fy_timer_stop.argtypes = [H, _dp]
     L.fy_launch_count.restype = C.c_longlong
     L.fy_launch_count.argtypes = [H]
     _lib = L
@@ -258,6 +260,14 @@ class Engine:
         out = np.zeros(8)
         self._ck(self.L.fy_get_phase_ms(self.h, _d(out)))
         return out
+
+    def timer_start(self):
+        self._ck(self.L.fy_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._ck(self.L.fy_timer_stop(self.h, C.byref(ms)))
+        return ms.value
 
     def launch_count(self):
         return int(self.L.fy_launch_count(self.h))

@@ -419,6 +419,22 @@ int fy_get_phase_ms(fy_handle h, double out[8])
     for (int i = 0; i < 8; ++i) out[i] = h->phaseMs[i];
     return FY_OK;
 }
+int fy_timer_start(fy_handle h)
+{
+    if (!h) return FY_ERR_INVALID;
+    FY_CUDA(cudaEventRecord(h->ev[6], h->stream));
+    return FY_OK;
+}
+int fy_timer_stop(fy_handle h, double* ms)
+{
+    if (!h || !ms) return FY_ERR_INVALID;
+    FY_CUDA(cudaEventRecord(h->ev[7], h->stream));
+    FY_CUDA(cudaEventSynchronize(h->ev[7]));
+    float f = 0;
+    FY_CUDA(cudaEventElapsedTime(&f, h->ev[6], h->ev[7]));
+    *ms = f;
+    return FY_OK;
+}
 long long fy_launch_count(fy_handle h) { return h ? h->launches : 0; }
 
 }  // extern "C"
