@@ -63,9 +63,9 @@ def lib():
     L.fy_locate.argtypes = [H, _dp, C.c_int, _ip, _ip]
     L.fy_find_cell.argtypes = [H, _dp, C.c_int, _ip]
     L.fy_coupling_begin.argtypes = [H, C.c_double]
-    L.fy_coupling_proc.argtypes = [H, _dp, C.c_int, _ip, _dp]
+    L.fy_coupling_proc.argtypes = [H, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.fy_coupling_end.argtypes = [H]
-    L.fy_set_particle_action.argtypes = [H, C.c_double, _dp, C.c_int, _ip, _dp]
+    L.fy_set_particle_action.argtypes = [H, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.fy_coupling_proc_device.argtypes = [H, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.fy_set_source_zero.argtypes = [H]
     L.fy_get_last_lists.argtypes = [H, C.c_int, _ip, _ip, _dp]
@@ -220,7 +220,7 @@ class Engine:
             found = np.empty(n, dtype=np.int32)
         if force is None:
             force = np.empty((n, 6), dtype=np.float64)
-        self._ck(self.L.fy_set_particle_action(self.h, dt, _d(pdata), n, _i(found), _d(force)))
+        self._ck(self.L.fy_set_particle_action(self.h, dt, pdata.ctypes.data, n, found.ctypes.data, force.ctypes.data))
         return found, force
 
     def coupling_begin(self, dt):
@@ -231,7 +231,7 @@ class Engine:
         n = pdata.shape[0]
         found = np.empty(n, dtype=np.int32)
         force = np.empty((n, 6), dtype=np.float64)
-        self._ck(self.L.fy_coupling_proc(self.h, _d(pdata), n, _i(found), _d(force)))
+        self._ck(self.L.fy_coupling_proc(self.h, pdata.ctypes.data, n, found.ctypes.data, force.ctypes.data))
         return found, force
 
     def coupling_end(self):
