@@ -1,0 +1,868 @@
+// oracle/fv_oracle.cc -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+//
+// CPU restatement ("port") of the fluid half of the reference's hot path:
+//   icoFoamYade/icoFoamYade.C:65-149     (PISO time step)
+//   pimpleFoamYade/pimpleFoamYade.C:60-114, UcEqn.H, pEqn.H, CourantNo.H, continuityErrs.H
+// The arithmetic of every fvm:: / fvc:: / solve call in those files belongs to OpenFOAM-6
+// (README.md:17), a third-party dependency that is NOT under /root/reference and is not installed
+// here, so each operator below restates OpenFOAM-6's published algorithm -- plain face loops over
+// LDU addressing, in OpenFOAM's own loop order -- and cites the reference call site it serves.
+// Case settings (schemes / solvers / tolerances) are not in the reference either; this file pins
+// the stock OpenFOAM-6 cavity set: ddt Euler; grad, div, laplacian Gauss linear (orthogonal
+// correction = none on a hex box); interpolate linear; p: PCG + DIC, U: smoothSolver symGaussSeidel.
+//
+// PARITY STATUS: the reference holds no tests or golden vectors for this half ("parity unpinned" at
+// the OpenFOAM boundary).  What pins this file instead is the solver log of the
+// stock OpenFOAM cavity tutorial (20x20x1 cells, first time step), see tests/test_fv_oracle.py.
+//
+// Build: make -C oracle oracle  ->  oracle/_build/liboracle.so  (-O2 -ffp-contract=off: the x86-64
+// wmake build of OpenFOAM has no FMA contraction).
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace
+{
+typedef std::vector<double> dvec;
+typedef std::vector<int> ivec;
+
+enum { BC_FIXED_VALUE = 0, BC_ZERO_GRADIENT = 1, BC_EMPTY = 2 };
+enum { PRECOND_DIC = 0, PRECOND_DIAGONAL = 1, PRECOND_NONE = 2 };
+
+const double SMALL = 1e-15;     // OpenFOAM `small` (double precision build)
+const double VSMALL = 1e-300;   // OpenFOAM `vSmall`
+
+struct Patch
+{
+    int start = 0, n = 0;       // range in the concatenated boundary-face arrays
+    int bcU = 0, bcP = 0;
+    double valueU[3] = {0, 0, 0};
+    double valueP = 0;
+};
+
+struct Mesh
+{
+    int nCells = 0, nFaces = 0, nB = 0;
+    dvec V;
+    ivec l, u;                  // owner ("lower") / neighbour ("upper") of internal faces
+    dvec Sf, magSf, w, dc;      // [Fi][3], [Fi], linear weights, deltaCoeffs
+    std::vector<Patch> patches;
+    ivec bCell;                 // [nB] faceCells
+    dvec bSf, bMagSf, bDc;      // [nB][3], [nB], [nB]
+    ivec ownStart;              // [N+1]
+    bool validCmpt[3] = {true, true, true};   // false for the direction "empty" patches remove
+};
+
+struct SolverPerf
+{
+    double initialResidual = 0, finalResidual = 0;
+    int nIterations = 0;
+};
+
+// ---------------------------------------------------------------------------------------------
+// lduMatrix primitives [OF-6 lduMatrixATmul.C / lduMatrixOperations.C]
+// ---------------------------------------------------------------------------------------------
+// Amul: Apsi = diag*psi; per face: Apsi[u] += lower*psi[l]; Apsi[l] += upper*psi[u]
+void Amul(const Mesh& m, const dvec& diag, const dvec& lower, const dvec& upper, const double* psi, double* Apsi)
+{
+    for (int c = 0; c < m.nCells; ++c) Apsi[c] = diag[c]*psi[c];
+    for (int f = 0; f < m.nFaces; ++f) {
+        Apsi[m.u[f]] += lower[f]*psi[m.l[f]];
+        Apsi[m.l[f]] += upper[f]*psi[m.u[f]];
+    }
+}
+
+// sumA: diag + sum of off-diagonals of the row
+void sumA(const Mesh& m, const dvec& diag, const dvec& lower, const dvec& upper, double* s)
+{
+    for (int c = 0; c < m.nCells; ++c) s[c] = diag[c];
+    for (int f = 0; f < m.nFaces; ++f) {
+        s[m.u[f]] += lower[f];
+        s[m.l[f]] += upper[f];
+    }
+}
+
+// residual: rA = source - diag*psi; per face: rA[u] -= lower*psi[l]; rA[l] -= upper*psi[u]
+void residual(const Mesh& m, const dvec& diag, const dvec& lower, const dvec& upper, const double* psi,
+              const double* source, double* rA)
+{
+    for (int c = 0; c < m.nCells; ++c) rA[c] = source[c] - diag[c]*psi[c];
+    for (int f = 0; f < m.nFaces; ++f) {
+        rA[m.u[f]] -= lower[f]*psi[m.l[f]];
+        rA[m.l[f]] -= upper[f]*psi[m.u[f]];
+    }
+}
+
+// negSumDiag: Diag[l] -= Lower; Diag[u] -= Upper, face order
+void negSumDiag(const Mesh& m, const dvec& lower, const dvec& upper, dvec& diag)
+{
+    diag.assign(m.nCells, 0.0);
+    for (int f = 0; f < m.nFaces; ++f) {
+        diag[m.l[f]] -= lower[f];
+        diag[m.u[f]] -= upper[f];
+    }
+}
+
+double sumMag(const double* a, int n)
+{
+    double s = 0;
+    for (int i = 0; i < n; ++i) s += std::fabs(a[i]);
+    return s;
+}
+double sumProd(const double* a, const double* b, int n)
+{
+    double s = 0;
+    for (int i = 0; i < n; ++i) s += a[i]*b[i];
+    return s;
+}
+
+// lduMatrix::solver::normFactor [OF-6 lduMatrixSolver.C]:
+//   tmp = sumA * gAverage(psi);  return gSum(mag(Apsi - tmp) + mag(source - tmp)) + 1e-20
+double normFactor(const Mesh& m, const dvec& diag, const dvec& lower, const dvec& upper, const double* psi,
+                  const double* source, const double* Apsi)
+{
+    dvec tmp(m.nCells);
+    sumA(m, diag, lower, upper, tmp.data());
+    double avg = 0;
+    for (int c = 0; c < m.nCells; ++c) avg += psi[c];
+    avg /= m.nCells;
+    double s = 0;
+    for (int c = 0; c < m.nCells; ++c) {
+        const double t = tmp[c]*avg;
+        s += std::fabs(Apsi[c] - t) + std::fabs(source[c] - t);
+    }
+    return s + 1e-20;
+}
+
+bool checkConvergence(const SolverPerf& sp, double tol, double relTol)
+{
+    return sp.finalResidual < tol || (relTol > 1e-20 && sp.finalResidual < relTol*sp.initialResidual);
+}
+
+// ---------------------------------------------------------------------------------------------
+// PCG [OF-6 PCG.C] with DIC [OF-6 DICPreconditioner.C] / diagonal / no preconditioner.
+// Serves pEqn.solve (icoFoamYade.C:125, pimpleFoamYade/pEqn.H:35).
+// ---------------------------------------------------------------------------------------------
+void dicReciprocalD(const Mesh& m, const dvec& diag, const dvec& upper, dvec& rD)
+{
+    rD = diag;
+    for (int f = 0; f < m.nFaces; ++f) rD[m.u[f]] -= upper[f]*upper[f]/rD[m.l[f]];
+    for (int c = 0; c < m.nCells; ++c) rD[c] = 1.0/rD[c];
+}
+
+void dicPrecondition(const Mesh& m, const dvec& upper, const dvec& rD, const double* rA, double* wA)
+{
+    for (int c = 0; c < m.nCells; ++c) wA[c] = rD[c]*rA[c];
+    for (int f = 0; f < m.nFaces; ++f) wA[m.u[f]] -= rD[m.u[f]]*upper[f]*wA[m.l[f]];
+    for (int f = m.nFaces - 1; f >= 0; --f) wA[m.l[f]] -= rD[m.l[f]]*upper[f]*wA[m.u[f]];
+}
+
+SolverPerf pcgSolve(const Mesh& m, const dvec& diag, const dvec& upper, const dvec& source, double* psi, double tol,
+                    double relTol, int maxIter, int precond)
+{
+    const int n = m.nCells;
+    SolverPerf sp;
+    dvec pA(n), wA(n), rA(n);
+    double wArA = 1e20, wArAold = wArA;     // solverPerformance::great_
+    Amul(m, diag, upper, upper, psi, wA.data());
+    for (int c = 0; c < n; ++c) rA[c] = source[c] - wA[c];
+    const double nf = normFactor(m, diag, upper, upper, psi, source.data(), wA.data());
+    sp.initialResidual = sumMag(rA.data(), n)/nf;
+    sp.finalResidual = sp.initialResidual;
+    if (!checkConvergence(sp, tol, relTol)) {
+        dvec rD;
+        if (precond == PRECOND_DIC) dicReciprocalD(m, diag, upper, rD);
+        else if (precond == PRECOND_DIAGONAL) { rD.resize(n); for (int c = 0; c < n; ++c) rD[c] = 1.0/diag[c]; }
+        do {
+            wArAold = wArA;
+            if (precond == PRECOND_DIC) dicPrecondition(m, upper, rD, rA.data(), wA.data());
+            else if (precond == PRECOND_DIAGONAL) { for (int c = 0; c < n; ++c) wA[c] = rD[c]*rA[c]; }
+            else { for (int c = 0; c < n; ++c) wA[c] = rA[c]; }
+            wArA = sumProd(wA.data(), rA.data(), n);
+            if (sp.nIterations == 0) {
+                for (int c = 0; c < n; ++c) pA[c] = wA[c];
+            } else {
+                const double beta = wArA/wArAold;
+                for (int c = 0; c < n; ++c) pA[c] = wA[c] + beta*pA[c];
+            }
+            Amul(m, diag, upper, upper, pA.data(), wA.data());
+            const double wApA = sumProd(wA.data(), pA.data(), n);
+            if (std::fabs(wApA)/nf < VSMALL) break;       // checkSingularity
+            const double alpha = wArA/wApA;
+            for (int c = 0; c < n; ++c) {
+                psi[c] += alpha*pA[c];
+                rA[c] -= alpha*wA[c];
+            }
+            sp.finalResidual = sumMag(rA.data(), n)/nf;
+        } while (sp.nIterations++ < maxIter && !checkConvergence(sp, tol, relTol));
+    }
+    return sp;
+}
+
+// ---------------------------------------------------------------------------------------------
+// smoothSolver + symGaussSeidel [OF-6 smoothSolver.C, symGaussSeidelSmoother.C], nSweeps = 1.
+// Serves solve(UEqn == -grad p) (icoFoamYade.C:93, pimpleFoamYade/UcEqn.H:24), one component at a time.
+// ---------------------------------------------------------------------------------------------
+void symGaussSeidelSweep(const Mesh& m, const dvec& diag, const dvec& lower, const dvec& upper, const double* source,
+                         double* psi)
+{
+    const int n = m.nCells;
+    dvec bPrime(source, source + n);
+    for (int c = 0; c < n; ++c) {
+        double psii = bPrime[c];
+        for (int f = m.ownStart[c]; f < m.ownStart[c + 1]; ++f) psii -= upper[f]*psi[m.u[f]];
+        psii /= diag[c];
+        for (int f = m.ownStart[c]; f < m.ownStart[c + 1]; ++f) bPrime[m.u[f]] -= lower[f]*psii;
+        psi[c] = psii;
+    }
+    for (int c = n - 1; c >= 0; --c) {
+        double psii = bPrime[c];
+        for (int f = m.ownStart[c]; f < m.ownStart[c + 1]; ++f) psii -= upper[f]*psi[m.u[f]];
+        psii /= diag[c];
+        for (int f = m.ownStart[c]; f < m.ownStart[c + 1]; ++f) bPrime[m.u[f]] -= lower[f]*psii;
+        psi[c] = psii;
+    }
+}
+
+SolverPerf smoothSolve(const Mesh& m, const dvec& diag, const dvec& lower, const dvec& upper, const dvec& source,
+                       double* psi, double tol, double relTol, int maxIter)
+{
+    const int n = m.nCells;
+    SolverPerf sp;
+    dvec Apsi(n), r(n);
+    Amul(m, diag, lower, upper, psi, Apsi.data());
+    const double nf = normFactor(m, diag, lower, upper, psi, source.data(), Apsi.data());
+    for (int c = 0; c < n; ++c) r[c] = source[c] - Apsi[c];
+    sp.initialResidual = sumMag(r.data(), n)/nf;
+    sp.finalResidual = sp.initialResidual;
+    if (!checkConvergence(sp, tol, relTol)) {
+        do {
+            symGaussSeidelSweep(m, diag, lower, upper, source.data(), psi);
+            residual(m, diag, lower, upper, psi, source.data(), r.data());
+            sp.finalResidual = sumMag(r.data(), n)/nf;
+        } while ((sp.nIterations += 1) < maxIter && !checkConvergence(sp, tol, relTol));
+    }
+    return sp;
+}
+
+// ---------------------------------------------------------------------------------------------
+// boundary values
+// ---------------------------------------------------------------------------------------------
+inline void patchU(const Mesh& m, const Patch& p, int b, const double* U, double* out)
+{
+    if (p.bcU == BC_FIXED_VALUE) { out[0] = p.valueU[0]; out[1] = p.valueU[1]; out[2] = p.valueU[2]; }
+    else { const int c = m.bCell[b]; out[0] = U[3*(size_t)c]; out[1] = U[3*(size_t)c + 1]; out[2] = U[3*(size_t)c + 2]; }
+}
+inline double patchP(const Mesh& m, const Patch& p, int b, const double* P)
+{
+    return p.bcP == BC_FIXED_VALUE ? p.valueP : P[m.bCell[b]];
+}
+
+// ---------------------------------------------------------------------------------------------
+// fvc operators [OF-6 gaussGrad.C, surfaceInterpolationScheme.C, fvcSurfaceIntegrate.C]
+// ---------------------------------------------------------------------------------------------
+// linear interpolate: lambda*(phiP - phiN) + phiN
+inline double lerp(double w, double P, double N) { return w*(P - N) + N; }
+
+// fvc::grad(U): (1/V) sum_f Sf (x) U_f  -> [N][9] row-major T_ij = Sf_i U_j.   icoFoamYade.C:71, pimpleFoamYade.C:76
+void gradVector(const Mesh& m, const double* U, double* g)
+{
+    std::fill(g, g + 9*(size_t)m.nCells, 0.0);
+    for (int f = 0; f < m.nFaces; ++f) {
+        const int P = m.l[f], N = m.u[f];
+        double uf[3];
+        for (int j = 0; j < 3; ++j) uf[j] = lerp(m.w[f], U[3*(size_t)P + j], U[3*(size_t)N + j]);
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                const double t = m.Sf[3*(size_t)f + i]*uf[j];
+                g[9*(size_t)P + 3*i + j] += t;
+                g[9*(size_t)N + 3*i + j] -= t;
+            }
+    }
+    for (const Patch& p : m.patches) {
+        if (p.bcU == BC_EMPTY) continue;
+        for (int b = p.start; b < p.start + p.n; ++b) {
+            double ub[3];
+            patchU(m, p, b, U, ub);
+            const int c = m.bCell[b];
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) g[9*(size_t)c + 3*i + j] += m.bSf[3*(size_t)b + i]*ub[j];
+        }
+    }
+    for (int c = 0; c < m.nCells; ++c)
+        for (int k = 0; k < 9; ++k) g[9*(size_t)c + k] /= m.V[c];
+}
+
+// fvc::grad(p) -> [N][3].   icoFoamYade.C:93,136; pimpleFoamYade.C:74
+void gradScalar(const Mesh& m, const double* p, double* g)
+{
+    std::fill(g, g + 3*(size_t)m.nCells, 0.0);
+    for (int f = 0; f < m.nFaces; ++f) {
+        const int P = m.l[f], N = m.u[f];
+        const double pf = lerp(m.w[f], p[P], p[N]);
+        for (int i = 0; i < 3; ++i) {
+            const double t = m.Sf[3*(size_t)f + i]*pf;
+            g[3*(size_t)P + i] += t;
+            g[3*(size_t)N + i] -= t;
+        }
+    }
+    for (const Patch& pt : m.patches) {
+        if (pt.bcP == BC_EMPTY) continue;
+        for (int b = pt.start; b < pt.start + pt.n; ++b) {
+            const double pb = patchP(m, pt, b, p);
+            const int c = m.bCell[b];
+            for (int i = 0; i < 3; ++i) g[3*(size_t)c + i] += m.bSf[3*(size_t)b + i]*pb;
+        }
+    }
+    for (int c = 0; c < m.nCells; ++c)
+        for (int k = 0; k < 3; ++k) g[3*(size_t)c + k] /= m.V[c];
+}
+
+// fvc::div(phi) = surfaceIntegrate: (1/V) sum_f +-phi_f.   icoFoamYade.C:120 and continuityErrs.H
+void divFlux(const Mesh& m, const double* phi, double* d)
+{
+    std::fill(d, d + m.nCells, 0.0);
+    for (int f = 0; f < m.nFaces; ++f) {
+        d[m.l[f]] += phi[f];
+        d[m.u[f]] -= phi[f];
+    }
+    for (const Patch& p : m.patches) {
+        if (p.bcU == BC_EMPTY) continue;
+        for (int b = p.start; b < p.start + p.n; ++b) d[m.bCell[b]] += phi[m.nFaces + b];
+    }
+    for (int c = 0; c < m.nCells; ++c) d[c] /= m.V[c];
+}
+
+// CourantNo.H (stock; icoFoamYade.C:68 / pimpleFoamYade/CourantNo.H:32-49): sumPhi = surfaceSum(mag(phi))
+void courant(const Mesh& m, const double* phi, double dt, double* CoNum, double* meanCoNum)
+{
+    dvec s(m.nCells, 0.0);
+    for (int f = 0; f < m.nFaces; ++f) {
+        const double a = std::fabs(phi[f]);
+        s[m.l[f]] += a;
+        s[m.u[f]] += a;
+    }
+    for (const Patch& p : m.patches) {
+        if (p.bcU == BC_EMPTY) continue;
+        for (int b = p.start; b < p.start + p.n; ++b) s[m.bCell[b]] += std::fabs(phi[m.nFaces + b]);
+    }
+    double mx = -1e300, sum = 0, sv = 0;
+    for (int c = 0; c < m.nCells; ++c) {
+        mx = std::max(mx, s[c]/m.V[c]);
+        sum += s[c];
+        sv += m.V[c];
+    }
+    *CoNum = 0.5*mx*dt;
+    *meanCoNum = 0.5*(sum/sv)*dt;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the icoFoamYade state and time step
+// ---------------------------------------------------------------------------------------------
+struct Ctl
+{
+    int nCorrectors = 2;
+    int nNonOrthCorrectors = 0;
+    int momentumPredictor = 1;
+    int pRefCell = 0;
+    double pRefValue = 0;
+    double pTol = 1e-6, pRelTol = 0.05, pFinalTol = 1e-6, pFinalRelTol = 0.0;
+    double UTol = 1e-5, URelTol = 0.0;
+    int maxIter = 1000;
+    int precond = PRECOND_DIC;
+};
+
+struct Stats
+{
+    double CoNum = 0, meanCoNum = 0;
+    SolverPerf U[3];
+    SolverPerf p[8];            // one per pressure solve of the step, in order
+    int nPSolves = 0;
+    double sumLocalContErr = 0, globalContErr = 0, cumulativeContErr = 0;
+    double corrSumLocal[8] = {0}, corrGlobal[8] = {0};   // continuityErrs.H after each PISO corrector
+};
+
+struct Ico
+{
+    Mesh m;
+    double nu = 0.01;
+    dvec U, p, phi;             // [N][3], [N], [Fi + nB]
+    dvec uSource;               // [N][3]
+    dvec vGrad;                 // [N][9]
+    Ctl ctl;
+    Stats st;
+    double cumulativeContErr = 0;
+    // intermediates of the last corrector, kept for stage-by-stage parity tests
+    dvec rAU, HbyA, phiHbyA, gradP, diagU, upperU, lowerU, sourceU, diagP, upperP, sourceP;
+    dvec icU, bcU;              // UEqn internalCoeffs / boundaryCoeffs [nB][3]
+    double tMomentum = 0, tPressure = 0, tOther = 0;
+};
+
+bool pNeedsReference(const Mesh& m)
+{
+    for (const Patch& p : m.patches)
+        if (p.bcP == BC_FIXED_VALUE && p.n > 0) return false;
+    return true;
+}
+
+double nowSec()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// UEqn = fvm::ddt(U) + fvm::div(phi,U) - fvm::laplacian(nu,U) == uSource          icoFoamYade.C:79-85
+// [OF-6 EulerDdtScheme::fvmDdt, gaussConvectionScheme::fvmDiv, gaussLaplacianScheme::fvmLaplacianUncorrected,
+//  fvMatrix operator+, operator-, operator==(fvMatrix, volField)]
+void assembleUEqn(Ico& s, double dt, const dvec& U0)
+{
+    const Mesh& m = s.m;
+    const int N = m.nCells, Fi = m.nFaces, nB = m.nB;
+    const double rDeltaT = 1.0/dt;
+    dvec diagD(N), lowerC(Fi), upperC(Fi), diagC, upperL(Fi), diagL;
+    s.sourceU.assign(3*(size_t)N, 0.0);
+    for (int c = 0; c < N; ++c) {
+        diagD[c] = rDeltaT*m.V[c];
+        for (int j = 0; j < 3; ++j) s.sourceU[3*(size_t)c + j] = rDeltaT*U0[3*(size_t)c + j]*m.V[c];
+    }
+    for (int f = 0; f < Fi; ++f) {
+        lowerC[f] = -m.w[f]*s.phi[f];
+        upperC[f] = lowerC[f] + s.phi[f];
+        upperL[f] = m.dc[f]*(s.nu*m.magSf[f]);
+    }
+    negSumDiag(m, lowerC, upperC, diagC);
+    negSumDiag(m, upperL, upperL, diagL);
+    s.diagU.resize(N);
+    s.upperU.resize(Fi);
+    s.lowerU.resize(Fi);
+    for (int c = 0; c < N; ++c) s.diagU[c] = (diagD[c] + diagC[c]) - diagL[c];
+    for (int f = 0; f < Fi; ++f) {
+        s.upperU[f] = upperC[f] - upperL[f];
+        s.lowerU[f] = lowerC[f] - upperL[f];
+    }
+    // boundary coefficients: convection  ic = phi_b*valueInternalCoeffs, bc = -phi_b*valueBoundaryCoeffs;
+    //                        laplacian   ic = gammaMagSf_b*gradientInternalCoeffs, bc = -gammaMagSf_b*gradientBoundaryCoeffs
+    s.icU.assign(3*(size_t)nB, 0.0);
+    s.bcU.assign(3*(size_t)nB, 0.0);
+    for (const Patch& p : m.patches) {
+        if (p.bcU == BC_EMPTY) continue;
+        for (int b = p.start; b < p.start + p.n; ++b) {
+            const double phib = s.phi[Fi + b];
+            const double gMagSf = s.nu*m.bMagSf[b];
+            for (int j = 0; j < 3; ++j) {
+                double icC, bcC, icL, bcL;
+                if (p.bcU == BC_FIXED_VALUE) {
+                    icC = phib*0.0;
+                    bcC = -phib*p.valueU[j];
+                    icL = gMagSf*(-1.0*m.bDc[b]);
+                    bcL = -gMagSf*(m.bDc[b]*p.valueU[j]);
+                } else {
+                    icC = phib*1.0;
+                    bcC = -phib*0.0;
+                    icL = gMagSf*0.0;
+                    bcL = -gMagSf*0.0;
+                }
+                s.icU[3*(size_t)b + j] = icC - icL;
+                s.bcU[3*(size_t)b + j] = bcC - bcL;
+            }
+        }
+    }
+    // == uSource : source += V*uSource
+    for (int c = 0; c < N; ++c)
+        for (int j = 0; j < 3; ++j) s.sourceU[3*(size_t)c + j] += m.V[c]*s.uSource[3*(size_t)c + j];
+}
+
+// solve(UEqn == -fvc::grad(p))  icoFoamYade.C:93  [OF-6 fvMatrix<Type>::solveSegregated]
+void momentumPredictor(Ico& s)
+{
+    const Mesh& m = s.m;
+    const int N = m.nCells;
+    s.gradP.resize(3*(size_t)N);
+    gradScalar(m, s.p.data(), s.gradP.data());
+    dvec src(s.sourceU);
+    for (int c = 0; c < N; ++c)
+        for (int j = 0; j < 3; ++j) src[3*(size_t)c + j] += m.V[c]*(-s.gradP[3*(size_t)c + j]);
+    for (int b = 0; b < m.nB; ++b)          // addBoundarySource (patch order, face order)
+        for (int j = 0; j < 3; ++j) src[3*(size_t)m.bCell[b] + j] += s.bcU[3*(size_t)b + j];
+    dvec psi(N), b1(N), dg(N);
+    for (int j = 0; j < 3; ++j) {
+        s.st.U[j] = SolverPerf();
+        if (!m.validCmpt[j]) continue;
+        dg = s.diagU;
+        for (int b = 0; b < m.nB; ++b) dg[m.bCell[b]] += s.icU[3*(size_t)b + j];      // addBoundaryDiag
+        for (int c = 0; c < N; ++c) { psi[c] = s.U[3*(size_t)c + j]; b1[c] = src[3*(size_t)c + j]; }
+        s.st.U[j] = smoothSolve(m, dg, s.lowerU, s.upperU, b1, psi.data(), s.ctl.UTol, s.ctl.URelTol, s.ctl.maxIter);
+        for (int c = 0; c < N; ++c) s.U[3*(size_t)c + j] = psi[c];
+    }
+}
+
+// rAU = 1/UEqn.A();  H = UEqn.H()       icoFoamYade.C:99-100  [OF-6 fvMatrix::A, fvMatrix::H, lduMatrix::H]
+void computeRAUandH(Ico& s, dvec& H)
+{
+    const Mesh& m = s.m;
+    const int N = m.nCells;
+    dvec D(s.diagU);
+    for (int b = 0; b < m.nB; ++b) {
+        const double* ic = &s.icU[3*(size_t)b];
+        D[m.bCell[b]] += (ic[0] + ic[1] + ic[2])/3.0;                                  // addCmptAvBoundaryDiag
+    }
+    s.rAU.resize(N);
+    for (int c = 0; c < N; ++c) s.rAU[c] = 1.0/(D[c]/m.V[c]);
+    H.assign(3*(size_t)N, 0.0);
+    dvec bd(N);
+    for (int j = 0; j < 3; ++j) {
+        if (!m.validCmpt[j]) continue;
+        std::fill(bd.begin(), bd.end(), 0.0);
+        for (int b = 0; b < m.nB; ++b) bd[m.bCell[b]] += s.icU[3*(size_t)b + j];
+        for (int c = 0; c < N; ++c) bd[c] = -bd[c];
+        for (int b = 0; b < m.nB; ++b) {
+            const double* ic = &s.icU[3*(size_t)b];
+            bd[m.bCell[b]] += (ic[0] + ic[1] + ic[2])/3.0;
+        }
+        for (int c = 0; c < N; ++c) H[3*(size_t)c + j] = bd[c]*s.U[3*(size_t)c + j];
+    }
+    dvec Hl(3*(size_t)N, 0.0);
+    for (int f = 0; f < m.nFaces; ++f) {
+        const int P = m.l[f], Nb = m.u[f];
+        for (int j = 0; j < 3; ++j) {
+            Hl[3*(size_t)Nb + j] -= s.lowerU[f]*s.U[3*(size_t)P + j];
+            Hl[3*(size_t)P + j] -= s.upperU[f]*s.U[3*(size_t)Nb + j];
+        }
+    }
+    for (size_t i = 0; i < 3*(size_t)N; ++i) H[i] += Hl[i] + s.sourceU[i];
+    for (int b = 0; b < m.nB; ++b)
+        for (int j = 0; j < 3; ++j) H[3*(size_t)m.bCell[b] + j] += s.bcU[3*(size_t)b + j];
+    for (int c = 0; c < N; ++c)
+        for (int j = 0; j < 3; ++j) H[3*(size_t)c + j] /= m.V[c];
+    for (int j = 0; j < 3; ++j)
+        if (!m.validCmpt[j]) for (int c = 0; c < N; ++c) H[3*(size_t)c + j] = 0.0;
+}
+
+// adjustPhi(phiHbyA, U, p)  icoFoamYade.C:108  [OF-6 adjustPhi.C]
+int adjustPhi(const Mesh& m, double* phi)
+{
+    if (!pNeedsReference(m)) return 0;
+    double massIn = 0, fixedMassOut = 0, adjustableMassOut = 0;
+    for (const Patch& p : m.patches) {
+        if (p.bcU == BC_EMPTY) continue;
+        for (int b = p.start; b < p.start + p.n; ++b) {
+            const double ph = phi[m.nFaces + b];
+            if (p.bcU == BC_FIXED_VALUE) { if (ph < 0) massIn -= ph; else fixedMassOut += ph; }
+            else { if (ph < 0) massIn -= ph; else adjustableMassOut += ph; }
+        }
+    }
+    double totalFlux = VSMALL;
+    for (int b = 0; b < m.nB; ++b) totalFlux += std::fabs(phi[m.nFaces + b]);
+    double massCorr = 1.0;
+    const double magAdj = std::fabs(adjustableMassOut);
+    if (magAdj > VSMALL && magAdj/totalFlux > SMALL) massCorr = (massIn - fixedMassOut)/adjustableMassOut;
+    else if (std::fabs(fixedMassOut - massIn)/totalFlux > 1e-8) return -1;   // FatalError in OpenFOAM
+    for (const Patch& p : m.patches) {
+        if (p.bcU != BC_ZERO_GRADIENT) continue;
+        for (int b = p.start; b < p.start + p.n; ++b)
+            if (phi[m.nFaces + b] > 0.0) phi[m.nFaces + b] *= massCorr;
+    }
+    return 0;
+}
+
+int icoSolve(Ico& s, double dt)
+{
+    const Mesh& m = s.m;
+    const int N = m.nCells, Fi = m.nFaces, nB = m.nB;
+    const double rDeltaT = 1.0/dt;
+    double t0 = nowSec();
+    const dvec U0(s.U), phi0(s.phi);                 // oldTime fields
+    s.st.nPSolves = 0;
+    assembleUEqn(s, dt, U0);
+    if (s.ctl.momentumPredictor) momentumPredictor(s);
+    s.tMomentum += nowSec() - t0;
+
+    dvec H, div(N), totalSource(N), dg(N), icP(nB), bcP(nB), rAUf(Fi);
+    s.HbyA.resize(3*(size_t)N);
+    s.phiHbyA.resize((size_t)Fi + nB);
+    s.upperP.resize(Fi);
+    for (int corr = 1; corr <= s.ctl.nCorrectors; ++corr) {
+        t0 = nowSec();
+        computeRAUandH(s, H);
+        for (int c = 0; c < N; ++c)
+            for (int j = 0; j < 3; ++j) s.HbyA[3*(size_t)c + j] = s.rAU[c]*H[3*(size_t)c + j];
+        // phiHbyA = fvc::flux(HbyA) + fvc::interpolate(rAU)*fvc::ddtCorr(U, phi)      icoFoamYade.C:101-106
+        // [OF-6 EulerDdtScheme::fvcDdtPhiCorr + ddtScheme::fvcDdtPhiCoeff]
+        for (int f = 0; f < Fi; ++f) {
+            const int P = m.l[f], Nb = m.u[f];
+            double flux = 0, u0f = 0;
+            for (int j = 0; j < 3; ++j) {
+                flux += m.Sf[3*(size_t)f + j]*lerp(m.w[f], s.HbyA[3*(size_t)P + j], s.HbyA[3*(size_t)Nb + j]);
+                u0f += m.Sf[3*(size_t)f + j]*lerp(m.w[f], U0[3*(size_t)P + j], U0[3*(size_t)Nb + j]);
+            }
+            const double phiCorr = phi0[f] - u0f;
+            const double coeff = 1.0 - std::min(std::fabs(phiCorr)/(std::fabs(phi0[f]) + SMALL), 1.0);
+            rAUf[f] = lerp(m.w[f], s.rAU[P], s.rAU[Nb]);
+            s.phiHbyA[f] = flux + rAUf[f]*((coeff*rDeltaT)*phiCorr);
+        }
+        for (const Patch& p : m.patches) {
+            for (int b = p.start; b < p.start + p.n; ++b) {
+                if (p.bcU == BC_EMPTY) { s.phiHbyA[Fi + b] = 0.0; continue; }
+                const int c = m.bCell[b];
+                double hb[3], u0b[3];
+                if (p.bcU == BC_FIXED_VALUE) { hb[0] = p.valueU[0]; hb[1] = p.valueU[1]; hb[2] = p.valueU[2]; }   // constrainHbyA
+                else { hb[0] = s.HbyA[3*(size_t)c]; hb[1] = s.HbyA[3*(size_t)c + 1]; hb[2] = s.HbyA[3*(size_t)c + 2]; }
+                patchU(m, p, b, U0.data(), u0b);
+                double flux = 0, u0f = 0;
+                for (int j = 0; j < 3; ++j) { flux += m.bSf[3*(size_t)b + j]*hb[j]; u0f += m.bSf[3*(size_t)b + j]*u0b[j]; }
+                const double phiCorr = phi0[Fi + b] - u0f;
+                double coeff = 1.0 - std::min(std::fabs(phiCorr)/(std::fabs(phi0[Fi + b]) + SMALL), 1.0);
+                if (p.bcU == BC_FIXED_VALUE) coeff = 0.0;                     // fixesValue() patches
+                s.phiHbyA[Fi + b] = flux + s.rAU[c]*((coeff*rDeltaT)*phiCorr);
+            }
+        }
+        if (adjustPhi(m, s.phiHbyA.data()) != 0) return -1;
+        // constrainPressure: fixedFluxPressure patches only -- none in the pinned BC set
+        s.tOther += nowSec() - t0;
+        for (int nonOrth = 0; nonOrth <= s.ctl.nNonOrthCorrectors; ++nonOrth) {
+            t0 = nowSec();
+            // pEqn: fvm::laplacian(rAU, p) == fvc::div(phiHbyA)                    icoFoamYade.C:118-121
+            for (int f = 0; f < Fi; ++f) s.upperP[f] = m.dc[f]*(rAUf[f]*m.magSf[f]);
+            negSumDiag(m, s.upperP, s.upperP, s.diagP);
+            for (const Patch& p : m.patches) {
+                for (int b = p.start; b < p.start + p.n; ++b) {
+                    icP[b] = 0.0;
+                    bcP[b] = 0.0;
+                    if (p.bcP != BC_FIXED_VALUE) continue;
+                    const double pGamma = s.rAU[m.bCell[b]]*m.bMagSf[b];
+                    icP[b] = pGamma*(-1.0*m.bDc[b]);
+                    bcP[b] = -pGamma*(m.bDc[b]*p.valueP);
+                }
+            }
+            divFlux(m, s.phiHbyA.data(), div.data());
+            s.sourceP.assign(N, 0.0);
+            for (int c = 0; c < N; ++c) s.sourceP[c] += m.V[c]*div[c];
+            if (pNeedsReference(m)) {                                               // icoFoamYade.C:123
+                s.sourceP[s.ctl.pRefCell] += s.diagP[s.ctl.pRefCell]*s.ctl.pRefValue;
+                s.diagP[s.ctl.pRefCell] += s.diagP[s.ctl.pRefCell];
+            }
+            // fvMatrix<scalar>::solveSegregated
+            dg = s.diagP;
+            totalSource = s.sourceP;
+            for (int b = 0; b < nB; ++b) { dg[m.bCell[b]] += icP[b]; totalSource[m.bCell[b]] += bcP[b]; }
+            const bool fin = (corr == s.ctl.nCorrectors) && (nonOrth == s.ctl.nNonOrthCorrectors);
+            SolverPerf sp = pcgSolve(m, dg, s.upperP, totalSource, s.p.data(), fin ? s.ctl.pFinalTol : s.ctl.pTol,
+                                     fin ? s.ctl.pFinalRelTol : s.ctl.pRelTol, s.ctl.maxIter, s.ctl.precond);
+            if (s.st.nPSolves < 8) s.st.p[s.st.nPSolves] = sp;
+            s.st.nPSolves++;
+            s.tPressure += nowSec() - t0;
+            if (nonOrth == s.ctl.nNonOrthCorrectors) {
+                // phi = phiHbyA - pEqn.flux()                                        icoFoamYade.C:127-130
+                for (int f = 0; f < Fi; ++f)
+                    s.phi[f] = s.phiHbyA[f] - (s.upperP[f]*s.p[m.u[f]] - s.upperP[f]*s.p[m.l[f]]);
+                for (int b = 0; b < nB; ++b) s.phi[Fi + b] = s.phiHbyA[Fi + b] - (icP[b]*s.p[m.bCell[b]] - bcP[b]);
+            }
+        }
+        t0 = nowSec();
+        // continuityErrs.H (stock)                                                 icoFoamYade.C:134
+        divFlux(m, s.phi.data(), div.data());
+        double sl = 0, sg = 0, sv = 0;
+        for (int c = 0; c < N; ++c) { sl += std::fabs(div[c])*m.V[c]; sg += div[c]*m.V[c]; sv += m.V[c]; }
+        s.st.sumLocalContErr = dt*(sl/sv);
+        s.st.globalContErr = dt*(sg/sv);
+        s.cumulativeContErr += s.st.globalContErr;
+        s.st.cumulativeContErr = s.cumulativeContErr;
+        if (corr <= 8) { s.st.corrSumLocal[corr - 1] = s.st.sumLocalContErr; s.st.corrGlobal[corr - 1] = s.st.globalContErr; }
+        // U = HbyA - rAU*fvc::grad(p)                                              icoFoamYade.C:136-137
+        s.gradP.resize(3*(size_t)N);
+        gradScalar(m, s.p.data(), s.gradP.data());
+        for (int c = 0; c < N; ++c)
+            for (int j = 0; j < 3; ++j) s.U[3*(size_t)c + j] = s.HbyA[3*(size_t)c + j] - s.rAU[c]*s.gradP[3*(size_t)c + j];
+        s.tOther += nowSec() - t0;
+    }
+    return 0;
+}
+
+Mesh* buildMesh(int nCells, const double* V, int nFaces, const int* owner, const int* neigh, const double* Sf,
+                const double* magSf, const double* w, const double* dc, int nPatches, const int* patchSize,
+                const int* bCell, const double* bSf, const double* bMagSf, const double* bDc, const int* bcU,
+                const double* valueU, const int* bcP, const double* valueP, Mesh& m)
+{
+    m.nCells = nCells;
+    m.nFaces = nFaces;
+    m.V.assign(V, V + nCells);
+    m.l.assign(owner, owner + nFaces);
+    m.u.assign(neigh, neigh + nFaces);
+    m.Sf.assign(Sf, Sf + 3*(size_t)nFaces);
+    m.magSf.assign(magSf, magSf + nFaces);
+    m.w.assign(w, w + nFaces);
+    m.dc.assign(dc, dc + nFaces);
+    int o = 0;
+    for (int i = 0; i < nPatches; ++i) {
+        Patch p;
+        p.start = o;
+        p.n = patchSize[i];
+        p.bcU = bcU[i];
+        p.bcP = bcP[i];
+        for (int j = 0; j < 3; ++j) p.valueU[j] = valueU[3*i + j];
+        p.valueP = valueP[i];
+        m.patches.push_back(p);
+        o += p.n;
+    }
+    m.nB = o;
+    m.bCell.assign(bCell, bCell + o);
+    m.bSf.assign(bSf, bSf + 3*(size_t)o);
+    m.bMagSf.assign(bMagSf, bMagSf + o);
+    m.bDc.assign(bDc, bDc + o);
+    m.ownStart.assign(nCells + 1, 0);
+    for (int f = 0; f < nFaces; ++f) m.ownStart[owner[f] + 1]++;
+    for (int c = 0; c < nCells; ++c) m.ownStart[c + 1] += m.ownStart[c];
+    for (const Patch& p : m.patches) {
+        if (p.bcU != BC_EMPTY || p.n == 0) continue;
+        const double* s = &m.bSf[3*(size_t)p.start];
+        int d = 0;
+        if (std::fabs(s[1]) > std::fabs(s[d])) d = 1;
+        if (std::fabs(s[2]) > std::fabs(s[d])) d = 2;
+        m.validCmpt[d] = false;
+    }
+    return &m;
+}
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C API (ctypes: oracle/port.py)
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+void* fvo_create(int nCells, const double* V, int nFaces, const int* owner, const int* neigh, const double* Sf,
+                 const double* magSf, const double* w, const double* dc, int nPatches, const int* patchSize,
+                 const int* bCell, const double* bSf, const double* bMagSf, const double* bDc, const int* bcU,
+                 const double* valueU, const int* bcP, const double* valueP)
+{
+    Ico* s = new Ico();
+    buildMesh(nCells, V, nFaces, owner, neigh, Sf, magSf, w, dc, nPatches, patchSize, bCell, bSf, bMagSf, bDc, bcU,
+              valueU, bcP, valueP, s->m);
+    const Mesh& m = s->m;
+    s->U.assign(3*(size_t)nCells, 0.0);
+    s->p.assign(nCells, 0.0);
+    s->phi.assign((size_t)nFaces + m.nB, 0.0);
+    s->uSource.assign(3*(size_t)nCells, 0.0);
+    s->vGrad.assign(9*(size_t)nCells, 0.0);
+    return s;
+}
+void fvo_destroy(void* h) { delete (Ico*)h; }
+
+// ctl: nCorrectors nNonOrth momentumPredictor pRefCell maxIter precond | pRefValue pTol pRelTol pFinalTol pFinalRelTol UTol URelTol nu
+void fvo_set_controls(void* h, const int* ic6, const double* dc8)
+{
+    Ico* s = (Ico*)h;
+    s->ctl.nCorrectors = ic6[0]; s->ctl.nNonOrthCorrectors = ic6[1]; s->ctl.momentumPredictor = ic6[2];
+    s->ctl.pRefCell = ic6[3]; s->ctl.maxIter = ic6[4]; s->ctl.precond = ic6[5];
+    s->ctl.pRefValue = dc8[0]; s->ctl.pTol = dc8[1]; s->ctl.pRelTol = dc8[2]; s->ctl.pFinalTol = dc8[3];
+    s->ctl.pFinalRelTol = dc8[4]; s->ctl.UTol = dc8[5]; s->ctl.URelTol = dc8[6]; s->nu = dc8[7];
+}
+
+// name: U p phi uSource vGrad rAU HbyA phiHbyA gradP diagU upperU lowerU sourceU diagP upperP sourceP
+double* fvo_field(void* h, const char* name, long* n)
+{
+    Ico* s = (Ico*)h;
+    const std::string k(name);
+    dvec* v = nullptr;
+    if (k == "U") v = &s->U; else if (k == "p") v = &s->p; else if (k == "phi") v = &s->phi;
+    else if (k == "uSource") v = &s->uSource; else if (k == "vGrad") v = &s->vGrad; else if (k == "rAU") v = &s->rAU;
+    else if (k == "HbyA") v = &s->HbyA; else if (k == "phiHbyA") v = &s->phiHbyA; else if (k == "gradP") v = &s->gradP;
+    else if (k == "diagU") v = &s->diagU; else if (k == "upperU") v = &s->upperU; else if (k == "lowerU") v = &s->lowerU;
+    else if (k == "sourceU") v = &s->sourceU; else if (k == "diagP") v = &s->diagP; else if (k == "upperP") v = &s->upperP;
+    else if (k == "sourceP") v = &s->sourceP;
+    if (!v) { if (n) *n = 0; return nullptr; }
+    if (n) *n = (long)v->size();
+    return v->data();
+}
+
+// phi = linearInterpolate(U) & Sf  (createPhi.H, icoFoamYade/createFields.H:152)
+void fvo_create_phi(void* h)
+{
+    Ico* s = (Ico*)h;
+    const Mesh& m = s->m;
+    for (int f = 0; f < m.nFaces; ++f) {
+        double a = 0;
+        for (int j = 0; j < 3; ++j) a += m.Sf[3*(size_t)f + j]*lerp(m.w[f], s->U[3*(size_t)m.l[f] + j], s->U[3*(size_t)m.u[f] + j]);
+        s->phi[f] = a;
+    }
+    for (const Patch& p : m.patches)
+        for (int b = p.start; b < p.start + p.n; ++b) {
+            double ub[3] = {0, 0, 0}, a = 0;
+            if (p.bcU != BC_EMPTY) patchU(m, p, b, s->U.data(), ub);
+            for (int j = 0; j < 3; ++j) a += m.bSf[3*(size_t)b + j]*ub[j];
+            s->phi[m.nFaces + b] = a;
+        }
+}
+
+// CourantNo.H + vGrad = fvc::grad(U)   (icoFoamYade.C:68-71): what runs before setParticleAction
+void fvo_ico_pre(void* h, double dt)
+{
+    Ico* s = (Ico*)h;
+    courant(s->m, s->phi.data(), dt, &s->st.CoNum, &s->st.meanCoNum);
+    gradVector(s->m, s->U.data(), s->vGrad.data());
+}
+
+// UEqn assembly, momentum predictor, PISO correctors (icoFoamYade.C:79-140); uSource is read from the state
+int fvo_ico_solve(void* h, double dt) { return icoSolve(*(Ico*)h, dt); }
+
+// out: CoNum meanCoNum sumLocal global cumulative nPSolves | U[3]x(init,final,iters) | p[8]x(init,final,iters) | corrSumLocal[8] | corrGlobal[8]
+void fvo_get_stats(void* h, double* out)
+{
+    Ico* s = (Ico*)h;
+    int o = 0;
+    out[o++] = s->st.CoNum; out[o++] = s->st.meanCoNum; out[o++] = s->st.sumLocalContErr;
+    out[o++] = s->st.globalContErr; out[o++] = s->st.cumulativeContErr; out[o++] = s->st.nPSolves;
+    for (int j = 0; j < 3; ++j) { out[o++] = s->st.U[j].initialResidual; out[o++] = s->st.U[j].finalResidual; out[o++] = s->st.U[j].nIterations; }
+    for (int k = 0; k < 8; ++k) { out[o++] = s->st.p[k].initialResidual; out[o++] = s->st.p[k].finalResidual; out[o++] = s->st.p[k].nIterations; }
+    for (int k = 0; k < 8; ++k) out[o++] = s->st.corrSumLocal[k];
+    for (int k = 0; k < 8; ++k) out[o++] = s->st.corrGlobal[k];
+}
+void fvo_get_times(void* h, double* out3)
+{
+    Ico* s = (Ico*)h;
+    out3[0] = s->tMomentum; out3[1] = s->tPressure; out3[2] = s->tOther;
+    s->tMomentum = s->tPressure = s->tOther = 0;
+}
+
+// stand-alone operators on the state's mesh (stage parity hooks)
+void fvo_grad_vector(void* h, const double* U, double* out9) { gradVector(((Ico*)h)->m, U, out9); }
+void fvo_grad_scalar(void* h, const double* p, double* out3) { gradScalar(((Ico*)h)->m, p, out3); }
+void fvo_div_flux(void* h, const double* phi, double* out) { divFlux(((Ico*)h)->m, phi, out); }
+
+// PCG on a caller-given symmetric LDU matrix over the state's addressing; out3 = init, final, iters
+void fvo_pcg(void* h, const double* diag, const double* upper, const double* source, double* psi, double tol,
+             double relTol, int maxIter, int precond, double* out3)
+{
+    const Mesh& m = ((Ico*)h)->m;
+    const dvec d(diag, diag + m.nCells), u(upper, upper + m.nFaces), b(source, source + m.nCells);
+    const SolverPerf sp = pcgSolve(m, d, u, b, psi, tol, relTol, maxIter, precond);
+    out3[0] = sp.initialResidual; out3[1] = sp.finalResidual; out3[2] = sp.nIterations;
+}
+// smoothSolver/symGaussSeidel on a caller-given asymmetric LDU matrix
+void fvo_smooth(void* h, const double* diag, const double* lower, const double* upper, const double* source,
+                double* psi, double tol, double relTol, int maxIter, double* out3)
+{
+    const Mesh& m = ((Ico*)h)->m;
+    const dvec d(diag, diag + m.nCells), lo(lower, lower + m.nFaces), u(upper, upper + m.nFaces), b(source, source + m.nCells);
+    const SolverPerf sp = smoothSolve(m, d, lo, u, b, psi, tol, relTol, maxIter);
+    out3[0] = sp.initialResidual; out3[1] = sp.finalResidual; out3[2] = sp.nIterations;
+}
+// one DIC application: wA = M^-1 rA
+void fvo_dic(void* h, const double* diag, const double* upper, const double* rA, double* wA)
+{
+    const Mesh& m = ((Ico*)h)->m;
+    const dvec d(diag, diag + m.nCells), u(upper, upper + m.nFaces);
+    dvec rD;
+    dicReciprocalD(m, d, u, rD);
+    dicPrecondition(m, u, rD, rA, wA);
+}
+void fvo_amul(void* h, const double* diag, const double* lower, const double* upper, const double* psi, double* out)
+{
+    const Mesh& m = ((Ico*)h)->m;
+    const dvec d(diag, diag + m.nCells), lo(lower, lower + m.nFaces), u(upper, upper + m.nFaces);
+    Amul(m, d, lo, u, psi, out);
+}
+
+}  // extern "C"

@@ -1,0 +1,156 @@
+"""CPU: pins the fluid-half oracle (oracle/fv_oracle.cc, this repo's restatement of the OpenFOAM-6 operators
+behind icoFoamYade.C:65-149).
+
+The reference ships no tests for this half and OpenFOAM is not installed here, so the pin is the solver log
+OpenFOAM itself prints for its stock `cavity` tutorial (icoFoam, blockMesh 20x20x1 on 0.1 x 0.1 x 0.01 m,
+lid U = (1 0 0), nu = 0.01, deltaT = 0.005, PISO nCorrectors 2, p: PCG/DIC 1e-06 relTol 0.05, pFinal relTol 0,
+U: smoothSolver symGaussSeidel 1e-05) -- the same operator sequence icoFoamYade runs with uSource = 0.  The
+numbers below are that log's first three time steps as OpenFOAM prints them (6 significant digits).  They were
+written down from the public tutorial log, not produced by this code; the oracle reproduces every one of them,
+which pins: Euler ddt, Gauss-linear convection / laplacian / gradient, boundary coefficients, the segregated
+solve, symGaussSeidel sweeps and its residual normalisation, A()/H(), ddtCorr, pEqn assembly + setReference,
+DIC-PCG with OpenFOAM's stopping rule, the flux update, continuityErrs and CourantNo.
+"""
+import numpy as np
+import pytest
+
+from oracle import meshgen, port
+
+pytestmark = pytest.mark.skipif(not port.available(), reason="oracle/_build/liboracle.so not built")
+
+
+def sig6(x):
+    return float("%.6g" % x)
+
+
+def cavity_mesh(n=20, nz=1):
+    m = meshgen.hex_box_ldu(n, n, nz, 0.1, 0.1, 0.01,
+                            patches=[("movingWall", ["ymax"]), ("fixedWalls", ["xmin", "xmax", "ymin"]),
+                                     ("frontAndBack", ["zmin", "zmax"])])
+    meshgen.set_bc(m, "movingWall", valueU=(1, 0, 0))
+    meshgen.set_bc(m, "frontAndBack", bcU=meshgen.BC_EMPTY, bcP=meshgen.BC_EMPTY)
+    return m
+
+
+# log.icoFoam of the stock cavity tutorial: (Courant mean, max), Ux (init, final, iters), Uy, p corrector 1,
+# sum local after corrector 1, p corrector 2, sum local after corrector 2
+CAVITY_LOG = [
+    dict(Co=(0.0, 0.0), Ux=(1.0, 8.90511e-06, 19), Uy=(0.0, 0.0, 0), p1=(1.0, 0.0492854, 12), c1=0.000466513,
+         p2=(0.590864, 2.65225e-07, 35), c2=2.74685e-09),
+    dict(Co=(0.0976825, 0.585607), Ux=(0.160686, 6.83031e-06, 19), Uy=(0.260828, 9.65939e-06, 18),
+         p1=(0.428925, 0.0103739, 22), c1=None, p2=(0.30209, 5.26569e-07, 33), c2=6.61987e-09),
+    dict(Co=(0.144686, 0.758934), Ux=(0.0447632, 9.12473e-06, 15), Uy=(0.0817804, 6.96014e-06, 17),
+         p1=(0.131584, 0.00445878, 11), c1=None, p2=(0.0973392, 9.15339e-07, 31), c2=7.57271e-09),
+]
+
+
+def test_openfoam_cavity_tutorial_log():
+    O = port.IcoOracle(cavity_mesh(), nu=0.01)
+    O.create_phi()
+    for ref in CAVITY_LOG:
+        O.pre(0.005)
+        O.solve(0.005)
+        st = O.stats()
+        assert (sig6(st["meanCoNum"]), sig6(st["CoNum"])) == ref["Co"]
+        for j, k in ((0, "Ux"), (1, "Uy")):
+            u = st["U"][j]
+            assert (sig6(u["initial"]), sig6(u["final"]), u["iters"]) == ref[k], k
+        assert st["U"][2]["iters"] == 0          # empty direction is not solved
+        for j, k in ((0, "p1"), (1, "p2")):
+            p = st["p"][j]
+            assert (sig6(p["initial"]), sig6(p["final"]), p["iters"]) == ref[k], k
+        if ref["c1"] is not None:
+            assert sig6(st["corrSumLocal"][0]) == ref["c1"]
+        assert sig6(st["corrSumLocal"][1]) == ref["c2"]
+        assert abs(st["globalContErr"]) < 1e-17
+    O.close()
+
+
+def _mesh3d(n=(6, 5, 4)):
+    m = meshgen.hex_box_ldu(*n, lx=1.0, ly=0.5, lz=2.0)
+    meshgen.set_bc(m, "xmin", valueU=(0.3, 0.0, 0.0))
+    meshgen.set_bc(m, "xmax", bcU=meshgen.BC_ZERO_GRADIENT, bcP=meshgen.BC_FIXED_VALUE, valueP=0.25)
+    return m
+
+
+def test_gradients_are_exact_for_linear_fields_in_the_interior():
+    m = _mesh3d((8, 7, 6))
+    O = port.IcoOracle(m)
+    C = m["C"]
+    A = np.array([[0.3, -1.0, 2.0], [0.7, 0.2, -0.4], [1.5, 0.0, 0.9]])      # U_j = sum_i C_i A_ij
+    U = C @ A
+    g = O.grad_vector(U).reshape(-1, 3, 3)
+    nx, ny, nz = m["n"]
+    idx = np.arange(m["nCells"]).reshape(nz, ny, nx)[1:-1, 1:-1, 1:-1].reshape(-1)
+    np.testing.assert_allclose(g[idx], np.broadcast_to(A, (idx.size, 3, 3)), rtol=0, atol=1e-12)
+    p = C @ np.array([2.0, -3.0, 0.5])
+    gp = O.grad_scalar(p)
+    np.testing.assert_allclose(gp[idx], np.broadcast_to([2.0, -3.0, 0.5], (idx.size, 3)), rtol=0, atol=1e-12)
+    O.close()
+
+
+def _ldu_dense(m, diag, lower, upper):
+    N = m["nCells"]
+    A = np.zeros((N, N))
+    A[np.arange(N), np.arange(N)] = diag
+    A[m["neighbour"], m["owner"]] = lower
+    A[m["owner"], m["neighbour"]] = upper
+    return A
+
+
+def test_ldu_kernels_against_dense_algebra():
+    m = _mesh3d()
+    O = port.IcoOracle(m)
+    rng = np.random.default_rng(3)
+    N, Fi = m["nCells"], m["nInternalFaces"]
+    upper = -rng.uniform(0.5, 1.5, Fi)
+    lower = -rng.uniform(0.5, 1.5, Fi)
+    diag = np.zeros(N)
+    np.subtract.at(diag, m["owner"], lower)
+    np.subtract.at(diag, m["neighbour"], upper)
+    diag += rng.uniform(0.1, 0.2, N)
+    psi = rng.standard_normal(N)
+    np.testing.assert_allclose(O.amul(diag, lower, upper, psi), _ldu_dense(m, diag, lower, upper) @ psi, rtol=1e-13)
+    # symmetric negative-definite (Laplacian-like) system: PCG to tight tolerance == dense solve
+    A = _ldu_dense(m, -diag, -upper, -upper)
+    b = rng.standard_normal(N)
+    for pre in ("DIC", "diagonal", "none"):
+        x, perf = O.pcg(-diag, -upper, b, np.zeros(N), tol=1e-14, relTol=0.0, preconditioner=pre)
+        np.testing.assert_allclose(x, np.linalg.solve(A, b), rtol=1e-9, atol=1e-11)
+        assert 0 < perf["iters"] < 200 and perf["final"] < 1e-14
+    # DIC: M = (L + D) D^-1 (D + L^T) with the recurrence D_u = a_uu - sum a_ul^2 / D_l
+    Asym = _ldu_dense(m, diag, upper, upper)
+    D = diag.copy()
+    for f in range(Fi):
+        D[m["neighbour"][f]] -= upper[f] ** 2 / D[m["owner"][f]]
+    Ls = np.tril(Asym, -1)
+    M = (Ls + np.diag(D)) @ np.diag(1.0 / D) @ (np.diag(D) + Ls.T)
+    r = rng.standard_normal(N)
+    np.testing.assert_allclose(O.dic(diag, upper, r), np.linalg.solve(M, r), rtol=1e-11)
+    # symGaussSeidel: converges to the dense solution of the asymmetric, diagonally dominant system
+    Aas = _ldu_dense(m, diag, lower, upper)
+    x, perf = O.smooth(diag, lower, upper, b, np.zeros(N), tol=1e-13)
+    np.testing.assert_allclose(x, np.linalg.solve(Aas, b), rtol=1e-8, atol=1e-10)
+    O.close()
+
+
+def test_channel_step_is_divergence_free_and_bounded():
+    """inlet (fixedValue U) / outlet (zeroGradient U, fixedValue p) box: two PISO steps leave a discretely
+    divergence-free flux field whose outflow equals the inflow."""
+    m = _mesh3d((12, 6, 5))
+    O = port.IcoOracle(m, nu=0.01)
+    O.field("U")[:] = (0.3, 0.0, 0.0)
+    O.create_phi()
+    for _ in range(2):
+        O.pre(0.01)
+        O.solve(0.01)
+    st = O.stats()
+    assert st["sumLocalContErr"] < 1e-8
+    phi = O.field("phi")
+    Fi = m["nInternalFaces"]
+    sizes = [p["faceCells"].size for p in m["patches"]]
+    inflow = phi[Fi:Fi + sizes[0]].sum()
+    outflow = phi[Fi + sizes[0]:Fi + sizes[0] + sizes[1]].sum()
+    assert inflow < 0 and abs(inflow + outflow) < 1e-7 * abs(inflow)
+    assert np.all(np.isfinite(O.field("U"))) and np.abs(O.field("U")).max() < 1.0
+    O.close()
