@@ -47,7 +47,8 @@ enum {
 /* boundary-condition kinds (the subset of OpenFOAM patch fields the synthetic cases use) */
 enum {
     FY_BC_FIXED_VALUE = 0,    /* fixedValue / noSlip / movingWall: value given per patch */
-    FY_BC_ZERO_GRADIENT = 1
+    FY_BC_ZERO_GRADIENT = 1,
+    FY_BC_EMPTY = 2           /* OpenFOAM `empty` (2-D cases): the faces take part in nothing */
 };
 
 /* A patch: nFaces boundary faces that all belong to one boundary-condition group.
@@ -181,6 +182,83 @@ int fy_set_source_zero(fy_handle h);
 /* Cell lists + normalised Gaussian weights of the last fy_coupling_proc (parity hooks):
  * h_counts [n], h_ids [n][12], h_weights [n][12] (FoamYade.C:293-316). Any pointer may be NULL.     */
 int fy_get_last_lists(fy_handle h, int n, int* h_counts, int* h_ids, double* h_weights);
+
+/* ---------------------------------------------------------------------------------------------
+ * the fluid half: icoFoamYade's time step (icoFoamYade/icoFoamYade.C:65-149) on the device
+ *
+ * The arithmetic is OpenFOAM-6's (Euler ddt; Gauss linear grad / div / laplacian; linear interpolation;
+ * p: PCG + DIC / diagonal / none, U: smoothSolver + symGaussSeidel -- the stock cavity fvSchemes /
+ * fvSolution, which the reference does not ship).  Supported meshes: a uniform hex box in blockMesh
+ * order (fy_mesh_desc.boxN set, LDU faces and patches consistent with it) whose boundary sides each
+ * carry one boundary condition; fy_fv_supported() says whether the mesh qualified.
+ * ------------------------------------------------------------------------------------------- */
+enum { FY_PRECOND_DIC = 0, FY_PRECOND_DIAGONAL = 1, FY_PRECOND_NONE = 2 };
+
+/* fvSolution: PISO sub-dictionary (icoFoamYade/createFields.H:166-168 reads pRefCell / pRefValue from it)
+ * and the p / pFinal / U solver entries.                                                              */
+typedef struct {
+    int nCorrectors;                /* PISO nCorrectors                      (stock cavity: 2) */
+    int nNonOrthogonalCorrectors;   /*                                       (0)               */
+    int momentumPredictor;          /* piso.momentumPredictor()              (1)               */
+    int pRefCell;
+    double pRefValue;
+    double pTol, pRelTol;           /* p      { tolerance 1e-06; relTol 0.05; } */
+    double pFinalTol, pFinalRelTol; /* pFinal { $p; relTol 0; }                 */
+    double UTol, URelTol;           /* U      { tolerance 1e-05; relTol 0; }    */
+    int maxIter;                    /* 1000 */
+    int preconditioner;             /* FY_PRECOND_* for p */
+} fy_piso_controls;
+
+typedef struct {
+    double initialResidual, finalResidual;
+    int nIterations;
+    int pad_;
+} fy_solver_perf;
+
+/* What the solver log of one time step prints: Courant number, the segregated U solves, every
+ * pressure solve in order, continuityErrs.H after each PISO corrector.                          */
+typedef struct {
+    double CoNum, meanCoNum;
+    fy_solver_perf U[3];
+    fy_solver_perf p[8];
+    int nPSolves;
+    int pad_;
+    double sumLocalContErr, globalContErr, cumulativeContErr;
+    double corrSumLocal[8], corrGlobal[8];
+} fy_ico_stats;
+
+/* 1 when the mesh given to fy_create qualified for the device FV path, else 0 (fy_last_error says why). */
+int fy_fv_supported(fy_handle h);
+/* defaults = the stock cavity set above */
+int fy_piso_default_controls(fy_piso_controls* c);
+int fy_set_piso_controls(fy_handle h, const fy_piso_controls* c);
+/* transportProperties nu of the fluid solve (fy_set_properties sets it too) */
+int fy_set_viscosity(fy_handle h, double nu);
+/* phi = linearInterpolate(U) & Sf   (createPhi.H, icoFoamYade/createFields.H:152) from the U on the device */
+int fy_create_phi(fy_handle h);
+/* CourantNo.H + vGrad = fvc::grad(U)   (icoFoamYade.C:68-71): everything before setParticleAction */
+int fy_ico_pre(fy_handle h, double dt);
+/* UEqn assembly with uSource, momentum predictor, PISO correctors (icoFoamYade.C:79-140).  Reads and
+ * updates the device fields U (FY_F_U), p (FY_F_P), phi (FY_F_PHI); reads uSource (FY_F_USOURCE).    */
+int fy_ico_solve(fy_handle h, double dt);
+int fy_get_ico_stats(fy_handle h, fy_ico_stats* out);
+
+/* Parity hooks: single operators on host data, in OpenFOAM's own layouts (cell fields [N][..], face
+ * fields and matrix coefficients in LDU face order: internal faces then boundary faces patch by patch). */
+int fy_fvc_grad_vector(fy_handle h, const double* h_U, double* h_out9);      /* fvc::grad(U), icoFoamYade.C:71  */
+int fy_fvc_grad_scalar(fy_handle h, const double* h_p, double* h_out3);      /* fvc::grad(p), icoFoamYade.C:136 */
+int fy_fvc_div_flux(fy_handle h, const double* h_phi, double* h_out);        /* fvc::div(phi), icoFoamYade.C:120 */
+/* lduMatrix solves over the mesh's addressing: out3 = initialResidual, finalResidual, nIterations */
+int fy_pcg_solve(fy_handle h, const double* h_diag, const double* h_upper, const double* h_source, double* h_psi,
+                 double tol, double relTol, int maxIter, int preconditioner, double out3[3]);
+int fy_smooth_solve(fy_handle h, const double* h_diag, const double* h_lower, const double* h_upper,
+                    const double* h_source, double* h_psi, double tol, double relTol, int maxIter, double out3[3]);
+int fy_dic_precondition(fy_handle h, const double* h_diag, const double* h_upper, const double* h_rA, double* h_wA);
+/* intermediates of the last PISO corrector: "rAU" [N], "HbyA" [N][3], "phiHbyA" [faces], "gradP" [N][3] */
+int fy_fv_get(fy_handle h, const char* name, double* h_dst);
+/* Device time (ms) of the phases of the last fy_ico_solve: [0] UEqn assembly + momentum predictor
+ * [1] pressure solves (PCG) [2] the rest of the correctors; and the last PCG's iteration time.      */
+int fy_get_fluid_ms(fy_handle h, double out[4]);
 
 /* Blocks until all work queued on the handle's stream is complete. */
 int fy_synchronize(fy_handle h);

@@ -1,0 +1,224 @@
+"""GPU: the sm_100a finite-volume / PISO kernels, called through the C ABI (include/fycuda.h), against the
+CPU oracle (oracle/fv_oracle.cc, pinned by the OpenFOAM cavity tutorial log in tests/test_fv_oracle.py).
+Bar: per-cell operators bit-exact (same operation order, no FMA contraction); solves and whole time steps
+within 1e-10 relative L2 (the only difference is the association of the global dot products / norms) with
+identical iteration counts."""
+import numpy as np
+import pytest
+
+from oracle import port
+from tests import cases, cases_fv
+from tests.test_fv_oracle import CAVITY_LOG, sig6
+
+pytestmark = pytest.mark.gpu
+TOL = cases.TOL
+
+
+def _rand_fields(mo, seed=0):
+    rng = np.random.default_rng(seed)
+    N = mo["nCells"]
+    nF = mo["nInternalFaces"] + sum(p["faceCells"].size for p in mo["patches"])
+    return rng.standard_normal((N, 3)), rng.standard_normal(N), rng.standard_normal(nF)
+
+
+@pytest.mark.parametrize("case", ["channel", "cavity3d", "cavity2d", "flat"])
+def test_fvc_operators_bit_exact(pkg, case):
+    if case == "channel":
+        mo, mp = cases_fv.channel(pkg, (13, 9, 7))
+    elif case == "cavity3d":
+        mo, mp = cases_fv.cavity3d(pkg, (8, 10, 12), (0.1, 0.2, 0.3))
+    elif case == "flat":
+        mo, mp = cases_fv.channel(pkg, (1, 6, 5))
+    else:
+        mo, mp = cases_fv.cavity2d(pkg, 12)
+    U, p, phi = _rand_fields(mo, 1)
+    O = port.IcoOracle(mo)
+    E = pkg.Engine(mp)
+    assert E.fv_supported(), E.L.fy_last_error(E.h).decode()
+    assert np.array_equal(E.grad_vector(U), O.grad_vector(U))
+    assert np.array_equal(E.grad_scalar(p), O.grad_scalar(p))
+    if case == "cavity2d":
+        Fi = mo["nInternalFaces"]
+        phi[Fi + 12 * 4:] = 0.0          # empty faces carry no flux
+    assert np.array_equal(E.div_flux(phi), O.div_flux(phi))
+    # face field round trip through the owner-slot layout
+    E.upload("phi", phi)
+    assert np.array_equal(E.download("phi"), phi)
+    E.close()
+    O.close()
+
+
+@pytest.mark.parametrize("n", [(9, 7, 5), (32, 32, 32)])
+def test_dic_precondition_bit_exact(pkg, n):
+    mo, mp = cases_fv.cavity3d(pkg, n)
+    rng = np.random.default_rng(2)
+    N, Fi = mo["nCells"], mo["nInternalFaces"]
+    upper = -rng.uniform(0.5, 1.5, Fi)
+    diag = np.zeros(N)
+    np.subtract.at(diag, mo["owner"], upper)
+    np.subtract.at(diag, mo["neighbour"], upper)
+    diag += rng.uniform(0.01, 0.05, N)
+    r = rng.standard_normal(N)
+    O = port.IcoOracle(mo)
+    E = pkg.Engine(mp)
+    assert np.array_equal(E.dic(diag, upper, r), O.dic(diag, upper, r))
+    E.close()
+    O.close()
+
+
+@pytest.mark.parametrize("pre", ["DIC", "diagonal", "none"])
+def test_pcg_matches_oracle(pkg, pre):
+    mo, mp = cases_fv.cavity3d(pkg, (24, 20, 16))
+    rng = np.random.default_rng(4)
+    N, Fi = mo["nCells"], mo["nInternalFaces"]
+    upper = rng.uniform(0.5, 1.5, Fi)              # negative-definite Laplacian-like matrix, as pEqn's
+    diag = np.zeros(N)
+    np.subtract.at(diag, mo["owner"], upper)
+    np.subtract.at(diag, mo["neighbour"], upper)
+    diag -= rng.uniform(0.001, 0.01, N)
+    b = rng.standard_normal(N)
+    O = port.IcoOracle(mo)
+    E = pkg.Engine(mp)
+    for tol, rel in ((1e-6, 0.05), (1e-10, 0.0)):
+        xo, po = O.pcg(diag, upper, b, np.zeros(N), tol=tol, relTol=rel, preconditioner=pre)
+        xe, pe = E.pcg(diag, upper, b, np.zeros(N), tol=tol, relTol=rel, preconditioner=pre)
+        assert pe["iters"] == po["iters"] and po["iters"] > 3
+        np.testing.assert_allclose(pe["initial"], po["initial"], rtol=1e-12)
+        np.testing.assert_allclose(pe["final"], po["final"], rtol=0.05)   # rounding of the dot products, amplified over the iterations
+        assert cases.rel_l2(xe, xo) <= TOL
+    # maxIter cap and an already-converged start behave like PCG.C
+    xo, po = O.pcg(diag, upper, b, np.zeros(N), tol=1e-14, relTol=0.0, maxIter=5, preconditioner=pre)
+    xe, pe = E.pcg(diag, upper, b, np.zeros(N), tol=1e-14, relTol=0.0, maxIter=5, preconditioner=pre)
+    assert pe["iters"] == po["iters"] == 6 and cases.rel_l2(xe, xo) <= TOL
+    xs, _ = O.pcg(diag, upper, b, np.zeros(N), tol=1e-13, relTol=0.0, preconditioner=pre)
+    xo, po = O.pcg(diag, upper, b, xs, tol=1e-6, relTol=0.0, preconditioner=pre)
+    xe, pe = E.pcg(diag, upper, b, xs, tol=1e-6, relTol=0.0, preconditioner=pre)
+    assert pe["iters"] == po["iters"] == 0 and np.array_equal(xe, xs)
+    E.close()
+    O.close()
+
+
+def test_smooth_solver_matches_oracle(pkg):
+    mo, mp = cases_fv.channel(pkg, (20, 14, 10))
+    rng = np.random.default_rng(5)
+    N, Fi = mo["nCells"], mo["nInternalFaces"]
+    upper = -rng.uniform(0.5, 1.5, Fi)
+    lower = -rng.uniform(0.5, 1.5, Fi)
+    diag = np.zeros(N)
+    np.subtract.at(diag, mo["owner"], lower)
+    np.subtract.at(diag, mo["neighbour"], upper)
+    diag += rng.uniform(0.5, 1.0, N)
+    b = rng.standard_normal(N)
+    O = port.IcoOracle(mo)
+    E = pkg.Engine(mp)
+    xo, po = O.smooth(diag, lower, upper, b, np.zeros(N), tol=1e-9)
+    xe, pe = E.smooth(diag, lower, upper, b, np.zeros(N), tol=1e-9)
+    assert pe["iters"] == po["iters"] and po["iters"] > 2
+    assert cases.rel_l2(xe, xo) <= 1e-13            # sweeps are bit-exact; only the stopping norm is summed differently
+    E.close()
+    O.close()
+
+
+def test_openfoam_cavity_tutorial_log_on_gpu(pkg):
+    """the device solver prints the stock cavity tutorial's log (see tests/test_fv_oracle.py for its provenance)"""
+    mo, mp = cases_fv.cavity2d(pkg, 20)
+    E = pkg.Engine(mp)
+    assert E.fv_supported(), E.L.fy_last_error(E.h).decode()
+    E.set_piso_controls(nu=0.01)
+    E.create_phi()
+    for ref in CAVITY_LOG:
+        E.ico_pre(0.005)
+        E.ico_solve(0.005)
+        st = E.ico_stats()
+        assert (sig6(st["meanCoNum"]), sig6(st["CoNum"])) == ref["Co"]
+        for j, k in ((0, "Ux"), (1, "Uy")):
+            u = st["U"][j]
+            assert (sig6(u["initial"]), sig6(u["final"]), u["iters"]) == ref[k], k
+        for j, k in ((0, "p1"), (1, "p2")):
+            q = st["p"][j]
+            assert (sig6(q["initial"]), sig6(q["final"]), q["iters"]) == ref[k], k
+        if ref["c1"] is not None:
+            assert sig6(st["corrSumLocal"][0]) == ref["c1"]
+        assert sig6(st["corrSumLocal"][1]) == ref["c2"]
+    E.close()
+
+
+@pytest.mark.parametrize("case", ["cavity3d", "channel", "cavity2d"])
+def test_ico_steps_match_oracle(pkg, case):
+    if case == "cavity3d":
+        mo, mp = cases_fv.cavity3d(pkg, (20, 20, 20))
+        U, p, dt, nu, ctl = np.zeros((mo["nCells"], 3)), np.zeros(mo["nCells"]), 0.004, 0.01, None
+    elif case == "channel":
+        mo, mp = cases_fv.channel(pkg, (28, 14, 12))
+        U, p = cases_fv.channel_init(mo["C"])
+        dt, nu, ctl = 0.02, 0.005, dict(nCorrectors=3, nNonOrthogonalCorrectors=1)
+    else:
+        mo, mp = cases_fv.cavity2d(pkg, 24)
+        U, p, dt, nu, ctl = np.zeros((mo["nCells"], 3)), np.zeros(mo["nCells"]), 0.004, 0.01, dict(preconditioner="diagonal")
+
+    def src(it, Ucur, vGrad):        # a momentum source that depends on the fields, like the particle reaction
+        s = np.zeros_like(Ucur)
+        s[:, 0] = 0.5 * np.sin(40.0 * mo["C"][:, 1]) - 0.2 * Ucur[:, 0]
+        s[:, 1] = 0.1 * vGrad[:, 3] * 1e-2
+        return s * (it + 1)
+
+    o = cases_fv.run_oracle_steps(mo, U, p, dt, 3, nu, ctl, src)
+    e = cases_fv.run_engine_steps(pkg, mp, U, p, dt, 3, nu, ctl, src)
+    cases_fv.compare_fluid(o, e)
+    assert abs(e["stats"][-1]["globalContErr"]) < 1e-8
+    assert e["stats"][-1]["sumLocalContErr"] < 1e-6
+
+
+def test_coupled_icoFoamYade_step(pkg):
+    """vGrad = grad(U) -> setParticleAction (point-force, the branch icoFoamYade hard-codes) -> UEqn/PISO ->
+    setSourceZero, engine vs (unmodified reference coupling + oracle fluid step)."""
+    from oracle import ref
+    n = 16
+    mo, mp = cases_fv.cavity3d(pkg, (n, n, n), (1.0, 1.0, 1.0))
+    N = mo["nCells"]
+    U0 = 0.2 * cases.fields_for(mo["C"])["U"]
+    pd = cases.particles(3000, 11, radius=0.1 / n, moving=True)
+    dt, nu = 2e-3, 1e-3
+    # oracle side
+    O = port.IcoOracle(mo, nu=nu)
+    O.field("U")[:] = U0
+    O.create_phi()
+    R = ref.RefFoamYade(mo, False)
+    R.set_properties(cases.RHOP, cases.RHOF, nu)
+    # engine side
+    E = pkg.Engine(mp)
+    E.set_properties(cases.RHOP, cases.RHOF, nu, False)
+    E.set_piso_controls(nu=nu)
+    E.upload("U", U0)
+    E.create_phi()
+    for step in range(2):
+        O.pre(dt)
+        R.field("U")[:] = O.field("U")
+        R.field("vGrad")[:] = O.field("vGrad")
+        fo, Fo = R.step(dt, pd, pieces=True)
+        O.field("uSource")[:] = R.field("uSource")
+        O.solve(dt)
+        R.set_source_zero()
+        E.ico_pre(dt)
+        fe, Fe = E.set_particle_action(dt, pd)
+        E.ico_solve(dt)
+        E.set_source_zero()
+        assert np.array_equal(fo, fe)
+        assert cases.rel_l2(Fe, Fo) <= TOL
+        assert cases.rel_l2(E.download("U"), O.field("U")) <= TOL
+        assert cases.rel_l2(E.download("p"), O.field("p")) <= TOL
+        assert not np.any(E.download("uSource"))
+    E.close()
+    R.close()
+    O.close()
+
+
+def test_unsupported_mesh_is_refused(pkg):
+    mp = pkg.box_mesh(6, 6, 6)
+    mp["V"] = mp["V"].copy()
+    mp["V"][5] *= 1.5
+    E = pkg.Engine(mp)
+    assert not E.fv_supported()
+    with pytest.raises(pkg.FyError):
+        E.ico_solve(1e-3)
+    E.close()

@@ -11,4 +11,4 @@ The directory name contains '-', so load it with
 (see __graft_entry__.load_package()).
 """
 from .binding import Engine, FyError, lib, lib_path, FIELD  # noqa: F401
-from .mesh import box_mesh  # noqa: F401
+from .mesh import box_mesh, set_bc, BC_FIXED_VALUE, BC_ZERO_GRADIENT, BC_EMPTY  # noqa: F401

@@ -21,6 +21,28 @@ class _PatchDesc(C.Structure):
                 ("bcU", C.c_int), ("valueU", C.c_double * 3), ("bcP", C.c_int), ("valueP", C.c_double)]
 
 
+class PisoControls(C.Structure):
+    _fields_ = [("nCorrectors", C.c_int), ("nNonOrthogonalCorrectors", C.c_int), ("momentumPredictor", C.c_int),
+                ("pRefCell", C.c_int), ("pRefValue", C.c_double), ("pTol", C.c_double), ("pRelTol", C.c_double),
+                ("pFinalTol", C.c_double), ("pFinalRelTol", C.c_double), ("UTol", C.c_double), ("URelTol", C.c_double),
+                ("maxIter", C.c_int), ("preconditioner", C.c_int)]
+
+
+class _SolverPerf(C.Structure):
+    _fields_ = [("initialResidual", C.c_double), ("finalResidual", C.c_double), ("nIterations", C.c_int),
+                ("pad_", C.c_int)]
+
+
+class _IcoStats(C.Structure):
+    _fields_ = [("CoNum", C.c_double), ("meanCoNum", C.c_double), ("U", _SolverPerf * 3), ("p", _SolverPerf * 8),
+                ("nPSolves", C.c_int), ("pad_", C.c_int), ("sumLocalContErr", C.c_double),
+                ("globalContErr", C.c_double), ("cumulativeContErr", C.c_double), ("corrSumLocal", C.c_double * 8),
+                ("corrGlobal", C.c_double * 8)]
+
+
+PRECOND = dict(DIC=0, diagonal=1, none=2)
+
+
 class _MeshDesc(C.Structure):
     _fields_ = [("nCells", C.c_int), ("C", _dp), ("V", _dp), ("nInternalFaces", C.c_int), ("owner", _ip),
                 ("neighbour", _ip), ("Sf", _dp), ("magSf", _dp), ("weights", _dp), ("deltaCoeffs", _dp),
@@ -76,6 +98,22 @@ def lib():
     L.fy_timer_stop.argtypes = [H, _dp]
     L.fy_launch_count.restype = C.c_longlong
     L.fy_launch_count.argtypes = [H]
+    L.fy_fv_supported.argtypes = [H]
+    L.fy_piso_default_controls.argtypes = [C.POINTER(PisoControls)]
+    L.fy_set_piso_controls.argtypes = [H, C.POINTER(PisoControls)]
+    L.fy_set_viscosity.argtypes = [H, C.c_double]
+    L.fy_create_phi.argtypes = [H]
+    L.fy_ico_pre.argtypes = [H, C.c_double]
+    L.fy_ico_solve.argtypes = [H, C.c_double]
+    L.fy_get_ico_stats.argtypes = [H, C.POINTER(_IcoStats)]
+    L.fy_fvc_grad_vector.argtypes = [H, _dp, _dp]
+    L.fy_fvc_grad_scalar.argtypes = [H, _dp, _dp]
+    L.fy_fvc_div_flux.argtypes = [H, _dp, _dp]
+    L.fy_pcg_solve.argtypes = [H, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int, C.c_int, _dp]
+    L.fy_smooth_solve.argtypes = [H, _dp, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int, _dp]
+    L.fy_dic_precondition.argtypes = [H, _dp, _dp, _dp, _dp]
+    L.fy_fv_get.argtypes = [H, C.c_char_p, _dp]
+    L.fy_get_fluid_ms.argtypes = [H, _dp]
     _lib = L
     return L
 
@@ -186,6 +224,8 @@ class Engine:
 
     def download(self, name, n=None):
         if name == "phi":
+            if n is None:
+                n = int(self.mesh["nInternalFaces"]) + sum(int(p["faceCells"].shape[0]) for p in self.mesh["patches"])
             out = np.empty(n, dtype=np.float64)
         else:
             w = _WIDTH[name]
@@ -271,3 +311,92 @@ class Engine:
 
     def launch_count(self):
         return int(self.L.fy_launch_count(self.h))
+
+    # ---- the fluid half (icoFoamYade time step) -------------------------------------------------
+    def fv_supported(self):
+        return bool(self.L.fy_fv_supported(self.h))
+
+    def set_piso_controls(self, **kw):
+        c = PisoControls()
+        self.L.fy_piso_default_controls(C.byref(c))
+        for k, v in kw.items():
+            if k == "preconditioner" and isinstance(v, str):
+                v = PRECOND[v]
+            if k == "nu":
+                self._ck(self.L.fy_set_viscosity(self.h, float(v)))
+                continue
+            if not hasattr(c, k):
+                raise KeyError(k)
+            setattr(c, k, v)
+        self._ck(self.L.fy_set_piso_controls(self.h, C.byref(c)))
+
+    def create_phi(self):
+        self._ck(self.L.fy_create_phi(self.h))
+
+    def ico_pre(self, dt):
+        self._ck(self.L.fy_ico_pre(self.h, dt))
+
+    def ico_solve(self, dt):
+        self._ck(self.L.fy_ico_solve(self.h, dt))
+
+    def fluid_step(self, dt):
+        """the fluid part of one icoFoamYade time step after setParticleAction (icoFoamYade.C:79-140)"""
+        self._ck(self.L.fy_ico_solve(self.h, dt))
+
+    def ico_stats(self):
+        st = _IcoStats()
+        self._ck(self.L.fy_get_ico_stats(self.h, C.byref(st)))
+        perf = lambda q: dict(initial=q.initialResidual, final=q.finalResidual, iters=q.nIterations)  # noqa: E731
+        return dict(CoNum=st.CoNum, meanCoNum=st.meanCoNum, U=[perf(st.U[j]) for j in range(3)],
+                    p=[perf(st.p[k]) for k in range(min(st.nPSolves, 8))], nPSolves=st.nPSolves,
+                    sumLocalContErr=st.sumLocalContErr, globalContErr=st.globalContErr,
+                    cumulativeContErr=st.cumulativeContErr, corrSumLocal=list(st.corrSumLocal),
+                    corrGlobal=list(st.corrGlobal))
+
+    def grad_vector(self, U):
+        out = np.empty((self.N, 9))
+        self._ck(self.L.fy_fvc_grad_vector(self.h, _d(_c64(U)), _d(out)))
+        return out
+
+    def grad_scalar(self, p):
+        out = np.empty((self.N, 3))
+        self._ck(self.L.fy_fvc_grad_scalar(self.h, _d(_c64(p)), _d(out)))
+        return out
+
+    def div_flux(self, phi):
+        out = np.empty(self.N)
+        self._ck(self.L.fy_fvc_div_flux(self.h, _d(_c64(phi)), _d(out)))
+        return out
+
+    def pcg(self, diag, upper, source, psi0, tol=1e-6, relTol=0.0, maxIter=1000, preconditioner="DIC"):
+        psi = _c64(psi0).copy()
+        out = np.zeros(3)
+        self._ck(self.L.fy_pcg_solve(self.h, _d(_c64(diag)), _d(_c64(upper)), _d(_c64(source)), _d(psi), tol, relTol,
+                                     maxIter, PRECOND[preconditioner], _d(out)))
+        return psi, dict(initial=out[0], final=out[1], iters=int(out[2]))
+
+    def smooth(self, diag, lower, upper, source, psi0, tol=1e-5, relTol=0.0, maxIter=1000):
+        psi = _c64(psi0).copy()
+        out = np.zeros(3)
+        self._ck(self.L.fy_smooth_solve(self.h, _d(_c64(diag)), _d(_c64(lower)), _d(_c64(upper)), _d(_c64(source)),
+                                        _d(psi), tol, relTol, maxIter, _d(out)))
+        return psi, dict(initial=out[0], final=out[1], iters=int(out[2]))
+
+    def dic(self, diag, upper, rA):
+        out = np.empty(self.N)
+        self._ck(self.L.fy_dic_precondition(self.h, _d(_c64(diag)), _d(_c64(upper)), _d(_c64(rA)), _d(out)))
+        return out
+
+    def fv_get(self, name):
+        nF = int(self.mesh["nInternalFaces"])
+        nB = sum(int(p["faceCells"].shape[0]) for p in self.mesh["patches"])
+        shape = dict(rAU=(self.N,), HbyA=(self.N, 3), gradP=(self.N, 3), diagU=(self.N,), sourceU=(self.N, 3),
+                     phiHbyA=(nF + nB,), phi=(nF + nB,), upperP=(nF,), upperU=(nF,), lowerU=(nF,))[name]
+        out = np.empty(shape)
+        self._ck(self.L.fy_fv_get(self.h, name.encode(), _d(out)))
+        return out
+
+    def fluid_ms(self):
+        out = np.zeros(4)
+        self._ck(self.L.fy_get_fluid_ms(self.h, _d(out)))
+        return out

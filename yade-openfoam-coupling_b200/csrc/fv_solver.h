@@ -1,5 +1,80 @@
-// fv_solver.h -- internal interface of the finite-volume / PISO half (fv_*.cu).
+// fv_solver.h -- internal interface of the finite-volume / PISO half (fv_box.cu).
 #pragma once
+#include <string>
+#include <vector>
+
+#include "fv_box.cuh"
 #include "fy_ctx.h"
 
+// solver state shared between the kernels of one linear solve (device memory; the host reads it back
+// only every few iterations, the iteration kernels themselves test `done`)
+struct FvSolveDev {
+    double tol, relTol;
+    int maxIter, precond;
+    double avg, normFactor, initRes, finalRes;
+    double wArA, wArAold, wApA, alpha, beta;
+    int nIter, done, singular, pad;
+};
+
+// device scalars of one time step (Courant number, continuity errors, adjustPhi)
+struct FvStepDev {
+    double CoNum, meanCoNum;
+    double sumLocal, global;
+    double corrSumLocal[8], corrGlobal[8];
+    double massIn, fixedMassOut, adjustableMassOut, totalFlux, massCorr;
+    int adjustFail, pad;
+};
+
+struct FvState {
+    bool supported = false;
+    std::string why;
+    BoxGeom g;
+    int nFi = 0, nB = 0;
+    int* dSlotOfFace = nullptr;         // [nFi + nB] OpenFOAM face order -> owner slot
+    std::vector<int> hSlotOfFace;
+    fy_piso_controls ctl;
+    double nu = 0.01;
+    double cumulativeContErr = 0;
+    fy_ico_stats stats;
+
+    // face fields (owner slots)
+    double *phi = nullptr, *phi0 = nullptr, *phiHbyA = nullptr;
+    // cell fields
+    double *U0 = nullptr, *HbyA = nullptr, *rAU = nullptr, *gradP = nullptr;
+    // UEqn: diag, lower/upper in owner slots [3N], source [N][3]; per-component solve arrays (SoA [3][N])
+    double *diagU = nullptr, *loU = nullptr, *upU = nullptr, *srcU = nullptr;
+    double *dgU = nullptr, *bU = nullptr, *psiU = nullptr, *bPrime = nullptr;
+    // pEqn
+    double *upP = nullptr, *dgP = nullptr, *bP = nullptr;
+    // Krylov vectors
+    double *rD = nullptr, *pA = nullptr, *wA = nullptr, *rA = nullptr;
+    // scratch for the parity hooks (LDU-order staging)
+    double *stage = nullptr;
+    size_t stageCap = 0;
+
+    FvRed red{nullptr, nullptr};
+    FvSolveDev* dSolve = nullptr;
+    FvSolveDev* hSolve = nullptr;       // pinned
+    FvStepDev* dStep = nullptr;
+    FvStepDev* hStep = nullptr;         // pinned
+    int cellGrid = 0;                   // blocks of the grid-stride cell kernels
+    int waveGrid = 0;                   // co-resident blocks of the cooperative wavefront kernels
+    int pcgBatch = 8;
+    double fluidMs[4] = {0, 0, 0, 0};
+};
+
+int fvCreate(fy_ctx* h, const fy_mesh_desc* m);
+int fvPcgSolve(fy_ctx* h, FvState* s, const double* dg, const double* up, const double* b, double* psi, double tol,
+               double relTol, int maxIter, int precond, fy_solver_perf* perf);
+int fvSmoothSolve(fy_ctx* h, FvState* s, const double* dg, const double* lo, const double* up, const double* b,
+                  double* psi, double tol, double relTol, int maxIter, fy_solver_perf* perf);
+int fvDicPrecondition(fy_ctx* h, FvState* s, const double* dg, const double* up, const double* rA, double* wA);
+int fvCreatePhi(fy_ctx* h, FvState* s);
+int fvGradVector(fy_ctx* h, FvState* s, const double* dU, double* dOut);
+int fvGradScalar(fy_ctx* h, FvState* s, const double* dP, double* dOut);
+int fvDivFlux(fy_ctx* h, FvState* s, const double* dPhiSlots, double* dOut);
+int fvFacesToSlots(fy_ctx* h, FvState* s, int n, const double* dFaces, double* dSlots);
+int fvSlotsToFaces(fy_ctx* h, FvState* s, int n, const double* dSlots, double* dFaces);
+int fvIcoPre(fy_ctx* h, FvState* s, double dt);
+int fvIcoSolve(fy_ctx* h, FvState* s, double dt);
 void fvDestroy(fy_ctx* h);

@@ -188,6 +188,8 @@ int fy_create(const fy_mesh_desc* m, int device, fy_handle* out)
     cudaMemsetAsync(h->dStamp, 0, N * sizeof(int), h->stream);
     rc = fyInitCouplingFields(h);
     if (rc) return fail(rc);
+    rc = fvCreate(h, m);                 // decides whether the mesh qualifies for the device FV path
+    if (rc) return fail(rc);
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) { h->err = "sync after create failed"; return fail(FY_ERR_CUDA); }
     *out = h;
     return FY_OK;
@@ -217,6 +219,7 @@ int fy_set_properties(fy_handle h, double rhoP, double rhoF, double nu, int gaus
     h->rhoP = rhoP; h->rhoF = rhoF; h->nu = nu;
     h->gaussian = gaussianInterp != 0;
     h->propsSet = true;
+    if (h->fv) h->fv->nu = nu;
     return FY_OK;
 }
 
@@ -252,12 +255,20 @@ int fy_upload_field(fy_handle h, int f, const double* src)
 {
     if (!h || f < 0 || f >= FY_F_COUNT || !src || !h->dField[f]) return FY_ERR_INVALID;
     FY_CUDA(cudaMemcpyAsync(h->dField[f], src, fieldCount(h, f) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (f == FY_F_PHI && h->fv && h->fv->supported) {      // OpenFOAM face order -> owner slots
+        int rc = fvFacesToSlots(h, h->fv, h->fv->nFi + h->fv->nB, h->dField[f], h->fv->phi);
+        if (rc) return rc;
+    }
     FY_CUDA(cudaStreamSynchronize(h->stream));
     return FY_OK;
 }
 int fy_download_field(fy_handle h, int f, double* dst)
 {
     if (!h || f < 0 || f >= FY_F_COUNT || !dst || !h->dField[f]) return FY_ERR_INVALID;
+    if (f == FY_F_PHI && h->fv && h->fv->supported) {
+        int rc = fvSlotsToFaces(h, h->fv, h->fv->nFi + h->fv->nB, h->fv->phi, h->dField[f]);
+        if (rc) return rc;
+    }
     FY_CUDA(cudaMemcpyAsync(dst, h->dField[f], fieldCount(h, f) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     FY_CUDA(cudaStreamSynchronize(h->stream));
     return FY_OK;

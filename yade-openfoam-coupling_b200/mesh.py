@@ -10,9 +10,12 @@ import numpy as np
 PATCH_NAMES = ("xmin", "xmax", "ymin", "ymax", "zmin", "zmax")
 BC_FIXED_VALUE = 0
 BC_ZERO_GRADIENT = 1
+BC_EMPTY = 2
 
 
-def box_mesh(nx, ny, nz, lx=1.0, ly=1.0, lz=1.0, origin=(0.0, 0.0, 0.0), faces=True):
+def box_mesh(nx, ny, nz, lx=1.0, ly=1.0, lz=1.0, origin=(0.0, 0.0, 0.0), faces=True, patches=None):
+    """`patches`: optional list of (name, [sides...]) grouping the six sides into boundary patches in boundary
+    order (e.g. the cavity tutorial's movingWall / fixedWalls / frontAndBack); default one patch per side."""
     hx, hy, hz = lx / nx, ly / ny, lz / nz
     N = nx * ny * nz
     k, j, i = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
@@ -49,17 +52,25 @@ def box_mesh(nx, ny, nz, lx=1.0, ly=1.0, lz=1.0, origin=(0.0, 0.0, 0.0), faces=T
     Sf[np.arange(Fi), d] = area[d]
     m.update(nInternalFaces=Fi, owner=owner, neighbour=neigh, Sf=Sf, magSf=area[d].copy(),
              weights=np.full(Fi, 0.5, dtype=np.float64), deltaCoeffs=(1.0 / dist)[d].copy())
+    side = dict(xmin=(i == 0, 0, -1.0), xmax=(i == nx - 1, 0, 1.0), ymin=(j == 0, 1, -1.0), ymax=(j == ny - 1, 1, 1.0),
+                zmin=(k == 0, 2, -1.0), zmax=(k == nz - 1, 2, 1.0))
+    groups = patches if patches is not None else [(nm, [nm]) for nm in PATCH_NAMES]
     patches = []
-    for name, mask, ax, sign in (("xmin", i == 0, 0, -1.0), ("xmax", i == nx - 1, 0, 1.0),
-                                 ("ymin", j == 0, 1, -1.0), ("ymax", j == ny - 1, 1, 1.0),
-                                 ("zmin", k == 0, 2, -1.0), ("zmax", k == nz - 1, 2, 1.0)):
-        fc = cid[mask].astype(np.int32)
-        nf = fc.shape[0]
-        psf = np.zeros((nf, 3), dtype=np.float64)
-        psf[:, ax] = sign * area[ax]
-        patches.append(dict(name=name, faceCells=fc, Sf=psf, magSf=np.full(nf, area[ax]),
-                            deltaCoeffs=np.full(nf, 1.0 / (0.5 * dist[ax])),
-                            bcU=BC_FIXED_VALUE, valueU=(0.0, 0.0, 0.0), bcP=BC_ZERO_GRADIENT, valueP=0.0))
+    for name, sides in groups:
+        fcs, sfs, mss, dcs = [], [], [], []
+        for sd in sides:
+            mask, ax, sign = side[sd]
+            fc = cid[mask].astype(np.int32)
+            nf = fc.shape[0]
+            psf = np.zeros((nf, 3), dtype=np.float64)
+            psf[:, ax] = sign * area[ax]
+            fcs.append(fc)
+            sfs.append(psf)
+            mss.append(np.full(nf, area[ax]))
+            dcs.append(np.full(nf, 1.0 / (0.5 * dist[ax])))
+        patches.append(dict(name=name, faceCells=np.concatenate(fcs), Sf=np.concatenate(sfs), magSf=np.concatenate(mss),
+                            deltaCoeffs=np.concatenate(dcs), bcU=BC_FIXED_VALUE, valueU=(0.0, 0.0, 0.0),
+                            bcP=BC_ZERO_GRADIENT, valueP=0.0))
     m["patches"] = patches
     return m
 
