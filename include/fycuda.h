@@ -259,6 +259,11 @@ int fy_fv_get(fy_handle h, const char* name, double* h_dst);
 /* Device time (ms) of the phases of the last fy_ico_solve: [0] UEqn assembly + momentum predictor
  * [1] pressure solves (PCG) [2] the rest of the correctors; and the last PCG's iteration time.      */
 int fy_get_fluid_ms(fy_handle h, double out[4]);
+/* Average device time (ms, CUDA events on the handle's stream) of each kernel class of the PCG iteration,
+ * sampled while profiling is on (fy_set_profiling): [0] preconditioner forward sweep [1] backward sweep
+ * (+ wA.rA) [2] search direction [3] Amul (+ wA.pA) [4] solution/residual update (+ sum|rA|);
+ * [5] samples taken [6] PCG iterations run since the last reset.                                        */
+int fy_get_kernel_ms(fy_handle h, double out[8], int reset);
 
 /* Blocks until all work queued on the handle's stream is complete. */
 int fy_synchronize(fy_handle h);

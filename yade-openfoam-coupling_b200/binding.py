@@ -114,6 +114,7 @@ def lib():
     L.fy_dic_precondition.argtypes = [H, _dp, _dp, _dp, _dp]
     L.fy_fv_get.argtypes = [H, C.c_char_p, _dp]
     L.fy_get_fluid_ms.argtypes = [H, _dp]
+    L.fy_get_kernel_ms.argtypes = [H, _dp, C.c_int]
     _lib = L
     return L
 
@@ -400,3 +401,9 @@ class Engine:
         out = np.zeros(4)
         self._ck(self.L.fy_get_fluid_ms(self.h, _d(out)))
         return out
+
+    def kernel_ms(self, reset=True):
+        out = np.zeros(8)
+        self._ck(self.L.fy_get_kernel_ms(self.h, _d(out), int(reset)))
+        return dict(precond_fwd=out[0], precond_bwd=out[1], direction=out[2], amul=out[3], update=out[4],
+                    samples=int(out[5]), pcg_iterations=int(out[6]))

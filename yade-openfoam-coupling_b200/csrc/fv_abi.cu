@@ -264,4 +264,23 @@ int fy_get_fluid_ms(fy_handle h, double out[4])
     return FY_OK;
 }
 
+int fy_get_kernel_ms(fy_handle h, double out[8], int reset)
+{
+    FvState* s;
+    int rc = needFv(h, &s);
+    if (rc) return rc;
+    if (!out) return FY_ERR_INVALID;
+    const double n = s->kernelSamples > 0 ? (double)s->kernelSamples : 1.0;
+    for (int q = 0; q < 5; ++q) out[q] = s->kernelMs[q] / n;
+    out[5] = (double)s->kernelSamples;
+    out[6] = (double)s->pcgIterations;
+    out[7] = 0;
+    if (reset) {
+        for (int q = 0; q < 5; ++q) s->kernelMs[q] = 0;
+        s->kernelSamples = 0;
+        s->pcgIterations = 0;
+    }
+    return FY_OK;
+}
+
 }  // extern "C"

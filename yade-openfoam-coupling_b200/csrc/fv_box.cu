@@ -931,25 +931,45 @@ int fvPcgSolve(fy_ctx* h, FvState* s, const double* dg, const double* up, const 
         FV_LAUNCH(k_recip, G, N, dg, s->rD, s->dSolve);
     }
     int queued = 0;
+    bool sampled = false;
+    const bool prof = h->profiling && s->pev[0];
     for (;;) {
         if ((rc = readSolve(h, s))) return rc;
+        if (sampled) {
+            for (int q = 0; q < 5; ++q) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, s->pev[q], s->pev[q + 1]);
+                s->kernelMs[q] += ms;
+            }
+            s->kernelSamples++;
+            sampled = false;
+        }
         if (s->hSolve->done) break;
         int batch = s->pcgBatch;
         if (queued >= 4 * batch) batch *= 2;
         for (int it = 0; it < batch; ++it) {
+            const bool ev = prof && it == 0;
+            if (ev) cudaEventRecord(s->pev[0], h->stream);
             if (precond == FV_PRECOND_DIC) {
                 if ((rc = launchWave<OpDicFwd, false, false>(h, s, OpDicFwd{s->rD, up, s->rA, s->wA}, s->dSolve))) return rc;
+                if (ev) cudaEventRecord(s->pev[1], h->stream);
                 if ((rc = launchWave<OpDicBwd, true, true>(h, s, OpDicBwd{s->rD, up, s->rA, s->wA}, s->dSolve))) return rc;
             } else {
+                if (ev) cudaEventRecord(s->pev[1], h->stream);
                 FV_LAUNCH(k_precond_diag, G, N, precond == FV_PRECOND_DIAGONAL ? s->rD : (const double*)nullptr, s->rA, s->wA,
                           s->red, s->dSolve);
             }
+            if (ev) cudaEventRecord(s->pev[2], h->stream);
             FV_LAUNCH(k_pcg_dir, G, N, s->wA, s->pA, s->dSolve);
+            if (ev) cudaEventRecord(s->pev[3], h->stream);
             FV_LAUNCH(k_pcg_amul, G, g, dg, up, s->pA, s->wA, s->red, s->dSolve);
+            if (ev) cudaEventRecord(s->pev[4], h->stream);
             FV_LAUNCH(k_pcg_update, G, N, s->pA, s->wA, psi, s->rA, s->red, s->dSolve);
+            if (ev) { cudaEventRecord(s->pev[5], h->stream); sampled = true; }
         }
         queued += batch;
     }
+    s->pcgIterations += s->hSolve->nIter;
     if (perf) {
         perf->initialResidual = s->hSolve->initRes;
         perf->finalResidual = s->hSolve->finalRes;
@@ -1271,6 +1291,7 @@ int fvCreate(fy_ctx* h, const fy_mesh_desc* m)
     if ((rc = devAlloc(h, &s->dStep, 1))) return rc;
     FY_CUDA(cudaHostAlloc((void**)&s->hSolve, sizeof(FvSolveDev), cudaHostAllocDefault));
     FY_CUDA(cudaHostAlloc((void**)&s->hStep, sizeof(FvStepDev), cudaHostAllocDefault));
+    for (auto& e : s->pev) cudaEventCreate(&e);
     // the face field phi lives in owner slots; the ABI's FY_F_PHI is served through the slot map
     FY_CUDA(cudaStreamSynchronize(h->stream));
     s->supported = true;
@@ -1285,6 +1306,7 @@ void fvDestroy(fy_ctx* h)
                     s->srcU, s->dgU, s->bU, s->psiU, s->bPrime, s->upP, s->dgP, s->bP, s->rD, s->pA, s->wA, s->rA, s->stage,
                     s->red.partial, s->red.ticket, s->dSolve, s->dStep};
     for (void* p : ptrs) if (p) cudaFree(p);
+    for (auto& e : s->pev) if (e) cudaEventDestroy(e);
     if (s->hSolve) cudaFreeHost(s->hSolve);
     if (s->hStep) cudaFreeHost(s->hStep);
     delete s;

@@ -61,6 +61,13 @@ struct FvState {
     int waveGrid = 0;                   // co-resident blocks of the cooperative wavefront kernels
     int pcgBatch = 8;
     double fluidMs[4] = {0, 0, 0, 0};
+    // profiling (fy_set_profiling): device time of each kernel class of the PCG iteration, sampled on the
+    // first iteration of every batch: [0] precondition forward [1] backward (+wA.rA) [2] search direction
+    // [3] Amul (+wA.pA) [4] update (+|rA|)
+    cudaEvent_t pev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double kernelMs[5] = {0, 0, 0, 0, 0};
+    long long kernelSamples = 0;
+    long long pcgIterations = 0;        // since the last fy_get_kernel_ms reset
 };
 
 int fvCreate(fy_ctx* h, const fy_mesh_desc* m);
