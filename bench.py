@@ -249,11 +249,11 @@ def run_engine(args):
             cand["k_point_force"] = (phase[3], 132.0 * P + 128.0 * N)
         if fluid and kms and kms["samples"] > 0:
             it_step = kms["pcg_iterations"] / float(nprof)
-            cand["k_wave<OpDicFwd> (DIC forward sweep)"] = (kms["precond_fwd"], 24.0 * N + 8.0 * 3 * N, it_step)
-            cand["k_wave<OpDicBwd> (DIC backward sweep + wA.rA)"] = (kms["precond_bwd"], 24.0 * N + 8.0 * 3 * N, it_step)
-            cand["k_pcg_amul"] = (kms["amul"], 24.0 * N + 8.0 * 3 * N, it_step)
-            cand["k_pcg_update"] = (kms["update"], 48.0 * N, it_step)
-            cand["k_pcg_dir"] = (kms["direction"], 24.0 * N, it_step)
+            cand["k_pencil<OpDicFwd> (DIC forward sweep)"] = (kms["precond_fwd"], 24.0 * N + 8.0 * 3 * N, it_step)
+            cand["k_pencil<OpDicBwd> (DIC backward sweep + wA.rA)"] = (kms["precond_bwd"], 24.0 * N + 8.0 * 3 * N, it_step)
+            cand["k_pen_amul"] = (kms["amul"], 24.0 * N + 8.0 * 3 * N, it_step)
+            cand["k_pen_update"] = (kms["update"], 48.0 * N, it_step)
+            cand["k_pen_dir"] = (kms["direction"], 24.0 * N, it_step)
         # dominant = largest share of the step
         def share(v):
             return v[0] * (v[2] if len(v) > 2 else 1.0)

@@ -48,7 +48,7 @@ def test_fvc_operators_bit_exact(pkg, case):
     O.close()
 
 
-@pytest.mark.parametrize("n", [(9, 7, 5), (32, 32, 32)])
+@pytest.mark.parametrize("n", [(9, 7, 5), (32, 32, 32), (12, 70, 9), (40, 33, 19), (5, 100, 3)])
 def test_dic_precondition_bit_exact(pkg, n):
     mo, mp = cases_fv.cavity3d(pkg, n)
     rng = np.random.default_rng(2)

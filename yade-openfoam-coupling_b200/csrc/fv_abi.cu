@@ -213,7 +213,8 @@ int fy_smooth_solve(fy_handle h, const double* diag, const double* lower, const 
     double *dD, *dLo, *dUp, *dB, *dPsi;
     if ((rc = stageMatrix(h, s, diag, lower, upper, source, psi, &dD, &dLo, &dUp, &dB, &dPsi))) return rc;
     fy_solver_perf perf{0, 0, 0, 0};
-    if ((rc = fvSmoothSolve(h, s, dD, dLo, dUp, dB, dPsi, tol, relTol, maxIter, &perf))) return rc;
+    if ((rc = fvSmoothSetMatrix(h, s, dLo, dUp))) return rc;
+    if ((rc = fvSmoothSolve(h, s, dD, dB, dPsi, tol, relTol, maxIter, &perf))) return rc;
     if (out3) { out3[0] = perf.initialResidual; out3[1] = perf.finalResidual; out3[2] = perf.nIterations; }
     return d2h(h, psi, dPsi, (size_t)s->g.N);
 }
@@ -250,6 +251,16 @@ int fy_fv_get(fy_handle h, const char* name, double* dst)
         const double* src = k == "phiHbyA" ? s->phiHbyA : (k == "phi" ? s->phi : (k == "upperP" ? s->upP : (k == "upperU" ? s->upU : s->loU)));
         if ((rc = fvSlotsToFaces(h, s, (int)nF, src, d))) return rc;
         return d2h(h, dst, d, nF);
+    }
+    if (k == "pencilTrace") {        // debug: [nJB*nz][4] time stamps (ns, relative to the earliest) of the last pencil launch
+        const size_t n = ((size_t)s->pen.g.nJB * (s->pen.g.nz + 8) * 3 + 64) * 32;
+        std::vector<unsigned long long> t(n);
+        FY_CUDA(cudaStreamSynchronize(h->stream));
+        FY_CUDA(cudaMemcpy(t.data(), s->pen.trace, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        unsigned long long t0 = ~0ull;
+        for (size_t q = 0; q < n; ++q) if (t[q] && t[q] < t0) t0 = t[q];
+        for (size_t q = 0; q < n; ++q) dst[q] = t[q] ? (double)(t[q] - t0) : -1.0;
+        return FY_OK;
     }
     h->err = "fy_fv_get: unknown field " + k;
     return FY_ERR_INVALID;

@@ -11,15 +11,11 @@
 // keep OpenFOAM's dependency order: on the lexicographic box cell (i,j,k) depends on (i-1,j,k), (i,j-1,k),
 // (i,j,k-1), so all cells of a hyperplane i+j+k = s are independent and are processed together
 // (wavefront schedule, one grid-wide barrier per plane inside one cooperative kernel).
-#include <cooperative_groups.h>
-
 #include <algorithm>
 #include <cmath>
 #include <cstring>
 
 #include "fv_solver.h"
-
-namespace cg = cooperative_groups;
 
 namespace {
 constexpr int BLK = 256;
@@ -329,289 +325,6 @@ __global__ void __launch_bounds__(BLK) k_store_component(int N, const double* __
 }
 
 // ---------------------------------------------------------------------------------------------
-// lduMatrix kernels on owner-slot coefficients (lo/up [3N]; for a symmetric matrix lo == up)
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double fvAmulCell(const BoxGeom& g, const double* __restrict__ dg, const double* __restrict__ lo,
-                                             const double* __restrict__ up, const double* __restrict__ x, int c, int i,
-                                             int j, int k)
-{
-    const int N = g.N;
-    double a = dg[c] * x[c];
-    if (k > 0) a += lo[2 * N + c - g.sz] * x[c - g.sz];
-    if (j > 0) a += lo[N + c - g.sy] * x[c - g.sy];
-    if (i > 0) a += lo[c - 1] * x[c - 1];
-    if (i < g.nx - 1) a += up[c] * x[c + 1];
-    if (j < g.ny - 1) a += up[N + c] * x[c + g.sy];
-    if (k < g.nz - 1) a += up[2 * N + c] * x[c + g.sz];
-    return a;
-}
-__device__ __forceinline__ double fvSumACell(const BoxGeom& g, const double* __restrict__ dg, const double* __restrict__ lo,
-                                             const double* __restrict__ up, int c, int i, int j, int k)
-{
-    const int N = g.N;
-    double a = dg[c];
-    if (k > 0) a += lo[2 * N + c - g.sz];
-    if (j > 0) a += lo[N + c - g.sy];
-    if (i > 0) a += lo[c - 1];
-    if (i < g.nx - 1) a += up[c];
-    if (j < g.ny - 1) a += up[N + c];
-    if (k < g.nz - 1) a += up[2 * N + c];
-    return a;
-}
-
-__global__ void k_solve_begin(FvSolveDev* st, double tol, double relTol, int maxIter, int precond)
-{
-    st->tol = tol; st->relTol = relTol; st->maxIter = maxIter; st->precond = precond;
-    st->avg = 0; st->normFactor = 0; st->initRes = 0; st->finalRes = 0;
-    st->wArA = 1e20; st->wArAold = 1e20; st->wApA = 0; st->alpha = 0; st->beta = 0;
-    st->nIter = 0; st->done = 0; st->singular = 0;
-}
-
-__device__ __forceinline__ bool fvConverged(const FvSolveDev* st)
-{
-    return st->finalRes < st->tol || (st->relTol > 1e-20 && st->finalRes < st->relTol * st->initRes);
-}
-
-// gAverage(psi)
-__global__ void __launch_bounds__(BLK) k_avg(int N, const double* __restrict__ psi, FvRed red, FvSolveDev* st)
-{
-    double v[1] = {0.0};
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < N; c += gridDim.x * blockDim.x) v[0] += psi[c];
-    fvGridReduce<1, false, BLK>(v, red, [=](const double* t) { st->avg = t[0] / N; });
-}
-
-// rA = source - A psi;  normFactor = sum(|Apsi - sumA avg| + |source - sumA avg|) + 1e-20;
-// initialResidual = sum|rA| / normFactor                              [OF-6 lduMatrix::solver::normFactor]
-__global__ void __launch_bounds__(BLK)
-k_solve_init(BoxGeom g, const double* __restrict__ dg, const double* __restrict__ lo, const double* __restrict__ up,
-             const double* __restrict__ b, const double* __restrict__ psi, double* __restrict__ rA, FvRed red,
-             FvSolveDev* st)
-{
-    double v[2] = {0.0, 0.0};
-    const double avg = st->avg;
-    FV_CELL_LOOP(g, c) {
-        int i, j, k;
-        fvIJK(g, c, i, j, k);
-        const double Apsi = fvAmulCell(g, dg, lo, up, psi, c, i, j, k);
-        const double t = fvSumACell(g, dg, lo, up, c, i, j, k) * avg;
-        const double r = b[c] - Apsi;
-        if (rA) rA[c] = r;
-        v[0] += fabs(Apsi - t) + fabs(b[c] - t);
-        v[1] += fabs(r);
-    }
-    fvGridReduce<2, false, BLK>(v, red, [=](const double* t) {
-        st->normFactor = t[0] + 1e-20;
-        st->initRes = t[1] / st->normFactor;
-        st->finalRes = st->initRes;
-        st->done = fvConverged(st) ? 1 : 0;
-    });
-}
-
-// lduMatrix::residual + gSumMag (smoothSolver's convergence test after each sweep)
-__global__ void __launch_bounds__(BLK)
-k_residual(BoxGeom g, const double* __restrict__ dg, const double* __restrict__ lo, const double* __restrict__ up,
-           const double* __restrict__ b, const double* __restrict__ psi, FvRed red, FvSolveDev* st)
-{
-    double v[1] = {0.0};
-    const int N = g.N;
-    FV_CELL_LOOP(g, c) {
-        int i, j, k;
-        fvIJK(g, c, i, j, k);
-        double r = b[c] - dg[c] * psi[c];
-        if (k > 0) r -= lo[2 * N + c - g.sz] * psi[c - g.sz];
-        if (j > 0) r -= lo[N + c - g.sy] * psi[c - g.sy];
-        if (i > 0) r -= lo[c - 1] * psi[c - 1];
-        if (i < g.nx - 1) r -= up[c] * psi[c + 1];
-        if (j < g.ny - 1) r -= up[N + c] * psi[c + g.sy];
-        if (k < g.nz - 1) r -= up[2 * N + c] * psi[c + g.sz];
-        v[0] += fabs(r);
-    }
-    fvGridReduce<1, false, BLK>(v, red, [=](const double* t) {
-        st->finalRes = t[0] / st->normFactor;
-        st->nIter += 1;                                               // nSweeps = 1
-        st->done = (!(st->nIter < st->maxIter) || fvConverged(st)) ? 1 : 0;
-    });
-}
-
-// ---------------------------------------------------------------------------------------------
-// wavefront engine: cells of the hyperplane i+j+k = s are independent in every sequential LDU
-// recurrence; one cooperative kernel walks the planes with a grid barrier between them.
-// ---------------------------------------------------------------------------------------------
-struct OpDicD {            // DIC calcReciprocalD, before the final 1/x: rD[u] -= upper^2 / rD[l]
-    const double* dg; const double* up; double* D;
-    __device__ __forceinline__ void cell(const BoxGeom& g, int c, int i, int j, int k, double&) const
-    {
-        const int N = g.N;
-        double r = dg[c];
-        if (k > 0) { const double u = up[2 * N + c - g.sz]; r -= u * u / D[c - g.sz]; }
-        if (j > 0) { const double u = up[N + c - g.sy]; r -= u * u / D[c - g.sy]; }
-        if (i > 0) { const double u = up[c - 1]; r -= u * u / D[c - 1]; }
-        D[c] = r;
-    }
-};
-struct OpDicFwd {          // wA = rD rA;  wA[u] -= rD[u] upper wA[l]   (faces ascending)
-    const double* rD; const double* up; const double* rA; double* wA;
-    __device__ __forceinline__ void cell(const BoxGeom& g, int c, int i, int j, int k, double&) const
-    {
-        const int N = g.N;
-        const double rd = rD[c];
-        double w = rd * rA[c];
-        if (k > 0) w -= rd * up[2 * N + c - g.sz] * wA[c - g.sz];
-        if (j > 0) w -= rd * up[N + c - g.sy] * wA[c - g.sy];
-        if (i > 0) w -= rd * up[c - 1] * wA[c - 1];
-        wA[c] = w;
-    }
-};
-struct OpDicBwd {          // wA[l] -= rD[l] upper wA[u]   (faces descending); accumulates wA.rA
-    const double* rD; const double* up; const double* rA; double* wA;
-    __device__ __forceinline__ void cell(const BoxGeom& g, int c, int i, int j, int k, double& acc) const
-    {
-        const int N = g.N;
-        const double rd = rD[c];
-        double w = wA[c];
-        if (k < g.nz - 1) w -= rd * up[2 * N + c] * wA[c + g.sz];
-        if (j < g.ny - 1) w -= rd * up[N + c] * wA[c + g.sy];
-        if (i < g.nx - 1) w -= rd * up[c] * wA[c + 1];
-        wA[c] = w;
-        acc += w * rA[c];
-    }
-};
-struct OpGsFwd {           // symGaussSeidel forward sweep; leaves bPrime (source minus the lower-side products)
-    const double* dg; const double* lo; const double* up; const double* b; double* psi; double* bPrime;
-    __device__ __forceinline__ void cell(const BoxGeom& g, int c, int i, int j, int k, double&) const
-    {
-        const int N = g.N;
-        double bp = b[c];
-        if (k > 0) bp -= lo[2 * N + c - g.sz] * psi[c - g.sz];
-        if (j > 0) bp -= lo[N + c - g.sy] * psi[c - g.sy];
-        if (i > 0) bp -= lo[c - 1] * psi[c - 1];
-        bPrime[c] = bp;
-        double x = bp;
-        if (i < g.nx - 1) x -= up[c] * psi[c + 1];
-        if (j < g.ny - 1) x -= up[N + c] * psi[c + g.sy];
-        if (k < g.nz - 1) x -= up[2 * N + c] * psi[c + g.sz];
-        psi[c] = x / dg[c];
-    }
-};
-struct OpGsBwd {           // symGaussSeidel backward sweep
-    const double* dg; const double* up; const double* bPrime; double* psi;
-    __device__ __forceinline__ void cell(const BoxGeom& g, int c, int i, int j, int k, double&) const
-    {
-        const int N = g.N;
-        double x = bPrime[c];
-        if (i < g.nx - 1) x -= up[c] * psi[c + 1];
-        if (j < g.ny - 1) x -= up[N + c] * psi[c + g.sy];
-        if (k < g.nz - 1) x -= up[2 * N + c] * psi[c + g.sz];
-        psi[c] = x / dg[c];
-    }
-};
-
-// DOT: after the sweep, reduce the per-thread accumulators into st->wArA (PCG search-direction update)
-template <class Op, bool REV, bool DOT>
-__global__ void __launch_bounds__(BLK) k_wave(BoxGeom g, Op op, FvRed red, FvSolveDev* st)
-{
-    if (st && st->done) return;                 // uniform across the grid: nobody reaches the barrier
-    cg::grid_group grid = cg::this_grid();
-    const int nJK = g.ny * g.nz, S = g.nx + g.ny + g.nz - 2;
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    double acc = 0.0;
-    for (int step = 0; step < S; ++step) {
-        const int s = REV ? S - 1 - step : step;
-        for (int jk = tid; jk < nJK; jk += nth) {
-            const int j = jk % g.ny, k = jk / g.ny, i = s - j - k;
-            if (i >= 0 && i < g.nx) op.cell(g, i + g.nx * (j + g.ny * k), i, j, k, acc);
-        }
-        grid.sync();
-    }
-    if (DOT) {
-        double v[1] = {acc};
-        fvGridReduce<1, false, BLK>(v, red, [=](const double* t) {
-            st->wArAold = st->wArA;
-            st->wArA = t[0];
-            st->beta = st->wArA / st->wArAold;
-        });
-    }
-}
-
-__global__ void __launch_bounds__(BLK) k_recip(int N, const double* __restrict__ a, double* __restrict__ out, const FvSolveDev* st)
-{
-    if (st && st->done) return;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < N; c += gridDim.x * blockDim.x) out[c] = 1.0 / a[c];
-}
-
-// diagonal / no preconditioner: wA = rD rA (or rA) with the wA.rA dot
-__global__ void __launch_bounds__(BLK)
-k_precond_diag(int N, const double* __restrict__ rD, const double* __restrict__ rA, double* __restrict__ wA, FvRed red,
-               FvSolveDev* st)
-{
-    if (st->done) return;
-    double v[1] = {0.0};
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < N; c += gridDim.x * blockDim.x) {
-        const double w = rD ? rD[c] * rA[c] : rA[c];
-        wA[c] = w;
-        v[0] += w * rA[c];
-    }
-    fvGridReduce<1, false, BLK>(v, red, [=](const double* t) {
-        st->wArAold = st->wArA;
-        st->wArA = t[0];
-        st->beta = st->wArA / st->wArAold;
-    });
-}
-
-// pA = wA (first iteration) | wA + beta pA
-__global__ void __launch_bounds__(BLK) k_pcg_dir(int N, const double* __restrict__ wA, double* __restrict__ pA, const FvSolveDev* st)
-{
-    if (st->done) return;
-    const bool first = st->nIter == 0;
-    const double beta = st->beta;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < N; c += gridDim.x * blockDim.x)
-        pA[c] = first ? wA[c] : wA[c] + beta * pA[c];
-}
-
-// wA = A pA; wApA = wA.pA; alpha = wArA/wApA (with the singularity test of PCG.C)
-__global__ void __launch_bounds__(BLK)
-k_pcg_amul(BoxGeom g, const double* __restrict__ dg, const double* __restrict__ up, const double* __restrict__ pA,
-           double* __restrict__ wA, FvRed red, FvSolveDev* st)
-{
-    if (st->done) return;
-    double v[1] = {0.0};
-    FV_CELL_LOOP(g, c) {
-        int i, j, k;
-        fvIJK(g, c, i, j, k);
-        const double a = fvAmulCell(g, dg, up, up, pA, c, i, j, k);
-        wA[c] = a;
-        v[0] += a * pA[c];
-    }
-    fvGridReduce<1, false, BLK>(v, red, [=](const double* t) {
-        st->wApA = t[0];
-        if (fabs(t[0]) / st->normFactor < FV_VSMALL) { st->singular = 1; st->done = 1; }
-        else st->alpha = st->wArA / t[0];
-    });
-}
-
-// psi += alpha pA; rA -= alpha wA; finalResidual = sum|rA|/normFactor; PCG.C's loop condition
-__global__ void __launch_bounds__(BLK)
-k_pcg_update(int N, const double* __restrict__ pA, const double* __restrict__ wA, double* __restrict__ psi,
-             double* __restrict__ rA, FvRed red, FvSolveDev* st)
-{
-    if (st->done) return;
-    const double alpha = st->alpha;
-    double v[1] = {0.0};
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < N; c += gridDim.x * blockDim.x) {
-        psi[c] += alpha * pA[c];
-        const double r = rA[c] - alpha * wA[c];
-        rA[c] = r;
-        v[0] += fabs(r);
-    }
-    fvGridReduce<1, false, BLK>(v, red, [=](const double* t) {
-        st->finalRes = t[0] / st->normFactor;
-        const bool cont = st->nIter < st->maxIter;                    // nIterations++ < maxIter_
-        st->nIter += 1;
-        if (!cont || fvConverged(st)) st->done = 1;
-    });
-}
-
-// ---------------------------------------------------------------------------------------------
 // PISO corrector kernels
 // ---------------------------------------------------------------------------------------------
 // HbyA = rAU*UEqn.H()                                                               icoFoamYade.C:100
@@ -887,132 +600,7 @@ k_correct_U(BoxGeom g, double dt, int corr, const double* __restrict__ phi, cons
         FY_CHECK_LAUNCH();                                                                  \
     } while (0)
 
-template <class Op, bool REV, bool DOT>
-int launchWave(fy_ctx* h, FvState* s, Op op, FvSolveDev* st)
-{
-    BoxGeom g = s->g;
-    FvRed red = s->red;
-    void* args[] = {&g, &op, &red, &st};
-    cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_wave<Op, REV, DOT>, dim3(s->waveGrid), dim3(BLK), args, 0,
-                                                h->stream);
-    h->launches++;
-    if (e != cudaSuccess) {
-        h->err = std::string("cooperative launch: ") + cudaGetErrorString(e);
-        return FY_ERR_CUDA;
-    }
-    return FY_OK;
-}
-
-int readSolve(fy_ctx* h, FvState* s)
-{
-    FY_CUDA(cudaMemcpyAsync(s->hSolve, s->dSolve, sizeof(FvSolveDev), cudaMemcpyDeviceToHost, h->stream));
-    FY_CUDA(cudaStreamSynchronize(h->stream));
-    return FY_OK;
-}
-
 }  // namespace
-
-// PCG on owner-slot coefficients (device pointers).  Iteration kernels are queued in batches and test the
-// device-side `done` flag themselves; the host looks at the state once per batch.
-int fvPcgSolve(fy_ctx* h, FvState* s, const double* dg, const double* up, const double* b, double* psi, double tol,
-               double relTol, int maxIter, int precond, fy_solver_perf* perf)
-{
-    const BoxGeom& g = s->g;
-    const int N = g.N, G = s->cellGrid;
-    int rc;
-    k_solve_begin<<<1, 1, 0, h->stream>>>(s->dSolve, tol, relTol, maxIter, precond);
-    FY_CHECK_LAUNCH();
-    FV_LAUNCH(k_avg, G, N, psi, s->red, s->dSolve);
-    FV_LAUNCH(k_solve_init, G, g, dg, up, up, b, psi, s->rA, s->red, s->dSolve);
-    if (precond == FV_PRECOND_DIC) {
-        if ((rc = launchWave<OpDicD, false, false>(h, s, OpDicD{dg, up, s->rD}, s->dSolve))) return rc;
-        FV_LAUNCH(k_recip, G, N, s->rD, s->rD, s->dSolve);
-    } else if (precond == FV_PRECOND_DIAGONAL) {
-        FV_LAUNCH(k_recip, G, N, dg, s->rD, s->dSolve);
-    }
-    int queued = 0;
-    bool sampled = false;
-    const bool prof = h->profiling && s->pev[0];
-    for (;;) {
-        if ((rc = readSolve(h, s))) return rc;
-        if (sampled) {
-            for (int q = 0; q < 5; ++q) {
-                float ms = 0;
-                cudaEventElapsedTime(&ms, s->pev[q], s->pev[q + 1]);
-                s->kernelMs[q] += ms;
-            }
-            s->kernelSamples++;
-            sampled = false;
-        }
-        if (s->hSolve->done) break;
-        int batch = s->pcgBatch;
-        if (queued >= 4 * batch) batch *= 2;
-        for (int it = 0; it < batch; ++it) {
-            const bool ev = prof && it == 0;
-            if (ev) cudaEventRecord(s->pev[0], h->stream);
-            if (precond == FV_PRECOND_DIC) {
-                if ((rc = launchWave<OpDicFwd, false, false>(h, s, OpDicFwd{s->rD, up, s->rA, s->wA}, s->dSolve))) return rc;
-                if (ev) cudaEventRecord(s->pev[1], h->stream);
-                if ((rc = launchWave<OpDicBwd, true, true>(h, s, OpDicBwd{s->rD, up, s->rA, s->wA}, s->dSolve))) return rc;
-            } else {
-                if (ev) cudaEventRecord(s->pev[1], h->stream);
-                FV_LAUNCH(k_precond_diag, G, N, precond == FV_PRECOND_DIAGONAL ? s->rD : (const double*)nullptr, s->rA, s->wA,
-                          s->red, s->dSolve);
-            }
-            if (ev) cudaEventRecord(s->pev[2], h->stream);
-            FV_LAUNCH(k_pcg_dir, G, N, s->wA, s->pA, s->dSolve);
-            if (ev) cudaEventRecord(s->pev[3], h->stream);
-            FV_LAUNCH(k_pcg_amul, G, g, dg, up, s->pA, s->wA, s->red, s->dSolve);
-            if (ev) cudaEventRecord(s->pev[4], h->stream);
-            FV_LAUNCH(k_pcg_update, G, N, s->pA, s->wA, psi, s->rA, s->red, s->dSolve);
-            if (ev) { cudaEventRecord(s->pev[5], h->stream); sampled = true; }
-        }
-        queued += batch;
-    }
-    s->pcgIterations += s->hSolve->nIter;
-    if (perf) {
-        perf->initialResidual = s->hSolve->initRes;
-        perf->finalResidual = s->hSolve->finalRes;
-        perf->nIterations = s->hSolve->nIter;
-    }
-    return FY_OK;
-}
-
-// smoothSolver + symGaussSeidel (nSweeps 1) on owner-slot coefficients (device pointers)
-int fvSmoothSolve(fy_ctx* h, FvState* s, const double* dg, const double* lo, const double* up, const double* b,
-                  double* psi, double tol, double relTol, int maxIter, fy_solver_perf* perf)
-{
-    const BoxGeom& g = s->g;
-    const int N = g.N, G = s->cellGrid;
-    int rc;
-    k_solve_begin<<<1, 1, 0, h->stream>>>(s->dSolve, tol, relTol, maxIter, 0);
-    FY_CHECK_LAUNCH();
-    FV_LAUNCH(k_avg, G, N, psi, s->red, s->dSolve);
-    FV_LAUNCH(k_solve_init, G, g, dg, lo, up, b, psi, (double*)nullptr, s->red, s->dSolve);
-    for (;;) {
-        if ((rc = readSolve(h, s))) return rc;
-        if (s->hSolve->done) break;
-        if ((rc = launchWave<OpGsFwd, false, false>(h, s, OpGsFwd{dg, lo, up, b, psi, s->bPrime}, s->dSolve))) return rc;
-        if ((rc = launchWave<OpGsBwd, true, false>(h, s, OpGsBwd{dg, up, s->bPrime, psi}, s->dSolve))) return rc;
-        FV_LAUNCH(k_residual, G, g, dg, lo, up, b, psi, s->red, s->dSolve);
-    }
-    if (perf) {
-        perf->initialResidual = s->hSolve->initRes;
-        perf->finalResidual = s->hSolve->finalRes;
-        perf->nIterations = s->hSolve->nIter;
-    }
-    return FY_OK;
-}
-
-int fvDicPrecondition(fy_ctx* h, FvState* s, const double* dg, const double* up, const double* rA, double* wA)
-{
-    int rc;
-    if ((rc = launchWave<OpDicD, false, false>(h, s, OpDicD{dg, up, s->rD}, nullptr))) return rc;
-    FV_LAUNCH(k_recip, s->cellGrid, s->g.N, s->rD, s->rD, (const FvSolveDev*)nullptr);
-    if ((rc = launchWave<OpDicFwd, false, false>(h, s, OpDicFwd{s->rD, up, rA, wA}, nullptr))) return rc;
-    if ((rc = launchWave<OpDicBwd, true, false>(h, s, OpDicBwd{s->rD, up, rA, wA}, nullptr))) return rc;
-    return FY_OK;
-}
 
 int fvCreatePhi(fy_ctx* h, FvState* s)
 {
@@ -1078,10 +666,11 @@ int fvIcoSolve(fy_ctx* h, FvState* s, double dt)
     if (ctl.momentumPredictor) {
         FV_LAUNCH(k_grad_scalar, G, g, p, s->gradP);
         FV_LAUNCH(k_usolve_setup, G, g, s->nu, s->phi, s->srcU, s->gradP, U, s->bU, s->psiU);
+        if ((rc = fvSmoothSetMatrix(h, s, s->loU, s->upU))) return rc;
         for (int m = 0; m < 3; ++m) {
             if (!g.valid[m]) continue;
-            if ((rc = fvSmoothSolve(h, s, s->dgU + (size_t)m * N, s->loU, s->upU, s->bU + (size_t)m * N,
-                                    s->psiU + (size_t)m * N, ctl.UTol, ctl.URelTol, ctl.maxIter, &s->stats.U[m])))
+            if ((rc = fvSmoothSolve(h, s, s->dgU + (size_t)m * N, s->bU + (size_t)m * N, s->psiU + (size_t)m * N, ctl.UTol,
+                                    ctl.URelTol, ctl.maxIter, &s->stats.U[m])))
                 return rc;
             FV_LAUNCH(k_store_component, G, N, s->psiU + (size_t)m * N, m, U);
         }
@@ -1275,17 +864,14 @@ int fvCreate(fy_ctx* h, const fy_mesh_desc* m)
     for (auto pp : bufs) if ((rc = devAlloc(h, pp, NS))) return rc;
     double** b3[] = {&s->U0, &s->HbyA, &s->gradP, &s->loU, &s->upU, &s->srcU, &s->dgU, &s->bU, &s->psiU, &s->upP};
     for (auto pp : b3) if ((rc = devAlloc(h, pp, N3))) return rc;
-    double** b1[] = {&s->rAU, &s->diagU, &s->bPrime, &s->dgP, &s->bP, &s->rD, &s->pA, &s->wA, &s->rA};
+    double** b1[] = {&s->rAU, &s->diagU, &s->dgP, &s->bP};
     for (auto pp : b1) if ((rc = devAlloc(h, pp, (size_t)N))) return rc;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     s->cellGrid = std::min((N + BLK - 1) / BLK, sms * 8);
-    int perSm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, (const void*)k_wave<OpGsFwd, false, false>, BLK, 0);
-    perSm = std::max(1, std::min(perSm, 4));
-    s->waveGrid = std::max(1, std::min((ny * nz + BLK - 1) / BLK, sms * perSm));
-    if ((rc = devAlloc(h, &s->red.partial, 4 * (size_t)std::max(s->cellGrid, s->waveGrid)))) return rc;
+    if ((rc = penCreate(h, s))) return rc;
+    if ((rc = devAlloc(h, &s->red.partial, 4 * (size_t)std::max(s->cellGrid, s->pen.rowGrid)))) return rc;
     if ((rc = devAlloc(h, &s->red.ticket, 1))) return rc;
     if ((rc = devAlloc(h, &s->dSolve, 1))) return rc;
     if ((rc = devAlloc(h, &s->dStep, 1))) return rc;
@@ -1303,9 +889,10 @@ void fvDestroy(fy_ctx* h)
     FvState* s = h->fv;
     if (!s) return;
     void* ptrs[] = {s->dSlotOfFace, s->phi, s->phi0, s->phiHbyA, s->U0, s->HbyA, s->rAU, s->gradP, s->diagU, s->loU, s->upU,
-                    s->srcU, s->dgU, s->bU, s->psiU, s->bPrime, s->upP, s->dgP, s->bP, s->rD, s->pA, s->wA, s->rA, s->stage,
+                    s->srcU, s->dgU, s->bU, s->psiU, s->upP, s->dgP, s->bP, s->stage,
                     s->red.partial, s->red.ticket, s->dSolve, s->dStep};
     for (void* p : ptrs) if (p) cudaFree(p);
+    penDestroy(s);
     for (auto& e : s->pev) if (e) cudaEventDestroy(e);
     if (s->hSolve) cudaFreeHost(s->hSolve);
     if (s->hStep) cudaFreeHost(s->hStep);

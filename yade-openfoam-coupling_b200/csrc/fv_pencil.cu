@@ -1,0 +1,1070 @@
+// fv_pencil.cu -- lduMatrix solvers of the fluid half on the device: PCG (DIC / diagonal / none) for the
+// pressure equation and smoothSolver + symGaussSeidel for the momentum predictor (the solvers the stock
+// fvSolution of icoFoam selects; the reference only calls `solve`, icoFoamYade.C:93,125).
+//
+// Every sequential recurrence runs as a warp-pencil pipeline in the skewed layout of fv_pencil.cuh; the
+// Krylov vector kernels (Amul, dots, axpys) run in the same layout so nothing is converted inside the
+// iteration.  The per-cell operation order is OpenFOAM's (see fv_box.cuh), global sums are deterministic
+// for a fixed launch geometry.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "fv_pencil.cuh"
+#include "fv_solver.h"
+
+namespace {
+constexpr int BLK = 256;
+constexpr double FV_VSMALL = 1e-300;
+constexpr int PEN_SPIN_LIMIT = 1 << 20;
+constexpr int PEN_WMAX = 8;                   // most warps per pencil group
+constexpr int PEN_D = 8;                      // input prefetch depth (rows)
+constexpr int PEN_CD = 16;                    // channel depth (rows), a multiple of D
+constexpr int PEN_GUARD = 64;                 // guard rows around every pencil array (>= 2D + 31)
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + TMA bulk copy (global -> shared), polled loads, chain stores
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smemU32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(uint64_t* b, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemU32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbarFenceInit() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbarExpectTx(uint64_t* b, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemU32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint64_t* b, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "PEN_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra PEN_DONE_%=;\n"
+        "bra PEN_WAIT_%=;\n"
+        "PEN_DONE_%=:\n"
+        "}\n" ::"r"(smemU32(b)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void mbarArrive(uint64_t* b)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smemU32(b)) : "memory");
+}
+// 8-byte asynchronous copy global -> shared (LDGSTS): every lane prefetches the words it will consume itself
+__device__ __forceinline__ void cpAsync8(uint32_t dst, const void* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src));
+}
+__device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cpAsyncWait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+// shared-memory accesses of the pencil loop: volatile asm keeps them in program order among themselves
+__device__ __forceinline__ double ldSharedV(uint32_t p)
+{
+    double v;
+    asm volatile("ld.volatile.shared.f64 %0, [%1];" : "=d"(v) : "r"(p));
+    return v;
+}
+__device__ __forceinline__ void stSharedV(uint32_t p, double v)
+{
+    asm volatile("st.volatile.shared.f64 [%0], %1;" ::"r"(p), "d"(v));
+}
+__device__ __forceinline__ double ldPoll(const double* p)
+{
+    unsigned long long v;
+#ifdef PEN_SYS_SCOPE
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+#else
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+#endif
+    return __longlong_as_double((long long)v);
+}
+__device__ __forceinline__ bool isSent(double v) { return (unsigned long long)__double_as_longlong(v) == PEN_SENT; }
+__device__ __forceinline__ void stChain(double* p, double v)
+{
+#ifdef PEN_SYS_SCOPE
+    asm volatile("st.volatile.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+#else
+    asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v));
+#endif
+}
+// out-of-line spin: keeps the hot loop small; gives up (and flags the launch) rather than hang the GPU
+__device__ __noinline__ double pollSlow(const double* p, int& fail)
+{
+    double v = ldPoll(p);
+    int spin = 0;
+#pragma unroll 1
+    while (isSent(v) && !fail) {
+        v = ldPoll(p);
+        if (++spin > PEN_SPIN_LIMIT) fail = 1;
+    }
+    return v;
+}
+__device__ __forceinline__ double sentValue() { return __longlong_as_double((long long)PEN_SENT); }
+
+// ---------------------------------------------------------------------------------------------
+// the recurrences.  in[] are the per-cell input streams, chain is the output array the neighbours'
+// values are taken from.  Each op is split into
+//   pre(a)                : everything that does not depend on a neighbour's new value (runs one step early)
+//   cell(c, vx, vy, vz)   : the dependent chain, in OpenFOAM's order (forward sweeps reach a cell through the
+//                           faces owned by c-nx*ny, c-nx, c-1, i.e. z, y, x; backward sweeps through the
+//                           cell's own faces in descending order, again z, y, x)
+//   post(...)             : side outputs
+// There are NO neighbour-exists predicates: the coefficient of a missing neighbour is stored as 0 and every
+// value a lane can see is finite (pads are 0, inactive lanes produce 0), so the missing term is an exact
+// "- 0*v".  (Only the sign of an exact zero result can differ from the sequential loop.)
+// ---------------------------------------------------------------------------------------------
+struct OpDicD {            // DICPreconditioner::calcReciprocalD: rD[u] -= upper^2 / rD[l]; then rD = 1/rD
+    static constexpr int NIN = 4, NC = 4;
+    static constexpr bool DOT = false;
+    const double* in[NIN];     // dg lowx lowy lowz
+    double* chain;             // D before the reciprocal
+    double* rD;
+    __device__ __forceinline__ void pre(const double (&a)[NIN], double (&c)[NC]) const
+    {
+        c[0] = a[0];
+        c[1] = a[1] * a[1];
+        c[2] = a[2] * a[2];
+        c[3] = a[3] * a[3];
+    }
+    __device__ __forceinline__ double cell(const double (&c)[NC], double vx, double vy, double vz, double&) const
+    {
+        double r = c[0];
+        r -= c[3] / (c[3] == 0.0 ? 1.0 : vz);       // no such face: u*u = 0, and v may be a pad's 0
+        r -= c[2] / (c[2] == 0.0 ? 1.0 : vy);
+        r -= c[1] / (c[1] == 0.0 ? 1.0 : vx);
+        return r;
+    }
+    __device__ __forceinline__ void post(long long pos, bool active, const double (&)[NC], double res, double, double&) const
+    {
+        if (active) rD[pos] = 1.0 / res;
+    }
+    __device__ __forceinline__ void fin(FvSolveDev*, double) const {}
+};
+struct OpDicFwd {          // wA = rD rA;  wA[u] -= rD[u] upper wA[l]   (faces ascending)
+    static constexpr int NIN = 5, NC = 4;
+    static constexpr bool DOT = false;
+    const double* in[NIN];     // rD rA lowx lowy lowz
+    double* chain;             // yA
+    __device__ __forceinline__ void pre(const double (&a)[NIN], double (&c)[NC]) const
+    {
+        c[0] = a[0] * a[1];
+        c[1] = a[0] * a[2];
+        c[2] = a[0] * a[3];
+        c[3] = a[0] * a[4];
+    }
+    __device__ __forceinline__ double cell(const double (&c)[NC], double vx, double vy, double vz, double&) const
+    {
+        double w = c[0];
+        w -= c[3] * vz;
+        w -= c[2] * vy;
+        w -= c[1] * vx;
+        return w;
+    }
+    __device__ __forceinline__ void post(long long, bool, const double (&)[NC], double, double, double&) const {}
+    __device__ __forceinline__ void fin(FvSolveDev*, double) const {}
+};
+struct OpDicBwd {          // wA[l] -= rD[l] upper wA[u]   (faces descending); accumulates wA.rA; re-arms yA
+    static constexpr int NIN = 6, NC = 5;
+    static constexpr bool DOT = true;
+    const double* in[NIN];     // yA rD upx upy upz rA
+    double* chain;             // zA
+    double* y;
+    __device__ __forceinline__ void pre(const double (&a)[NIN], double (&c)[NC]) const
+    {
+        c[0] = a[0];
+        c[1] = a[1] * a[2];
+        c[2] = a[1] * a[3];
+        c[3] = a[1] * a[4];
+        c[4] = a[5];
+    }
+    __device__ __forceinline__ double cell(const double (&c)[NC], double vx, double vy, double vz, double&) const
+    {
+        double w = c[0];
+        w -= c[3] * vz;
+        w -= c[2] * vy;
+        w -= c[1] * vx;
+        return w;
+    }
+    __device__ __forceinline__ void post(long long pos, bool active, const double (&c)[NC], double res, double, double& acc) const
+    {
+        acc += res * c[4];
+        if (active) y[pos] = sentValue();
+    }
+    __device__ __forceinline__ void fin(FvSolveDev* st, double tot) const
+    {
+        if (!st) return;
+        st->wArAold = st->wArA;
+        st->wArA = tot;
+        st->beta = st->wArA / st->wArAold;
+    }
+};
+struct OpGsFwd {           // GaussSeidelSmoother forward sweep: new values below; old values above arrive pre-multiplied (e)
+    static constexpr int NIN = 8, NC = 8;
+    static constexpr bool DOT = false;
+    const double* in[NIN];     // b lowx lowy lowz ex ey ez dg
+    double* chain;             // psi after the forward sweep
+    double* bPrime;
+    double* psiOld;            // consumed by k_pen_gs_upper before the sweep: re-armed here for the backward sweep
+    __device__ __forceinline__ void pre(const double (&a)[NIN], double (&c)[NC]) const
+    {
+#pragma unroll
+        for (int x = 0; x < NIN; ++x) c[x] = a[x];
+    }
+    __device__ __forceinline__ double cell(const double (&c)[NC], double vx, double vy, double vz, double& side) const
+    {
+        double bp = c[0];
+        bp -= c[3] * vz;
+        bp -= c[2] * vy;
+        bp -= c[1] * vx;
+        side = bp;
+        double x = bp;
+        x -= c[4];                                  // upper[x+] psi_old[c+1]   (0 when there is no such face)
+        x -= c[5];
+        x -= c[6];
+        return x / c[7];
+    }
+    __device__ __forceinline__ void post(long long pos, bool active, const double (&)[NC], double, double side, double&) const
+    {
+        if (active) {
+            bPrime[pos] = side;
+            psiOld[pos] = sentValue();
+        }
+    }
+    __device__ __forceinline__ void fin(FvSolveDev*, double) const {}
+};
+struct OpGsBwd {           // GaussSeidelSmoother backward sweep (own faces in ascending order: x, y, z)
+    static constexpr int NIN = 5, NC = 5;
+    static constexpr bool DOT = false;
+    const double* in[NIN];     // bPrime upx upy upz dg
+    double* chain;             // psi
+    double* mid;               // forward-sweep values: dead now, re-armed for the next iteration
+    __device__ __forceinline__ void pre(const double (&a)[NIN], double (&c)[NC]) const
+    {
+#pragma unroll
+        for (int x = 0; x < NIN; ++x) c[x] = a[x];
+    }
+    __device__ __forceinline__ double cell(const double (&c)[NC], double vx, double vy, double vz, double&) const
+    {
+        double x = c[0];
+        x -= c[1] * vx;
+        x -= c[2] * vy;
+        x -= c[3] * vz;
+        return x / c[4];
+    }
+    __device__ __forceinline__ void post(long long pos, bool active, const double (&)[NC], double, double, double&) const
+    {
+        if (active) mid[pos] = sentValue();
+    }
+    __device__ __forceinline__ void fin(FvSolveDev*, double) const {}
+};
+
+struct PenCtl {
+    unsigned int* ticket;      // [0] next ticket  [1] warps finished
+    int* error;                // set when a poll gave up
+    double* partial;           // per-warp partial sums
+    FvSolveDev* st;            // may be null
+    int dbg;                   // debug switches (FY_PENCIL_DBG)
+    unsigned long long* trace; // optional [warps][8] time stamps / wait cycles
+};
+
+// One CTA per pencil group (j-block jb, plane group kq): W COMPUTE warps, each owning ONE k-plane of the
+// 32-lane j-block, plus two HELPER warps.  Per step a compute lane does one cell.  It prefetches its own
+// inputs (8-byte cp.async into a private shared-memory ring, D rows ahead) and reads them one step early,
+// so that the neighbour-independent products overlap the previous step's dependent chain.  Neighbour
+// values that cross warps arrive through shared-memory channels of sentinel-armed slots (data and flag in
+// one 8-byte word, per-lane producer/consumer):
+//   z channel w : the 32 values of plane w-1's row -- written by compute warp w-1, or, for the group's
+//                 first plane, by the Z HELPER, which polls the output array of the group behind in L2;
+//   y channel w : the edge lane's y-neighbour -- written by the Y HELPER, which polls the last lane of the
+//                 neighbouring j-block's rows in L2 (one helper lane per plane).
+// So the compute warps never touch L2 for a dependency and never spin on anything but shared memory.
+// Tickets are handed out in dependency order (a group's producers always hold smaller tickets), so the
+// pipeline cannot deadlock whatever the residency.  All memory operations of the loops are volatile asm
+// (kept in program order, which IS the software pipeline); the arithmetic between them is left to the
+// scheduler.  The loops have no bounds tests: Tp is a multiple of 2D and every array carries guard rows.
+struct PenWarp {               // per-warp constants of one sweep
+    uint32_t ringS, zInS, zOutS, yInS;
+    int s0, nx, Tp, row00;
+    bool zOut, edge;
+    long long slab;
+};
+
+__device__ __forceinline__ void penStampAt(unsigned long long* tr, int t0, int Tp)
+{
+    if (!tr) return;
+    const int wh = 8 + t0 / PEN_D;
+    if (wh < 32 && (threadIdx.x & 31) == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        tr[wh] = t;
+    }
+}
+
+template <class Op, bool REV, bool ZIN, bool YIN>
+__device__ __forceinline__ void penSweep(const Op& op, const PenWarp& w, double& acc, unsigned long long* tr)
+{
+    constexpr int NIN = Op::NIN, NC = Op::NC, D = PEN_D, CD = PEN_CD;
+    constexpr unsigned int FULL = 0xffffffffu;
+    constexpr int RS = REV ? -32 : 32;                     // row stride in sweep order (doubles)
+    const double* inB[NIN];
+#pragma unroll
+    for (int x = 0; x < NIN; ++x) inB[x] = op.in[x] + w.slab + w.row00;
+    double* const chainB = op.chain + w.slab + w.row00;
+    const long long posB = w.slab + w.row00;
+
+    // row s of the sweep is fetched by commit group s into ring slot s mod D
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+#pragma unroll
+        for (int x = 0; x < NIN; ++x) cpAsync8(w.ringS + (d * NIN + x) * 256, inB[x] + d * RS);
+        cpAsyncCommit();
+    }
+    double prev = 0.0, cn[NC];
+    cpAsyncWait<D - 1>();
+    {
+        double a[NIN];
+#pragma unroll
+        for (int x = 0; x < NIN; ++x) a[x] = ldSharedV(w.ringS + x * 256);
+        op.pre(a, cn);
+    }
+    double vzN = ZIN ? ldSharedV(w.zInS) : 0.0;            // channel reads run one row ahead as well
+    double vyN = YIN ? ldSharedV(w.yInS) : 0.0;
+    // The row loop is deliberately NOT unrolled: one warp executes it alone, and a body that overflows the
+    // instruction cache costs more than the few slot-index instructions saved.
+#pragma unroll 1
+    for (int t = 0; t < w.Tp; ++t) {
+        const uint32_t rs = (uint32_t)(t & (D - 1)) * (NIN * 256);            // this row's ring slot
+        const uint32_t rsN = (uint32_t)((t + 1) & (D - 1)) * (NIN * 256);     // next row's
+        const uint32_t cs = (uint32_t)(t & (CD - 1));                         // channel slots
+        const uint32_t csN = (uint32_t)((t + 1) & (CD - 1));
+        const int e = t * RS;                                                 // element offset of this row
+        if ((t & (D - 1)) == 0) {
+            penStampAt(tr, t, w.Tp);
+            if (w.zOut) {                                                     // flow control, once per block of D rows
+                int spin = 0;
+                while (!isSent(ldSharedV(w.zOutS + (cs + D - 1) * 256)) && ++spin < PEN_SPIN_LIMIT) {}
+            }
+        }
+        // (A) next row's inputs: read them now, use them after this row's chain
+        cpAsyncWait<D - 2>();
+        double an[NIN];
+#pragma unroll
+        for (int x = 0; x < NIN; ++x) an[x] = ldSharedV(w.ringS + rsN + x * 256);
+        // (B) refill the slot this row came from (its values already sit in cn)
+#pragma unroll
+        for (int x = 0; x < NIN; ++x) cpAsync8(w.ringS + rs + x * 256, inB[x] + e + D * RS);
+        cpAsyncCommit();
+        // (C) the dependent chain
+        const bool active = (unsigned)(t - w.s0) < (unsigned)w.nx;
+        const double vx = prev;
+        double vy = REV ? __shfl_down_sync(FULL, prev, 1) : __shfl_up_sync(FULL, prev, 1);
+        double vz = 0.0;
+        if (ZIN) {
+            double v = vzN;
+            int spin = 0;
+            while (isSent(v) && ++spin < PEN_SPIN_LIMIT) v = ldSharedV(w.zInS + cs * 256);
+            stSharedV(w.zInS + cs * 256, sentValue());
+            vzN = ldSharedV(w.zInS + csN * 256);
+            vz = v;
+        }
+        if (YIN) {
+            double v = vyN;
+            int spin = 0;
+            while (w.edge && isSent(v) && ++spin < PEN_SPIN_LIMIT) v = ldSharedV(w.yInS + cs * 8);   // only the edge lane owns the slot
+            if (w.edge) stSharedV(w.yInS + cs * 8, sentValue());
+            vyN = ldSharedV(w.yInS + csN * 8);
+            vy = w.edge ? v : vy;
+        }
+        double side = 0.0;
+        double res = op.cell(cn, vx, vy, vz, side);
+        res = active ? res : 0.0;
+        if (w.zOut) stSharedV(w.zOutS + cs * 256, res);
+        stChain(chainB + e, res);
+        op.post(posB + e, active, cn, res, side, acc);
+        prev = res;
+        // (D) neighbour-independent products of the next row
+        op.pre(an, cn);
+    }
+    cpAsyncWait<0>();
+}
+
+// Z helper: streams the rows of the plane behind the group (another CTA's output, in L2) into z channel 0.
+// Eight rows are kept in flight; when the wanted row is still armed, every armed row is re-requested at once.
+template <bool REV>
+__device__ __forceinline__ void penHelpZ(const double* zRow0, uint32_t chanS, int Tp, int& fail, unsigned long long* tr, int dbg)
+{
+    constexpr int D = PEN_D, CD = PEN_CD;
+    constexpr int RS = REV ? -32 : 32;
+    const double* zB = zRow0;
+    double r[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) r[d] = ldPoll(zB + d * RS);
+    for (int t0 = 0; t0 < Tp; t0 += D) {
+        const uint32_t cb = (uint32_t)(t0 & (CD - 1)) * 256;
+        penStampAt(tr, t0, Tp);
+        {
+            int spin = 0;
+            while (!isSent(ldSharedV(chanS + cb + (D - 1) * 256)) && ++spin < PEN_SPIN_LIMIT) {}
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            int spin = 0;
+            while (isSent(r[d]) && !fail) {
+                r[d] = ldPoll(zB + d * RS);
+                if (++spin > PEN_SPIN_LIMIT) fail = 1;
+            }
+            stSharedV(chanS + cb + d * 256, r[d]);
+            r[d] = ldPoll(zB + (d + D) * RS);
+        }
+        zB += D * RS;
+    }
+}
+
+// Y helper: lane q < W serves compute warp q: the y-neighbour of its edge lane, row by row, from the
+// neighbouring j-block's output in L2 into y channel q.  Lane q runs q rows behind lane 0, like its plane.
+template <bool REV>
+__device__ __forceinline__ void penHelpY(const double* yRow0, bool on, int q, uint32_t chanS, int Tp, int& fail)
+{
+    constexpr int D = PEN_D, CD = PEN_CD;
+    constexpr int RS = REV ? -32 : 32;
+    const double* yB = yRow0 - (long long)q * RS;          // row n of the loop is this lane's row n - q
+    double r[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) r[d] = ldPoll(yB + d * RS);
+    for (int t0 = 0; t0 < Tp + D * ((PEN_WMAX + D - 1) / D); t0 += D) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const int n = t0 + d - q;                      // this lane's row
+            double v = r[d];
+            if (on && n >= 0 && n < Tp) {
+                const uint32_t slot = chanS + (uint32_t)(n & (CD - 1)) * 8;
+                int spin = 0;
+                while (isSent(v) && !fail) {
+                    v = ldPoll(yB + d * RS);
+                    if (++spin > PEN_SPIN_LIMIT) fail = 1;
+                }
+                spin = 0;
+                while (!isSent(ldSharedV(slot)) && ++spin < PEN_SPIN_LIMIT) {}
+                stSharedV(slot, v);
+            }
+            r[d] = ldPoll(yB + (d + D) * RS);
+        }
+        yB += D * RS;
+    }
+}
+
+template <class Op, bool REV>
+__global__ void __launch_bounds__(32 * (PEN_WMAX + 2)) k_pencil(PencilGeom g, Op op, PenCtl ctl)
+{
+    constexpr int NIN = Op::NIN, D = PEN_D, CD = PEN_CD;
+    constexpr unsigned int FULL = 0xffffffffu;
+    extern __shared__ __align__(128) unsigned char penSmem[];
+    __shared__ unsigned int shTicket;
+    if (ctl.st && ctl.st->done) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = (blockDim.x >> 5) - 2;
+    // shared memory: input rings [W][D][NIN][32] | z channels [W][CD][32] (channel w feeds compute warp w) | y channels [W][CD]
+    double* const zChan = reinterpret_cast<double*>(penSmem) + (size_t)W * (D * NIN * 32);
+    double* const yChan = zChan + (size_t)W * (CD * 32);
+    for (int x = threadIdx.x; x < W * CD * 33; x += blockDim.x) zChan[x] = sentValue();
+    if (threadIdx.x == 0) shTicket = atomicAdd(ctl.ticket, 1u);
+    __syncthreads();
+    const unsigned int tk = shTicket;
+    const int nKQ = (g.nz + W - 1) / W;
+    int kq = (int)tk / g.nJB, jb = (int)tk - kq * g.nJB;
+    if (REV) { kq = nKQ - 1 - kq; jb = g.nJB - 1 - jb; }
+    const int slotId = (kq * g.nJB + jb) * (W + 2) + warp;
+    constexpr int KS = REV ? -1 : 1;
+    auto planeOf = [&](int wq) { return REV ? kq * W + W - 1 - wq : kq * W + wq; };
+    auto stamp = [&](int wh) {
+        if (ctl.trace && lane == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            ctl.trace[(size_t)slotId * 32 + wh] = t;
+        }
+    };
+    stamp(0);
+    unsigned long long* const trw = ctl.trace ? ctl.trace + (size_t)slotId * 32 : nullptr;
+    double acc = 0.0;
+    int fail = 0;
+    const bool yCol = REV ? jb < g.nJB - 1 : jb > 0;       // this j-block has a y-producer block
+    // edge lane: (i, j-1) sits in slab jb-1 at row m+31, lane 31; (i, j+1) in slab jb+1 at row m-31, lane 0
+    const long long yOff = REV ? ((long long)g.Tp - 31) * 32 - 31 : -(((long long)g.Tp - 31) * 32 - 31);
+    const int row00 = REV ? (g.Tp - 1) * 32 : 0;
+    constexpr int EDGE = REV ? 31 : 0;
+    if (warp < W) {
+        const int k = planeOf(warp);
+        if (k < g.nz) {
+            const int j = jb * 32 + lane;
+            const bool jvalid = j < g.ny;
+            PenWarp w;
+            w.ringS = smemU32(reinterpret_cast<double*>(penSmem) + (size_t)warp * (D * NIN * 32) + lane);
+            w.zInS = smemU32(zChan + (size_t)warp * (CD * 32) + lane);
+            w.zOutS = w.zInS + CD * 256;
+            w.yInS = smemU32(yChan + (size_t)warp * CD);
+            // Sweep row s touches memory row m = s (forward) or Tp-1-s (backward); lane l then sits on the x index
+            // i = m - l.  s - s0 counts the lane's cells in sweep order: active for 0 <= s - s0 < nx.
+            w.s0 = jvalid ? (REV ? g.Tp - g.nx - lane : lane) : (1 << 30);
+            w.nx = g.nx;
+            w.Tp = g.Tp;
+            w.row00 = row00;
+            w.slab = (((long long)k * g.nJB + jb) * g.Tp) * 32 + lane;
+            const int kBehind = k - KS, kAhead = k + KS;
+            const bool zin = kBehind >= 0 && kBehind < g.nz;
+            w.zOut = kAhead >= 0 && kAhead < g.nz && warp < W - 1;
+            w.edge = lane == EDGE;
+            if (zin && yCol) penSweep<Op, REV, true, true>(op, w, acc, trw);
+            else if (zin) penSweep<Op, REV, true, false>(op, w, acc, trw);
+            else if (yCol) penSweep<Op, REV, false, true>(op, w, acc, trw);
+            else penSweep<Op, REV, false, false>(op, w, acc, trw);
+        }
+    } else if (warp == W) {
+        const int k0 = planeOf(0), kBehind = k0 - KS;
+        if (k0 < g.nz && kBehind >= 0 && kBehind < g.nz)
+            penHelpZ<REV>(op.chain + (((long long)kBehind * g.nJB + jb) * g.Tp) * 32 + lane + row00, smemU32(zChan + lane), g.Tp, fail, trw, ctl.dbg);
+    } else {
+        const int q = lane < W ? lane : 0;
+        const int k = planeOf(q);
+        const bool on = yCol && lane < W && k < g.nz;
+        const double* y0 = op.chain + (((long long)(on ? k : 0) * g.nJB + jb) * g.Tp) * 32 + EDGE + yOff + row00;
+        if (yCol) penHelpY<REV>(y0, on, q, smemU32(yChan + (size_t)q * CD), g.Tp, fail);
+    }
+
+    stamp(3);
+    if (Op::DOT) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(FULL, acc, o);
+        if (lane == 0) ctl.partial[slotId] = acc;
+    }
+    fail = __any_sync(FULL, fail);
+    unsigned int last = 0;
+    if (lane == 0) {
+        if (fail) atomicExch(ctl.error, 1);
+        __threadfence();
+        last = (atomicAdd(ctl.ticket + 1, 1u) == gridDim.x * (W + 2) - 1) ? 1u : 0u;
+    }
+    last = __shfl_sync(FULL, last, 0);
+    if (!last) return;
+    __threadfence();
+    if (Op::DOT) {
+        const volatile double* p = ctl.partial;
+        double x = 0.0;
+        for (unsigned int b = lane; b < gridDim.x * (W + 2); b += 32) x += p[b];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(FULL, x, o);
+        if (lane == 0) op.fin(ctl.st, x);
+    }
+    if (lane == 0) {
+        ctl.ticket[0] = 0u;
+        ctl.ticket[1] = 0u;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout conversion (natural x-fastest cell order <-> pencil layout)
+// ---------------------------------------------------------------------------------------------
+#define PEN_ROW_LOOP(g, c)                                                                                  \
+    for (long long row_ = (long long)blockIdx.x * (BLK / 32) + (threadIdx.x >> 5); row_ < (g).nRows;        \
+         row_ += (long long)gridDim.x * (BLK / 32))                                                         \
+        for (PenCell c = penDecode((g), row_, threadIdx.x & 31); c.valid; c.valid = false)
+
+__device__ __forceinline__ int penNat(const PencilGeom& g, const PenCell& c) { return c.i + g.nx * (c.j + g.ny * c.k); }
+
+// matrix: dg [N], lo / up owner slots [3N] (natural) -> PenMatrix
+__global__ void __launch_bounds__(BLK)
+k_pen_matrix(PencilGeom g, const double* __restrict__ dg, const double* __restrict__ lo, const double* __restrict__ up,
+             PenMatrix M)
+{
+    const int sd[3] = {1, g.nx, g.nx * g.ny};
+    PEN_ROW_LOOP(g, c) {
+        const int n = penNat(g, c);
+        const int v[3] = {c.i, c.j, c.k}, nd[3] = {g.nx, g.ny, g.nz};
+        if (dg) M.dg[c.pos] = dg[n];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            if (M.low[d]) M.low[d][c.pos] = v[d] > 0 ? lo[(size_t)d * g.N + n - sd[d]] : 0.0;
+            if (M.up[d]) M.up[d][c.pos] = v[d] < nd[d] - 1 ? up[(size_t)d * g.N + n] : 0.0;
+        }
+    }
+}
+__global__ void __launch_bounds__(BLK) k_pen_from_nat(PencilGeom g, const double* __restrict__ nat, double* __restrict__ pen)
+{
+    PEN_ROW_LOOP(g, c) pen[c.pos] = nat[penNat(g, c)];
+}
+__global__ void __launch_bounds__(BLK) k_pen_to_nat(PencilGeom g, const double* __restrict__ pen, double* __restrict__ nat)
+{
+    PEN_ROW_LOOP(g, c) nat[penNat(g, c)] = pen[c.pos];
+}
+// arms up to three chain arrays with the sentinel
+__global__ void __launch_bounds__(BLK) k_pen_arm(PencilGeom g, double* a0, double* a1, double* a2, const FvSolveDev* st)
+{
+    const double sv = sentValue();
+    PEN_ROW_LOOP(g, c) {
+        if (a0) a0[c.pos] = sv;
+        if (a1) a1[c.pos] = sv;
+        if (a2) a2[c.pos] = sv;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// lduMatrix kernels in pencil layout
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double penAmulCell(const PencilGeom& g, const PenMatrix& M, const double* __restrict__ x,
+                                              const PenCell& c)
+{
+    const long long p = c.pos;
+    double a = M.dg[p] * x[p];
+    if (c.k > 0) a += M.low[2][p] * x[p - g.zStride];
+    if (c.j > 0) a += M.low[1][p] * x[penYm(g, c)];
+    if (c.i > 0) a += M.low[0][p] * x[p - 32];
+    if (c.i < g.nx - 1) a += M.up[0][p] * x[p + 32];
+    if (c.j < g.ny - 1) a += M.up[1][p] * x[penYp(g, c)];
+    if (c.k < g.nz - 1) a += M.up[2][p] * x[p + g.zStride];
+    return a;
+}
+__device__ __forceinline__ double penSumACell(const PencilGeom& g, const PenMatrix& M, const PenCell& c)
+{
+    const long long p = c.pos;
+    double a = M.dg[p];
+    if (c.k > 0) a += M.low[2][p];
+    if (c.j > 0) a += M.low[1][p];
+    if (c.i > 0) a += M.low[0][p];
+    if (c.i < g.nx - 1) a += M.up[0][p];
+    if (c.j < g.ny - 1) a += M.up[1][p];
+    if (c.k < g.nz - 1) a += M.up[2][p];
+    return a;
+}
+
+__global__ void k_solve_begin(FvSolveDev* st, double tol, double relTol, int maxIter, int precond)
+{
+    st->tol = tol; st->relTol = relTol; st->maxIter = maxIter; st->precond = precond;
+    st->avg = 0; st->normFactor = 0; st->initRes = 0; st->finalRes = 0;
+    st->wArA = 1e20; st->wArAold = 1e20; st->wApA = 0; st->alpha = 0; st->beta = 0;
+    st->nIter = 0; st->done = 0; st->singular = 0;
+}
+__device__ __forceinline__ bool fvConverged(const FvSolveDev* st)
+{
+    return st->finalRes < st->tol || (st->relTol > 1e-20 && st->finalRes < st->relTol * st->initRes);
+}
+
+// gAverage(psi)
+__global__ void __launch_bounds__(BLK) k_pen_avg(PencilGeom g, const double* __restrict__ psi, FvRed red, FvSolveDev* st)
+{
+    double v[1] = {0.0};
+    PEN_ROW_LOOP(g, c) v[0] += psi[c.pos];
+    const int N = g.N;
+    fvGridReduce<1, false, BLK>(v, red, [=](const double* t) { st->avg = t[0] / N; });
+}
+
+// rA = source - A psi;  normFactor = sum(|Apsi - sumA avg| + |source - sumA avg|) + 1e-20;
+// initialResidual = sum|rA| / normFactor                              [OF-6 lduMatrix::solver::normFactor]
+__global__ void __launch_bounds__(BLK)
+k_pen_solve_init(PencilGeom g, PenMatrix M, const double* __restrict__ b, const double* __restrict__ psi,
+                 double* __restrict__ rA, FvRed red, FvSolveDev* st)
+{
+    double v[2] = {0.0, 0.0};
+    const double avg = st->avg;
+    PEN_ROW_LOOP(g, c) {
+        const double Apsi = penAmulCell(g, M, psi, c);
+        const double t = penSumACell(g, M, c) * avg;
+        const double r = b[c.pos] - Apsi;
+        if (rA) rA[c.pos] = r;
+        v[0] += fabs(Apsi - t) + fabs(b[c.pos] - t);
+        v[1] += fabs(r);
+    }
+    fvGridReduce<2, false, BLK>(v, red, [=](const double* t) {
+        st->normFactor = t[0] + 1e-20;
+        st->initRes = t[1] / st->normFactor;
+        st->finalRes = st->initRes;
+        st->done = fvConverged(st) ? 1 : 0;
+    });
+}
+
+// lduMatrix::residual + gSumMag (smoothSolver's convergence test after each sweep)
+__global__ void __launch_bounds__(BLK)
+k_pen_residual(PencilGeom g, PenMatrix M, const double* __restrict__ b, const double* __restrict__ psi, FvRed red,
+               FvSolveDev* st)
+{
+    if (st->done) return;
+    double v[1] = {0.0};
+    PEN_ROW_LOOP(g, c) {
+        const long long p = c.pos;
+        double r = b[p] - M.dg[p] * psi[p];
+        if (c.k > 0) r -= M.low[2][p] * psi[p - g.zStride];
+        if (c.j > 0) r -= M.low[1][p] * psi[penYm(g, c)];
+        if (c.i > 0) r -= M.low[0][p] * psi[p - 32];
+        if (c.i < g.nx - 1) r -= M.up[0][p] * psi[p + 32];
+        if (c.j < g.ny - 1) r -= M.up[1][p] * psi[penYp(g, c)];
+        if (c.k < g.nz - 1) r -= M.up[2][p] * psi[p + g.zStride];
+        v[0] += fabs(r);
+    }
+    fvGridReduce<1, false, BLK>(v, red, [=](const double* t) {
+        st->finalRes = t[0] / st->normFactor;
+        st->nIter += 1;                                               // nSweeps = 1
+        st->done = (!(st->nIter < st->maxIter) || fvConverged(st)) ? 1 : 0;
+    });
+}
+
+// Gauss-Seidel: the products upper*psi_old of the faces a cell owns, taken before the forward sweep
+// overwrites anything (the sweep subtracts them in the same x+, y+, z+ order)
+__global__ void __launch_bounds__(BLK)
+k_pen_gs_upper(PencilGeom g, PenMatrix M, const double* __restrict__ psi, double* __restrict__ ex, double* __restrict__ ey,
+               double* __restrict__ ez, const FvSolveDev* st)
+{
+    if (st->done) return;
+    PEN_ROW_LOOP(g, c) {
+        const long long p = c.pos;
+        ex[p] = c.i < g.nx - 1 ? M.up[0][p] * psi[p + 32] : 0.0;
+        ey[p] = c.j < g.ny - 1 ? M.up[1][p] * psi[penYp(g, c)] : 0.0;
+        ez[p] = c.k < g.nz - 1 ? M.up[2][p] * psi[p + g.zStride] : 0.0;
+    }
+}
+
+// diagonal / no preconditioner: zA = rD rA (or rA) with the wA.rA dot
+__global__ void __launch_bounds__(BLK)
+k_pen_precond_diag(PencilGeom g, const double* __restrict__ rD, const double* __restrict__ rA, double* __restrict__ zA,
+                   FvRed red, FvSolveDev* st)
+{
+    if (st->done) return;
+    double v[1] = {0.0};
+    PEN_ROW_LOOP(g, c) {
+        const double w = rD ? rD[c.pos] * rA[c.pos] : rA[c.pos];
+        zA[c.pos] = w;
+        v[0] += w * rA[c.pos];
+    }
+    fvGridReduce<1, false, BLK>(v, red, [=](const double* t) {
+        st->wArAold = st->wArA;
+        st->wArA = t[0];
+        st->beta = st->wArA / st->wArAold;
+    });
+}
+__global__ void __launch_bounds__(BLK) k_pen_recip(PencilGeom g, const double* __restrict__ a, double* __restrict__ out)
+{
+    PEN_ROW_LOOP(g, c) out[c.pos] = 1.0 / a[c.pos];
+}
+
+// pA = zA (first iteration) | zA + beta pA;  re-arms zA for the next backward sweep
+__global__ void __launch_bounds__(BLK)
+k_pen_dir(PencilGeom g, double* __restrict__ zA, double* __restrict__ pA, const FvSolveDev* st)
+{
+    if (st->done) return;
+    const bool first = st->nIter == 0;
+    const double beta = st->beta;
+    const double sv = sentValue();
+    PEN_ROW_LOOP(g, c) {
+        const double z = zA[c.pos];
+        pA[c.pos] = first ? z : z + beta * pA[c.pos];
+        zA[c.pos] = sv;
+    }
+}
+
+// wA = A pA; wApA = wA.pA; alpha = wArA/wApA (with the singularity test of PCG.C)
+__global__ void __launch_bounds__(BLK)
+k_pen_amul(PencilGeom g, PenMatrix M, const double* __restrict__ pA, double* __restrict__ wA, FvRed red, FvSolveDev* st)
+{
+    if (st->done) return;
+    double v[1] = {0.0};
+    PEN_ROW_LOOP(g, c) {
+        const double a = penAmulCell(g, M, pA, c);
+        wA[c.pos] = a;
+        v[0] += a * pA[c.pos];
+    }
+    fvGridReduce<1, false, BLK>(v, red, [=](const double* t) {
+        st->wApA = t[0];
+        if (fabs(t[0]) / st->normFactor < FV_VSMALL) { st->singular = 1; st->done = 1; }
+        else st->alpha = st->wArA / t[0];
+    });
+}
+
+// psi += alpha pA; rA -= alpha wA; finalResidual = sum|rA|/normFactor; PCG.C's loop condition
+__global__ void __launch_bounds__(BLK)
+k_pen_update(PencilGeom g, const double* __restrict__ pA, const double* __restrict__ wA, double* __restrict__ psi,
+             double* __restrict__ rA, FvRed red, FvSolveDev* st)
+{
+    if (st->done) return;
+    const double alpha = st->alpha;
+    double v[1] = {0.0};
+    PEN_ROW_LOOP(g, c) {
+        psi[c.pos] += alpha * pA[c.pos];
+        const double r = rA[c.pos] - alpha * wA[c.pos];
+        rA[c.pos] = r;
+        v[0] += fabs(r);
+    }
+    fvGridReduce<1, false, BLK>(v, red, [=](const double* t) {
+        st->finalRes = t[0] / st->normFactor;
+        const bool cont = st->nIter < st->maxIter;                    // nIterations++ < maxIter_
+        st->nIter += 1;
+        if (!cont || fvConverged(st)) st->done = 1;
+    });
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+#define PEN_LAUNCH(kernel, ...)                                                             \
+    do {                                                                                    \
+        kernel<<<s->pen.rowGrid, BLK, 0, h->stream>>>(__VA_ARGS__);                         \
+        FY_CHECK_LAUNCH();                                                                  \
+    } while (0)
+
+template <class Op, bool REV>
+int launchPencil(fy_ctx* h, FvState* s, const Op& op, FvSolveDev* st)
+{
+    PenState& P = s->pen;
+    // warps per group: as many as the shared-memory budget allows (each owns D*NIN rows + one channel)
+    const int perWarp = PEN_D * Op::NIN * 256 + PEN_CD * 33 * 8;
+    int W = std::max(1, std::min(std::min(P.W, PEN_WMAX), P.smemBudget / perWarp));
+    W = std::min(W, P.g.nz);
+    const size_t smem = (size_t)W * perWarp;
+    static bool attrDone = false;
+    if (!attrDone) {
+        FY_CUDA(cudaFuncSetAttribute((const void*)k_pencil<Op, REV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attrDone = true;
+    }
+    PenCtl ctl{P.ticket, P.error, P.partial, st, P.dbg, P.traceOn ? P.trace : nullptr};
+    const int grid = P.g.nJB * ((P.g.nz + W - 1) / W);
+    k_pencil<Op, REV><<<grid, 32 * (W + 2), smem, h->stream>>>(P.g, op, ctl);
+    FY_CHECK_LAUNCH();
+    return FY_OK;
+}
+
+int readSolve(fy_ctx* h, FvState* s)
+{
+    FY_CUDA(cudaMemcpyAsync(s->hSolve, s->dSolve, sizeof(FvSolveDev), cudaMemcpyDeviceToHost, h->stream));
+    FY_CUDA(cudaMemcpyAsync(s->pen.hError, s->pen.error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    FY_CUDA(cudaStreamSynchronize(h->stream));
+    if (*s->pen.hError) {
+        h->err = "pencil pipeline: a neighbour value never arrived (poll limit reached)";
+        return FY_ERR_CUDA;
+    }
+    return FY_OK;
+}
+
+PenMatrix penMatrixOf(PenState& P, int which)      // 0: p (symmetric: low built from upper)  1: U
+{
+    PenMatrix M;
+    double** c = which == 0 ? P.mP : P.mU;
+    M.dg = c[0];
+    for (int d = 0; d < 3; ++d) { M.low[d] = c[1 + d]; M.up[d] = c[4 + d]; }
+    return M;
+}
+}  // namespace
+
+int penCreate(fy_ctx* h, FvState* s)
+{
+    PenState& P = s->pen;
+    const BoxGeom& b = s->g;
+    PencilGeom& g = P.g;
+    g.nx = b.nx; g.ny = b.ny; g.nz = b.nz; g.N = b.N;
+    g.nJB = (b.ny + 31) / 32;
+    g.Tp = ((b.nx + 31 + PEN_CD - 1) / PEN_CD) * PEN_CD;
+    g.nRows = (long long)b.nz * g.nJB * g.Tp;
+    g.NP = g.nRows * 32;
+    g.zStride = (long long)g.nJB * g.Tp * 32;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    P.rowGrid = (int)std::max<long long>(1, std::min<long long>((g.nRows + BLK / 32 - 1) / (BLK / 32), (long long)sms * 8));
+    P.W = 8;
+    if (const char* e = std::getenv("FY_PENCIL_W")) { const int w = std::atoi(e); if (w >= 1 && w <= PEN_WMAX) P.W = w; }
+    P.smemBudget = 200 * 1024;
+    if (const char* e = std::getenv("FY_PENCIL_SMEM_KB")) { const int k = std::atoi(e); if (k >= 16 && k <= 216) P.smemBudget = k * 1024; }
+    // every array carries PEN_GUARD rows of zeros in front and behind: the sweeps prefetch D rows past either end
+    const size_t guard = (size_t)PEN_GUARD * 32, bytes = ((size_t)g.NP + 2 * guard) * sizeof(double);
+    auto alloc = [&](double*& p) -> int {
+        double* raw = nullptr;
+        FY_CUDA(cudaMalloc((void**)&raw, bytes));
+        FY_CUDA(cudaMemsetAsync(raw, 0, bytes, h->stream));
+        p = raw + guard;
+        return FY_OK;
+    };
+    int rc;
+    for (auto& p : P.mP) if ((rc = alloc(p))) return rc;
+    for (auto& p : P.mU) if ((rc = alloc(p))) return rc;
+    for (auto& p : P.v) if ((rc = alloc(p))) return rc;
+    const int maxWarps = g.nJB * (g.nz + PEN_WMAX) * 3 + 64;
+    FY_CUDA(cudaMalloc((void**)&P.partial, (size_t)maxWarps * sizeof(double)));
+    FY_CUDA(cudaMalloc((void**)&P.trace, (size_t)maxWarps * 32 * sizeof(unsigned long long)));
+    FY_CUDA(cudaMemsetAsync(P.trace, 0, (size_t)maxWarps * 32 * sizeof(unsigned long long), h->stream));
+    P.traceOn = std::getenv("FY_PENCIL_TRACE") != nullptr;
+    if (const char* e = std::getenv("FY_PENCIL_DBG")) P.dbg = std::atoi(e);
+    FY_CUDA(cudaMalloc((void**)&P.ticket, 2 * sizeof(unsigned int)));
+    FY_CUDA(cudaMemsetAsync(P.ticket, 0, 2 * sizeof(unsigned int), h->stream));
+    FY_CUDA(cudaMalloc((void**)&P.error, sizeof(int)));
+    FY_CUDA(cudaMemsetAsync(P.error, 0, sizeof(int), h->stream));
+    FY_CUDA(cudaHostAlloc((void**)&P.hError, sizeof(int), cudaHostAllocDefault));
+    *P.hError = 0;
+    return FY_OK;
+}
+
+void penDestroy(FvState* s)
+{
+    PenState& P = s->pen;
+    const size_t guard = (size_t)PEN_GUARD * 32;
+    for (auto p : P.mP) if (p) cudaFree(p - guard);
+    for (auto p : P.mU) if (p) cudaFree(p - guard);
+    for (auto p : P.v) if (p) cudaFree(p - guard);
+    if (P.partial) cudaFree(P.partial);
+    if (P.trace) cudaFree(P.trace);
+    if (P.ticket) cudaFree(P.ticket);
+    if (P.error) cudaFree(P.error);
+    if (P.hError) cudaFreeHost(P.hError);
+}
+
+// vector roles inside the shared pool P.v[]
+enum { V_B = 0, V_X, V_RD, V_D, V_RA, V_PA, V_WA, V_YA, V_ZA, V_BPRIME = V_RA, V_MID = V_PA, V_EX = V_WA, V_EY = V_YA, V_EZ = V_ZA };
+
+// PCG on owner-slot coefficients (device pointers, natural cell order).  Iteration kernels are queued in
+// batches and test the device-side `done` flag themselves; the host looks at the state once per batch.
+int fvPcgSolve(fy_ctx* h, FvState* s, const double* dg, const double* up, const double* b, double* psi, double tol,
+               double relTol, int maxIter, int precond, fy_solver_perf* perf)
+{
+    PenState& P = s->pen;
+    const PencilGeom& g = P.g;
+    int rc;
+    PenMatrix M = penMatrixOf(P, 0);
+    double** v = P.v;
+    PEN_LAUNCH(k_pen_matrix, g, dg, up, up, M);
+    PEN_LAUNCH(k_pen_from_nat, g, b, v[V_B]);
+    PEN_LAUNCH(k_pen_from_nat, g, psi, v[V_X]);
+    k_solve_begin<<<1, 1, 0, h->stream>>>(s->dSolve, tol, relTol, maxIter, precond);
+    FY_CHECK_LAUNCH();
+    PEN_LAUNCH(k_pen_avg, g, v[V_X], s->red, s->dSolve);
+    PEN_LAUNCH(k_pen_solve_init, g, M, v[V_B], v[V_X], v[V_RA], s->red, s->dSolve);
+    if (precond == FV_PRECOND_DIC) {
+        PEN_LAUNCH(k_pen_arm, g, v[V_D], v[V_YA], v[V_ZA], s->dSolve);
+        OpDicD op{{M.dg, M.low[0], M.low[1], M.low[2]}, v[V_D], v[V_RD]};
+        if ((rc = launchPencil<OpDicD, false>(h, s, op, s->dSolve))) return rc;
+    } else if (precond == FV_PRECOND_DIAGONAL) {
+        PEN_LAUNCH(k_pen_recip, g, M.dg, v[V_RD]);
+    }
+    int queued = 0;
+    bool sampled = false;
+    const bool prof = h->profiling && s->pev[0];
+    for (;;) {
+        if ((rc = readSolve(h, s))) return rc;
+        if (sampled) {
+            for (int q = 0; q < 5; ++q) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, s->pev[q], s->pev[q + 1]);
+                s->kernelMs[q] += ms;
+            }
+            s->kernelSamples++;
+            sampled = false;
+        }
+        if (s->hSolve->done) break;
+        int batch = s->pcgBatch;
+        if (queued >= 4 * batch) batch *= 2;
+        for (int it = 0; it < batch; ++it) {
+            const bool ev = prof && it == 0;
+            if (ev) cudaEventRecord(s->pev[0], h->stream);
+            if (precond == FV_PRECOND_DIC) {
+                OpDicFwd f{{v[V_RD], v[V_RA], M.low[0], M.low[1], M.low[2]}, v[V_YA]};
+                if ((rc = launchPencil<OpDicFwd, false>(h, s, f, s->dSolve))) return rc;
+                if (ev) cudaEventRecord(s->pev[1], h->stream);
+                OpDicBwd bw{{v[V_YA], v[V_RD], M.up[0], M.up[1], M.up[2], v[V_RA]}, v[V_ZA], v[V_YA]};
+                if ((rc = launchPencil<OpDicBwd, true>(h, s, bw, s->dSolve))) return rc;
+            } else {
+                if (ev) cudaEventRecord(s->pev[1], h->stream);
+                PEN_LAUNCH(k_pen_precond_diag, g, precond == FV_PRECOND_DIAGONAL ? v[V_RD] : (const double*)nullptr, v[V_RA],
+                           v[V_ZA], s->red, s->dSolve);
+            }
+            if (ev) cudaEventRecord(s->pev[2], h->stream);
+            PEN_LAUNCH(k_pen_dir, g, v[V_ZA], v[V_PA], s->dSolve);
+            if (ev) cudaEventRecord(s->pev[3], h->stream);
+            PEN_LAUNCH(k_pen_amul, g, M, v[V_PA], v[V_WA], s->red, s->dSolve);
+            if (ev) cudaEventRecord(s->pev[4], h->stream);
+            PEN_LAUNCH(k_pen_update, g, v[V_PA], v[V_WA], v[V_X], v[V_RA], s->red, s->dSolve);
+            if (ev) { cudaEventRecord(s->pev[5], h->stream); sampled = true; }
+        }
+        queued += batch;
+    }
+    PEN_LAUNCH(k_pen_to_nat, g, v[V_X], psi);
+    s->pcgIterations += s->hSolve->nIter;
+    if (perf) {
+        perf->initialResidual = s->hSolve->initRes;
+        perf->finalResidual = s->hSolve->finalRes;
+        perf->nIterations = s->hSolve->nIter;
+    }
+    return FY_OK;
+}
+
+// Uploads the (component-independent) off-diagonals of the momentum matrix into the pencil layout.
+int fvSmoothSetMatrix(fy_ctx* h, FvState* s, const double* lo, const double* up)
+{
+    PenState& P = s->pen;
+    PenMatrix M = penMatrixOf(P, 1);
+    M.dg = nullptr;
+    PEN_LAUNCH(k_pen_matrix, P.g, (const double*)nullptr, lo, up, M);
+    return FY_OK;
+}
+
+// smoothSolver + symGaussSeidel (nSweeps 1); off-diagonals as set by fvSmoothSetMatrix
+int fvSmoothSolve(fy_ctx* h, FvState* s, const double* dg, const double* b, double* psi, double tol, double relTol,
+                  int maxIter, fy_solver_perf* perf)
+{
+    PenState& P = s->pen;
+    const PencilGeom& g = P.g;
+    int rc;
+    PenMatrix M = penMatrixOf(P, 1);
+    double** v = P.v;
+    PEN_LAUNCH(k_pen_from_nat, g, dg, M.dg);
+    PEN_LAUNCH(k_pen_from_nat, g, b, v[V_B]);
+    PEN_LAUNCH(k_pen_from_nat, g, psi, v[V_X]);
+    k_solve_begin<<<1, 1, 0, h->stream>>>(s->dSolve, tol, relTol, maxIter, 0);
+    FY_CHECK_LAUNCH();
+    PEN_LAUNCH(k_pen_avg, g, v[V_X], s->red, s->dSolve);
+    PEN_LAUNCH(k_pen_solve_init, g, M, v[V_B], v[V_X], (double*)nullptr, s->red, s->dSolve);
+    PEN_LAUNCH(k_pen_arm, g, v[V_MID], (double*)nullptr, (double*)nullptr, s->dSolve);
+    for (;;) {
+        if ((rc = readSolve(h, s))) return rc;
+        if (s->hSolve->done) break;
+        for (int it = 0; it < s->gsBatch; ++it) {
+            PEN_LAUNCH(k_pen_gs_upper, g, M, v[V_X], v[V_EX], v[V_EY], v[V_EZ], s->dSolve);
+            OpGsFwd f{{v[V_B], M.low[0], M.low[1], M.low[2], v[V_EX], v[V_EY], v[V_EZ], M.dg}, v[V_MID], v[V_BPRIME], v[V_X]};
+            if ((rc = launchPencil<OpGsFwd, false>(h, s, f, s->dSolve))) return rc;
+            OpGsBwd bw{{v[V_BPRIME], M.up[0], M.up[1], M.up[2], M.dg}, v[V_X], v[V_MID]};
+            if ((rc = launchPencil<OpGsBwd, true>(h, s, bw, s->dSolve))) return rc;
+            PEN_LAUNCH(k_pen_residual, g, M, v[V_B], v[V_X], s->red, s->dSolve);
+        }
+    }
+    PEN_LAUNCH(k_pen_to_nat, g, v[V_X], psi);
+    if (perf) {
+        perf->initialResidual = s->hSolve->initRes;
+        perf->finalResidual = s->hSolve->finalRes;
+        perf->nIterations = s->hSolve->nIter;
+    }
+    return FY_OK;
+}
+
+int fvDicPrecondition(fy_ctx* h, FvState* s, const double* dg, const double* up, const double* rA, double* wA)
+{
+    PenState& P = s->pen;
+    const PencilGeom& g = P.g;
+    int rc;
+    PenMatrix M = penMatrixOf(P, 0);
+    double** v = P.v;
+    PEN_LAUNCH(k_pen_matrix, g, dg, up, up, M);
+    PEN_LAUNCH(k_pen_from_nat, g, rA, v[V_RA]);
+    PEN_LAUNCH(k_pen_arm, g, v[V_D], v[V_YA], v[V_ZA], (const FvSolveDev*)nullptr);
+    OpDicD op{{M.dg, M.low[0], M.low[1], M.low[2]}, v[V_D], v[V_RD]};
+    if ((rc = launchPencil<OpDicD, false>(h, s, op, nullptr))) return rc;
+    OpDicFwd f{{v[V_RD], v[V_RA], M.low[0], M.low[1], M.low[2]}, v[V_YA]};
+    if ((rc = launchPencil<OpDicFwd, false>(h, s, f, nullptr))) return rc;
+    OpDicBwd bw{{v[V_YA], v[V_RD], M.up[0], M.up[1], M.up[2], v[V_RA]}, v[V_ZA], v[V_YA]};
+    if ((rc = launchPencil<OpDicBwd, true>(h, s, bw, nullptr))) return rc;
+    PEN_LAUNCH(k_pen_to_nat, g, v[V_ZA], wA);
+    FY_CUDA(cudaMemcpyAsync(P.hError, P.error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    FY_CUDA(cudaStreamSynchronize(h->stream));
+    if (*P.hError) {
+        h->err = "pencil pipeline: a neighbour value never arrived (poll limit reached)";
+        return FY_ERR_CUDA;
+    }
+    return FY_OK;
+}

@@ -1,0 +1,83 @@
+// fv_pencil.cuh -- the "pencil" layout the sequential LDU recurrences (DIC factorisation, DIC forward /
+// backward substitution, Gauss-Seidel sweeps) and the Krylov kernels around them run in.
+//
+// WHY.  OpenFOAM's DIC / Gauss-Seidel loops are sequential over the face list; on the lexicographic hex
+// box cell (i,j,k) depends on (i-1,j,k), (i,j-1,k), (i,j,k-1).  A hyperplane wavefront with one grid
+// barrier per plane costs ~3.5 us x (nx+ny+nz-2) planes = 1.3 ms per sweep at 128^3 against ~20 us of
+// HBM time.  Here one WARP owns a pencil of cells instead -- 32 consecutive j (one per lane), all i, and
+// K consecutive k-planes -- and walks it in nx+31+K-1 steps: at step t lane l works on i = t-l-q of plane
+// q.  The x-dependency stays in a register, the y-dependency is one __shfl from the neighbouring lane,
+// the z-dependency between the K planes of a warp is a register of the previous step.  Only two values
+// cross warps: the z-neighbour of the warp's first plane and the y-neighbour of its edge lane.  They are
+// read straight from the output array in L2, which is pre-filled with a signalling-NaN sentinel: the
+// consumer polls the 8-byte word until it is not the sentinel (data and flag in one store, no fence, no
+// grid barrier).  The operation order inside a cell is exactly OpenFOAM's, so results stay bit-identical
+// to the sequential loops.
+//
+// LAYOUT (HBM).  So that every warp access is one contiguous 256-byte row, the solver's vectors and
+// matrix coefficients live in a skewed layout: slab (k, jb = j/32) holds Tp rows ("slots") of 32 lanes,
+//     pos(i,j,k) = ((k*nJB + jb)*Tp + i + (j&31))*32 + (j&31),       Tp = roundup(nx+31, PEN_S)
+// i.e. row m of a slab holds the 32 mutually independent cells i = m-lane that a warp processes in one
+// step (for both sweep directions).  Rows are fetched PEN_S at a time by TMA bulk copies
+// (cp.async.bulk + mbarrier) into a shared-memory ring several chunks ahead of the computation.  The
+// layout costs (nx+31)/nx extra storage; pads are never read by a valid cell.
+#pragma once
+#include <cstdint>
+
+#include "fv_box.cuh"
+
+constexpr int PEN_S = 4;                                         // rows per TMA chunk
+constexpr unsigned long long PEN_SENT = 0x7FF4DEADBEEF5A5AULL;   // signalling NaN: arithmetic never produces it
+
+struct PencilGeom {
+    int nx, ny, nz, N;
+    int nJB;               // j-blocks of 32 lanes
+    int Tp;                // rows per slab
+    long long nRows;       // nz*nJB*Tp
+    long long NP;          // nRows*32 doubles per vector
+    long long zStride;     // nJB*Tp*32: distance between (i,j,k) and (i,j,k+1)
+};
+
+struct PenCell {
+    bool valid;
+    int i, j, k, lane;
+    long long pos;
+};
+
+__device__ __forceinline__ PenCell penDecode(const PencilGeom& g, long long row, int lane)
+{
+    PenCell c;
+    const int sb = (int)(row / g.Tp);
+    const int m = (int)(row - (long long)sb * g.Tp);
+    c.k = sb / g.nJB;
+    const int jb = sb - c.k * g.nJB;
+    c.lane = lane;
+    c.i = m - lane;
+    c.j = jb * 32 + lane;
+    c.valid = c.i >= 0 && c.i < g.nx && c.j < g.ny;
+    c.pos = row * 32 + lane;
+    return c;
+}
+__host__ __device__ __forceinline__ long long penPos(const PencilGeom& g, int i, int j, int k)
+{
+    return (((long long)k * g.nJB + (j >> 5)) * g.Tp + i + (j & 31)) * 32 + (j & 31);
+}
+// position of (i, j-1, k) / (i, j+1, k)
+__device__ __forceinline__ long long penYm(const PencilGeom& g, const PenCell& c)
+{
+    return c.lane > 0 ? c.pos - 33 : c.pos - (long long)g.Tp * 32 + 31 * 32 + 31;
+}
+__device__ __forceinline__ long long penYp(const PencilGeom& g, const PenCell& c)
+{
+    return c.lane < 31 ? c.pos + 33 : c.pos + (long long)g.Tp * 32 - 31 * 32 - 31;
+}
+
+// an LDU matrix in pencil layout: low[d] = coefficient of the face towards the lower neighbour in
+// direction d (lduMatrix::lower of the face owned by that neighbour -- or ::upper of it for the DIC
+// recurrences of a symmetric matrix, where both are the same array), up[d] = lduMatrix::upper of the
+// cell's own +d face.  Zero where there is no such neighbour.
+struct PenMatrix {
+    double* dg;
+    double* low[3];
+    double* up[3];
+};

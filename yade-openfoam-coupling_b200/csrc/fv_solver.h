@@ -4,6 +4,7 @@
 #include <vector>
 
 #include "fv_box.cuh"
+#include "fv_pencil.cuh"
 #include "fy_ctx.h"
 
 // solver state shared between the kernels of one linear solve (device memory; the host reads it back
@@ -25,6 +26,25 @@ struct FvStepDev {
     int adjustFail, pad;
 };
 
+// pencil-layout solver state (fv_pencil.cu): matrices, the shared pool of Krylov / smoother vectors, and
+// the bookkeeping of the warp-pencil pipelines
+struct PenState {
+    PencilGeom g;
+    int rowGrid = 0;                    // blocks of the row-structured vector kernels
+    int W = 8;                          // warps per pencil group (CTA)
+    int smemBudget = 200 * 1024;        // bytes of shared memory per pencil group
+    double* mP[7] = {nullptr};          // pEqn: dg, low[3], up[3]
+    double* mU[7] = {nullptr};          // UEqn: dg (current component), low[3], up[3]
+    double* v[9] = {nullptr};           // vectors (roles: see fv_pencil.cu)
+    double* partial = nullptr;          // per-pencil partial sums
+    unsigned long long* trace = nullptr; // [nJB*nz][4] debug time stamps of the last pencil launch (FY_PENCIL_TRACE)
+    bool traceOn = false;
+    int dbg = 0;
+    unsigned int* ticket = nullptr;     // [2]
+    int* error = nullptr;
+    int* hError = nullptr;              // pinned
+};
+
 struct FvState {
     bool supported = false;
     std::string why;
@@ -43,11 +63,9 @@ struct FvState {
     double *U0 = nullptr, *HbyA = nullptr, *rAU = nullptr, *gradP = nullptr;
     // UEqn: diag, lower/upper in owner slots [3N], source [N][3]; per-component solve arrays (SoA [3][N])
     double *diagU = nullptr, *loU = nullptr, *upU = nullptr, *srcU = nullptr;
-    double *dgU = nullptr, *bU = nullptr, *psiU = nullptr, *bPrime = nullptr;
+    double *dgU = nullptr, *bU = nullptr, *psiU = nullptr;
     // pEqn
     double *upP = nullptr, *dgP = nullptr, *bP = nullptr;
-    // Krylov vectors
-    double *rD = nullptr, *pA = nullptr, *wA = nullptr, *rA = nullptr;
     // scratch for the parity hooks (LDU-order staging)
     double *stage = nullptr;
     size_t stageCap = 0;
@@ -58,8 +76,9 @@ struct FvState {
     FvStepDev* dStep = nullptr;
     FvStepDev* hStep = nullptr;         // pinned
     int cellGrid = 0;                   // blocks of the grid-stride cell kernels
-    int waveGrid = 0;                   // co-resident blocks of the cooperative wavefront kernels
     int pcgBatch = 8;
+    int gsBatch = 2;
+    PenState pen;
     double fluidMs[4] = {0, 0, 0, 0};
     // profiling (fy_set_profiling): device time of each kernel class of the PCG iteration, sampled on the
     // first iteration of every batch: [0] precondition forward [1] backward (+wA.rA) [2] search direction
@@ -73,8 +92,11 @@ struct FvState {
 int fvCreate(fy_ctx* h, const fy_mesh_desc* m);
 int fvPcgSolve(fy_ctx* h, FvState* s, const double* dg, const double* up, const double* b, double* psi, double tol,
                double relTol, int maxIter, int precond, fy_solver_perf* perf);
-int fvSmoothSolve(fy_ctx* h, FvState* s, const double* dg, const double* lo, const double* up, const double* b,
-                  double* psi, double tol, double relTol, int maxIter, fy_solver_perf* perf);
+int fvSmoothSetMatrix(fy_ctx* h, FvState* s, const double* lo, const double* up);
+int fvSmoothSolve(fy_ctx* h, FvState* s, const double* dg, const double* b, double* psi, double tol, double relTol,
+                  int maxIter, fy_solver_perf* perf);
+int penCreate(fy_ctx* h, FvState* s);
+void penDestroy(FvState* s);
 int fvDicPrecondition(fy_ctx* h, FvState* s, const double* dg, const double* up, const double* rA, double* wA);
 int fvCreatePhi(fy_ctx* h, FvState* s);
 int fvGradVector(fy_ctx* h, FvState* s, const double* dU, double* dOut);
