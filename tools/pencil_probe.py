@@ -37,18 +37,17 @@ w = E.dic(diag, upper, r)
 G = E.L
 nJB = (n + 31) // 32
 W = int(os.environ.get("FY_PENCIL_W", "8"))
-tr = np.empty((nJB * (n + 8) * 3 + 64) * 32)
+tr = np.empty((nJB * (n + 8 * 8 + 64) * 4 + 64) * 32)
 E._ck(G.fy_fv_get(E.h, b"pencilTrace", tr.ctypes.data_as(C.POINTER(C.c_double))))
 nKQ = (n + W - 1) // W
-tr = tr[: nKQ * nJB * (W + 2) * 32].reshape(nKQ, nJB, W + 2, 32)
+NW = 2 * W + 1
+tr = tr[: nKQ * nJB * NW * 32].reshape(nKQ, nJB, NW, 32)
 base = tr[..., 0][tr[..., 0] >= 0].min()
 print("last launch (backward sweep): span %.1f us" % ((tr[..., 3].max() - base) / 1e3))
 f = lambda a: " ".join("%5.1f" % ((x - base) / 1e3) for x in a)
-for jb in (nJB - 1,):
-    print("column jb=%d (dependency order: kq descending): time at the start of each block of 8 rows" % jb)
-    for kq in range(nKQ - 1, max(nKQ - 4, -1), -1):
+for jb in range(nJB - 1, -1, -1):
+    print("column jb=%d (kq descending): [start of block 0, 1, 10, 19 | end] of warp 0 and warp W-1" % jb)
+    for kq in range(nKQ - 1, -1, -1):
         c = tr[kq, jb]
-        print("  kq %2d zh: %s" % (kq, f(c[W, 8:30])))
-        print("  kq %2d w0: %s" % (kq, f(c[0, 8:30])))
-        print("  kq %2d w%d: %s" % (kq, W - 1, f(c[W - 1, 8:30])))
+        print("  kq %2d w0: %s | %s   w%d: %s | %s" % (kq, f(c[0, [8, 9, 18, 27]]), f(c[0, [3]]), W - 1, f(c[W - 1, [8, 9, 18, 27]]), f(c[W - 1, [3]])))
 E.close()

@@ -19,7 +19,8 @@ constexpr double FV_VSMALL = 1e-300;
 constexpr int PEN_SPIN_LIMIT = 1 << 20;
 constexpr int PEN_WMAX = 8;                   // most warps per pencil group
 constexpr int PEN_D = 8;                      // input prefetch depth (rows)
-constexpr int PEN_CD = 16;                    // channel depth (rows), a multiple of D
+constexpr int PEN_CD = 16;                    // z channel depth (rows), a multiple of D
+constexpr int PEN_CY = 32;                    // y channel depth (rows): one slot per y-helper lane
 constexpr int PEN_GUARD = 64;                 // guard rows around every pencil array (>= 2D + 31)
 
 // ---------------------------------------------------------------------------------------------
@@ -104,6 +105,45 @@ __device__ __noinline__ double pollSlow(const double* p, int& fail)
         v = ldPoll(p);
         if (++spin > PEN_SPIN_LIMIT) fail = 1;
     }
+    return v;
+}
+// thread-block cluster: rank, barrier, distributed shared memory (the z channel between the CTAs of a cluster)
+__device__ __forceinline__ uint32_t clusterRank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t clusterSize()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void clusterSync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapToRank(uint32_t localS, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(localS), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ double ldClusterV(uint32_t p)
+{
+    double v;
+    asm volatile("ld.volatile.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(p));
+    return v;
+}
+__device__ __forceinline__ void stClusterV(uint32_t p, double v)
+{
+    asm volatile("st.volatile.shared::cluster.f64 [%0], %1;" ::"r"(p), "d"(v));
+}
+__device__ __forceinline__ uint32_t ldClusterU32(uint32_t p)
+{
+    uint32_t v;
+    asm volatile("ld.volatile.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(p));
     return v;
 }
 __device__ __forceinline__ double sentValue() { return __longlong_as_double((long long)PEN_SENT); }
@@ -292,7 +332,7 @@ struct PenCtl {
 struct PenWarp {               // per-warp constants of one sweep
     uint32_t ringS, zInS, zOutS, yInS;
     int s0, nx, Tp, row00;
-    bool zOut, edge;
+    bool zOut, zRemote, edge;       // zRemote: the z channel written lives in the next CTA of the cluster (DSMEM)
     long long slab;
 };
 
@@ -344,12 +384,14 @@ __device__ __forceinline__ void penSweep(const Op& op, const PenWarp& w, double&
         const uint32_t rsN = (uint32_t)((t + 1) & (D - 1)) * (NIN * 256);     // next row's
         const uint32_t cs = (uint32_t)(t & (CD - 1));                         // channel slots
         const uint32_t csN = (uint32_t)((t + 1) & (CD - 1));
+        const uint32_t ys = (uint32_t)(t & (PEN_CY - 1)), ysN = (uint32_t)((t + 1) & (PEN_CY - 1));
         const int e = t * RS;                                                 // element offset of this row
         if ((t & (D - 1)) == 0) {
             penStampAt(tr, t, w.Tp);
             if (w.zOut) {                                                     // flow control, once per block of D rows
                 int spin = 0;
-                while (!isSent(ldSharedV(w.zOutS + (cs + D - 1) * 256)) && ++spin < PEN_SPIN_LIMIT) {}
+                if (w.zRemote) { while (!isSent(ldClusterV(w.zOutS + (cs + D - 1) * 256)) && ++spin < PEN_SPIN_LIMIT) {} }
+                else { while (!isSent(ldSharedV(w.zOutS + (cs + D - 1) * 256)) && ++spin < PEN_SPIN_LIMIT) {} }
             }
         }
         // (A) next row's inputs: read them now, use them after this row's chain
@@ -377,15 +419,18 @@ __device__ __forceinline__ void penSweep(const Op& op, const PenWarp& w, double&
         if (YIN) {
             double v = vyN;
             int spin = 0;
-            while (w.edge && isSent(v) && ++spin < PEN_SPIN_LIMIT) v = ldSharedV(w.yInS + cs * 8);   // only the edge lane owns the slot
-            if (w.edge) stSharedV(w.yInS + cs * 8, sentValue());
-            vyN = ldSharedV(w.yInS + csN * 8);
+            while (w.edge && isSent(v) && ++spin < PEN_SPIN_LIMIT) v = ldSharedV(w.yInS + ys * 8);   // only the edge lane owns the slot
+            if (w.edge) stSharedV(w.yInS + ys * 8, sentValue());
+            vyN = ldSharedV(w.yInS + ysN * 8);
             vy = w.edge ? v : vy;
         }
         double side = 0.0;
         double res = op.cell(cn, vx, vy, vz, side);
         res = active ? res : 0.0;
-        if (w.zOut) stSharedV(w.zOutS + cs * 256, res);
+        if (w.zOut) {
+            if (w.zRemote) stClusterV(w.zOutS + cs * 256, res);
+            else stSharedV(w.zOutS + cs * 256, res);
+        }
         stChain(chainB + e, res);
         op.post(posB + e, active, cn, res, side, acc);
         prev = res;
@@ -417,7 +462,13 @@ __device__ __forceinline__ void penHelpZ(const double* zRow0, uint32_t chanS, in
         for (int d = 0; d < D; ++d) {
             int spin = 0;
             while (isSent(r[d]) && !fail) {
-                r[d] = ldPoll(zB + d * RS);
+                // one L2 round trip costs several row times: re-request EVERY row of the ring that has not
+                // arrived, so that a round trip brings all the rows produced meanwhile
+#pragma unroll
+                for (int x = 0; x < D; ++x) {
+                    const int off = (x >= d ? x : x + D) * RS;     // rows d.. belong to this block, rows < d to the next
+                    if (isSent(r[x])) r[x] = ldPoll(zB + off);
+                }
                 if (++spin > PEN_SPIN_LIMIT) fail = 1;
             }
             stSharedV(chanS + cb + d * 256, r[d]);
@@ -427,59 +478,55 @@ __device__ __forceinline__ void penHelpZ(const double* zRow0, uint32_t chanS, in
     }
 }
 
-// Y helper: lane q < W serves compute warp q: the y-neighbour of its edge lane, row by row, from the
-// neighbouring j-block's output in L2 into y channel q.  Lane q runs q rows behind lane 0, like its plane.
+// Y helpers: one warp per compute warp.  It fetches the y-neighbour of the plane's edge lane -- the last lane
+// of the neighbouring j-block's rows, another CTA's output in L2 -- 32 rows at a time: lane l polls row
+// 32b + l on its own and drops it into slot l of the plane's y channel as soon as the consumer has taken
+// the previous block's row from it.  Every lane waits independently, so a value is delivered one L2 round
+// trip after it was produced however close the two j-blocks run.
 template <bool REV>
-__device__ __forceinline__ void penHelpY(const double* yRow0, bool on, int q, uint32_t chanS, int Tp, int& fail)
+__device__ __forceinline__ void penHelpY(const double* yRow0, uint32_t chanS, int Tp, int& fail)
 {
-    constexpr int D = PEN_D, CD = PEN_CD;
     constexpr int RS = REV ? -32 : 32;
-    const double* yB = yRow0 - (long long)q * RS;          // row n of the loop is this lane's row n - q
-    double r[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) r[d] = ldPoll(yB + d * RS);
-    for (int t0 = 0; t0 < Tp + D * ((PEN_WMAX + D - 1) / D); t0 += D) {
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-            const int n = t0 + d - q;                      // this lane's row
-            double v = r[d];
-            if (on && n >= 0 && n < Tp) {
-                const uint32_t slot = chanS + (uint32_t)(n & (CD - 1)) * 8;
-                int spin = 0;
-                while (isSent(v) && !fail) {
-                    v = ldPoll(yB + d * RS);
-                    if (++spin > PEN_SPIN_LIMIT) fail = 1;
-                }
-                spin = 0;
-                while (!isSent(ldSharedV(slot)) && ++spin < PEN_SPIN_LIMIT) {}
-                stSharedV(slot, v);
-            }
-            r[d] = ldPoll(yB + (d + D) * RS);
+    const int lane = threadIdx.x & 31;
+    const uint32_t slot = chanS + (uint32_t)lane * 8;
+    for (int b0 = 0; b0 < Tp; b0 += PEN_CY) {
+        const double* a = yRow0 + (long long)(b0 + lane) * RS;
+        double v = ldPoll(a);
+        int spin = 0;
+        while (isSent(v) && !fail) {
+            v = ldPoll(a);
+            if (++spin > PEN_SPIN_LIMIT) fail = 1;
         }
-        yB += D * RS;
+        spin = 0;
+        while (!isSent(ldSharedV(slot)) && ++spin < PEN_SPIN_LIMIT) {}
+        stSharedV(slot, v);
     }
 }
 
 template <class Op, bool REV>
-__global__ void __launch_bounds__(32 * (PEN_WMAX + 2)) k_pencil(PencilGeom g, Op op, PenCtl ctl)
+__global__ void __launch_bounds__(32 * (2 * PEN_WMAX + 1)) k_pencil(PencilGeom g, Op op, PenCtl ctl)
 {
     constexpr int NIN = Op::NIN, D = PEN_D, CD = PEN_CD;
     constexpr unsigned int FULL = 0xffffffffu;
     extern __shared__ __align__(128) unsigned char penSmem[];
     __shared__ unsigned int shTicket;
     if (ctl.st && ctl.st->done) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = (blockDim.x >> 5) - 2;
-    // shared memory: input rings [W][D][NIN][32] | z channels [W][CD][32] (channel w feeds compute warp w) | y channels [W][CD]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5, W = (NW - 1) >> 1;
+    // warps: [0,W) compute | W: z helper | (W, 2W]: y helpers
+    // shared memory: input rings [W][D][NIN][32] | z channels [W][CD][32] (channel w feeds compute warp w) | y channels [W][CY]
     double* const zChan = reinterpret_cast<double*>(penSmem) + (size_t)W * (D * NIN * 32);
     double* const yChan = zChan + (size_t)W * (CD * 32);
-    for (int x = threadIdx.x; x < W * CD * 33; x += blockDim.x) zChan[x] = sentValue();
-    if (threadIdx.x == 0) shTicket = atomicAdd(ctl.ticket, 1u);
-    __syncthreads();
-    const unsigned int tk = shTicket;
-    const int nKQ = (g.nz + W - 1) / W;
-    int kq = (int)tk / g.nJB, jb = (int)tk - kq * g.nJB;
-    if (REV) { kq = nKQ - 1 - kq; jb = g.nJB - 1 - jb; }
-    const int slotId = (kq * g.nJB + jb) * (W + 2) + warp;
+    for (int x = threadIdx.x; x < W * (CD * 32 + PEN_CY); x += blockDim.x) zChan[x] = sentValue();
+    // one ticket per cluster; the C CTAs of a cluster take C consecutive plane groups of one j-block
+    const int C = (int)clusterSize(), rank = (int)clusterRank();
+    if (rank == 0 && threadIdx.x == 0) shTicket = atomicAdd(ctl.ticket, 1u);
+    clusterSync();                                         // channels armed and the ticket taken, cluster-wide
+    const unsigned int tk = ldClusterU32(mapToRank(smemU32(&shTicket), 0));
+    const int nKQ = (g.nz + W - 1) / W, nCl = (nKQ + C - 1) / C;
+    int cl = (int)tk / g.nJB, jb = (int)tk - cl * g.nJB;
+    if (REV) { cl = nCl - 1 - cl; jb = g.nJB - 1 - jb; }
+    const int kq = REV ? cl * C + C - 1 - rank : cl * C + rank;           // may be >= nKQ: a CTA without planes
+    const int slotId = (kq * g.nJB + jb) * NW + warp;
     constexpr int KS = REV ? -1 : 1;
     auto planeOf = [&](int wq) { return REV ? kq * W + W - 1 - wq : kq * W + wq; };
     auto stamp = [&](int wh) {
@@ -507,7 +554,7 @@ __global__ void __launch_bounds__(32 * (PEN_WMAX + 2)) k_pencil(PencilGeom g, Op
             w.ringS = smemU32(reinterpret_cast<double*>(penSmem) + (size_t)warp * (D * NIN * 32) + lane);
             w.zInS = smemU32(zChan + (size_t)warp * (CD * 32) + lane);
             w.zOutS = w.zInS + CD * 256;
-            w.yInS = smemU32(yChan + (size_t)warp * CD);
+            w.yInS = smemU32(yChan + (size_t)warp * PEN_CY);
             // Sweep row s touches memory row m = s (forward) or Tp-1-s (backward); lane l then sits on the x index
             // i = m - l.  s - s0 counts the lane's cells in sweep order: active for 0 <= s - s0 < nx.
             w.s0 = jvalid ? (REV ? g.Tp - g.nx - lane : lane) : (1 << 30);
@@ -517,7 +564,9 @@ __global__ void __launch_bounds__(32 * (PEN_WMAX + 2)) k_pencil(PencilGeom g, Op
             w.slab = (((long long)k * g.nJB + jb) * g.Tp) * 32 + lane;
             const int kBehind = k - KS, kAhead = k + KS;
             const bool zin = kBehind >= 0 && kBehind < g.nz;
-            w.zOut = kAhead >= 0 && kAhead < g.nz && warp < W - 1;
+            w.zRemote = warp == W - 1;
+            w.zOut = kAhead >= 0 && kAhead < g.nz && (warp < W - 1 || rank < C - 1);
+            if (w.zRemote) w.zOutS = mapToRank(smemU32(zChan + lane), (uint32_t)(rank < C - 1 ? rank + 1 : rank));
             w.edge = lane == EDGE;
             if (zin && yCol) penSweep<Op, REV, true, true>(op, w, acc, trw);
             else if (zin) penSweep<Op, REV, true, false>(op, w, acc, trw);
@@ -526,14 +575,14 @@ __global__ void __launch_bounds__(32 * (PEN_WMAX + 2)) k_pencil(PencilGeom g, Op
         }
     } else if (warp == W) {
         const int k0 = planeOf(0), kBehind = k0 - KS;
-        if (k0 < g.nz && kBehind >= 0 && kBehind < g.nz)
+        if (rank == 0 && k0 < g.nz && kBehind >= 0 && kBehind < g.nz)
             penHelpZ<REV>(op.chain + (((long long)kBehind * g.nJB + jb) * g.Tp) * 32 + lane + row00, smemU32(zChan + lane), g.Tp, fail, trw, ctl.dbg);
-    } else {
-        const int q = lane < W ? lane : 0;
+
+    } else if (yCol) {
+        const int q = warp - W - 1;
         const int k = planeOf(q);
-        const bool on = yCol && lane < W && k < g.nz;
-        const double* y0 = op.chain + (((long long)(on ? k : 0) * g.nJB + jb) * g.Tp) * 32 + EDGE + yOff + row00;
-        if (yCol) penHelpY<REV>(y0, on, q, smemU32(yChan + (size_t)q * CD), g.Tp, fail);
+        if (k < g.nz)
+            penHelpY<REV>(op.chain + (((long long)k * g.nJB + jb) * g.Tp) * 32 + EDGE + yOff + row00, smemU32(yChan + (size_t)q * PEN_CY), g.Tp, fail);
     }
 
     stamp(3);
@@ -547,7 +596,7 @@ __global__ void __launch_bounds__(32 * (PEN_WMAX + 2)) k_pencil(PencilGeom g, Op
     if (lane == 0) {
         if (fail) atomicExch(ctl.error, 1);
         __threadfence();
-        last = (atomicAdd(ctl.ticket + 1, 1u) == gridDim.x * (W + 2) - 1) ? 1u : 0u;
+        last = (atomicAdd(ctl.ticket + 1, 1u) == gridDim.x * NW - 1) ? 1u : 0u;
     }
     last = __shfl_sync(FULL, last, 0);
     if (!last) return;
@@ -555,7 +604,7 @@ __global__ void __launch_bounds__(32 * (PEN_WMAX + 2)) k_pencil(PencilGeom g, Op
     if (Op::DOT) {
         const volatile double* p = ctl.partial;
         double x = 0.0;
-        for (unsigned int b = lane; b < gridDim.x * (W + 2); b += 32) x += p[b];
+        for (unsigned int b = lane; b < gridDim.x * NW; b += 32) x += p[b];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(FULL, x, o);
         if (lane == 0) op.fin(ctl.st, x);
@@ -818,7 +867,7 @@ int launchPencil(fy_ctx* h, FvState* s, const Op& op, FvSolveDev* st)
 {
     PenState& P = s->pen;
     // warps per group: as many as the shared-memory budget allows (each owns D*NIN rows + one channel)
-    const int perWarp = PEN_D * Op::NIN * 256 + PEN_CD * 33 * 8;
+    const int perWarp = PEN_D * Op::NIN * 256 + PEN_CD * 256 + PEN_CY * 8;
     int W = std::max(1, std::min(std::min(P.W, PEN_WMAX), P.smemBudget / perWarp));
     W = std::min(W, P.g.nz);
     const size_t smem = (size_t)W * perWarp;
@@ -828,9 +877,25 @@ int launchPencil(fy_ctx* h, FvState* s, const Op& op, FvSolveDev* st)
         attrDone = true;
     }
     PenCtl ctl{P.ticket, P.error, P.partial, st, P.dbg, P.traceOn ? P.trace : nullptr};
-    const int grid = P.g.nJB * ((P.g.nz + W - 1) / W);
-    k_pencil<Op, REV><<<grid, 32 * (W + 2), smem, h->stream>>>(P.g, op, ctl);
-    FY_CHECK_LAUNCH();
+    // clusters of C consecutive plane groups hand the z-neighbour over through distributed shared memory
+    const int nKQ = (P.g.nz + W - 1) / W;
+    int C = 1;
+    while (C * 2 <= P.cluster && C < nKQ) C *= 2;
+    const int nCl = (nKQ + C - 1) / C;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(P.g.nJB * nCl * C));
+    cfg.blockDim = dim3(32 * (2 * W + 1));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    FY_CUDA(cudaLaunchKernelEx(&cfg, k_pencil<Op, REV>, P.g, op, ctl));
+    h->launches++;
     return FY_OK;
 }
 
@@ -863,7 +928,7 @@ int penCreate(fy_ctx* h, FvState* s)
     PencilGeom& g = P.g;
     g.nx = b.nx; g.ny = b.ny; g.nz = b.nz; g.N = b.N;
     g.nJB = (b.ny + 31) / 32;
-    g.Tp = ((b.nx + 31 + PEN_CD - 1) / PEN_CD) * PEN_CD;
+    g.Tp = ((b.nx + 31 + PEN_CY - 1) / PEN_CY) * PEN_CY;
     g.nRows = (long long)b.nz * g.nJB * g.Tp;
     g.NP = g.nRows * 32;
     g.zStride = (long long)g.nJB * g.Tp * 32;
@@ -872,6 +937,8 @@ int penCreate(fy_ctx* h, FvState* s)
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     P.rowGrid = (int)std::max<long long>(1, std::min<long long>((g.nRows + BLK / 32 - 1) / (BLK / 32), (long long)sms * 8));
     P.W = 8;
+    P.cluster = 8;
+    if (const char* e = std::getenv("FY_PENCIL_CLUSTER")) { const int c = std::atoi(e); if (c >= 1 && c <= 8) P.cluster = c; }
     if (const char* e = std::getenv("FY_PENCIL_W")) { const int w = std::atoi(e); if (w >= 1 && w <= PEN_WMAX) P.W = w; }
     P.smemBudget = 200 * 1024;
     if (const char* e = std::getenv("FY_PENCIL_SMEM_KB")) { const int k = std::atoi(e); if (k >= 16 && k <= 216) P.smemBudget = k * 1024; }
@@ -888,7 +955,7 @@ int penCreate(fy_ctx* h, FvState* s)
     for (auto& p : P.mP) if ((rc = alloc(p))) return rc;
     for (auto& p : P.mU) if ((rc = alloc(p))) return rc;
     for (auto& p : P.v) if ((rc = alloc(p))) return rc;
-    const int maxWarps = g.nJB * (g.nz + PEN_WMAX) * 3 + 64;
+    const int maxWarps = g.nJB * (g.nz + 8 * PEN_WMAX + 64) * 4 + 64;
     FY_CUDA(cudaMalloc((void**)&P.partial, (size_t)maxWarps * sizeof(double)));
     FY_CUDA(cudaMalloc((void**)&P.trace, (size_t)maxWarps * 32 * sizeof(unsigned long long)));
     FY_CUDA(cudaMemsetAsync(P.trace, 0, (size_t)maxWarps * 32 * sizeof(unsigned long long), h->stream));
