@@ -249,11 +249,12 @@ def run_engine(args):
             cand["k_point_force"] = (phase[3], 132.0 * P + 128.0 * N)
         if fluid and kms and kms["samples"] > 0:
             it_step = kms["pcg_iterations"] / float(nprof)
-            cand["k_pencil<OpDicFwd> (DIC forward sweep)"] = (kms["precond_fwd"], 24.0 * N + 8.0 * 3 * N, it_step)
-            cand["k_pencil<OpDicBwd> (DIC backward sweep + wA.rA)"] = (kms["precond_bwd"], 24.0 * N + 8.0 * 3 * N, it_step)
-            cand["k_pen_amul"] = (kms["amul"], 24.0 * N + 8.0 * 3 * N, it_step)
-            cand["k_pen_update"] = (kms["update"], 48.0 * N, it_step)
-            cand["k_pen_dir"] = (kms["direction"], 24.0 * N, it_step)
+            # pencil-layout kernels: algorithmic bytes = 8 B x (streams read + written) per cell (kernels)
+            cand["k_pencil<OpDicFwd> (DIC forward sweep)"] = (kms["precond_fwd"], 48.0 * N, it_step)       # rD rA low[3] -> y
+            cand["k_pencil<OpDicBwd> (DIC backward sweep + wA.rA)"] = (kms["precond_bwd"], 64.0 * N, it_step)  # y rD up[3] rA -> z, re-arm y
+            cand["k_pen_amul"] = (kms["amul"], 72.0 * N, it_step)                                         # dg low[3] up[3] p -> w
+            cand["k_pen_update"] = (kms["update"], 48.0 * N, it_step)                                     # p w x r -> x r
+            cand["k_pen_dir"] = (kms["direction"], 32.0 * N, it_step)                                     # z p -> p, re-arm z
         # dominant = largest share of the step
         def share(v):
             return v[0] * (v[2] if len(v) > 2 else 1.0)

@@ -54,6 +54,40 @@ def lib():
     return _lib
 
 
+HOST_LIB_PATH = os.path.join(_HERE, "_build", "libhost_harness.so")
+_host = None
+
+
+def host_available():
+    return os.path.exists(HOST_LIB_PATH)
+
+
+def host_lib():
+    """oracle/_build/libhost_harness.so: the same fake Yade peer and fields around the PRODUCT's host class
+    (yade-openfoam-coupling_b200/host/FoamYadeB200.H -> libfycuda.so).  GPU tests only."""
+    global _host
+    if _host is None:
+        L = C.CDLL(HOST_LIB_PATH)
+        L.ref_create.restype = C.c_void_p
+        L.ref_create.argtypes = [C.c_int, _dp, _dp, C.c_int, _dp, _ip, _dp, C.c_int, C.c_int]
+        L.ref_destroy.argtypes = [C.c_void_p]
+        L.ref_set_properties.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+        L.ref_field.restype = _dp
+        L.ref_field.argtypes = [C.c_void_p, C.c_char_p]
+        L.ref_get_constants.argtypes = [C.c_void_p, _dp]
+        L.ref_set_logging.argtypes = [C.c_int]
+        L.ref_get_trace.restype = C.c_int
+        L.ref_get_trace.argtypes = [C.c_char_p, C.c_int]
+        L.ref_get_counts.argtypes = [C.POINTER(C.c_long)]
+        L.ref_get_dt.argtypes = [_dp, C.c_void_p]
+        L.ref_get_bbox.restype = C.c_int
+        L.ref_get_bbox.argtypes = [_dp, C.c_int]
+        L.ref_step.argtypes = [C.c_void_p, C.c_double, C.c_double, _dp, C.c_int, _ip, _ip, _dp]
+        L.ref_set_source_zero.argtypes = [C.c_void_p]
+        _host = L
+    return _host
+
+
 def _d(a):
     return a.ctypes.data_as(_dp)
 
@@ -74,8 +108,8 @@ FIELD_WIDTH = dict(U=3, gradP=3, divT=3, ddtU=3, uSource=3, uParticle=3, vGrad=9
 class RefFoamYade:
     """The reference Foam::FoamYade object on a mesh given by oracle.meshgen.hex_box()."""
 
-    def __init__(self, mesh, gaussian, n_yade=1):
-        self.L = lib()
+    def __init__(self, mesh, gaussian, n_yade=1, host=False):
+        self.L = host_lib() if host else lib()
         self.mesh = mesh
         self.N = mesh["V"].shape[0]
         self.gaussian = bool(gaussian)

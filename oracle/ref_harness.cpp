@@ -26,7 +26,16 @@
 //                       the quadratic list scan of buildCellPartList
 //                       (F.C:265-289) -- same additions in the same order, so
 //                       the same bits, but O(pairs).
+#ifdef FY_HOST_CLASS
+// second build of this harness (oracle/_build/libhost_harness.so): the SAME fake Yade peer and fields drive
+// the product's OpenFOAM-side host class (yade-openfoam-coupling_b200/host/FoamYadeB200.H) instead of the
+// reference, so a GPU test can compare wire traces and replies message for message.
+#include "FoamYadeB200.H"
+typedef Foam::FoamYadeB200 FyClass;
+#else
 #include "FoamYade.H"
+typedef Foam::FoamYade FyClass;
+#endif
 #include "PstreamGlobals.H"
 
 #include <chrono>
@@ -178,7 +187,7 @@ struct Ref
     Foam::volTensorField vGrad;
     Foam::volScalarField uSourceDrag, alpha;
     Foam::uniformDimensionedVectorField g;
-    Foam::FoamYade* fy = nullptr;
+    FyClass* fy = nullptr;
     void* fyStorage = nullptr;
     bool gaussian = false;
     // captured cell lists of the last step (after canonical truncation when applied)
@@ -260,9 +269,14 @@ void* ref_create(int nCells, const double* C, const double* V, int nPoints, cons
     g_peer.clearStep();
     // `bool serialYade` (F.H:91) is only ever set to true (F.C:31): give the object zeroed storage so
     // that the parallel protocol is what runs when Y > 1.
-    r->fyStorage = std::calloc(1, sizeof(Foam::FoamYade));
-    r->fy = new (r->fyStorage) Foam::FoamYade(r->mesh, r->U, r->gradP, r->vGrad, r->divT, r->ddtU, r->g,
+    r->fyStorage = std::calloc(1, sizeof(FyClass));
+    r->fy = new (r->fyStorage) FyClass(r->mesh, r->U, r->gradP, r->vGrad, r->divT, r->ddtU, r->g,
                                                r->uSourceDrag, r->alpha, r->uSource, r->uParticle, gaussian != 0);
+#ifdef FY_HOST_CLASS
+    if (r->box.nx > 0)
+        r->fy->setHexBox(r->box.nx, r->box.ny, r->box.nz, Foam::point(r->box.x0, r->box.y0, r->box.z0),
+                         Foam::vector(r->box.hx, r->box.hy, r->box.hz));
+#endif
     return r;
 }
 
@@ -270,7 +284,7 @@ void ref_destroy(void* h)
 {
     Ref* r = (Ref*)h;
     if (!r) return;
-    r->fy->~FoamYade();
+    r->fy->~FyClass();
     std::free(r->fyStorage);
     delete r;     // the k-d nodes are leaked by the reference itself (MT.C:28)
 }
@@ -296,7 +310,7 @@ double* ref_field(void* h, const char* name)
 
 void ref_get_constants(void* h, double* out4)
 {
-    Foam::FoamYade* fy = ((Ref*)h)->fy;
+    FyClass* fy = ((Ref*)h)->fy;
     out4[0] = fy->interpRange; out4[1] = fy->sigmaInterp; out4[2] = fy->interpRangeCu; out4[3] = fy->sigmaPi;
 }
 
@@ -322,6 +336,7 @@ int ref_get_bbox(double* out, int cap)
     return m;
 }
 
+#ifndef FY_HOST_CLASS
 // raw k-d "range" query of the reference (MT.C:148-179); ids is [n][stride], counts [n] (count may exceed 12)
 void ref_locate(void* h, const double* xyz, int n, int* ids, int* counts, int stride)
 {
@@ -333,6 +348,8 @@ void ref_locate(void* h, const double* xyz, int n, int* ids, int* counts, int st
         for (int j = 0; j < stride; ++j) ids[(size_t)i*stride + j] = (j < (int)l.size()) ? l[j] : -1;
     }
 }
+
+#endif
 
 int ref_find_cell(void* h, const double* xyz)
 {
@@ -349,6 +366,7 @@ void ref_step(void* h, double dt, double yadeDT, const double* pdata, int n, con
     collectOutputs(r, n, found, force6);
 }
 
+#ifndef FY_HOST_CLASS
 // same sequence through the public pieces (see header comment). truncate12: canonical list form;
 // dense: order-preserving dense accumulate instead of the quadratic scan. Records cell lists and phase times.
 void ref_step_pieces(void* h, double dt, double yadeDT, const double* pdata, int n, const int* split,
@@ -437,6 +455,8 @@ void ref_get_times(void* h, double* out5)
     Ref* r = (Ref*)h;
     out5[0] = r->tLocate; out5[1] = r->tWeights; out5[2] = r->tAccum; out5[3] = r->tForce; out5[4] = r->tSend;
 }
+
+#endif
 
 void ref_set_source_zero(void* h) { ((Ref*)h)->fy->setSourceZero(); }
 

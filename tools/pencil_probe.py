@@ -37,7 +37,7 @@ w = E.dic(diag, upper, r)
 G = E.L
 nJB = (n + 31) // 32
 W = int(os.environ.get("FY_PENCIL_W", "8"))
-tr = np.empty((nJB * (n + 8 * 8 + 64) * 4 + 64) * 32)
+tr = np.empty((nJB * (n + 16 * 8 + 64) * 4 + 64) * 32)
 E._ck(G.fy_fv_get(E.h, b"pencilTrace", tr.ctypes.data_as(C.POINTER(C.c_double))))
 nKQ = (n + W - 1) // W
 NW = 2 * W + 1

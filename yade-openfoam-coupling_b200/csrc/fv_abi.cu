@@ -253,7 +253,7 @@ int fy_fv_get(fy_handle h, const char* name, double* dst)
         return d2h(h, dst, d, nF);
     }
     if (k == "pencilTrace") {        // debug: [nJB*nz][4] time stamps (ns, relative to the earliest) of the last pencil launch
-        const size_t n = ((size_t)s->pen.g.nJB * (s->pen.g.nz + 8 * 8 + 64) * 4 + 64) * 32;
+        const size_t n = ((size_t)s->pen.g.nJB * (s->pen.g.nz + 16 * 8 + 64) * 4 + 64) * 32;
         std::vector<unsigned long long> t(n);
         FY_CUDA(cudaStreamSynchronize(h->stream));
         FY_CUDA(cudaMemcpy(t.data(), s->pen.trace, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));

@@ -874,6 +874,7 @@ int launchPencil(fy_ctx* h, FvState* s, const Op& op, FvSolveDev* st)
     static bool attrDone = false;
     if (!attrDone) {
         FY_CUDA(cudaFuncSetAttribute((const void*)k_pencil<Op, REV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        FY_CUDA(cudaFuncSetAttribute((const void*)k_pencil<Op, REV>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         attrDone = true;
     }
     PenCtl ctl{P.ticket, P.error, P.partial, st, P.dbg, P.traceOn ? P.trace : nullptr};
@@ -894,6 +895,15 @@ int launchPencil(fy_ctx* h, FvState* s, const Op& op, FvSolveDev* st)
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (C > 8) {                                           // 16-CTA clusters are non-portable: check that one fits
+        int nClusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nClusters, k_pencil<Op, REV>, &cfg) != cudaSuccess || nClusters < 1) {
+            cudaGetLastError();
+            C = 8;
+            attr[0].val.clusterDim.x = 8;
+            cfg.gridDim = dim3((unsigned)(P.g.nJB * ((nKQ + 7) / 8) * 8));
+        }
+    }
     FY_CUDA(cudaLaunchKernelEx(&cfg, k_pencil<Op, REV>, P.g, op, ctl));
     h->launches++;
     return FY_OK;
@@ -937,8 +947,8 @@ int penCreate(fy_ctx* h, FvState* s)
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     P.rowGrid = (int)std::max<long long>(1, std::min<long long>((g.nRows + BLK / 32 - 1) / (BLK / 32), (long long)sms * 8));
     P.W = 8;
-    P.cluster = 8;
-    if (const char* e = std::getenv("FY_PENCIL_CLUSTER")) { const int c = std::atoi(e); if (c >= 1 && c <= 8) P.cluster = c; }
+    P.cluster = 16;
+    if (const char* e = std::getenv("FY_PENCIL_CLUSTER")) { const int c = std::atoi(e); if (c >= 1 && c <= 16) P.cluster = c; }
     if (const char* e = std::getenv("FY_PENCIL_W")) { const int w = std::atoi(e); if (w >= 1 && w <= PEN_WMAX) P.W = w; }
     P.smemBudget = 200 * 1024;
     if (const char* e = std::getenv("FY_PENCIL_SMEM_KB")) { const int k = std::atoi(e); if (k >= 16 && k <= 216) P.smemBudget = k * 1024; }
@@ -955,7 +965,7 @@ int penCreate(fy_ctx* h, FvState* s)
     for (auto& p : P.mP) if ((rc = alloc(p))) return rc;
     for (auto& p : P.mU) if ((rc = alloc(p))) return rc;
     for (auto& p : P.v) if ((rc = alloc(p))) return rc;
-    const int maxWarps = g.nJB * (g.nz + 8 * PEN_WMAX + 64) * 4 + 64;
+    const int maxWarps = g.nJB * (g.nz + 16 * PEN_WMAX + 64) * 4 + 64;
     FY_CUDA(cudaMalloc((void**)&P.partial, (size_t)maxWarps * sizeof(double)));
     FY_CUDA(cudaMalloc((void**)&P.trace, (size_t)maxWarps * 32 * sizeof(unsigned long long)));
     FY_CUDA(cudaMemsetAsync(P.trace, 0, (size_t)maxWarps * 32 * sizeof(unsigned long long), h->stream));

@@ -32,7 +32,7 @@ struct PenState {
     PencilGeom g;
     int rowGrid = 0;                    // blocks of the row-structured vector kernels
     int W = 8;                          // compute warps per pencil group (CTA)
-    int cluster = 8;                    // largest thread-block cluster (plane groups chained through DSMEM)
+    int cluster = 16;                   // largest thread-block cluster (plane groups chained through DSMEM)
     int smemBudget = 200 * 1024;        // bytes of shared memory per pencil group
     double* mP[7] = {nullptr};          // pEqn: dg, low[3], up[3]
     double* mU[7] = {nullptr};          // UEqn: dg (current component), low[3], up[3]
