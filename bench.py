@@ -134,7 +134,7 @@ def run_engine(args):
     gaussian = args.coupling == "gaussian"
     _, mp, U0, p0 = flow_case(wl, pkg)
     N = mp["nCells"]
-    pd = cases.particles(P, seed + 1000 * rank, radius=0.1 / nx, moving=True)
+    pd = cases.particles(P, pkg.replicas.particle_seed(seed, rank), radius=0.1 / nx, moving=True)
     E = pkg.Engine(mp, device=local)
     E.set_properties(cases.RHOP, cases.RHOF, nu, gaussian)
     fluid = not args.coupling_only
@@ -233,10 +233,7 @@ def run_engine(args):
     kms = E.kernel_ms(reset=True) if fluid else None
     E.set_profiling(False)
 
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
+    ms, ms_e2e = pkg.replicas.slowest_rank_ms([ms, ms_e2e], dist if world > 1 else None, "cuda")
     if rank == 0:
         peak, which = peaks()
         Fi = 3 * N - nx * ny - ny * nz - nx * nz
@@ -263,7 +260,7 @@ def run_engine(args):
         ach = kbytes / (kms_dom * 1e-3) / 1e9 if kms_dom > 0 else 0.0
         line = {
             "metric": METRIC,
-            "value": world * args.steps / (ms * 1e-3), "unit": "coupled timesteps/s",
+            "value": pkg.replicas.job_throughput(world, args.steps, ms), "unit": "coupled timesteps/s",
             "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%s: %s" % (wl, desc), "cells": N, "internal_faces": Fi, "particles_per_gpu": P,
@@ -271,7 +268,7 @@ def run_engine(args):
                        "fvSolution": "PISO nCorrectors 2; p PCG/DIC 1e-06 relTol 0.05 (pFinal 0); U smoothSolver symGaussSeidel 1e-05",
                        "l2": "flushed between timed steps (256 MiB write)",
                        "partition": "one domain replica per GPU" if world > 1 else "single domain"},
-            "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "coupled timesteps/s",
+            "e2e": {"value": pkg.replicas.job_throughput(world, args.steps, ms_e2e), "unit": "coupled timesteps/s",
                     "h2d_bytes_per_step": 80 * P, "d2h_bytes_per_step": 52 * P},
             "gpu_launches": int(launches),
             "pcg_iterations_per_step": (float(np.mean(p_iters)) if p_iters else None),
