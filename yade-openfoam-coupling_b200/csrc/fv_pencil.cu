@@ -18,7 +18,9 @@ constexpr int BLK = 256;
 constexpr double FV_VSMALL = 1e-300;
 constexpr int PEN_SPIN_LIMIT = 1 << 20;
 constexpr int PEN_WMAX = 8;                   // most warps per pencil group
-constexpr int PEN_D = 8;                      // input prefetch depth (rows)
+constexpr int PEN_D = 8;                      // rows per flow-control block / helper ring depth
+// input prefetch depth (rows) of a sweep with NIN input streams: as deep as ~22 KB of ring per warp allows
+__host__ __device__ constexpr int penDepth(int nin) { return nin > 0 ? 8 : 8; }   // deeper rings were measured slower (more shared memory, no fewer stalls)
 constexpr int PEN_CD = 16;                    // z channel depth (rows), a multiple of D
 constexpr int PEN_CY = 32;                    // y channel depth (rows): one slot per y-helper lane
 constexpr int PEN_GUARD = 64;                 // guard rows around every pencil array (>= 2D + 31)
@@ -350,22 +352,25 @@ __device__ __forceinline__ void penStampAt(unsigned long long* tr, int t0, int T
 template <class Op, bool REV, bool ZIN, bool YIN>
 __device__ __forceinline__ void penSweep(const Op& op, const PenWarp& w, double& acc, unsigned long long* tr)
 {
-    constexpr int NIN = Op::NIN, NC = Op::NC, D = PEN_D, CD = PEN_CD;
+    constexpr int NIN = Op::NIN, NC = Op::NC, D = penDepth(Op::NIN), FB = PEN_D, CD = PEN_CD;
     constexpr unsigned int FULL = 0xffffffffu;
     constexpr int RS = REV ? -32 : 32;                     // row stride in sweep order (doubles)
-    const double* inB[NIN];
+    // running pointers (one 64-bit add per stream and row; no per-row address arithmetic from scratch)
+    const double* inP[NIN];
 #pragma unroll
-    for (int x = 0; x < NIN; ++x) inB[x] = op.in[x] + w.slab + w.row00;
-    double* const chainB = op.chain + w.slab + w.row00;
-    const long long posB = w.slab + w.row00;
+    for (int x = 0; x < NIN; ++x) inP[x] = op.in[x] + w.slab + w.row00;
+    double* chainP = op.chain + w.slab + w.row00;
+    long long pos = w.slab + w.row00;
 
     // row s of the sweep is fetched by commit group s into ring slot s mod D
 #pragma unroll
     for (int d = 0; d < D; ++d) {
 #pragma unroll
-        for (int x = 0; x < NIN; ++x) cpAsync8(w.ringS + (d * NIN + x) * 256, inB[x] + d * RS);
+        for (int x = 0; x < NIN; ++x) cpAsync8(w.ringS + (d * NIN + x) * 256, inP[x] + d * RS);
         cpAsyncCommit();
     }
+#pragma unroll
+    for (int x = 0; x < NIN; ++x) inP[x] += D * RS;        // from here on: the row D ahead of the current one
     double prev = 0.0, cn[NC];
     cpAsyncWait<D - 1>();
     {
@@ -376,22 +381,24 @@ __device__ __forceinline__ void penSweep(const Op& op, const PenWarp& w, double&
     }
     double vzN = ZIN ? ldSharedV(w.zInS) : 0.0;            // channel reads run one row ahead as well
     double vyN = YIN ? ldSharedV(w.yInS) : 0.0;
+    uint32_t rs = 0;                                       // ring slot of the current row (bytes)
+    int act = -w.s0;                                       // t - s0: the lane's cell index in sweep order
     // The row loop is deliberately NOT unrolled: one warp executes it alone, and a body that overflows the
     // instruction cache costs more than the few slot-index instructions saved.
 #pragma unroll 1
     for (int t = 0; t < w.Tp; ++t) {
-        const uint32_t rs = (uint32_t)(t & (D - 1)) * (NIN * 256);            // this row's ring slot
-        const uint32_t rsN = (uint32_t)((t + 1) & (D - 1)) * (NIN * 256);     // next row's
+        const uint32_t rsN = (rs + NIN * 256 == D * NIN * 256) ? 0u : rs + NIN * 256;     // next row's ring slot
         const uint32_t cs = (uint32_t)(t & (CD - 1));                         // channel slots
         const uint32_t csN = (uint32_t)((t + 1) & (CD - 1));
         const uint32_t ys = (uint32_t)(t & (PEN_CY - 1)), ysN = (uint32_t)((t + 1) & (PEN_CY - 1));
-        const int e = t * RS;                                                 // element offset of this row
-        if ((t & (D - 1)) == 0) {
+        if ((t & (FB - 1)) == 0) {
+#ifdef PEN_PROFILE
             penStampAt(tr, t, w.Tp);
+#endif
             if (w.zOut) {                                                     // flow control, once per block of D rows
                 int spin = 0;
-                if (w.zRemote) { while (!isSent(ldClusterV(w.zOutS + (cs + D - 1) * 256)) && ++spin < PEN_SPIN_LIMIT) {} }
-                else { while (!isSent(ldSharedV(w.zOutS + (cs + D - 1) * 256)) && ++spin < PEN_SPIN_LIMIT) {} }
+                if (w.zRemote) { while (!isSent(ldClusterV(w.zOutS + (cs + FB - 1) * 256)) && ++spin < PEN_SPIN_LIMIT) {} }
+                else { while (!isSent(ldSharedV(w.zOutS + (cs + FB - 1) * 256)) && ++spin < PEN_SPIN_LIMIT) {} }
             }
         }
         // (A) next row's inputs: read them now, use them after this row's chain
@@ -401,10 +408,13 @@ __device__ __forceinline__ void penSweep(const Op& op, const PenWarp& w, double&
         for (int x = 0; x < NIN; ++x) an[x] = ldSharedV(w.ringS + rsN + x * 256);
         // (B) refill the slot this row came from (its values already sit in cn)
 #pragma unroll
-        for (int x = 0; x < NIN; ++x) cpAsync8(w.ringS + rs + x * 256, inB[x] + e + D * RS);
+        for (int x = 0; x < NIN; ++x) {
+            cpAsync8(w.ringS + rs + x * 256, inP[x]);
+            inP[x] += RS;
+        }
         cpAsyncCommit();
         // (C) the dependent chain
-        const bool active = (unsigned)(t - w.s0) < (unsigned)w.nx;
+        const bool active = (unsigned)act < (unsigned)w.nx;
         const double vx = prev;
         double vy = REV ? __shfl_down_sync(FULL, prev, 1) : __shfl_up_sync(FULL, prev, 1);
         double vz = 0.0;
@@ -431,11 +441,15 @@ __device__ __forceinline__ void penSweep(const Op& op, const PenWarp& w, double&
             if (w.zRemote) stClusterV(w.zOutS + cs * 256, res);
             else stSharedV(w.zOutS + cs * 256, res);
         }
-        stChain(chainB + e, res);
-        op.post(posB + e, active, cn, res, side, acc);
+        stChain(chainP, res);
+        op.post(pos, active, cn, res, side, acc);
         prev = res;
         // (D) neighbour-independent products of the next row
         op.pre(an, cn);
+        chainP += RS;
+        pos += RS;
+        rs = rsN;
+        ++act;
     }
     cpAsyncWait<0>();
 }
@@ -506,7 +520,7 @@ __device__ __forceinline__ void penHelpY(const double* yRow0, uint32_t chanS, in
 template <class Op, bool REV>
 __global__ void __launch_bounds__(32 * (2 * PEN_WMAX + 1)) k_pencil(PencilGeom g, Op op, PenCtl ctl)
 {
-    constexpr int NIN = Op::NIN, D = PEN_D, CD = PEN_CD;
+    constexpr int NIN = Op::NIN, D = penDepth(Op::NIN), CD = PEN_CD;
     constexpr unsigned int FULL = 0xffffffffu;
     extern __shared__ __align__(128) unsigned char penSmem[];
     __shared__ unsigned int shTicket;
@@ -813,6 +827,22 @@ k_pen_dir(PencilGeom g, double* __restrict__ zA, double* __restrict__ pA, const 
     }
 }
 
+// Amul of a SYMMETRIC matrix: the coefficient towards a lower neighbour is that neighbour's own upper coefficient,
+// which the neighbouring rows stream anyway -- three coefficient arrays less to fetch from HBM (same values, same sums)
+__device__ __forceinline__ double penAmulCellSym(const PencilGeom& g, const PenMatrix& M, const double* __restrict__ x,
+                                                 const PenCell& c)
+{
+    const long long p = c.pos;
+    double a = M.dg[p] * x[p];
+    if (c.k > 0) a += M.up[2][p - g.zStride] * x[p - g.zStride];
+    if (c.j > 0) { const long long q = penYm(g, c); a += M.up[1][q] * x[q]; }
+    if (c.i > 0) a += M.up[0][p - 32] * x[p - 32];
+    if (c.i < g.nx - 1) a += M.up[0][p] * x[p + 32];
+    if (c.j < g.ny - 1) a += M.up[1][p] * x[penYp(g, c)];
+    if (c.k < g.nz - 1) a += M.up[2][p] * x[p + g.zStride];
+    return a;
+}
+
 // wA = A pA; wApA = wA.pA; alpha = wArA/wApA (with the singularity test of PCG.C)
 __global__ void __launch_bounds__(BLK)
 k_pen_amul(PencilGeom g, PenMatrix M, const double* __restrict__ pA, double* __restrict__ wA, FvRed red, FvSolveDev* st)
@@ -820,7 +850,7 @@ k_pen_amul(PencilGeom g, PenMatrix M, const double* __restrict__ pA, double* __r
     if (st->done) return;
     double v[1] = {0.0};
     PEN_ROW_LOOP(g, c) {
-        const double a = penAmulCell(g, M, pA, c);
+        const double a = penAmulCellSym(g, M, pA, c);
         wA[c.pos] = a;
         v[0] += a * pA[c.pos];
     }
@@ -867,7 +897,7 @@ int launchPencil(fy_ctx* h, FvState* s, const Op& op, FvSolveDev* st)
 {
     PenState& P = s->pen;
     // warps per group: as many as the shared-memory budget allows (each owns D*NIN rows + one channel)
-    const int perWarp = PEN_D * Op::NIN * 256 + PEN_CD * 256 + PEN_CY * 8;
+    const int perWarp = penDepth(Op::NIN) * Op::NIN * 256 + PEN_CD * 256 + PEN_CY * 8;
     int W = std::max(1, std::min(std::min(P.W, PEN_WMAX), P.smemBudget / perWarp));
     W = std::min(W, P.g.nz);
     const size_t smem = (size_t)W * perWarp;
@@ -945,12 +975,14 @@ int penCreate(fy_ctx* h, FvState* s)
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    P.rowGrid = (int)std::max<long long>(1, std::min<long long>((g.nRows + BLK / 32 - 1) / (BLK / 32), (long long)sms * 8));
+    int rowMult = 8;
+    if (const char* e = std::getenv("FY_ROWGRID_MULT")) { const int m = std::atoi(e); if (m >= 1 && m <= 128) rowMult = m; }
+    P.rowGrid = (int)std::max<long long>(1, std::min<long long>((g.nRows + BLK / 32 - 1) / (BLK / 32), (long long)sms * rowMult));
     P.W = 8;
     P.cluster = 16;
     if (const char* e = std::getenv("FY_PENCIL_CLUSTER")) { const int c = std::atoi(e); if (c >= 1 && c <= 16) P.cluster = c; }
     if (const char* e = std::getenv("FY_PENCIL_W")) { const int w = std::atoi(e); if (w >= 1 && w <= PEN_WMAX) P.W = w; }
-    P.smemBudget = 200 * 1024;
+    P.smemBudget = 216 * 1024;
     if (const char* e = std::getenv("FY_PENCIL_SMEM_KB")) { const int k = std::atoi(e); if (k >= 16 && k <= 216) P.smemBudget = k * 1024; }
     // every array carries PEN_GUARD rows of zeros in front and behind: the sweeps prefetch D rows past either end
     const size_t guard = (size_t)PEN_GUARD * 32, bytes = ((size_t)g.NP + 2 * guard) * sizeof(double);
