@@ -49,6 +49,19 @@ def peaks():
     return 6650.0, "fallback"
 
 
+def ncu_traffic(kernel_label):
+    """DRAM bytes per launch (read + write) of the kernel class from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "r1f_ncu_traffic.json")
+    try:
+        ks = json.load(open(p))["kernels"]
+    except Exception:
+        return None
+    for name, v in ks.items():
+        if kernel_label.startswith(name):
+            return (v["dram_read_MB"] + v["dram_write_MB"]) * 1e6
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -257,6 +270,7 @@ def run_engine(args):
             return v[0] * (v[2] if len(v) > 2 else 1.0)
         kname = max(cand, key=lambda k: share(cand[k]))
         kms_dom, kbytes = cand[kname][0], cand[kname][1]
+        traffic = ncu_traffic(kname) if wl == "C2" else None
         ach = kbytes / (kms_dom * 1e-3) / 1e9 if kms_dom > 0 else 0.0
         line = {
             "metric": METRIC,
@@ -278,19 +292,37 @@ def run_engine(args):
             "kernel_ms": {k: {"ms": v[0], "alg_GBps": (v[1] / (v[0] * 1e-3) / 1e9 if v[0] > 0 else None),
                               "launches_per_step": (v[2] if len(v) > 2 else 1)} for k, v in cand.items()},
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": None, "peak_source": which, "kernel_ms": kms_dom},
+                         "frac": ach / peak, "traffic": traffic, "peak_source": which, "kernel_ms": kms_dom,
+                         "algorithmic_bytes": kbytes,
+                         "traffic_source": "profiles/r1f_ncu_traffic.json (ncu --set full, dram read+write per launch)" if traffic else None},
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:
             state = dict(U=E.download("U"), p=E.download("p"), phi=E.download("phi")) if fluid else None
-            line["cpu_baseline"] = cpu_baseline(args, state=state)
+            ref_out = {}
+            line["cpu_baseline"] = cpu_baseline(args, state=state, out=ref_out)
+            if fluid and ref_out:
+                # the same step (same start fields, same particle sample) on the engine: parity at the full mesh size
+                Ps = ref_out["pd"].shape[0]
+                E.upload("U", state["U"]); E.upload("p", state["p"]); E.upload("phi", state["phi"])
+                E.ico_pre(dt)
+                fe, Fe = E.set_particle_action(dt, ref_out["pd"])
+                E.ico_solve(dt)
+                E.set_source_zero()
+                st = E.ico_stats()
+                line["parity_full_size"] = {
+                    "cells": N, "particles": int(Ps),
+                    "U_rel_l2": cases.rel_l2(E.download("U"), ref_out["U"]), "p_rel_l2": cases.rel_l2(E.download("p"), ref_out["p"]),
+                    "force_rel_l2": cases.rel_l2(Fe, ref_out["force"]), "found_equal": bool(np.array_equal(fe, ref_out["found"])),
+                    "p_iters_engine": [q["iters"] for q in st["p"]], "p_iters_cpu": ref_out["p_iters"],
+                    "against": "oracle/_ref (unmodified FoamYade.C, canonical <=12 lists) + oracle/fv_oracle.cc, one step from the engine's state"}
         print(json.dumps(line))
     E.close()
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_baseline(args, state=None, steps=1, warmup=0):
+def cpu_baseline(args, state=None, steps=1, warmup=0, out=None):
     """The reference CPU path of one coupled step on the box's host cores (1 core: FoamYade.C and an OpenFOAM
     rank are single-threaded by construction): the reference's own coupling code (oracle/_ref, unmodified
     FoamYade.C) on a bounded particle sample + the oracle's restatement of the OpenFOAM fluid step on the
@@ -326,7 +358,7 @@ def cpu_baseline(args, state=None, steps=1, warmup=0):
             R.field("U")[:] = O.field("U")
             R.field("vGrad")[:] = O.field("vGrad")
         t1 = time.time()
-        R.step(dt, pd, pieces=True, truncate12=True, dense=True)
+        found_cpu, force_cpu = R.step(dt, pd, pieces=True, truncate12=True, dense=True)
         if fluid:
             O.field("uSource")[:] = R.field("uSource")
         R.set_source_zero()
@@ -339,6 +371,9 @@ def cpu_baseline(args, state=None, steps=1, warmup=0):
             t_fl += (t1 - t0) + (t3 - t2)
             if fluid:
                 iters.append(sum(q["iters"] for q in O.stats()["p"]))
+    if out is not None and fluid and steps == 1 and warmup == 0:
+        out.update(pd=pd, U=O.field("U").copy(), p=O.field("p").copy(), found=found_cpu.copy(), force=force_cpu.copy(),
+                   p_iters=[q["iters"] for q in O.stats()["p"]])
     R.close()
     if O:
         O.close()

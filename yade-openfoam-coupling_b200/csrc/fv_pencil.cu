@@ -498,7 +498,7 @@ __device__ __forceinline__ void penHelpZ(const double* zRow0, uint32_t chanS, in
 // the previous block's row from it.  Every lane waits independently, so a value is delivered one L2 round
 // trip after it was produced however close the two j-blocks run.
 template <bool REV>
-__device__ __forceinline__ void penHelpY(const double* yRow0, uint32_t chanS, int Tp, int& fail)
+__device__ __forceinline__ void penHelpY(const double* yRow0, uint32_t chanS, int Tp, int& fail, unsigned napNs)
 {
     constexpr int RS = REV ? -32 : 32;
     const int lane = threadIdx.x & 31;
@@ -508,11 +508,12 @@ __device__ __forceinline__ void penHelpY(const double* yRow0, uint32_t chanS, in
         double v = ldPoll(a);
         int spin = 0;
         while (isSent(v) && !fail) {
+            if (napNs) __nanosleep(napNs);                 // the row is still being produced: do not hog the LSU
             v = ldPoll(a);
             if (++spin > PEN_SPIN_LIMIT) fail = 1;
         }
         spin = 0;
-        while (!isSent(ldSharedV(slot)) && ++spin < PEN_SPIN_LIMIT) {}
+        while (!isSent(ldSharedV(slot)) && ++spin < PEN_SPIN_LIMIT) { if (napNs) __nanosleep(napNs); }
         stSharedV(slot, v);
     }
 }
@@ -596,7 +597,7 @@ __global__ void __launch_bounds__(32 * (2 * PEN_WMAX + 1)) k_pencil(PencilGeom g
         const int q = warp - W - 1;
         const int k = planeOf(q);
         if (k < g.nz)
-            penHelpY<REV>(op.chain + (((long long)k * g.nJB + jb) * g.Tp) * 32 + EDGE + yOff + row00, smemU32(yChan + (size_t)q * PEN_CY), g.Tp, fail);
+            penHelpY<REV>(op.chain + (((long long)k * g.nJB + jb) * g.Tp) * 32 + EDGE + yOff + row00, smemU32(yChan + (size_t)q * PEN_CY), g.Tp, fail, (unsigned)(ctl.dbg >> 8));
     }
 
     stamp(3);
