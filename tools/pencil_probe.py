@@ -46,8 +46,8 @@ base = tr[..., 0][tr[..., 0] >= 0].min()
 print("last launch (backward sweep): span %.1f us" % ((tr[..., 3].max() - base) / 1e3))
 f = lambda a: " ".join("%5.1f" % ((x - base) / 1e3) for x in a)
 for jb in range(nJB - 1, -1, -1):
-    print("column jb=%d (kq descending): [start of block 0, 1, 10, 19 | end] of warp 0 and warp W-1" % jb)
-    for kq in range(nKQ - 1, -1, -1):
+    print("column jb=%d: [start of block 0, 1, 10, 19 | end] of warp 0 and warp W-1" % jb)
+    for kq in (range(nKQ) if os.environ.get("FY_PROBE_FWD") else range(nKQ - 1, -1, -1)):
         c = tr[kq, jb]
         print("  kq %2d w0: %s | %s   w%d: %s | %s" % (kq, f(c[0, [8, 9, 18, 27]]), f(c[0, [3]]), W - 1, f(c[W - 1, [8, 9, 18, 27]]), f(c[W - 1, [3]])))
 E.close()

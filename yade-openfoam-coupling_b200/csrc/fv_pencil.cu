@@ -1168,7 +1168,7 @@ int fvDicPrecondition(fy_ctx* h, FvState* s, const double* dg, const double* up,
     OpDicFwd f{{v[V_RD], v[V_RA], M.low[0], M.low[1], M.low[2]}, v[V_YA]};
     if ((rc = launchPencil<OpDicFwd, false>(h, s, f, nullptr))) return rc;
     OpDicBwd bw{{v[V_YA], v[V_RD], M.up[0], M.up[1], M.up[2], v[V_RA]}, v[V_ZA], v[V_YA]};
-    if ((rc = launchPencil<OpDicBwd, true>(h, s, bw, nullptr))) return rc;
+    if (!(P.dbg & 64) && (rc = launchPencil<OpDicBwd, true>(h, s, bw, nullptr))) return rc;      // dbg 64: dev probe of the forward sweep
     PEN_LAUNCH(k_pen_to_nat, g, v[V_ZA], wA);
     FY_CUDA(cudaMemcpyAsync(P.hError, P.error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     FY_CUDA(cudaStreamSynchronize(h->stream));
