@@ -175,6 +175,20 @@ int fy_set_particle_action(fy_handle h, double dt, const double* h_pdata, int n,
  * no host synchronisation.                                                                            */
 int fy_coupling_proc_device(fy_handle h, const double* d_pdata, int n, int* d_found, double* d_force);
 
+/* Particle-sharded multi-GPU coupling: the passes of fy_coupling_proc_device one at a time, so
+ * that ranks holding different slices of ONE Yade buffer can sum the per-cell partial results between them (the
+ * reference does the same sum with MPI_Allreduce over the Foam ranks, FoamYade.C:511-516, for the forces):
+ *   pass 0  locate + Gaussian weights + per-cell accumulate (FoamYade.C:187-225, 293-316, 261-290) -> d_found;
+ *           then all-reduce SUM the accumulators (fy_device_accumulators: pvol [N], upAcc [N][3]) and MAX the stamps [N]
+ *   pass 1  setCellVolFraction (FoamYade.C:318-328) from the reduced accumulators: identical on every rank
+ *   pass 2  forces of this rank's particles (FoamYade.C:331-453) -> d_force (+ d_found in point-force mode); then
+ *           all-reduce SUM uSource [N][3] and uSourceDrag [N]
+ * Every rank must make the same sequence of calls.                                                                  */
+int fy_coupling_pass_device(fy_handle h, int pass, const double* d_pdata, int n, int* d_found, double* d_force);
+int fy_device_accumulators(fy_handle h, double** d_pvol, double** d_upAcc, int** d_stamp);
+/* The handle's CUDA stream (a cudaStream_t), so that a caller can order its own work (e.g. NCCL) with the engine's. */
+int fy_stream(fy_handle h, void** cuda_stream);
+
 /* FoamYade::setSourceZero (FoamYade.C:556-566): uSource = 0; Gaussian: alpha = 1, uSourceDrag = 0,
  * uParticle = 0.  Host-bound output fields are reset too.                                          */
 int fy_set_source_zero(fy_handle h);

@@ -90,6 +90,9 @@ def lib():
     L.fy_set_particle_action.argtypes = [H, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.fy_coupling_proc_device.argtypes = [H, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.fy_set_source_zero.argtypes = [H]
+    L.fy_coupling_pass_device.argtypes = [H, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.fy_device_accumulators.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    L.fy_stream.argtypes = [H, C.POINTER(C.c_void_p)]
     L.fy_get_last_lists.argtypes = [H, C.c_int, _ip, _ip, _dp]
     L.fy_synchronize.argtypes = [H]
     L.fy_set_profiling.argtypes = [H, C.c_int]
@@ -280,6 +283,20 @@ class Engine:
 
     def coupling_proc_device(self, d_pdata, n, d_found, d_force):
         self._ck(self.L.fy_coupling_proc_device(self.h, d_pdata, n, d_found, d_force))
+
+    def coupling_pass_device(self, p, d_pdata, n, d_found, d_force):
+        self._ck(self.L.fy_coupling_pass_device(self.h, int(p), C.c_void_p(d_pdata), int(n), C.c_void_p(d_found),
+                                                 C.c_void_p(d_force)))
+
+    def device_accumulators(self):
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._ck(self.L.fy_device_accumulators(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def stream(self):
+        s = C.c_void_p()
+        self._ck(self.L.fy_stream(self.h, C.byref(s)))
+        return s.value or 0
 
     def set_source_zero(self):
         self._ck(self.L.fy_set_source_zero(self.h))

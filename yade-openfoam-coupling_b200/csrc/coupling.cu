@@ -452,6 +452,52 @@ int fyCouplingProcDevice(fy_ctx* h, const double* d_pdata, int n, int* d_found, 
     return FY_OK;
 }
 
+// The three passes of fyCouplingProcDevice separately (particle-sharded multi-GPU mode):
+// the caller reduces the per-cell partial sums across ranks between the passes.
+//   pass 0  locate + weights + per-cell accumulate of THIS rank's particles        -> dPvol, dUpAcc, dStamp
+//   pass 1  void fraction from the (reduced) accumulators                          -> alpha, uParticle
+//   pass 2  forces of this rank's particles, reaction scattered                    -> uSource, uSourceDrag partials
+int fyCouplingPass(fy_ctx* h, int pass, const double* d_pdata, int n, int* d_found, double* d_force)
+{
+    if (!h->propsSet) { h->err = "fy_set_properties must be called first"; return FY_ERR_INVALID; }
+    const ForceConst fc{h->rhoF, h->nu, 1e-09};
+    int rc;
+    if (pass == 0) {
+        h->lastN = n;
+        h->procSerial++;                                   // every rank makes the same calls: same serial everywhere
+        if (!h->gaussian || n <= 0) return FY_OK;
+        if ((rc = fyReserve(h, h->dIds, (size_t)n * FY_MAXLIST))) return rc;
+        if ((rc = fyReserve(h, h->dCnt, (size_t)n))) return rc;
+        if ((rc = fyReserve(h, h->dW, (size_t)n * FY_MAXLIST))) return rc;
+        const GaussConst gc{h->maxDist, 2 * std::pow(h->sigmaInterp, 2), h->interpRangeCu, h->sigmaPi};
+        k_locate_gauss<<<fyGrid(n, 128), 128, 0, h->stream>>>(h->dTree, h->nTree, d_pdata, n, gc, h->procSerial, h->dIds.p,
+                                                              h->dCnt.p, h->dW.p, d_found, h->dPvol, h->dUpAcc, h->dStamp);
+        FY_CHECK_LAUNCH();
+    } else if (pass == 1) {
+        if (!h->gaussian) return FY_OK;
+        k_void_fraction<<<fyGrid(h->nCells, 256), 256, 0, h->stream>>>(h->nCells, h->procSerial, h->dStamp, h->dPvol, h->dUpAcc,
+                                                                       h->dV, h->dField[FY_F_ALPHA], h->dField[FY_F_UPARTICLE]);
+        FY_CHECK_LAUNCH();
+    } else {
+        if (n <= 0) return FY_OK;
+        if (h->gaussian) {
+            k_force_gauss<<<fyGrid(n, 128), 128, 0, h->stream>>>(
+                d_pdata, n, h->dIds.p, h->dCnt.p, h->dW.p, fc, h->dField[FY_F_U], h->dField[FY_F_ALPHA],
+                h->dField[FY_F_UPARTICLE], h->dField[FY_F_GRADP], h->dField[FY_F_DIVT], h->dV, h->dField[FY_F_USOURCEDRAG],
+                h->dField[FY_F_USOURCE], d_force);
+        } else {
+            if (h->boxN[0] <= 0) { h->err = "point-force mode needs the hex-box findCell (mesh.boxN)"; return FY_ERR_UNSUPPORTED; }
+            if ((rc = fyReserve(h, h->dCell, (size_t)n))) return rc;
+            const BoxConst b{h->boxN[0], h->boxN[1], h->boxN[2], h->boxGeom[0], h->boxGeom[1], h->boxGeom[2],
+                             h->boxGeom[3], h->boxGeom[4], h->boxGeom[5]};
+            k_point_force<<<fyGrid(n, 256), 256, 0, h->stream>>>(d_pdata, n, b, fc, h->dField[FY_F_U], h->dField[FY_F_VGRAD],
+                                                                h->dV, h->dField[FY_F_USOURCE], h->dCell.p, d_found, d_force);
+        }
+        FY_CHECK_LAUNCH();
+    }
+    return FY_OK;
+}
+
 int fySourceZeroDevice(fy_ctx* h)
 {
     k_source_zero<<<fyGrid(3LL * h->nCells, 256), 256, 0, h->stream>>>(h->nCells, h->gaussian ? 1 : 0,

@@ -334,6 +334,28 @@ int fy_coupling_proc_device(fy_handle h, const double* d_pdata, int n, int* d_fo
     return fyCouplingProcDevice(h, d_pdata, n, d_found, d_force);
 }
 
+int fy_coupling_pass_device(fy_handle h, int pass, const double* d_pdata, int n, int* d_found, double* d_force)
+{
+    if (!h || n < 0 || pass < 0 || pass > 2) return FY_ERR_INVALID;
+    return fyCouplingPass(h, pass, d_pdata, n, d_found, d_force);
+}
+
+int fy_device_accumulators(fy_handle h, double** d_pvol, double** d_upAcc, int** d_stamp)
+{
+    if (!h) return FY_ERR_INVALID;
+    if (d_pvol) *d_pvol = h->dPvol;
+    if (d_upAcc) *d_upAcc = h->dUpAcc;
+    if (d_stamp) *d_stamp = h->dStamp;
+    return FY_OK;
+}
+
+int fy_stream(fy_handle h, void** cuda_stream)
+{
+    if (!h || !cuda_stream) return FY_ERR_INVALID;
+    *cuda_stream = (void*)h->stream;
+    return FY_OK;
+}
+
 int fy_coupling_proc(fy_handle h, const double* pdata, int n, int* found, double* force)
 {
     if (!h || n < 0 || (n > 0 && (!pdata || !found || !force))) return FY_ERR_INVALID;

@@ -153,5 +153,6 @@ void fyBuildKdTree(const double* C, int n, std::vector<FyKdNode>& out);
 int fyLaunchLocate(fy_ctx* h, const double* d_xyz, int stride, int n, int* d_ids, int* d_cnt);
 int fyLaunchFindCell(fy_ctx* h, const double* d_xyz, int stride, int n, int* d_cell);
 int fyCouplingProcDevice(fy_ctx* h, const double* d_pdata, int n, int* d_found, double* d_force);
+int fyCouplingPass(fy_ctx* h, int pass, const double* d_pdata, int n, int* d_found, double* d_force);
 int fySourceZeroDevice(fy_ctx* h);
 int fyInitCouplingFields(fy_ctx* h);
