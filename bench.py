@@ -35,6 +35,7 @@ WORKLOADS = {
     "C1": (32, 32, 32, 1000, 42, "cavity", 5e-3, 0.01, "icoFoamYade lid-driven cavity 32^3 cells, 1k particles"),
     "C2": (128, 128, 128, 1000000, 7, "channel", 5e-3, 1e-6, "icoFoamYade channel 128^3 cells, 1M particles, fp64, 1xB200"),
     "C2s": (64, 64, 64, 125000, 7, "channel", 1e-2, 1e-6, "icoFoamYade channel 64^3 cells, 125k particles (reduced C2)"),
+    "C2p": (128, 128, 128, 10000000, 7, "channel", 5e-3, 1e-6, "icoFoamYade channel 128^3 cells, 10M particles (particle-bound, for --partition particles)"),
 }
 UIN = 0.3
 
@@ -147,7 +148,16 @@ def run_engine(args):
     gaussian = args.coupling == "gaussian"
     _, mp, U0, p0 = flow_case(wl, pkg)
     N = mp["nCells"]
-    pd = cases.particles(P, pkg.replicas.particle_seed(seed, rank), radius=0.1 / nx, moving=True)
+    sharded = args.partition == "particles" and world > 1
+    if sharded:
+        # ONE domain, ONE particle buffer split over the ranks (strong scaling of the coupling half; the fluid
+        # solve is replicated on every rank from identical inputs)
+        lo, hi = pkg.sharded.shard_range(P, rank, world)
+        pd = cases.particles(P, seed, radius=0.1 / nx, moving=True)[lo:hi].copy()
+        P_total, P = P, hi - lo
+    else:
+        pd = cases.particles(P, pkg.replicas.particle_seed(seed, rank), radius=0.1 / nx, moving=True)
+        P_total = P
     E = pkg.Engine(mp, device=local)
     E.set_properties(cases.RHOP, cases.RHOF, nu, gaussian)
     fluid = not args.coupling_only
@@ -168,11 +178,18 @@ def run_engine(args):
     h_force = torch.empty(P, 6, dtype=torch.float64).pin_memory()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
+    S = None
+    if sharded:
+        S = pkg.sharded.ShardedCoupling(E, dist, pkg.sharded.device_views(E), gaussian, pkg.sharded.external_stream_ctx(E))
+
     def step_device():
         if fluid:
             E.ico_pre(dt)
-        E.coupling_begin(dt)
-        E.coupling_proc_device(d_pd.data_ptr(), P, d_found.data_ptr(), d_force.data_ptr())
+        if S is not None:
+            S.step(dt, d_pd.data_ptr(), P, d_found.data_ptr(), d_force.data_ptr())
+        else:
+            E.coupling_begin(dt)
+            E.coupling_proc_device(d_pd.data_ptr(), P, d_found.data_ptr(), d_force.data_ptr())
         if fluid:
             E.ico_solve(dt)
         E.set_source_zero()
@@ -180,8 +197,16 @@ def run_engine(args):
     def step_e2e():
         if fluid:
             E.ico_pre(dt)
-        L.fy_set_particle_action(E.h, dt, ctypes.c_void_p(h_pd.data_ptr()), P, ctypes.c_void_p(h_found.data_ptr()),
-                                 ctypes.c_void_p(h_force.data_ptr()))
+        if S is not None:
+            with S.stream_ctx():
+                d_pd.copy_(h_pd, non_blocking=True)
+            S.step(dt, d_pd.data_ptr(), P, d_found.data_ptr(), d_force.data_ptr())
+            with S.stream_ctx():
+                h_found.copy_(d_found, non_blocking=True)
+                h_force.copy_(d_force, non_blocking=True)
+        else:
+            L.fy_set_particle_action(E.h, dt, ctypes.c_void_p(h_pd.data_ptr()), P, ctypes.c_void_p(h_found.data_ptr()),
+                                     ctypes.c_void_p(h_force.data_ptr()))
         if fluid:
             E.ico_solve(dt)
         E.set_source_zero()
@@ -274,15 +299,18 @@ def run_engine(args):
         ach = kbytes / (kms_dom * 1e-3) / 1e9 if kms_dom > 0 else 0.0
         line = {
             "metric": METRIC,
-            "value": pkg.replicas.job_throughput(world, args.steps, ms), "unit": "coupled timesteps/s",
+            "value": pkg.replicas.job_throughput(1 if sharded else world, args.steps, ms), "unit": "coupled timesteps/s",
             "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
             "config": {"workload": "%s: %s" % (wl, desc), "cells": N, "internal_faces": Fi, "particles_per_gpu": P,
+                       "particles_total": P_total if sharded else P * world,
                        "coupling": args.coupling, "fluid_solve": bool(fluid), "flow": flow, "dt": dt, "nu": nu,
                        "fvSolution": "PISO nCorrectors 2; p PCG/DIC 1e-06 relTol 0.05 (pFinal 0); U smoothSolver symGaussSeidel 1e-05",
                        "l2": "flushed between timed steps (256 MiB write)",
-                       "partition": "one domain replica per GPU" if world > 1 else "single domain"},
-            "e2e": {"value": pkg.replicas.job_throughput(world, args.steps, ms_e2e), "unit": "coupled timesteps/s",
+                       "partition": ("one domain, particle buffer sharded over the GPUs, NCCL all-reduce of the cell sums, fluid solve replicated"
+                                     if sharded else ("one domain replica per GPU" if world > 1 else "single domain"))},
+            "e2e": {"value": pkg.replicas.job_throughput(1 if sharded else world, args.steps, ms_e2e), "unit": "coupled timesteps/s",
                     "h2d_bytes_per_step": 80 * P, "d2h_bytes_per_step": 52 * P},
             "gpu_launches": int(launches),
             "pcg_iterations_per_step": (float(np.mean(p_iters)) if p_iters else None),
@@ -317,9 +345,12 @@ def run_engine(args):
                     "p_iters_engine": [q["iters"] for q in st["p"]], "p_iters_cpu": ref_out["p_iters"],
                     "against": "oracle/_ref (unmodified FoamYade.C, canonical <=12 lists) + oracle/fv_oracle.cc, one step from the engine's state"}
         print(json.dumps(line))
-    E.close()
+    torch.cuda.synchronize()
+    S = None
     if world > 1:
-        dist.destroy_process_group()
+        dist.barrier()
+        dist.destroy_process_group()         # before the engine (and the stream NCCL was ordered on) goes away
+    E.close()
 
 
 def cpu_baseline(args, state=None, steps=1, warmup=0, out=None):
@@ -420,6 +451,9 @@ def main():
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--coupling", default="gaussian", choices=["gaussian", "point"])
     ap.add_argument("--coupling-only", action="store_true")
+    ap.add_argument("--partition", default="replicas", choices=["replicas", "particles"],
+                    help="N > 1: independent domain replicas (weak scaling, default) or one domain with the particle "
+                         "buffer sharded over the GPUs (strong scaling of the coupling half)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-particles", type=int, default=200000)
     args = ap.parse_args()
