@@ -334,6 +334,7 @@ struct PenCtl {
 struct PenWarp {               // per-warp constants of one sweep
     uint32_t ringS, zInS, zOutS, yInS;
     int s0, nx, Tp, row00;
+    unsigned napNs;
     bool zOut, zRemote, edge;       // zRemote: the z channel written lives in the next CTA of the cluster (DSMEM)
     long long slab;
 };
@@ -421,7 +422,10 @@ __device__ __forceinline__ void penSweep(const Op& op, const PenWarp& w, double&
         if (ZIN) {
             double v = vzN;
             int spin = 0;
-            while (isSent(v) && ++spin < PEN_SPIN_LIMIT) v = ldSharedV(w.zInS + cs * 256);
+            while (isSent(v) && ++spin < PEN_SPIN_LIMIT) {
+                if (w.napNs) __nanosleep(w.napNs);         // the producer is still on this row: leave it the issue slots
+                v = ldSharedV(w.zInS + cs * 256);
+            }
             stSharedV(w.zInS + cs * 256, sentValue());
             vzN = ldSharedV(w.zInS + csN * 256);
             vz = v;
@@ -583,6 +587,7 @@ __global__ void __launch_bounds__(32 * (2 * PEN_WMAX + 1)) k_pencil(PencilGeom g
             w.zOut = kAhead >= 0 && kAhead < g.nz && (warp < W - 1 || rank < C - 1);
             if (w.zRemote) w.zOutS = mapToRank(smemU32(zChan + lane), (uint32_t)(rank < C - 1 ? rank + 1 : rank));
             w.edge = lane == EDGE;
+            w.napNs = (unsigned)(ctl.dbg >> 20);
             if (zin && yCol) penSweep<Op, REV, true, true>(op, w, acc, trw);
             else if (zin) penSweep<Op, REV, true, false>(op, w, acc, trw);
             else if (yCol) penSweep<Op, REV, false, true>(op, w, acc, trw);
@@ -597,7 +602,7 @@ __global__ void __launch_bounds__(32 * (2 * PEN_WMAX + 1)) k_pencil(PencilGeom g
         const int q = warp - W - 1;
         const int k = planeOf(q);
         if (k < g.nz)
-            penHelpY<REV>(op.chain + (((long long)k * g.nJB + jb) * g.Tp) * 32 + EDGE + yOff + row00, smemU32(yChan + (size_t)q * PEN_CY), g.Tp, fail, (unsigned)(ctl.dbg >> 8));
+            penHelpY<REV>(op.chain + (((long long)k * g.nJB + jb) * g.Tp) * 32 + EDGE + yOff + row00, smemU32(yChan + (size_t)q * PEN_CY), g.Tp, fail, (unsigned)((ctl.dbg >> 8) & 0xfff));
     }
 
     stamp(3);
