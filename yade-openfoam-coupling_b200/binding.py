@@ -51,7 +51,8 @@ class _MeshDesc(C.Structure):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libfycuda.so")
+    # FY_LIBFYCUDA: a differently-built libfycuda.so (dev A/B runs); the product path is the in-tree library
+    return os.environ.get("FY_LIBFYCUDA") or os.path.join(_HERE, "libfycuda.so")
 
 
 _lib = None
