@@ -66,6 +66,37 @@ def test_dic_precondition_bit_exact(pkg, n):
     O.close()
 
 
+@pytest.mark.parametrize("n,cluster,warps", [((8, 8, 150), "16", "8"), ((6, 40, 70), "2", "4"), ((10, 33, 37), "1", "8"),
+                                             ((9, 70, 20), "4", "2"), ((5, 5, 300), "8", "1")])
+def test_sweeps_across_clusters_and_helpers(pkg, monkeypatch, n, cluster, warps):
+    """every hand-off route of the pencil pipeline: shared-memory channels, DSMEM between the CTAs of a cluster,
+    the L2 z-helper between clusters (nz > planes per cluster) and the y-helpers between j-blocks (ny > 32)"""
+    monkeypatch.setenv("FY_PENCIL_CLUSTER", cluster)
+    monkeypatch.setenv("FY_PENCIL_W", warps)
+    mo, mp = cases_fv.cavity3d(pkg, n)
+    rng = np.random.default_rng(7)
+    N, Fi = mo["nCells"], mo["nInternalFaces"]
+    upper = -rng.uniform(0.5, 1.5, Fi)
+    lower = -rng.uniform(0.5, 1.5, Fi)
+    diag = np.zeros(N)
+    np.subtract.at(diag, mo["owner"], upper)
+    np.subtract.at(diag, mo["neighbour"], upper)
+    diag += rng.uniform(0.01, 0.05, N)
+    r = rng.standard_normal(N)
+    O = port.IcoOracle(mo)
+    E = pkg.Engine(mp)
+    assert np.array_equal(E.dic(diag, upper, r), O.dic(diag, upper, r))
+    dg = np.zeros(N)
+    np.subtract.at(dg, mo["owner"], lower)
+    np.subtract.at(dg, mo["neighbour"], upper)
+    dg += rng.uniform(0.5, 1.0, N)
+    xo, po = O.smooth(dg, lower, upper, r, np.zeros(N), tol=1e-9)
+    xe, pe = E.smooth(dg, lower, upper, r, np.zeros(N), tol=1e-9)
+    assert pe["iters"] == po["iters"] and cases.rel_l2(xe, xo) <= 1e-13
+    E.close()
+    O.close()
+
+
 @pytest.mark.parametrize("pre", ["DIC", "diagonal", "none"])
 def test_pcg_matches_oracle(pkg, pre):
     mo, mp = cases_fv.cavity3d(pkg, (24, 20, 16))
