@@ -17,6 +17,8 @@
 #include <cmath>
 #include <cstdio>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "fy_ctx.h"
 
 namespace {
@@ -155,22 +157,25 @@ struct GaussConst {
 };
 
 __global__ void __launch_bounds__(128)
-k_locate_gauss(const FyKdNode* __restrict__ tree, int nTree, const double* __restrict__ pdata, int n, GaussConst gc,
-               int serial, int* __restrict__ ids, int* __restrict__ cnt, double* __restrict__ wts,
-               int* __restrict__ found, double* __restrict__ pvolAcc, double* __restrict__ upAcc,
-               int* __restrict__ stamp)
+k_locate_gauss(const FyKdNode* __restrict__ tree, int nTree, const double* __restrict__ pdata, int n,
+               const int* __restrict__ perm, GaussConst gc, int serial, int* __restrict__ ids, int* __restrict__ cnt,
+               double* __restrict__ wts, int* __restrict__ found, double* __restrict__ pvolAcc,
+               double* __restrict__ upAcc, int* __restrict__ stamp)
 {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
+    // thread t works on particle perm[t] (particles sorted by position so that a warp shares tree paths and cells);
+    // cell lists / weights are kept in sorted order, structure-of-arrays: ids[j*n + t]
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int p = perm[t];
     const double* rec = pdata + (size_t)p * 10;
     const double px = rec[0], py = rec[1], pz = rec[2];
     Trail tr;
     kdDescend(tree, nTree, px, py, pz, gc.maxDist, tr);
     const int k = tr.nImp < FY_MAXLIST ? tr.nImp : FY_MAXLIST;
-    cnt[p] = k;
+    cnt[t] = k;
     found[p] = k > 0 ? 1 : -1;                                       // F.C:204,222 / 141
     if (k == 0) {
-        for (int j = 0; j < FY_MAXLIST; ++j) ids[(size_t)p * FY_MAXLIST + j] = -1;
+        for (int j = 0; j < FY_MAXLIST; ++j) ids[(size_t)j * n + t] = -1;
         return;
     }
     // weights (F.C:301-314): the squared distance is the same number the descent computed
@@ -191,8 +196,8 @@ k_locate_gauss(const FyKdNode* __restrict__ tree, int nTree, const double* __res
     for (int j = 0; j < FY_MAXLIST; ++j) {
         if (j < k) {
             const double wj = w[j] / allwt;                          // F.C:313
-            ids[(size_t)p * FY_MAXLIST + j] = id[j];
-            wts[(size_t)p * FY_MAXLIST + j] = wj;
+            ids[(size_t)j * n + t] = id[j];
+            wts[(size_t)j * n + t] = wj;
             const int c = id[j];
             // F.C:271-272 / 278-279: pVol*weight ; (linearVelocity*weight)*pVol
             atomicAdd(&pvolAcc[c], vol * wj);
@@ -201,8 +206,8 @@ k_locate_gauss(const FyKdNode* __restrict__ tree, int nTree, const double* __res
             atomicAdd(&upAcc[3 * (size_t)c + 2], vz * wj * vol);
             stamp[c] = serial;
         } else {
-            ids[(size_t)p * FY_MAXLIST + j] = -1;
-            wts[(size_t)p * FY_MAXLIST + j] = 0.0;
+            ids[(size_t)j * n + t] = -1;
+            wts[(size_t)j * n + t] = 0.0;
         }
     }
 }
@@ -234,16 +239,17 @@ struct ForceConst {
 };
 
 __global__ void __launch_bounds__(128)
-k_force_gauss(const double* __restrict__ pdata, int n, const int* __restrict__ ids, const int* __restrict__ cnt,
-              const double* __restrict__ wts, ForceConst fc, const double* __restrict__ U,
+k_force_gauss(const double* __restrict__ pdata, int n, const int* __restrict__ perm, const int* __restrict__ ids,
+              const int* __restrict__ cnt, const double* __restrict__ wts, ForceConst fc, const double* __restrict__ U,
               const double* __restrict__ alpha, const double* __restrict__ uParticle,
               const double* __restrict__ gradP, const double* __restrict__ divT, const double* __restrict__ V,
               double* __restrict__ uSourceDrag, double* __restrict__ uSource, double* __restrict__ force)
 {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int p = perm[t];
     double* F = force + (size_t)p * 6;
-    const int k = cnt[p];
+    const int k = cnt[t];
     if (k <= 0) {
         F[0] = F[1] = F[2] = F[3] = F[4] = F[5] = 0.0;                // F.C:142 zero-initialised buffer
         return;
@@ -261,8 +267,8 @@ k_force_gauss(const double* __restrict__ pdata, int n, const int* __restrict__ i
     double dtx = 0, dty = 0, dtz = 0, pgx = 0, pgy = 0, pgz = 0;
     const double twoNu = 2.0 * nu;
     for (int j = 0; j < k; ++j) {
-        const int c = ids[(size_t)p * FY_MAXLIST + j];
-        const double wj = wts[(size_t)p * FY_MAXLIST + j];
+        const int c = ids[(size_t)j * n + t];
+        const double wj = wts[(size_t)j * n + t];
         id[j] = c;
         w[j] = wj;
         ufx += U[3 * (size_t)c] * wj;
@@ -405,6 +411,66 @@ int fyLaunchFindCell(fy_ctx* h, const double* d_xyz, int stride, int n, int* d_c
 }
 
 // One YadeProc's worth of FoamYade.C:612-628 on device-resident buffers.
+namespace {
+// sort key: the particle's cell on a 128^3 grid over the mesh bounding box, x fastest like the cells
+__global__ void k_particle_keys(const double* __restrict__ pdata, int n, double x0, double y0, double z0, double sx,
+                                double sy, double sz, unsigned int* __restrict__ key, int* __restrict__ idx)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const double* r = pdata + (size_t)p * 10;
+    const int ix = min(127, max(0, (int)((r[0] - x0) * sx)));
+    const int iy = min(127, max(0, (int)((r[1] - y0) * sy)));
+    const int iz = min(127, max(0, (int)((r[2] - z0) * sz)));
+    key[p] = (unsigned int)(ix + 128 * (iy + 128 * iz));
+    idx[p] = p;
+}
+// lists of the last buffer back in wire order, array-of-structures (parity hook fy_get_last_lists)
+__global__ void k_unpermute_lists(int n, const int* __restrict__ perm, const int* __restrict__ cnt, const int* __restrict__ ids,
+                                  const double* __restrict__ wts, int* __restrict__ cntOut, int* __restrict__ idsOut,
+                                  double* __restrict__ wtsOut)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int p = perm[t];
+    cntOut[p] = cnt[t];
+    for (int j = 0; j < FY_MAXLIST; ++j) {
+        idsOut[(size_t)p * FY_MAXLIST + j] = ids[(size_t)j * n + t];
+        wtsOut[(size_t)p * FY_MAXLIST + j] = wts[(size_t)j * n + t];
+    }
+}
+}  // namespace
+
+// Sorts the buffer's particles by position (radix sort of 21-bit cell keys; the permutation only -- records stay
+// where Yade put them).  Result: h->dPerm.
+int fySortParticles(fy_ctx* h, const double* d_pdata, int n)
+{
+    int rc;
+    if ((rc = fyReserve(h, h->dKey, (size_t)n))) return rc;
+    if ((rc = fyReserve(h, h->dKey2, (size_t)n))) return rc;
+    if ((rc = fyReserve(h, h->dIdx, (size_t)n))) return rc;
+    if ((rc = fyReserve(h, h->dPerm, (size_t)n))) return rc;
+    const double ex = h->bbox[3] - h->bbox[0], ey = h->bbox[4] - h->bbox[1], ez = h->bbox[5] - h->bbox[2];
+    k_particle_keys<<<fyGrid(n, 256), 256, 0, h->stream>>>(d_pdata, n, h->bbox[0], h->bbox[1], h->bbox[2],
+                                                          ex > 0 ? 128.0 / ex : 0.0, ey > 0 ? 128.0 / ey : 0.0,
+                                                          ez > 0 ? 128.0 / ez : 0.0, h->dKey.p, h->dIdx.p);
+    FY_CHECK_LAUNCH();
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, h->dKey.p, h->dKey2.p, h->dIdx.p, h->dPerm.p, n, 0, 21, h->stream);
+    if ((rc = fyReserve(h, h->dSortTmp, bytes))) return rc;
+    FY_CUDA(cub::DeviceRadixSort::SortPairs(h->dSortTmp.p, bytes, h->dKey.p, h->dKey2.p, h->dIdx.p, h->dPerm.p, n, 0, 21,
+                                            h->stream));
+    h->launches += 4;
+    return FY_OK;
+}
+
+int fyUnpermuteLists(fy_ctx* h, int n, int* d_cnt, int* d_ids, double* d_wts)
+{
+    k_unpermute_lists<<<fyGrid(n, 128), 128, 0, h->stream>>>(n, h->dPerm.p, h->dCnt.p, h->dIds.p, h->dW.p, d_cnt, d_ids, d_wts);
+    FY_CHECK_LAUNCH();
+    return FY_OK;
+}
+
 int fyCouplingProcDevice(fy_ctx* h, const double* d_pdata, int n, int* d_found, double* d_force)
 {
     if (!h->propsSet) { h->err = "fy_set_properties must be called first"; return FY_ERR_INVALID; }
@@ -420,7 +486,8 @@ int fyCouplingProcDevice(fy_ctx* h, const double* d_pdata, int n, int* d_found, 
         h->procSerial++;
         const GaussConst gc{h->maxDist, 2 * std::pow(h->sigmaInterp, 2), h->interpRangeCu, h->sigmaPi};
         if (prof) cudaEventRecord(h->ev[1], h->stream);
-        k_locate_gauss<<<fyGrid(n, 128), 128, 0, h->stream>>>(h->dTree, h->nTree, d_pdata, n, gc, h->procSerial,
+        if ((rc = fySortParticles(h, d_pdata, n))) return rc;
+        k_locate_gauss<<<fyGrid(n, 128), 128, 0, h->stream>>>(h->dTree, h->nTree, d_pdata, n, h->dPerm.p, gc, h->procSerial,
                                                               h->dIds.p, h->dCnt.p, h->dW.p, d_found, h->dPvol,
                                                               h->dUpAcc, h->dStamp);
         FY_CHECK_LAUNCH();
@@ -431,7 +498,7 @@ int fyCouplingProcDevice(fy_ctx* h, const double* d_pdata, int n, int* d_found, 
         FY_CHECK_LAUNCH();
         if (prof) cudaEventRecord(h->ev[3], h->stream);
         k_force_gauss<<<fyGrid(n, 128), 128, 0, h->stream>>>(
-            d_pdata, n, h->dIds.p, h->dCnt.p, h->dW.p, fc, h->dField[FY_F_U], h->dField[FY_F_ALPHA],
+            d_pdata, n, h->dPerm.p, h->dIds.p, h->dCnt.p, h->dW.p, fc, h->dField[FY_F_U], h->dField[FY_F_ALPHA],
             h->dField[FY_F_UPARTICLE], h->dField[FY_F_GRADP], h->dField[FY_F_DIVT], h->dV,
             h->dField[FY_F_USOURCEDRAG], h->dField[FY_F_USOURCE], d_force);
         FY_CHECK_LAUNCH();
@@ -470,8 +537,10 @@ int fyCouplingPass(fy_ctx* h, int pass, const double* d_pdata, int n, int* d_fou
         if ((rc = fyReserve(h, h->dCnt, (size_t)n))) return rc;
         if ((rc = fyReserve(h, h->dW, (size_t)n * FY_MAXLIST))) return rc;
         const GaussConst gc{h->maxDist, 2 * std::pow(h->sigmaInterp, 2), h->interpRangeCu, h->sigmaPi};
-        k_locate_gauss<<<fyGrid(n, 128), 128, 0, h->stream>>>(h->dTree, h->nTree, d_pdata, n, gc, h->procSerial, h->dIds.p,
-                                                              h->dCnt.p, h->dW.p, d_found, h->dPvol, h->dUpAcc, h->dStamp);
+        if ((rc = fySortParticles(h, d_pdata, n))) return rc;
+        k_locate_gauss<<<fyGrid(n, 128), 128, 0, h->stream>>>(h->dTree, h->nTree, d_pdata, n, h->dPerm.p, gc, h->procSerial,
+                                                              h->dIds.p, h->dCnt.p, h->dW.p, d_found, h->dPvol, h->dUpAcc,
+                                                              h->dStamp);
         FY_CHECK_LAUNCH();
     } else if (pass == 1) {
         if (!h->gaussian) return FY_OK;
@@ -482,7 +551,7 @@ int fyCouplingPass(fy_ctx* h, int pass, const double* d_pdata, int n, int* d_fou
         if (n <= 0) return FY_OK;
         if (h->gaussian) {
             k_force_gauss<<<fyGrid(n, 128), 128, 0, h->stream>>>(
-                d_pdata, n, h->dIds.p, h->dCnt.p, h->dW.p, fc, h->dField[FY_F_U], h->dField[FY_F_ALPHA],
+                d_pdata, n, h->dPerm.p, h->dIds.p, h->dCnt.p, h->dW.p, fc, h->dField[FY_F_U], h->dField[FY_F_ALPHA],
                 h->dField[FY_F_UPARTICLE], h->dField[FY_F_GRADP], h->dField[FY_F_DIVT], h->dV, h->dField[FY_F_USOURCEDRAG],
                 h->dField[FY_F_USOURCE], d_force);
         } else {

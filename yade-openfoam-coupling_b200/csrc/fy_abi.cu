@@ -204,7 +204,8 @@ int fy_destroy(fy_handle h)
     void* ptrs[] = {h->dC, h->dV, h->dOwner, h->dNeigh, h->dOwnStart, h->dLosort, h->dLosortStart, h->dSf, h->dMagSf,
                     h->dWeights, h->dDeltaCoeffs, h->dBFaceCells, h->dBPatch, h->dBSf, h->dBMagSf, h->dBDeltaCoeffs,
                     h->dBStart, h->dBOrder, h->dTree, h->dPvol, h->dUpAcc, h->dStamp, h->dPdata.p, h->dFound.p,
-                    h->dForce.p, h->dIds.p, h->dCnt.p, h->dW.p, h->dCell.p};
+                    h->dForce.p, h->dIds.p, h->dCnt.p, h->dW.p, h->dCell.p, h->dKey.p, h->dKey2.p, h->dIdx.p, h->dPerm.p,
+                    h->dSortTmp.p, h->dListCnt.p, h->dListIds.p, h->dListW.p};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& f : h->dField) if (f) cudaFree(f);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
@@ -426,9 +427,16 @@ int fy_get_last_lists(fy_handle h, int n, int* counts, int* ids, double* weights
     if (!h || n < 0 || n > h->lastN) return FY_ERR_INVALID;
     if (n == 0) return FY_OK;
     if (!h->gaussian) { h->err = "fy_get_last_lists: Gaussian mode only"; return FY_ERR_INVALID; }
-    if (counts) FY_CUDA(cudaMemcpyAsync(counts, h->dCnt.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    if (ids) FY_CUDA(cudaMemcpyAsync(ids, h->dIds.p, (size_t)n * FY_MAXLIST * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    if (weights) FY_CUDA(cudaMemcpyAsync(weights, h->dW.p, (size_t)n * FY_MAXLIST * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    // the lists live in sorted order, structure-of-arrays: back to wire order first (all lastN of them)
+    const int m = h->lastN;
+    int rc;
+    if ((rc = fyReserve(h, h->dListCnt, (size_t)m))) return rc;
+    if ((rc = fyReserve(h, h->dListIds, (size_t)m * FY_MAXLIST))) return rc;
+    if ((rc = fyReserve(h, h->dListW, (size_t)m * FY_MAXLIST))) return rc;
+    if ((rc = fyUnpermuteLists(h, m, h->dListCnt.p, h->dListIds.p, h->dListW.p))) return rc;
+    if (counts) FY_CUDA(cudaMemcpyAsync(counts, h->dListCnt.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (ids) FY_CUDA(cudaMemcpyAsync(ids, h->dListIds.p, (size_t)n * FY_MAXLIST * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (weights) FY_CUDA(cudaMemcpyAsync(weights, h->dListW.p, (size_t)n * FY_MAXLIST * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     FY_CUDA(cudaStreamSynchronize(h->stream));
     return FY_OK;
 }

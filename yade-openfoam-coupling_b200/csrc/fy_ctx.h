@@ -93,10 +93,16 @@ struct fy_ctx {
     FyBuf<double> dPdata;         // [n][10]
     FyBuf<int> dFound;            // [n]
     FyBuf<double> dForce;         // [n][6]
-    FyBuf<int> dIds;              // [n][12]
+    FyBuf<int> dIds;              // [12][n] cell lists, in SORTED particle order (structure of arrays)
     FyBuf<int> dCnt;              // [n]
-    FyBuf<double> dW;             // [n][12]
+    FyBuf<double> dW;             // [12][n] normalised weights
     FyBuf<int> dCell;             // [n] point-force cell
+    // position sort of the current buffer (Gaussian mode): keys, identity, permutation (sorted slot -> wire index)
+    FyBuf<unsigned int> dKey, dKey2;
+    FyBuf<int> dIdx, dPerm;
+    FyBuf<char> dSortTmp;
+    FyBuf<int> dListCnt, dListIds;   // staging of fy_get_last_lists (wire order)
+    FyBuf<double> dListW;
     int lastN = 0;
 
     // ---- profiling
@@ -153,6 +159,8 @@ void fyBuildKdTree(const double* C, int n, std::vector<FyKdNode>& out);
 int fyLaunchLocate(fy_ctx* h, const double* d_xyz, int stride, int n, int* d_ids, int* d_cnt);
 int fyLaunchFindCell(fy_ctx* h, const double* d_xyz, int stride, int n, int* d_cell);
 int fyCouplingProcDevice(fy_ctx* h, const double* d_pdata, int n, int* d_found, double* d_force);
+int fySortParticles(fy_ctx* h, const double* d_pdata, int n);
+int fyUnpermuteLists(fy_ctx* h, int n, int* d_cnt, int* d_ids, double* d_wts);
 int fyCouplingPass(fy_ctx* h, int pass, const double* d_pdata, int n, int* d_found, double* d_force);
 int fySourceZeroDevice(fy_ctx* h);
 int fyInitCouplingFields(fy_ctx* h);
