@@ -1013,6 +1013,7 @@ int penCreate(fy_ctx* h, FvState* s)
     FY_CUDA(cudaMalloc((void**)&P.trace, (size_t)maxWarps * 32 * sizeof(unsigned long long)));
     FY_CUDA(cudaMemsetAsync(P.trace, 0, (size_t)maxWarps * 32 * sizeof(unsigned long long), h->stream));
     P.traceOn = std::getenv("FY_PENCIL_TRACE") != nullptr;
+    if (const char* e = std::getenv("FY_PCG_GRAPH")) P.useGraphs = std::atoi(e) != 0;
     if (const char* e = std::getenv("FY_PENCIL_DBG")) P.dbg = std::atoi(e);
     FY_CUDA(cudaMalloc((void**)&P.ticket, 2 * sizeof(unsigned int)));
     FY_CUDA(cudaMemsetAsync(P.ticket, 0, 2 * sizeof(unsigned int), h->stream));
@@ -1030,6 +1031,7 @@ void penDestroy(FvState* s)
     for (auto p : P.mP) if (p) cudaFree(p - guard);
     for (auto p : P.mU) if (p) cudaFree(p - guard);
     for (auto p : P.v) if (p) cudaFree(p - guard);
+    for (auto& ge : P.pcgGraph) if (ge) { cudaGraphExecDestroy(ge); ge = nullptr; }
     if (P.partial) cudaFree(P.partial);
     if (P.trace) cudaFree(P.trace);
     if (P.ticket) cudaFree(P.ticket);
@@ -1064,9 +1066,48 @@ int fvPcgSolve(fy_ctx* h, FvState* s, const double* dg, const double* up, const 
     } else if (precond == FV_PRECOND_DIAGONAL) {
         PEN_LAUNCH(k_pen_recip, g, M.dg, v[V_RD]);
     }
-    int queued = 0;
     bool sampled = false;
     const bool prof = h->profiling && s->pev[0];
+    // one PCG iteration = 5 launches whose arguments never change (the vector pool and the matrix arrays are fixed
+    // for the engine's life): a batch of iterations is captured once into a CUDA graph and replayed
+    auto enqueueIteration = [&](bool ev) -> int {
+        if (ev) cudaEventRecord(s->pev[0], h->stream);
+        if (precond == FV_PRECOND_DIC) {
+            OpDicFwd f{{v[V_RD], v[V_RA], M.low[0], M.low[1], M.low[2]}, v[V_YA]};
+            if ((rc = launchPencil<OpDicFwd, false>(h, s, f, s->dSolve))) return rc;
+            if (ev) cudaEventRecord(s->pev[1], h->stream);
+            OpDicBwd bw{{v[V_YA], v[V_RD], M.up[0], M.up[1], M.up[2], v[V_RA]}, v[V_ZA], v[V_YA]};
+            if ((rc = launchPencil<OpDicBwd, true>(h, s, bw, s->dSolve))) return rc;
+        } else {
+            if (ev) cudaEventRecord(s->pev[1], h->stream);
+            PEN_LAUNCH(k_pen_precond_diag, g, precond == FV_PRECOND_DIAGONAL ? v[V_RD] : (const double*)nullptr, v[V_RA],
+                       v[V_ZA], s->red, s->dSolve);
+        }
+        if (ev) cudaEventRecord(s->pev[2], h->stream);
+        PEN_LAUNCH(k_pen_dir, g, v[V_ZA], v[V_PA], s->dSolve);
+        if (ev) cudaEventRecord(s->pev[3], h->stream);
+        PEN_LAUNCH(k_pen_amul, g, M, v[V_PA], v[V_WA], s->red, s->dSolve);
+        if (ev) cudaEventRecord(s->pev[4], h->stream);
+        PEN_LAUNCH(k_pen_update, g, v[V_PA], v[V_WA], v[V_X], v[V_RA], s->red, s->dSolve);
+        if (ev) cudaEventRecord(s->pev[5], h->stream);
+        return FY_OK;
+    };
+    const int batch = s->pcgBatch;
+    cudaGraphExec_t& gexec = P.pcgGraph[precond];
+    const bool useGraph = P.useGraphs && !prof && !P.traceOn;
+    if (useGraph && !gexec && P.graphWarm[precond]) {
+        // (every kernel has run eagerly once by now: function attributes set, modules loaded)
+        const long long l0 = h->launches;
+        cudaGraph_t graph = nullptr;
+        FY_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        for (int it = 0; it < batch; ++it)
+            if ((rc = enqueueIteration(false))) { cudaStreamEndCapture(h->stream, &graph); if (graph) cudaGraphDestroy(graph); return rc; }
+        FY_CUDA(cudaStreamEndCapture(h->stream, &graph));
+        FY_CUDA(cudaGraphInstantiate(&gexec, graph, 0));
+        cudaGraphDestroy(graph);
+        P.graphLaunches = (int)(h->launches - l0);
+        h->launches = l0;
+    }
     for (;;) {
         if ((rc = readSolve(h, s))) return rc;
         if (sampled) {
@@ -1079,31 +1120,16 @@ int fvPcgSolve(fy_ctx* h, FvState* s, const double* dg, const double* up, const 
             sampled = false;
         }
         if (s->hSolve->done) break;
-        int batch = s->pcgBatch;
-        if (queued >= 4 * batch) batch *= 2;
-        for (int it = 0; it < batch; ++it) {
-            const bool ev = prof && it == 0;
-            if (ev) cudaEventRecord(s->pev[0], h->stream);
-            if (precond == FV_PRECOND_DIC) {
-                OpDicFwd f{{v[V_RD], v[V_RA], M.low[0], M.low[1], M.low[2]}, v[V_YA]};
-                if ((rc = launchPencil<OpDicFwd, false>(h, s, f, s->dSolve))) return rc;
-                if (ev) cudaEventRecord(s->pev[1], h->stream);
-                OpDicBwd bw{{v[V_YA], v[V_RD], M.up[0], M.up[1], M.up[2], v[V_RA]}, v[V_ZA], v[V_YA]};
-                if ((rc = launchPencil<OpDicBwd, true>(h, s, bw, s->dSolve))) return rc;
-            } else {
-                if (ev) cudaEventRecord(s->pev[1], h->stream);
-                PEN_LAUNCH(k_pen_precond_diag, g, precond == FV_PRECOND_DIAGONAL ? v[V_RD] : (const double*)nullptr, v[V_RA],
-                           v[V_ZA], s->red, s->dSolve);
+        if (useGraph && gexec) {
+            FY_CUDA(cudaGraphLaunch(gexec, h->stream));
+            h->launches += P.graphLaunches;
+        } else {
+            P.graphWarm[precond] = true;
+            for (int it = 0; it < batch; ++it) {
+                if ((rc = enqueueIteration(prof && it == 0))) return rc;
+                if (prof && it == 0) sampled = true;
             }
-            if (ev) cudaEventRecord(s->pev[2], h->stream);
-            PEN_LAUNCH(k_pen_dir, g, v[V_ZA], v[V_PA], s->dSolve);
-            if (ev) cudaEventRecord(s->pev[3], h->stream);
-            PEN_LAUNCH(k_pen_amul, g, M, v[V_PA], v[V_WA], s->red, s->dSolve);
-            if (ev) cudaEventRecord(s->pev[4], h->stream);
-            PEN_LAUNCH(k_pen_update, g, v[V_PA], v[V_WA], v[V_X], v[V_RA], s->red, s->dSolve);
-            if (ev) { cudaEventRecord(s->pev[5], h->stream); sampled = true; }
         }
-        queued += batch;
     }
     PEN_LAUNCH(k_pen_to_nat, g, v[V_X], psi);
     s->pcgIterations += s->hSolve->nIter;

@@ -40,6 +40,10 @@ struct PenState {
     double* partial = nullptr;          // per-pencil partial sums
     unsigned long long* trace = nullptr; // [nJB*nz][4] debug time stamps of the last pencil launch (FY_PENCIL_TRACE)
     bool traceOn = false;
+    bool useGraphs = true;              // replay a batch of PCG iterations as one CUDA graph (FY_PCG_GRAPH=0 disables)
+    cudaGraphExec_t pcgGraph[3] = {nullptr, nullptr, nullptr};     // per preconditioner
+    int graphLaunches = 0;              // kernel launches inside one graph replay
+    bool graphWarm[3] = {false, false, false};   // the iteration kernels have run eagerly at least once
     int dbg = 0;
     unsigned int* ticket = nullptr;     // [2]
     int* error = nullptr;
