@@ -200,29 +200,40 @@ def test_ico_steps_match_oracle(pkg, case):
     assert e["stats"][-1]["sumLocalContErr"] < 1e-6
 
 
-def test_coupled_icoFoamYade_step(pkg):
-    """vGrad = grad(U) -> setParticleAction (point-force, the branch icoFoamYade hard-codes) -> UEqn/PISO ->
-    setSourceZero, engine vs (unmodified reference coupling + oracle fluid step)."""
+@pytest.mark.parametrize("config", ["small_point", "C1_point", "C1_gaussian"])
+def test_coupled_icoFoamYade_step(pkg, config):
+    """vGrad = grad(U) -> setParticleAction -> UEqn/PISO -> setSourceZero, engine vs (unmodified reference coupling +
+    oracle fluid step).  C1 = BASELINE.json configs[0]: lid-driven cavity, 32^3 cells, 1k particles (seed 42); the
+    point-force branch is the one icoFoamYade hard-codes (icoFoamYade.C:53), the Gaussian one is the operator's other
+    constructor setting (FoamYade.H:117)."""
     from oracle import ref
-    n = 16
-    mo, mp = cases_fv.cavity3d(pkg, (n, n, n), (1.0, 1.0, 1.0))
-    N = mo["nCells"]
-    U0 = 0.2 * cases.fields_for(mo["C"])["U"]
-    pd = cases.particles(3000, 11, radius=0.1 / n, moving=True)
-    dt, nu = 2e-3, 1e-3
+    if config == "small_point":
+        n, P, seed, gaussian, steps, dt, nu = 16, 3000, 11, False, 2, 2e-3, 1e-3
+        mo, mp = cases_fv.cavity3d(pkg, (n, n, n), (1.0, 1.0, 1.0))
+        U0 = 0.2 * cases.fields_for(mo["C"])["U"]
+    else:
+        n, P, seed, gaussian, steps, dt, nu = 32, 1000, 42, config == "C1_gaussian", 4, 5e-3, 0.01
+        mo, mp = cases_fv.cavity3d(pkg, (n, n, n), (1.0, 1.0, 1.0))
+        U0 = np.zeros((mo["nCells"], 3))
+    pd = cases.particles(P, seed, radius=0.1 / n, moving=True)
+    f = cases.fields_for(mo["C"])
     # oracle side
     O = port.IcoOracle(mo, nu=nu)
     O.field("U")[:] = U0
     O.create_phi()
-    R = ref.RefFoamYade(mo, False)
+    R = ref.RefFoamYade(mo, gaussian)
     R.set_properties(cases.RHOP, cases.RHOF, nu)
     # engine side
     E = pkg.Engine(mp)
-    E.set_properties(cases.RHOP, cases.RHOF, nu, False)
+    E.set_properties(cases.RHOP, cases.RHOF, nu, gaussian)
     E.set_piso_controls(nu=nu)
     E.upload("U", U0)
     E.create_phi()
-    for step in range(2):
+    if gaussian:                      # gradP / divT are solver-owned inputs of the Gaussian branch: same values both sides
+        for k in ("gradP", "divT"):
+            R.field(k)[:] = 1e-2 * f[k]
+            E.upload(k, 1e-2 * f[k])
+    for step in range(steps):
         O.pre(dt)
         R.field("U")[:] = O.field("U")
         R.field("vGrad")[:] = O.field("vGrad")
@@ -239,6 +250,8 @@ def test_coupled_icoFoamYade_step(pkg):
         assert cases.rel_l2(E.download("U"), O.field("U")) <= TOL
         assert cases.rel_l2(E.download("p"), O.field("p")) <= TOL
         assert not np.any(E.download("uSource"))
+        so, se = O.stats(), E.ico_stats()
+        assert [q["iters"] for q in so["p"]] == [q["iters"] for q in se["p"]]
     E.close()
     R.close()
     O.close()
