@@ -31,36 +31,9 @@ constexpr int PEN_CY = 32;                    // y channel depth (rows): one slo
 constexpr int PEN_GUARD = 64;                 // guard rows around every pencil array (>= 2D + 31)
 
 // ---------------------------------------------------------------------------------------------
-// PTX helpers: mbarrier + TMA bulk copy (global -> shared), polled loads, chain stores
+// PTX helpers: cp.async staging, polled loads / chain stores (gpu-scope relaxed), shared-memory and DSMEM channels
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smemU32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbarInit(uint64_t* b, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemU32(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbarFenceInit() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbarExpectTx(uint64_t* b, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemU32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbarWait(uint64_t* b, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "PEN_WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra PEN_DONE_%=;\n"
-        "bra PEN_WAIT_%=;\n"
-        "PEN_DONE_%=:\n"
-        "}\n" ::"r"(smemU32(b)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void mbarArrive(uint64_t* b)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smemU32(b)) : "memory");
-}
 // 8-byte asynchronous copy global -> shared (LDGSTS): every lane prefetches the words it will consume itself
 __device__ __forceinline__ void cpAsync8(uint32_t dst, const void* src)
 {
@@ -101,18 +74,6 @@ __device__ __forceinline__ void stChain(double* p, double v)
 #else
     asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v));
 #endif
-}
-// out-of-line spin: keeps the hot loop small; gives up (and flags the launch) rather than hang the GPU
-__device__ __noinline__ double pollSlow(const double* p, int& fail)
-{
-    double v = ldPoll(p);
-    int spin = 0;
-#pragma unroll 1
-    while (isSent(v) && !fail) {
-        v = ldPoll(p);
-        if (++spin > PEN_SPIN_LIMIT) fail = 1;
-    }
-    return v;
 }
 // thread-block cluster: rank, barrier, distributed shared memory (the z channel between the CTAs of a cluster)
 __device__ __forceinline__ uint32_t clusterRank()

@@ -8,25 +8,25 @@
 // K consecutive k-planes -- and walks it in nx+31+K-1 steps: at step t lane l works on i = t-l-q of plane
 // q.  The x-dependency stays in a register, the y-dependency is one __shfl from the neighbouring lane,
 // the z-dependency between the K planes of a warp is a register of the previous step.  Only two values
-// cross warps: the z-neighbour of the warp's first plane and the y-neighbour of its edge lane.  They are
-// read straight from the output array in L2, which is pre-filled with a signalling-NaN sentinel: the
-// consumer polls the 8-byte word until it is not the sentinel (data and flag in one store, no fence, no
-// grid barrier).  The operation order inside a cell is exactly OpenFOAM's, so results stay bit-identical
-// to the sequential loops.
+// cross warps: the z-neighbour of the warp's first plane and the y-neighbour of its edge lane.  They travel
+// as 8-byte words that are data and flag at once: every slot is pre-armed with a signalling-NaN sentinel and
+// the consumer polls it until it is not the sentinel (no fence, no grid barrier) -- through shared-memory
+// channels inside a CTA, distributed shared memory inside a thread-block cluster, and, between clusters and
+// j-blocks, through the output array itself in L2 (read by helper warps).  The operation order inside a cell is
+// exactly OpenFOAM's, so results stay bit-identical to the sequential loops.  See fv_pencil.cu (k_pencil).
 //
 // LAYOUT (HBM).  So that every warp access is one contiguous 256-byte row, the solver's vectors and
 // matrix coefficients live in a skewed layout: slab (k, jb = j/32) holds Tp rows ("slots") of 32 lanes,
-//     pos(i,j,k) = ((k*nJB + jb)*Tp + i + (j&31))*32 + (j&31),       Tp = roundup(nx+31, PEN_S)
+//     pos(i,j,k) = ((k*nJB + jb)*Tp + i + (j&31))*32 + (j&31),       Tp = roundup(nx+31, 32)
 // i.e. row m of a slab holds the 32 mutually independent cells i = m-lane that a warp processes in one
-// step (for both sweep directions).  Rows are fetched PEN_S at a time by TMA bulk copies
-// (cp.async.bulk + mbarrier) into a shared-memory ring several chunks ahead of the computation.  The
-// layout costs (nx+31)/nx extra storage; pads are never read by a valid cell.
+// step (for both sweep directions).  Every lane prefetches its own words with 8-byte cp.async into a private
+// shared-memory ring 8 rows ahead.  The layout costs (nx+31)/nx extra storage; pads are zero, never armed, and
+// every array carries guard rows so that the sweeps need no bounds tests.
 #pragma once
 #include <cstdint>
 
 #include "fv_box.cuh"
 
-constexpr int PEN_S = 4;                                         // rows per TMA chunk
 constexpr unsigned long long PEN_SENT = 0x7FF4DEADBEEF5A5AULL;   // signalling NaN: arithmetic never produces it
 
 struct PencilGeom {
