@@ -4,11 +4,10 @@
 // WHY.  OpenFOAM's DIC / Gauss-Seidel loops are sequential over the face list; on the lexicographic hex
 // box cell (i,j,k) depends on (i-1,j,k), (i,j-1,k), (i,j,k-1).  A hyperplane wavefront with one grid
 // barrier per plane costs ~3.5 us x (nx+ny+nz-2) planes = 1.3 ms per sweep at 128^3 against ~20 us of
-// HBM time.  Here one WARP owns a pencil of cells instead -- 32 consecutive j (one per lane), all i, and
-// K consecutive k-planes -- and walks it in nx+31+K-1 steps: at step t lane l works on i = t-l-q of plane
-// q.  The x-dependency stays in a register, the y-dependency is one __shfl from the neighbouring lane,
-// the z-dependency between the K planes of a warp is a register of the previous step.  Only two values
-// cross warps: the z-neighbour of the warp's first plane and the y-neighbour of its edge lane.  They travel
+// HBM time.  Here one WARP owns a pencil of cells instead -- 32 consecutive j (one per lane), all i, one
+// k-plane -- and walks it in nx+31 steps: at step t lane l works on i = t-l.  The x-dependency stays in a
+// register, the y-dependency is one __shfl from the neighbouring lane.  Only two values cross warps: the
+// z-neighbour (the same row of the plane behind) and the y-neighbour of the warp's edge lane.  They travel
 // as 8-byte words that are data and flag at once: every slot is pre-armed with a signalling-NaN sentinel and
 // the consumer polls it until it is not the sentinel (no fence, no grid barrier) -- through shared-memory
 // channels inside a CTA, distributed shared memory inside a thread-block cluster, and, between clusters and
