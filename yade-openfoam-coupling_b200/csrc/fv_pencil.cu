@@ -25,7 +25,13 @@ constexpr int PEN_SPIN_LIMIT = 1 << 20;
 constexpr int PEN_WMAX = 8;                   // most warps per pencil group
 constexpr int PEN_D = 8;                      // rows per flow-control block / helper ring depth
 // input prefetch depth (rows) of a sweep with NIN input streams: as deep as ~22 KB of ring per warp allows
-__host__ __device__ constexpr int penDepth(int nin) { return nin > 0 ? 8 : 8; }   // deeper rings were measured slower (more shared memory, no fewer stalls)
+#ifndef PEN_DEPTH
+#define PEN_DEPTH 8
+#endif
+#ifndef PEN_FBLOCK
+#define PEN_FBLOCK 8
+#endif
+__host__ __device__ constexpr int penDepth(int nin) { return nin > 0 ? PEN_DEPTH : PEN_DEPTH; }   // deeper rings were measured slower (more shared memory, no fewer stalls)
 constexpr int PEN_CD = 16;                    // z channel depth (rows), a multiple of D
 constexpr int PEN_CY = 32;                    // y channel depth (rows): one slot per y-helper lane
 constexpr int PEN_GUARD = 64;                 // guard rows around every pencil array (>= 2D + 31)
@@ -319,7 +325,7 @@ __device__ __forceinline__ void penStampAt(unsigned long long* tr, int t0, int T
 template <class Op, bool REV, bool ZIN, bool YIN>
 __device__ __forceinline__ void penSweep(const Op& op, const PenWarp& w, double& acc, unsigned long long* tr)
 {
-    constexpr int NIN = Op::NIN, NC = Op::NC, D = penDepth(Op::NIN), FB = PEN_D, CD = PEN_CD;
+    constexpr int NIN = Op::NIN, NC = Op::NC, D = penDepth(Op::NIN), FB = PEN_FBLOCK, CD = PEN_CD;
     constexpr unsigned int FULL = 0xffffffffu;
     constexpr int RS = REV ? -32 : 32;                     // row stride in sweep order (doubles)
     // running pointers (one 64-bit add per stream and row; no per-row address arithmetic from scratch)
