@@ -252,6 +252,24 @@ int fy_set_viscosity(fy_handle h, double nu);
 int fy_create_phi(fy_handle h);
 /* CourantNo.H + vGrad = fvc::grad(U)   (icoFoamYade.C:68-71): everything before setParticleAction */
 int fy_ico_pre(fy_handle h, double dt);
+/* pimpleFoamYade's pre-coupling block (pimpleFoamYade/pimpleFoamYade.C:71-76): CourantNo.H, then on the device
+ * fields  FY_F_DDTU  = fvc::ddt(Uc) + fvc::div(phic, Uc)     FY_F_GRADP = fvc::grad(p)
+ *         FY_F_DIVT  = 2 nu fvc::laplacian(alphac, Uc)       FY_F_VGRAD = fvc::grad(Uc)
+ * from U (FY_F_U), p (FY_F_P), phi (FY_F_PHI) and the void fraction field as it stands (FY_F_ALPHA: setSourceZero reset
+ * it to 1 at the end of the previous step, as in the reference's loop; its patches hold 1.0) -- the inputs the Gaussian branch of setParticleAction reads, so that with the
+ * fluid state resident no host field crosses PCIe.  The Euler fvc::ddt term is identically zero at that point of
+ * the time step (Uc.oldTime() has just been stored from Uc).                                                    */
+int fy_pimple_pre(fy_handle h, double dt);
+/* pimpleFoamYade's fluid step after setParticleAction (pimpleFoamYade/pimpleFoamYade.C:82-104 with UcEqn.H, pEqn.H,
+ * continuityErrs.H; one outer corrector, laminar): alphacf = interpolate(alphac), alphaPhic = alphacf*phic,
+ *   UcEqn = ddt(alphac,Uc) + div(alphaPhic,Uc) - Sp(ddt(alphac) + div(alphaPhic),Uc) + divDevRhoReff(Uc) == Sp(uSourceDrag,Uc)
+ *   phicForces = flux(rAUc*uSource) + rAUcf*(g & Sf);  momentum predictor == reconstruct(phicForces/rAUcf - snGrad(p)*magSf)
+ *   PISO: phiHbyA = flux(HbyA) + alphacf*rAUcf*ddtCorr + phicForces;  laplacian(alphacf*rAUcf, p) == ddt(alphac) + div(alphacf*phiHbyA)
+ *         phic = phiHbyA - flux/alphacf;  Uc = HbyA + rAUc*reconstruct((phicForces - flux/alphacf)/rAUcf)
+ * Reads the device fields the coupling pass left (FY_F_ALPHA, FY_F_USOURCE, FY_F_USOURCEDRAG), updates U, p, phi;
+ * g = gravitational acceleration (NULL = 0).  fy_piso_controls / fy_get_ico_stats serve this solver too.  Patch types
+ * as for icoFoam (no fixedFluxPressure, so walls + gravity are not a consistent case).                            */
+int fy_pimple_solve(fy_handle h, double dt, const double g[3]);
 /* UEqn assembly with uSource, momentum predictor, PISO correctors (icoFoamYade.C:79-140).  Reads and
  * updates the device fields U (FY_F_U), p (FY_F_P), phi (FY_F_PHI); reads uSource (FY_F_USOURCE).    */
 int fy_ico_solve(fy_handle h, double dt);
@@ -262,13 +280,17 @@ int fy_get_ico_stats(fy_handle h, fy_ico_stats* out);
 int fy_fvc_grad_vector(fy_handle h, const double* h_U, double* h_out9);      /* fvc::grad(U), icoFoamYade.C:71  */
 int fy_fvc_grad_scalar(fy_handle h, const double* h_p, double* h_out3);      /* fvc::grad(p), icoFoamYade.C:136 */
 int fy_fvc_div_flux(fy_handle h, const double* h_phi, double* h_out);        /* fvc::div(phi), icoFoamYade.C:120 */
+int fy_fvc_div_phi_vector(fy_handle h, const double* h_phi, const double* h_U, double* h_out3);   /* fvc::div(phic, Uc), pimpleFoamYade.C:73 */
+/* fvc::laplacian(gamma, U), pimpleFoamYade.C:75; gammaB = value of gamma on the patches (alphac: 1.0) */
+int fy_fvc_laplacian_gamma_vector(fy_handle h, const double* h_gamma, double gammaB, const double* h_U, double* h_out3);
 /* lduMatrix solves over the mesh's addressing: out3 = initialResidual, finalResidual, nIterations */
 int fy_pcg_solve(fy_handle h, const double* h_diag, const double* h_upper, const double* h_source, double* h_psi,
                  double tol, double relTol, int maxIter, int preconditioner, double out3[3]);
 int fy_smooth_solve(fy_handle h, const double* h_diag, const double* h_lower, const double* h_upper,
                     const double* h_source, double* h_psi, double tol, double relTol, int maxIter, double out3[3]);
 int fy_dic_precondition(fy_handle h, const double* h_diag, const double* h_upper, const double* h_rA, double* h_wA);
-/* intermediates of the last PISO corrector: "rAU" [N], "HbyA" [N][3], "phiHbyA" [faces], "gradP" [N][3] */
+/* intermediates of the last PISO corrector: "rAU" [N], "HbyA" [N][3], "phiHbyA" [faces], "gradP" [N][3];
+ * after fy_pimple_solve also "phicForces" [faces], "divDev" [N][3]                                         */
 int fy_fv_get(fy_handle h, const char* name, double* h_dst);
 /* Device time (ms) of the phases of the last fy_ico_solve: [0] UEqn assembly + momentum predictor
  * [1] pressure solves (PCG) [2] the rest of the correctors; and the last PCG's iteration time.      */

@@ -337,6 +337,66 @@ void divFlux(const Mesh& m, const double* phi, double* d)
     for (int c = 0; c < m.nCells; ++c) d[c] /= m.V[c];
 }
 
+// fvc::div(phi, U) = surfaceIntegrate(phi_f * interpolate(U))  -> [N][3]
+// [OF-6 gaussConvectionScheme.C fvcDiv, linear].   pimpleFoamYade.C:73 (second term of ddtU_f)
+void divPhiU(const Mesh& m, const double* phi, const double* U, double* d)
+{
+    std::fill(d, d + 3*(size_t)m.nCells, 0.0);
+    for (int f = 0; f < m.nFaces; ++f) {
+        const int P = m.l[f], N = m.u[f];
+        for (int j = 0; j < 3; ++j) {
+            const double t = phi[f]*lerp(m.w[f], U[3*(size_t)P + j], U[3*(size_t)N + j]);
+            d[3*(size_t)P + j] += t;
+            d[3*(size_t)N + j] -= t;
+        }
+    }
+    for (const Patch& p : m.patches) {
+        if (p.bcU == BC_EMPTY) continue;
+        for (int b = p.start; b < p.start + p.n; ++b) {
+            double ub[3];
+            patchU(m, p, b, U, ub);
+            const int c = m.bCell[b];
+            for (int j = 0; j < 3; ++j) d[3*(size_t)c + j] += phi[m.nFaces + b]*ub[j];
+        }
+    }
+    for (int c = 0; c < m.nCells; ++c)
+        for (int j = 0; j < 3; ++j) d[3*(size_t)c + j] /= m.V[c];
+}
+
+// fvc::laplacian(gamma, U) = surfaceIntegrate((interpolate(gamma)*magSf) * snGrad(U))  -> [N][3]
+// [OF-6 gaussLaplacianScheme.C fvcLaplacian + uncorrectedSnGrad / snGradScheme::snGrad: deltaCoeffs*(U_N - U_P);
+//  fixedValue patch snGrad = deltaCoeffs_b*(U_b - U_P), zeroGradient patch snGrad = 0; the non-orthogonal
+//  correction of "corrected" is identically zero on the hex box].  gammaB = value of gamma on every non-empty patch:
+//  pimpleFoamYade's alphac has `calculated` patches (pim/createFields.H: built from a dimensionedScalar) that hold the
+//  1.0 FoamYade::initFields assigns field-wide (F.C:67); FoamYade only ever writes cell values afterwards.
+//  pimpleFoamYade.C:75 (divT = 2 nu fvc::laplacian(alphac, Uc))
+void laplacianGammaU(const Mesh& m, const double* gamma, double gammaB, const double* U, double* d)
+{
+    std::fill(d, d + 3*(size_t)m.nCells, 0.0);
+    for (int f = 0; f < m.nFaces; ++f) {
+        const int P = m.l[f], N = m.u[f];
+        const double gm = lerp(m.w[f], gamma[P], gamma[N])*m.magSf[f];
+        for (int j = 0; j < 3; ++j) {
+            const double t = gm*(m.dc[f]*(U[3*(size_t)N + j] - U[3*(size_t)P + j]));
+            d[3*(size_t)P + j] += t;
+            d[3*(size_t)N + j] -= t;
+        }
+    }
+    for (const Patch& p : m.patches) {
+        if (p.bcU == BC_EMPTY) continue;
+        for (int b = p.start; b < p.start + p.n; ++b) {
+            const int c = m.bCell[b];
+            const double gm = gammaB*m.bMagSf[b];
+            for (int j = 0; j < 3; ++j) {
+                const double sn = p.bcU == BC_FIXED_VALUE ? m.bDc[b]*(p.valueU[j] - U[3*(size_t)c + j]) : 0.0;
+                d[3*(size_t)c + j] += gm*sn;
+            }
+        }
+    }
+    for (int c = 0; c < m.nCells; ++c)
+        for (int j = 0; j < 3; ++j) d[3*(size_t)c + j] /= m.V[c];
+}
+
 // CourantNo.H (stock; icoFoamYade.C:68 / pimpleFoamYade/CourantNo.H:32-49): sumPhi = surfaceSum(mag(phi))
 void courant(const Mesh& m, const double* phi, double dt, double* CoNum, double* meanCoNum)
 {
@@ -399,6 +459,7 @@ struct Ico
     // intermediates of the last corrector, kept for stage-by-stage parity tests
     dvec rAU, HbyA, phiHbyA, gradP, diagU, upperU, lowerU, sourceU, diagP, upperP, sourceP;
     dvec icU, bcU;              // UEqn internalCoeffs / boundaryCoeffs [nB][3]
+    struct Pim* pim = nullptr;  // pimpleFoamYade intermediates (allocated on first use)
     double tMomentum = 0, tPressure = 0, tOther = 0;
 };
 
@@ -681,6 +742,420 @@ int icoSolve(Ico& s, double dt)
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// pimpleFoamYade: UcEqn.H + pEqn.H + continuityErrs.H  (pimpleFoamYade.C:82-104 with nOuterCorrectors 1, laminar)
+//
+// PARITY UNPINNED: the reference ships no case, log or test for this solver and OpenFOAM is not installed, so this
+// restates OpenFOAM-6's operators from their definitions (each cited) without a golden vector behind it.  Pinned
+// case settings (the reference has none): Euler; Gauss linear everywhere; laplacian/snGrad uncorrected (orthogonal
+// box); no relaxationFactors (UcEqn.relax() and p.relax() are then no-ops); simulationType laminar -> Stokes model,
+// divDevRhoReff(U) = - fvc::div((alpha*nuEff)*dev2(T(fvc::grad(U)))) - fvm::laplacian(alpha*nuEff, U)
+// [OF-6 linearViscousStress.C]; no fixedFluxPressure patch (constrainPressure is a no-op).
+//
+// Boundary values that matter: alphac / uSource / uSourceDrag have `calculated` patches (pim/createFields.H builds
+// them from dimensioned constants).  alphac's hold 1.0 (F.C:67 assigns the whole field), uSource's hold 0; FoamYade
+// writes cell values only and correctBoundaryConditions() of a calculated patch does nothing (pim.C:83-88).
+//
+// Old-time fields: Uc.oldTime() is stored by fvc::ddt(Uc) at pim.C:73 (before the step changes Uc) and phic.oldTime()
+// by the first phic assignment, i.e. both are the previous step's, as in icoFoam.  alphac.oldTime() is stored at
+// pim.C:83 (correctBoundaryConditions -> storeOldTimes), AFTER FoamYade wrote this step's void fraction into the
+// cells through operator[] -- so alphac.oldTime() == alphac and fvc::ddt(alphac) is identically +0.  The arithmetic
+// shape is kept (alpha0 is passed separately) so a driver that stores old times differently can say so.
+// ---------------------------------------------------------------------------------------------
+struct Pim
+{
+    dvec alphaf;                // alphacf [Fi + nB]
+    dvec alphaPhi;              // alphaPhic
+    dvec rAUf;                  // rAUcf
+    dvec phicForces;            // [Fi + nB]
+    dvec recon;                 // last fvc::reconstruct result [N][3]
+    dvec divDev;                // fvc::div((alpha nu) dev2(T(grad U))) [N][3]
+    dvec spDiv;                 // fvc::ddt(alphac) + fvc::div(alphaPhic) [N]
+    dvec invT;                  // inv(surfaceSum(SfHat*Sf)) [N][9]
+};
+
+inline double det9(const double* t)
+{
+    return (t[0]*t[4]*t[8] + t[1]*t[5]*t[6] + t[2]*t[3]*t[7]) - (t[0]*t[5]*t[7] + t[1]*t[3]*t[8] + t[2]*t[4]*t[6]);
+}
+// [OF-6 TensorI.H inv(const Tensor&, const Cmpt dett)]
+inline void inv9(const double* t, double* r)
+{
+    const double d = det9(t);
+    r[0] = (t[4]*t[8] - t[7]*t[5])/d; r[1] = (t[2]*t[7] - t[1]*t[8])/d; r[2] = (t[1]*t[5] - t[2]*t[4])/d;
+    r[3] = (t[6]*t[5] - t[3]*t[8])/d; r[4] = (t[0]*t[8] - t[2]*t[6])/d; r[5] = (t[3]*t[2] - t[0]*t[5])/d;
+    r[6] = (t[3]*t[7] - t[4]*t[6])/d; r[7] = (t[1]*t[6] - t[0]*t[7])/d; r[8] = (t[0]*t[4] - t[3]*t[1])/d;
+}
+
+// inv(surfaceSum(SfHat*mesh.Sf())) with tensorField inv()'s removal of the directions an empty patch pair leaves
+// without faces [OF-6 fvcReconstruct.C, tensorField.C inv(Field<tensor>&, const UList<tensor>&)]
+void reconstructTensor(const Mesh& m, dvec& invT)
+{
+    const int N = m.nCells;
+    dvec T(9*(size_t)N, 0.0);
+    for (int f = 0; f < m.nFaces; ++f)
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                const double t = (m.Sf[3*(size_t)f + i]/m.magSf[f])*m.Sf[3*(size_t)f + j];
+                T[9*(size_t)m.l[f] + 3*i + j] += t;
+                T[9*(size_t)m.u[f] + 3*i + j] += t;
+            }
+    for (const Patch& p : m.patches) {
+        if (p.bcU == BC_EMPTY) continue;
+        for (int b = p.start; b < p.start + p.n; ++b)
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j)
+                    T[9*(size_t)m.bCell[b] + 3*i + j] += (m.bSf[3*(size_t)b + i]/m.bMagSf[b])*m.bSf[3*(size_t)b + j];
+    }
+    invT.assign(9*(size_t)N, 0.0);
+    if (N == 0) return;
+    double scale = 0;
+    for (int k = 0; k < 9; ++k) scale += T[k]*T[k];
+    bool rm[3];
+    for (int d = 0; d < 3; ++d) rm[d] = (T[4*d]*T[4*d])/scale < SMALL;
+    for (int c = 0; c < N; ++c) {
+        double t[9];
+        for (int k = 0; k < 9; ++k) t[k] = T[9*(size_t)c + k];
+        for (int d = 0; d < 3; ++d) if (rm[d]) t[4*d] += 1.0;
+        inv9(t, &invT[9*(size_t)c]);
+        for (int d = 0; d < 3; ++d) if (rm[d]) invT[9*(size_t)c + 4*d] -= 1.0;
+    }
+}
+
+// fvc::reconstruct(ssf) = inv(surfaceSum(SfHat*Sf)) & surfaceSum(SfHat*ssf)     [OF-6 fvcReconstruct.C]
+void reconstruct(const Mesh& m, const dvec& invT, const double* ssf, double* out)
+{
+    const int N = m.nCells;
+    dvec v(3*(size_t)N, 0.0);
+    for (int f = 0; f < m.nFaces; ++f)
+        for (int i = 0; i < 3; ++i) {
+            const double t = (m.Sf[3*(size_t)f + i]/m.magSf[f])*ssf[f];
+            v[3*(size_t)m.l[f] + i] += t;
+            v[3*(size_t)m.u[f] + i] += t;
+        }
+    for (const Patch& p : m.patches) {
+        if (p.bcU == BC_EMPTY) continue;
+        for (int b = p.start; b < p.start + p.n; ++b)
+            for (int i = 0; i < 3; ++i) v[3*(size_t)m.bCell[b] + i] += (m.bSf[3*(size_t)b + i]/m.bMagSf[b])*ssf[m.nFaces + b];
+    }
+    for (int c = 0; c < N; ++c) {
+        const double* t = &invT[9*(size_t)c];
+        const double* a = &v[3*(size_t)c];
+        for (int i = 0; i < 3; ++i) out[3*(size_t)c + i] = t[3*i]*a[0] + t[3*i + 1]*a[1] + t[3*i + 2]*a[2];
+    }
+}
+
+// fvc::snGrad(p)*mesh.magSf()  [OF-6 snGradScheme::snGrad; fixedValue patch: deltaCoeffs*(p_b - p_P), zeroGradient: 0]
+void snGradPMagSf(const Mesh& m, const double* p, double* out)
+{
+    for (int f = 0; f < m.nFaces; ++f) out[f] = (m.dc[f]*(p[m.u[f]] - p[m.l[f]]))*m.magSf[f];
+    for (const Patch& pt : m.patches)
+        for (int b = pt.start; b < pt.start + pt.n; ++b) {
+            double sn = 0.0;
+            if (pt.bcP == BC_FIXED_VALUE) sn = m.bDc[b]*(pt.valueP - p[m.bCell[b]]);
+            out[m.nFaces + b] = pt.bcP == BC_EMPTY ? 0.0 : sn*m.bMagSf[b];
+        }
+}
+
+// fvc::div((alpha*nuEff)*dev2(T(fvc::grad(U))))  [OF-6 linearViscousStress::divDevRhoReff, gaussDivScheme::fvcDiv,
+// gaussGrad::correctBoundaryConditions for the patch values of grad(U), TensorI.H dev2 / T]
+void divDevTerm(const Mesh& m, const double* alpha, double alphaB, double nu, const double* U, double* out)
+{
+    const int N = m.nCells;
+    dvec g(9*(size_t)N), X(9*(size_t)N);
+    gradVector(m, U, g.data());
+    auto dev2T = [](const double* gr, double a, double* x) {
+        double t[9];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) t[3*i + j] = gr[3*j + i];
+        const double tr = t[0] + t[4] + t[8];
+        const double sph = (2.0/3.0)*tr;
+        t[0] -= sph; t[4] -= sph; t[8] -= sph;
+        for (int k = 0; k < 9; ++k) x[k] = a*t[k];
+    };
+    for (int c = 0; c < N; ++c) dev2T(&g[9*(size_t)c], alpha[c]*nu, &X[9*(size_t)c]);
+    std::fill(out, out + 3*(size_t)N, 0.0);
+    for (int f = 0; f < m.nFaces; ++f) {
+        const int P = m.l[f], Nb = m.u[f];
+        for (int j = 0; j < 3; ++j) {
+            double t = 0;
+            for (int i = 0; i < 3; ++i) t += m.Sf[3*(size_t)f + i]*lerp(m.w[f], X[9*(size_t)P + 3*i + j], X[9*(size_t)Nb + 3*i + j]);
+            out[3*(size_t)P + j] += t;
+            out[3*(size_t)Nb + j] -= t;
+        }
+    }
+    for (const Patch& p : m.patches) {
+        if (p.bcU == BC_EMPTY) continue;
+        for (int b = p.start; b < p.start + p.n; ++b) {
+            const int c = m.bCell[b];
+            double n[3], sn[3], gb[9], nG[3], xb[9];
+            for (int i = 0; i < 3; ++i) n[i] = m.bSf[3*(size_t)b + i]/m.bMagSf[b];
+            for (int j = 0; j < 3; ++j)
+                sn[j] = p.bcU == BC_FIXED_VALUE ? m.bDc[b]*(p.valueU[j] - U[3*(size_t)c + j]) : 0.0;
+            for (int k = 0; k < 9; ++k) gb[k] = g[9*(size_t)c + k];
+            for (int j = 0; j < 3; ++j) nG[j] = n[0]*gb[j] + n[1]*gb[3 + j] + n[2]*gb[6 + j];
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) gb[3*i + j] += n[i]*(sn[j] - nG[j]);
+            dev2T(gb, alphaB*nu, xb);
+            for (int j = 0; j < 3; ++j) {
+                double t = 0;
+                for (int i = 0; i < 3; ++i) t += m.bSf[3*(size_t)b + i]*xb[3*i + j];
+                out[3*(size_t)c + j] += t;
+            }
+        }
+    }
+    for (int c = 0; c < N; ++c)
+        for (int j = 0; j < 3; ++j) out[3*(size_t)c + j] /= m.V[c];
+}
+
+// UcEqn  (pim/UcEqn.H:3-11)
+void assembleUcEqn(Ico& s, Pim& q, double dt, const dvec& U0, const double* alpha, const double* alpha0, double alphaB,
+                   const double* uSourceDrag)
+{
+    const Mesh& m = s.m;
+    const int N = m.nCells, Fi = m.nFaces, nB = m.nB;
+    const double rDeltaT = 1.0/dt;
+    // alphacf = fvc::interpolate(alphac); alphaPhic = alphacf*phic            pim.C:84-85
+    q.alphaf.resize((size_t)Fi + nB);
+    q.alphaPhi.resize((size_t)Fi + nB);
+    for (int f = 0; f < Fi; ++f) q.alphaf[f] = lerp(m.w[f], alpha[m.l[f]], alpha[m.u[f]]);
+    for (int b = 0; b < nB; ++b) q.alphaf[Fi + b] = alphaB;
+    for (int f = 0; f < Fi + nB; ++f) q.alphaPhi[f] = q.alphaf[f]*s.phi[f];
+    // fvm::ddt(alphac, Uc)   [OF-6 EulerDdtScheme::fvmDdt(alpha, vf)]
+    dvec diagD(N), lowerC(Fi), upperC(Fi), diagC, upperL(Fi), diagL;
+    s.sourceU.assign(3*(size_t)N, 0.0);
+    for (int c = 0; c < N; ++c) {
+        diagD[c] = (rDeltaT*alpha[c])*m.V[c];
+        for (int j = 0; j < 3; ++j) s.sourceU[3*(size_t)c + j] = ((rDeltaT*alpha0[c])*U0[3*(size_t)c + j])*m.V[c];
+    }
+    // fvm::div(alphaPhic, Uc), fvm::laplacian(alpha*nuEff, Uc)
+    for (int f = 0; f < Fi; ++f) {
+        lowerC[f] = -m.w[f]*q.alphaPhi[f];
+        upperC[f] = lowerC[f] + q.alphaPhi[f];
+        const double gf = lerp(m.w[f], alpha[m.l[f]]*s.nu, alpha[m.u[f]]*s.nu);
+        upperL[f] = m.dc[f]*(gf*m.magSf[f]);
+    }
+    negSumDiag(m, lowerC, upperC, diagC);
+    negSumDiag(m, upperL, upperL, diagL);
+    // fvm::Sp(fvc::ddt(alphac) + fvc::div(alphaPhic), Uc)
+    q.spDiv.resize(N);
+    divFlux(m, q.alphaPhi.data(), q.spDiv.data());
+    for (int c = 0; c < N; ++c) q.spDiv[c] = rDeltaT*(alpha[c] - alpha0[c]) + q.spDiv[c];
+    // ((ddt + div) - Sp) + divDevRhoReff == Sp(uSourceDrag)
+    s.diagU.resize(N);
+    s.upperU.resize(Fi);
+    s.lowerU.resize(Fi);
+    for (int c = 0; c < N; ++c)
+        s.diagU[c] = (((diagD[c] + diagC[c]) - m.V[c]*q.spDiv[c]) + (-diagL[c])) - m.V[c]*uSourceDrag[c];
+    for (int f = 0; f < Fi; ++f) {
+        s.upperU[f] = upperC[f] + (-upperL[f]);
+        s.lowerU[f] = lowerC[f] + (-upperL[f]);
+    }
+    s.icU.assign(3*(size_t)nB, 0.0);
+    s.bcU.assign(3*(size_t)nB, 0.0);
+    for (const Patch& p : m.patches) {
+        if (p.bcU == BC_EMPTY) continue;
+        for (int b = p.start; b < p.start + p.n; ++b) {
+            const double phib = q.alphaPhi[Fi + b];
+            const double gMagSf = (alphaB*s.nu)*m.bMagSf[b];
+            for (int j = 0; j < 3; ++j) {
+                double icC, bcC, icL, bcL;
+                if (p.bcU == BC_FIXED_VALUE) {
+                    icC = phib*0.0;
+                    bcC = -phib*p.valueU[j];
+                    icL = gMagSf*(-1.0*m.bDc[b]);
+                    bcL = -gMagSf*(m.bDc[b]*p.valueU[j]);
+                } else {
+                    icC = phib*1.0;
+                    bcC = -phib*0.0;
+                    icL = gMagSf*0.0;
+                    bcL = -gMagSf*0.0;
+                }
+                s.icU[3*(size_t)b + j] = icC + (-icL);
+                s.bcU[3*(size_t)b + j] = bcC + (-bcL);
+            }
+        }
+    }
+    // explicit part of divDevRhoReff: the matrix gets  source -= V*(-fvc::div(...))
+    q.divDev.resize(3*(size_t)N);
+    divDevTerm(m, alpha, alphaB, s.nu, s.U.data(), q.divDev.data());
+    for (int c = 0; c < N; ++c)
+        for (int j = 0; j < 3; ++j) s.sourceU[3*(size_t)c + j] -= m.V[c]*(-q.divDev[3*(size_t)c + j]);
+}
+
+int pimpleSolve(Ico& s, Pim& q, double dt, const double* alpha, const double* alpha0, const double* uSourceDrag,
+                const double* gvec)
+{
+    const Mesh& m = s.m;
+    const int N = m.nCells, Fi = m.nFaces, nB = m.nB, nF = Fi + nB;
+    const double rDeltaT = 1.0/dt, alphaB = 1.0;
+    double t0 = nowSec();
+    const dvec U0(s.U), phi0(s.phi);
+    s.st.nPSolves = 0;
+    if (q.invT.size() != 9*(size_t)N) reconstructTensor(m, q.invT);
+    assembleUcEqn(s, q, dt, U0, alpha, alpha0, alphaB, uSourceDrag);
+
+    // rAUc = 1/UcEqn.A(); rAUcf = fvc::interpolate(rAUc)       (A() does not depend on Uc: computed once)
+    dvec H;
+    computeRAUandH(s, H);
+    q.rAUf.resize(nF);
+    for (int f = 0; f < Fi; ++f) q.rAUf[f] = lerp(m.w[f], s.rAU[m.l[f]], s.rAU[m.u[f]]);
+    for (int b = 0; b < nB; ++b) q.rAUf[Fi + b] = s.rAU[m.bCell[b]];
+    // phicForces = fvc::flux(rAUc*uSource) + rAUcf*(g & Sf)                   pim/UcEqn.H:17-20
+    q.phicForces.assign(nF, 0.0);
+    for (int f = 0; f < Fi; ++f) {
+        const int P = m.l[f], Nb = m.u[f];
+        double flux = 0, gS = 0;
+        for (int j = 0; j < 3; ++j) {
+            flux += m.Sf[3*(size_t)f + j]*lerp(m.w[f], s.rAU[P]*s.uSource[3*(size_t)P + j], s.rAU[Nb]*s.uSource[3*(size_t)Nb + j]);
+            gS += gvec[j]*m.Sf[3*(size_t)f + j];
+        }
+        q.phicForces[f] = flux + q.rAUf[f]*gS;
+    }
+    for (const Patch& p : m.patches) {
+        if (p.bcU == BC_EMPTY) continue;
+        for (int b = p.start; b < p.start + p.n; ++b) {
+            double flux = 0, gS = 0;
+            for (int j = 0; j < 3; ++j) {
+                flux += m.bSf[3*(size_t)b + j]*(s.rAU[m.bCell[b]]*0.0);
+                gS += gvec[j]*m.bSf[3*(size_t)b + j];
+            }
+            q.phicForces[Fi + b] = flux + q.rAUf[Fi + b]*gS;
+        }
+    }
+    dvec ssf(nF), snG(nF);
+    q.recon.resize(3*(size_t)N);
+    if (s.ctl.momentumPredictor) {
+        // solve(UcEqn == fvc::reconstruct(phicForces/rAUcf - fvc::snGrad(p)*mesh.magSf()))   pim/UcEqn.H:22-33
+        snGradPMagSf(m, s.p.data(), snG.data());
+        for (int f = 0; f < nF; ++f) ssf[f] = q.phicForces[f]/q.rAUf[f] - snG[f];
+        reconstruct(m, q.invT, ssf.data(), q.recon.data());
+        dvec src(s.sourceU);
+        for (int c = 0; c < N; ++c)
+            for (int j = 0; j < 3; ++j) src[3*(size_t)c + j] += m.V[c]*q.recon[3*(size_t)c + j];
+        for (int b = 0; b < nB; ++b)
+            for (int j = 0; j < 3; ++j) src[3*(size_t)m.bCell[b] + j] += s.bcU[3*(size_t)b + j];
+        dvec psi(N), b1(N), dg(N);
+        for (int j = 0; j < 3; ++j) {
+            s.st.U[j] = SolverPerf();
+            if (!m.validCmpt[j]) continue;
+            dg = s.diagU;
+            for (int b = 0; b < nB; ++b) dg[m.bCell[b]] += s.icU[3*(size_t)b + j];
+            for (int c = 0; c < N; ++c) { psi[c] = s.U[3*(size_t)c + j]; b1[c] = src[3*(size_t)c + j]; }
+            s.st.U[j] = smoothSolve(m, dg, s.lowerU, s.upperU, b1, psi.data(), s.ctl.UTol, s.ctl.URelTol, s.ctl.maxIter);
+            for (int c = 0; c < N; ++c) s.U[3*(size_t)c + j] = psi[c];
+        }
+    }
+    s.tMomentum += nowSec() - t0;
+
+    dvec div(N), totalSource(N), dg(N), icP(nB), bcP(nB), aphi(nF), fluxByA(nF);
+    s.HbyA.resize(3*(size_t)N);
+    s.phiHbyA.resize(nF);
+    s.upperP.resize(Fi);
+    for (int corr = 1; corr <= s.ctl.nCorrectors; ++corr) {
+        t0 = nowSec();
+        // HbyA = constrainHbyA(rAUc*UcEqn.H(), Uc, p)                                       pim/pEqn.H:2
+        computeRAUandH(s, H);
+        for (int c = 0; c < N; ++c)
+            for (int j = 0; j < 3; ++j) s.HbyA[3*(size_t)c + j] = s.rAU[c]*H[3*(size_t)c + j];
+        // phiHbyA = fvc::flux(HbyA) + alphacf*rAUcf*fvc::ddtCorr(Uc, phic)                  pim/pEqn.H:4-11
+        for (int f = 0; f < Fi; ++f) {
+            const int P = m.l[f], Nb = m.u[f];
+            double flux = 0, u0f = 0;
+            for (int j = 0; j < 3; ++j) {
+                flux += m.Sf[3*(size_t)f + j]*lerp(m.w[f], s.HbyA[3*(size_t)P + j], s.HbyA[3*(size_t)Nb + j]);
+                u0f += m.Sf[3*(size_t)f + j]*lerp(m.w[f], U0[3*(size_t)P + j], U0[3*(size_t)Nb + j]);
+            }
+            const double phiCorr = phi0[f] - u0f;
+            const double coeff = 1.0 - std::min(std::fabs(phiCorr)/(std::fabs(phi0[f]) + SMALL), 1.0);
+            s.phiHbyA[f] = flux + (q.alphaf[f]*q.rAUf[f])*((coeff*rDeltaT)*phiCorr);
+        }
+        for (const Patch& p : m.patches) {
+            for (int b = p.start; b < p.start + p.n; ++b) {
+                if (p.bcU == BC_EMPTY) { s.phiHbyA[Fi + b] = 0.0; continue; }
+                const int c = m.bCell[b];
+                double hb[3], u0b[3];
+                if (p.bcU == BC_FIXED_VALUE) { hb[0] = p.valueU[0]; hb[1] = p.valueU[1]; hb[2] = p.valueU[2]; }
+                else { hb[0] = s.HbyA[3*(size_t)c]; hb[1] = s.HbyA[3*(size_t)c + 1]; hb[2] = s.HbyA[3*(size_t)c + 2]; }
+                patchU(m, p, b, U0.data(), u0b);
+                double flux = 0, u0f = 0;
+                for (int j = 0; j < 3; ++j) { flux += m.bSf[3*(size_t)b + j]*hb[j]; u0f += m.bSf[3*(size_t)b + j]*u0b[j]; }
+                const double phiCorr = phi0[Fi + b] - u0f;
+                double coeff = 1.0 - std::min(std::fabs(phiCorr)/(std::fabs(phi0[Fi + b]) + SMALL), 1.0);
+                if (p.bcU == BC_FIXED_VALUE) coeff = 0.0;
+                s.phiHbyA[Fi + b] = flux + (q.alphaf[Fi + b]*q.rAUf[Fi + b])*((coeff*rDeltaT)*phiCorr);
+            }
+        }
+        if (adjustPhi(m, s.phiHbyA.data()) != 0) return -1;                                  // pim/pEqn.H:13-16
+        for (int f = 0; f < nF; ++f) s.phiHbyA[f] += q.phicForces[f];                        // pim/pEqn.H:18
+        s.tOther += nowSec() - t0;
+        for (int nonOrth = 0; nonOrth <= s.ctl.nNonOrthCorrectors; ++nonOrth) {
+            t0 = nowSec();
+            // fvm::laplacian(alphacf*rAUcf, p) == fvc::ddt(alphac) + fvc::div(alphacf*phiHbyA)   pim/pEqn.H:26-31
+            for (int f = 0; f < Fi; ++f) s.upperP[f] = m.dc[f]*((q.alphaf[f]*q.rAUf[f])*m.magSf[f]);
+            negSumDiag(m, s.upperP, s.upperP, s.diagP);
+            for (const Patch& p : m.patches) {
+                for (int b = p.start; b < p.start + p.n; ++b) {
+                    icP[b] = 0.0;
+                    bcP[b] = 0.0;
+                    if (p.bcP != BC_FIXED_VALUE) continue;
+                    const double pGamma = (q.alphaf[Fi + b]*q.rAUf[Fi + b])*m.bMagSf[b];
+                    icP[b] = pGamma*(-1.0*m.bDc[b]);
+                    bcP[b] = -pGamma*(m.bDc[b]*p.valueP);
+                }
+            }
+            for (int f = 0; f < nF; ++f) aphi[f] = q.alphaf[f]*s.phiHbyA[f];
+            divFlux(m, aphi.data(), div.data());
+            s.sourceP.assign(N, 0.0);
+            for (int c = 0; c < N; ++c) s.sourceP[c] += m.V[c]*(rDeltaT*(alpha[c] - alpha0[c]) + div[c]);
+            if (pNeedsReference(m)) {
+                s.sourceP[s.ctl.pRefCell] += s.diagP[s.ctl.pRefCell]*s.ctl.pRefValue;
+                s.diagP[s.ctl.pRefCell] += s.diagP[s.ctl.pRefCell];
+            }
+            dg = s.diagP;
+            totalSource = s.sourceP;
+            for (int b = 0; b < nB; ++b) { dg[m.bCell[b]] += icP[b]; totalSource[m.bCell[b]] += bcP[b]; }
+            const bool fin = (corr == s.ctl.nCorrectors) && (nonOrth == s.ctl.nNonOrthCorrectors);
+            SolverPerf sp = pcgSolve(m, dg, s.upperP, totalSource, s.p.data(), fin ? s.ctl.pFinalTol : s.ctl.pTol,
+                                     fin ? s.ctl.pFinalRelTol : s.ctl.pRelTol, s.ctl.maxIter, s.ctl.precond);
+            if (s.st.nPSolves < 8) s.st.p[s.st.nPSolves] = sp;
+            s.st.nPSolves++;
+            s.tPressure += nowSec() - t0;
+            if (nonOrth == s.ctl.nNonOrthCorrectors) {
+                t0 = nowSec();
+                // phic = phiHbyA - pEqn.flux()/alphacf                                       pim/pEqn.H:39
+                for (int f = 0; f < Fi; ++f) fluxByA[f] = (s.upperP[f]*s.p[m.u[f]] - s.upperP[f]*s.p[m.l[f]])/q.alphaf[f];
+                for (int b = 0; b < nB; ++b) fluxByA[Fi + b] = (icP[b]*s.p[m.bCell[b]] - bcP[b])/q.alphaf[Fi + b];
+                for (int f = 0; f < nF; ++f) s.phi[f] = s.phiHbyA[f] - fluxByA[f];
+                // Uc = HbyA + rAUc*fvc::reconstruct((phicForces - pEqn.flux()/alphacf)/rAUcf)  pim/pEqn.H:43-45
+                for (int f = 0; f < nF; ++f) ssf[f] = (q.phicForces[f] - fluxByA[f])/q.rAUf[f];
+                reconstruct(m, q.invT, ssf.data(), q.recon.data());
+                for (int c = 0; c < N; ++c)
+                    for (int j = 0; j < 3; ++j)
+                        s.U[3*(size_t)c + j] = s.HbyA[3*(size_t)c + j] + s.rAU[c]*q.recon[3*(size_t)c + j];
+                s.tOther += nowSec() - t0;
+            }
+        }
+        t0 = nowSec();
+        // continuityErrs.H: contErr = fvc::ddt(alphac) + fvc::div(alphacf*phic)         pim/continuityErrs.H:32-46
+        for (int f = 0; f < nF; ++f) aphi[f] = q.alphaf[f]*s.phi[f];
+        divFlux(m, aphi.data(), div.data());
+        double sl = 0, sg = 0, sv = 0;
+        for (int c = 0; c < N; ++c) {
+            const double e = rDeltaT*(alpha[c] - alpha0[c]) + div[c];
+            sl += std::fabs(e)*m.V[c]; sg += e*m.V[c]; sv += m.V[c];
+        }
+        s.st.sumLocalContErr = dt*(sl/sv);
+        s.st.globalContErr = dt*(sg/sv);
+        s.cumulativeContErr += s.st.globalContErr;
+        s.st.cumulativeContErr = s.cumulativeContErr;
+        if (corr <= 8) { s.st.corrSumLocal[corr - 1] = s.st.sumLocalContErr; s.st.corrGlobal[corr - 1] = s.st.globalContErr; }
+        s.tOther += nowSec() - t0;
+    }
+    return 0;
+}
+
+
 Mesh* buildMesh(int nCells, const double* V, int nFaces, const int* owner, const int* neigh, const double* Sf,
                 const double* magSf, const double* w, const double* dc, int nPatches, const int* patchSize,
                 const int* bCell, const double* bSf, const double* bMagSf, const double* bDc, const int* bcU,
@@ -748,7 +1223,12 @@ void* fvo_create(int nCells, const double* V, int nFaces, const int* owner, cons
     s->vGrad.assign(9*(size_t)nCells, 0.0);
     return s;
 }
-void fvo_destroy(void* h) { delete (Ico*)h; }
+void fvo_destroy(void* h)
+{
+    Ico* s = (Ico*)h;
+    delete s->pim;
+    delete s;
+}
 
 // ctl: nCorrectors nNonOrth momentumPredictor pRefCell maxIter precond | pRefValue pTol pRelTol pFinalTol pFinalRelTol UTol URelTol nu
 void fvo_set_controls(void* h, const int* ic6, const double* dc8)
@@ -830,6 +1310,68 @@ void fvo_get_times(void* h, double* out3)
 void fvo_grad_vector(void* h, const double* U, double* out9) { gradVector(((Ico*)h)->m, U, out9); }
 void fvo_grad_scalar(void* h, const double* p, double* out3) { gradScalar(((Ico*)h)->m, p, out3); }
 void fvo_div_flux(void* h, const double* phi, double* out) { divFlux(((Ico*)h)->m, phi, out); }
+
+void fvo_div_phi_vector(void* h, const double* phi, const double* U, double* out3) { divPhiU(((Ico*)h)->m, phi, U, out3); }
+void fvo_laplacian_gamma_vector(void* h, const double* gamma, double gammaB, const double* U, double* out3)
+{
+    laplacianGammaU(((Ico*)h)->m, gamma, gammaB, U, out3);
+}
+
+// pimpleFoamYade.C:73-76 -- the four fields the solver hands to FoamYade before setParticleAction:
+//   ddtU_f = fvc::ddt(Uc) + fvc::div(phic, Uc);  gradP = fvc::grad(p);  divT = 2*nu*fvc::laplacian(alphac, Uc);
+//   vGrad = fvc::grad(Uc)
+// fvc::ddt(Uc) is evaluated BEFORE Uc is touched in the new time step: GeometricField::oldTime() stores
+// Uc.oldTime() := Uc at that first access [OF-6 GeometricField.C storeOldTimes], so the Euler term
+// rDeltaT*(Uc - Uc.oldTime()) is rDeltaT*0 = +0 and ddtU_f = 0 + div(phic, Uc).
+void fvo_pimple_pre(void* h, double dt, const double* alpha, double* ddtU3, double* gradP3, double* divT3, double* vGrad9)
+{
+    Ico* s = (Ico*)h;
+    const Mesh& m = s->m;
+    const double rDeltaT = 1.0/dt;
+    courant(m, s->phi.data(), dt, &s->st.CoNum, &s->st.meanCoNum);      // pimpleFoamYade.C:71 #include "CourantNo.H"
+    divPhiU(m, s->phi.data(), s->U.data(), ddtU3);
+    for (size_t k = 0; k < 3*(size_t)m.nCells; ++k) ddtU3[k] = rDeltaT*(s->U[k] - s->U[k]) + ddtU3[k];
+    gradScalar(m, s->p.data(), gradP3);
+    laplacianGammaU(m, alpha, 1.0, s->U.data(), divT3);
+    const double twoNu = 2*s->nu;
+    for (size_t k = 0; k < 3*(size_t)m.nCells; ++k) divT3[k] = twoNu*divT3[k];
+    gradVector(m, s->U.data(), vGrad9);
+}
+
+// UcEqn.H + pEqn.H + continuityErrs.H (pimpleFoamYade.C:82-104); alpha0 = alphac.oldTime() (== alpha in the reference,
+// see the note above pimpleSolve), g = gravitational acceleration; uSource is read from the state
+int fvo_pimple_solve(void* h, double dt, const double* alpha, const double* alpha0, const double* uSourceDrag, const double* g3)
+{
+    Ico* s = (Ico*)h;
+    if (!s->pim) s->pim = new Pim();
+    return pimpleSolve(*s, *s->pim, dt, alpha, alpha0, uSourceDrag, g3);
+}
+// pimple intermediates of the last step: phicForces alphaf rAUf recon divDev spDiv
+double* fvo_pimple_field(void* h, const char* name, long* n)
+{
+    Ico* s = (Ico*)h;
+    const std::string k(name);
+    dvec* v = nullptr;
+    if (s->pim) {
+        if (k == "phicForces") v = &s->pim->phicForces; else if (k == "alphaf") v = &s->pim->alphaf;
+        else if (k == "rAUf") v = &s->pim->rAUf; else if (k == "recon") v = &s->pim->recon;
+        else if (k == "divDev") v = &s->pim->divDev; else if (k == "spDiv") v = &s->pim->spDiv;
+    }
+    if (!v) { if (n) *n = 0; return nullptr; }
+    if (n) *n = (long)v->size();
+    return v->data();
+}
+void fvo_reconstruct(void* h, const double* ssf, double* out3)
+{
+    Ico* s = (Ico*)h;
+    if (!s->pim) s->pim = new Pim();
+    if (s->pim->invT.size() != 9*(size_t)s->m.nCells) reconstructTensor(s->m, s->pim->invT);
+    reconstruct(s->m, s->pim->invT, ssf, out3);
+}
+void fvo_div_dev(void* h, const double* alpha, double alphaB, double nu, const double* U, double* out3)
+{
+    divDevTerm(((Ico*)h)->m, alpha, alphaB, nu, U, out3);
+}
 
 // PCG on a caller-given symmetric LDU matrix over the state's addressing; out3 = init, final, iters
 void fvo_pcg(void* h, const double* diag, const double* upper, const double* source, double* psi, double tol,

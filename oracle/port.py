@@ -42,6 +42,15 @@ def lib():
         L.fvo_grad_vector.argtypes = [C.c_void_p, _dp, _dp]
         L.fvo_grad_scalar.argtypes = [C.c_void_p, _dp, _dp]
         L.fvo_div_flux.argtypes = [C.c_void_p, _dp, _dp]
+        L.fvo_div_phi_vector.argtypes = [C.c_void_p, _dp, _dp, _dp]
+        L.fvo_laplacian_gamma_vector.argtypes = [C.c_void_p, _dp, C.c_double, _dp, _dp]
+        L.fvo_pimple_solve.restype = C.c_int
+        L.fvo_pimple_solve.argtypes = [C.c_void_p, C.c_double, _dp, _dp, _dp, _dp]
+        L.fvo_pimple_field.restype = _dp
+        L.fvo_pimple_field.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_long)]
+        L.fvo_reconstruct.argtypes = [C.c_void_p, _dp, _dp]
+        L.fvo_div_dev.argtypes = [C.c_void_p, _dp, C.c_double, C.c_double, _dp, _dp]
+        L.fvo_pimple_pre.argtypes = [C.c_void_p, C.c_double, _dp, _dp, _dp, _dp, _dp]
         L.fvo_pcg.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int, C.c_int, _dp]
         L.fvo_smooth.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int, _dp]
         L.fvo_dic.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp]
@@ -167,6 +176,50 @@ class IcoOracle:
         out = np.empty(self.N)
         self.L.fvo_div_flux(self.h, _d(_c(phi)), _d(out))
         return out
+
+    def div_phi_vector(self, phi, U):
+        out = np.empty((self.N, 3))
+        self.L.fvo_div_phi_vector(self.h, _d(_c(phi)), _d(_c(U)), _d(out))
+        return out
+
+    def laplacian_gamma_vector(self, gamma, U, gammaB=1.0):
+        out = np.empty((self.N, 3))
+        self.L.fvo_laplacian_gamma_vector(self.h, _d(_c(gamma)), gammaB, _d(_c(U)), _d(out))
+        return out
+
+    def reconstruct(self, ssf):
+        out = np.empty((self.N, 3))
+        self.L.fvo_reconstruct(self.h, _d(_c(ssf)), _d(out))
+        return out
+
+    def div_dev(self, alpha, U, nu, alphaB=1.0):
+        """fvc::div((alpha*nuEff)*dev2(T(fvc::grad(U)))) -- the explicit part of the laminar divDevRhoReff"""
+        out = np.empty((self.N, 3))
+        self.L.fvo_div_dev(self.h, _d(_c(alpha)), alphaB, nu, _d(_c(U)), _d(out))
+        return out
+
+    def pimple_solve(self, dt, alpha, uSourceDrag, g=(0.0, 0.0, 0.0), alpha0=None):
+        """UcEqn.H + pEqn.H + continuityErrs.H (pimpleFoamYade.C:82-104); reads the state's uSource"""
+        a = _c(alpha).reshape(-1)
+        a0 = a if alpha0 is None else _c(alpha0).reshape(-1)
+        rc = self.L.fvo_pimple_solve(self.h, dt, _d(a), _d(a0), _d(_c(uSourceDrag).reshape(-1)), _d(_c(g)))
+        if rc != 0:
+            raise RuntimeError("adjustPhi: continuity error cannot be removed by adjusting the outflow")
+
+    def pimple_field(self, name):
+        n = C.c_long()
+        p = self.L.fvo_pimple_field(self.h, name.encode(), C.byref(n))
+        if not p or n.value == 0:
+            raise KeyError(name)
+        a = np.ctypeslib.as_array(p, shape=(n.value,))
+        return a.reshape(-1, 3) if name in ("recon", "divDev") else a
+
+    def pimple_pre(self, dt, alpha):
+        """pimpleFoamYade.C:73-76 on the state's U, p, phi: returns ddtU, gradP, divT, vGrad."""
+        ddtU, gradP, divT = np.empty((self.N, 3)), np.empty((self.N, 3)), np.empty((self.N, 3))
+        vGrad = np.empty((self.N, 9))
+        self.L.fvo_pimple_pre(self.h, dt, _d(_c(alpha)), _d(ddtU), _d(gradP), _d(divT), _d(vGrad))
+        return ddtU, gradP, divT, vGrad
 
     def pcg(self, diag, upper, source, psi0, tol=1e-6, relTol=0.0, maxIter=1000, preconditioner="DIC"):
         psi = _c(psi0).copy()

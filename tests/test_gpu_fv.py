@@ -41,6 +41,10 @@ def test_fvc_operators_bit_exact(pkg, case):
         Fi = mo["nInternalFaces"]
         phi[Fi + 12 * 4:] = 0.0          # empty faces carry no flux
     assert np.array_equal(E.div_flux(phi), O.div_flux(phi))
+    # pimpleFoamYade.C:73,75: fvc::div(phic, Uc) and fvc::laplacian(alphac, Uc)
+    gamma = np.random.default_rng(5).uniform(0.3, 1.0, mo["nCells"])
+    assert np.array_equal(E.div_phi_vector(phi, U), O.div_phi_vector(phi, U))
+    assert np.array_equal(E.laplacian_gamma_vector(gamma, U), O.laplacian_gamma_vector(gamma, U))
     # face field round trip through the owner-slot layout
     E.upload("phi", phi)
     assert np.array_equal(E.download("phi"), phi)
@@ -252,6 +256,149 @@ def test_coupled_icoFoamYade_step(pkg, config):
         assert not np.any(E.download("uSource"))
         so, se = O.stats(), E.ico_stats()
         assert [q["iters"] for q in so["p"]] == [q["iters"] for q in se["p"]]
+    E.close()
+    R.close()
+    O.close()
+
+
+def _pimple_drive(mo, it):
+    """synthetic void fraction / implicit drag / momentum source / gravity of one step (what a coupling pass leaves)"""
+    C = mo["C"]
+    lo, hi = C.min(0), C.max(0)
+    ctr = np.array([0.4, 0.55, 0.5])
+    x = np.where(hi > lo, (C - lo) / np.where(hi > lo, hi - lo, 1.0), ctr)
+    blob = np.exp(-(((x - ctr) ** 2).sum(1)) / 0.04)
+    alpha = 1.0 - (0.35 + 0.05 * it) * blob
+    drag = -(40.0 + 10.0 * it) * (1.0 - alpha)
+    src = np.stack([0.3 * (1.0 - alpha) * np.sin(5.0 * x[:, 1]), -0.8 * (1.0 - alpha), 0.1 * blob * x[:, 0]], 1)
+    return alpha, drag, src
+
+
+@pytest.mark.parametrize("case", ["cavity3d", "channel", "cavity2d", "no_predictor"])
+def test_pimpleFoamYade_steps_match_oracle(pkg, case):
+    """UcEqn.H + pEqn.H + continuityErrs.H (pimpleFoamYade.C:82-104) on the device against oracle/fv_oracle.cc's
+    pimpleSolve, with a non-uniform void fraction, implicit drag, a momentum source and gravity.  What is assembled
+    before the first linear solve (explicit stress term, UcEqn diagonal and source, 1/A, phicForces) is bit-exact;
+    the fields after each step agree to 1e-10 with identical iteration counts."""
+    ctl, g = {}, (0.0, -0.2, 0.05)
+    if case in ("cavity3d", "no_predictor"):
+        mo, mp = cases_fv.cavity3d(pkg, (18, 16, 14), (1.0, 0.9, 0.8))
+        U, p, dt, nu = 0.2 * cases.fields_for(mo["C"])["U"], np.zeros(mo["nCells"]), 2e-3, 1e-2
+        if case == "no_predictor":
+            ctl = dict(momentumPredictor=0, nCorrectors=3)
+    elif case == "channel":
+        mo, mp = cases_fv.channel(pkg, (28, 14, 12))
+        U, p = cases_fv.channel_init(mo["C"])
+        dt, nu, ctl = 0.02, 0.005, dict(nCorrectors=2, nNonOrthogonalCorrectors=1)
+    else:
+        mo, mp = cases_fv.cavity2d(pkg, 24)
+        U, p, dt, nu, g = np.zeros((mo["nCells"], 3)), np.zeros(mo["nCells"]), 0.004, 0.01, (0.0, -0.2, 0.0)
+    N = mo["nCells"]
+    O = port.IcoOracle(mo, nu=nu, **ctl)
+    O.field("U")[:] = U
+    O.field("p")[:] = p
+    O.create_phi()
+    E = pkg.Engine(mp)
+    assert E.fv_supported(), E.L.fy_last_error(E.h).decode()
+    E.set_piso_controls(nu=nu, **ctl)
+    E.upload("U", U)
+    E.upload("p", p)
+    E.create_phi()
+    for it in range(3):
+        alpha, drag, src = _pimple_drive(mo, it)
+        O.field("uSource")[:] = src
+        O.pimple_solve(dt, alpha, drag, g)
+        E.upload("alpha", alpha)
+        E.upload("uSourceDrag", drag)
+        E.upload("uSource", src)
+        E.pimple_solve(dt, g)
+        if it == 0:
+            assert np.array_equal(E.fv_get("divDev"), O.pimple_field("divDev"))
+            assert np.array_equal(E.fv_get("diagU"), O.field("diagU"))
+            assert np.array_equal(E.fv_get("sourceU"), O.field("sourceU"))
+            assert np.array_equal(E.fv_get("rAU"), O.field("rAU"))
+            assert np.array_equal(E.fv_get("phicForces"), O.pimple_field("phicForces"))
+            assert np.any(O.pimple_field("divDev")) and np.any(O.pimple_field("phicForces"))
+        so, se = O.stats(), E.ico_stats()
+        assert [q["iters"] for q in so["p"]] == [q["iters"] for q in se["p"]], it
+        assert [q["iters"] for q in so["U"]] == [q["iters"] for q in se["U"]], it
+        for k in ("U", "p", "phi"):
+            assert cases.rel_l2(E.download(k), O.field(k)) <= TOL, (k, it)
+        assert cases.rel_l2(E.fv_get("HbyA"), O.field("HbyA")) <= TOL
+        assert cases.rel_l2(E.fv_get("phiHbyA"), O.field("phiHbyA")) <= TOL
+        assert abs(se["sumLocalContErr"] - so["sumLocalContErr"]) <= 1e-6 * so["sumLocalContErr"] + 1e-18
+        assert se["sumLocalContErr"] < 1e-6
+    E.close()
+    O.close()
+
+
+@pytest.mark.parametrize("case", ["cavity3d", "channel"])
+def test_coupled_pimpleFoamYade_step(pkg, case):
+    """The whole pimpleFoamYade time step with every field resident on the device (pimpleFoamYade.C:71-108): CourantNo,
+    ddtU_f / gradP / divT / vGrad, Gaussian setParticleAction, UcEqn + PISO with the void fraction, implicit drag and
+    momentum source the coupling pass just wrote, setSourceZero -- against oracle operators + the UNMODIFIED reference
+    operator (oracle/_ref).  divT is evaluated with the alphac setSourceZero reset to 1 at the end of the previous step,
+    as in the reference's loop."""
+    from oracle import ref
+    if case == "cavity3d":
+        mo, mp = cases_fv.cavity3d(pkg, (24, 24, 24), (1.0, 1.0, 1.0))
+        U0, p0, dt, nu = 0.3 * cases.fields_for(mo["C"])["U"], None, 2e-3, 1e-3
+    else:
+        mo, mp = cases_fv.channel(pkg, (28, 14, 12))
+        U0, p0 = cases_fv.channel_init(mo["C"])
+        dt, nu = 5e-3, 5e-3
+    N = mo["nCells"]
+    lo, hi = mo["C"].min(0), mo["C"].max(0)
+    pd = cases.particles(1500, 9, radius=0.25 * float(np.cbrt(mo["V"][0])), moving=True)
+    pd[:, 0:3] = lo + (0.1 + 0.8 * (pd[:, 0:3] - pd[:, 0:3].min(0)) / np.ptp(pd[:, 0:3], axis=0)) * (hi - lo)
+    O = port.IcoOracle(mo, nu=nu)
+    O.field("U")[:] = U0
+    if p0 is not None:
+        O.field("p")[:] = p0
+    O.create_phi()
+    R = ref.RefFoamYade(mo, True)
+    R.set_properties(cases.RHOP, cases.RHOF, nu)
+    E = pkg.Engine(mp)
+    E.set_properties(cases.RHOP, cases.RHOF, nu, True)
+    E.set_piso_controls(nu=nu)
+    E.upload("U", U0)
+    if p0 is not None:
+        E.upload("p", p0)
+    E.create_phi()
+    for step in range(3):
+        ddtU, gradP, divT, vGrad = O.pimple_pre(dt, R.field("alpha").reshape(N))
+        for k, v in (("U", O.field("U")), ("ddtU", ddtU), ("gradP", gradP), ("divT", divT), ("vGrad", vGrad)):
+            R.field(k)[:] = v.reshape(R.field(k).shape)
+        fo, Fo = R.step(dt, pd, pieces=True)
+        O.field("uSource")[:] = R.field("uSource")
+        alphaO = R.field("alpha").reshape(N).copy()
+        O.pimple_solve(dt, alphaO, R.field("uSourceDrag").reshape(N))
+        R.set_source_zero()
+
+        E.pimple_pre(dt)
+        got = {k: E.download(k) for k in ("ddtU", "gradP", "divT", "vGrad")}
+        fe, Fe = E.set_particle_action(dt, pd)
+        alphaE = E.download("alpha")
+        E.pimple_solve(dt)
+        E.set_source_zero()
+
+        for k, want in (("ddtU", ddtU), ("gradP", gradP), ("divT", divT), ("vGrad", vGrad)):
+            if step == 0:
+                assert np.array_equal(got[k].reshape(want.shape), want), k      # identical inputs: bit-exact operators
+            else:
+                assert cases.rel_l2(got[k].reshape(want.shape), want) <= TOL, (k, step)
+        assert np.any(divT) and np.any(vGrad)
+        assert np.array_equal(fo, fe)
+        assert cases.rel_l2(Fe, Fo) <= TOL
+        assert cases.rel_l2(alphaE.reshape(N), alphaO) <= TOL
+        assert alphaO.min() < 1.0                     # the void fraction really enters UcEqn / pEqn
+        assert cases.rel_l2(E.download("U"), O.field("U")) <= TOL
+        assert cases.rel_l2(E.download("p"), O.field("p")) <= TOL
+        assert cases.rel_l2(E.download("phi"), O.field("phi")) <= TOL
+        assert not np.any(E.download("uSource")) and np.all(E.download("alpha") == 1.0)
+        so, se = O.stats(), E.ico_stats()
+        assert [q["iters"] for q in so["p"]] == [q["iters"] for q in se["p"]]
+        assert abs(se["CoNum"] - so["CoNum"]) <= 1e-12 * max(so["CoNum"], 1e-300)
     E.close()
     R.close()
     O.close()

@@ -113,6 +113,10 @@ def lib():
     L.fy_fvc_grad_vector.argtypes = [H, _dp, _dp]
     L.fy_fvc_grad_scalar.argtypes = [H, _dp, _dp]
     L.fy_fvc_div_flux.argtypes = [H, _dp, _dp]
+    L.fy_fvc_div_phi_vector.argtypes = [H, _dp, _dp, _dp]
+    L.fy_fvc_laplacian_gamma_vector.argtypes = [H, _dp, C.c_double, _dp, _dp]
+    L.fy_pimple_pre.argtypes = [H, C.c_double]
+    L.fy_pimple_solve.argtypes = [H, C.c_double, _dp]
     L.fy_pcg_solve.argtypes = [H, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int, C.c_int, _dp]
     L.fy_smooth_solve.argtypes = [H, _dp, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int, _dp]
     L.fy_dic_precondition.argtypes = [H, _dp, _dp, _dp, _dp]
@@ -355,6 +359,15 @@ class Engine:
     def ico_pre(self, dt):
         self._ck(self.L.fy_ico_pre(self.h, dt))
 
+    def pimple_pre(self, dt):
+        """pimpleFoamYade.C:71-76 on the device fields: CourantNo, ddtU, gradP, divT, vGrad"""
+        self._ck(self.L.fy_pimple_pre(self.h, dt))
+
+    def pimple_solve(self, dt, g=(0.0, 0.0, 0.0)):
+        """pimpleFoamYade.C:82-104 (UcEqn.H, pEqn.H, continuityErrs.H) on the device fields"""
+        gv = _c64(g)
+        self._ck(self.L.fy_pimple_solve(self.h, dt, _d(gv)))
+
     def ico_solve(self, dt):
         self._ck(self.L.fy_ico_solve(self.h, dt))
 
@@ -387,6 +400,16 @@ class Engine:
         self._ck(self.L.fy_fvc_div_flux(self.h, _d(_c64(phi)), _d(out)))
         return out
 
+    def div_phi_vector(self, phi, U):
+        out = np.empty((self.N, 3))
+        self._ck(self.L.fy_fvc_div_phi_vector(self.h, _d(_c64(phi)), _d(_c64(U)), _d(out)))
+        return out
+
+    def laplacian_gamma_vector(self, gamma, U, gammaB=1.0):
+        out = np.empty((self.N, 3))
+        self._ck(self.L.fy_fvc_laplacian_gamma_vector(self.h, _d(_c64(gamma)), gammaB, _d(_c64(U)), _d(out)))
+        return out
+
     def pcg(self, diag, upper, source, psi0, tol=1e-6, relTol=0.0, maxIter=1000, preconditioner="DIC"):
         psi = _c64(psi0).copy()
         out = np.zeros(3)
@@ -410,7 +433,8 @@ class Engine:
         nF = int(self.mesh["nInternalFaces"])
         nB = sum(int(p["faceCells"].shape[0]) for p in self.mesh["patches"])
         shape = dict(rAU=(self.N,), HbyA=(self.N, 3), gradP=(self.N, 3), diagU=(self.N,), sourceU=(self.N, 3),
-                     phiHbyA=(nF + nB,), phi=(nF + nB,), upperP=(nF,), upperU=(nF,), lowerU=(nF,))[name]
+                     phiHbyA=(nF + nB,), phi=(nF + nB,), upperP=(nF,), upperU=(nF,), lowerU=(nF,),
+                     phicForces=(nF + nB,), divDev=(self.N, 3))[name]
         out = np.empty(shape)
         self._ck(self.L.fy_fv_get(self.h, name.encode(), _d(out)))
         return out

@@ -100,6 +100,25 @@ int fy_ico_pre(fy_handle h, double dt)
     return fvIcoPre(h, s, dt);
 }
 
+int fy_pimple_pre(fy_handle h, double dt)
+{
+    FvState* s;
+    int rc = needFv(h, &s);
+    if (rc) return rc;
+    if (!(dt > 0)) { h->err = "fy_pimple_pre: dt must be positive"; return FY_ERR_INVALID; }
+    return fvPimplePre(h, s, dt);
+}
+
+int fy_pimple_solve(fy_handle h, double dt, const double g[3])
+{
+    FvState* s;
+    int rc = needFv(h, &s);
+    if (rc) return rc;
+    if (!(dt > 0)) { h->err = "fy_pimple_solve: dt must be positive"; return FY_ERR_INVALID; }
+    const double zero[3] = {0, 0, 0};
+    return fvPimpleSolve(h, s, dt, g ? g : zero);
+}
+
 int fy_ico_solve(fy_handle h, double dt)
 {
     FvState* s;
@@ -160,6 +179,38 @@ int fy_fvc_div_flux(fy_handle h, const double* phi, double* out)
     if ((rc = fvFacesToSlots(h, s, (int)nF, d, d + nF))) return rc;
     if ((rc = fvDivFlux(h, s, d + nF, d + nF + NS))) return rc;
     return d2h(h, out, d + nF + NS, N);
+}
+
+int fy_fvc_div_phi_vector(fy_handle h, const double* phi, const double* U, double* out3)
+{
+    FvState* s;
+    int rc = needFv(h, &s);
+    if (rc) return rc;
+    if (!phi || !U || !out3) return FY_ERR_INVALID;
+    const size_t N = (size_t)s->g.N, nF = (size_t)s->nFi + s->nB, NS = (size_t)s->g.nSlots;
+    double* d;
+    if ((rc = stage(h, s, nF + NS + 6 * N, &d))) return rc;
+    double *dSlots = d + nF, *dU = dSlots + NS, *dOut = dU + 3 * N;
+    if ((rc = h2d(h, d, phi, nF))) return rc;
+    if ((rc = h2d(h, dU, U, 3 * N))) return rc;
+    if ((rc = fvFacesToSlots(h, s, (int)nF, d, dSlots))) return rc;
+    if ((rc = fvDivPhiVector(h, s, dSlots, dU, dOut))) return rc;
+    return d2h(h, out3, dOut, 3 * N);
+}
+
+int fy_fvc_laplacian_gamma_vector(fy_handle h, const double* gamma, double gammaB, const double* U, double* out3)
+{
+    FvState* s;
+    int rc = needFv(h, &s);
+    if (rc) return rc;
+    if (!gamma || !U || !out3) return FY_ERR_INVALID;
+    const size_t N = (size_t)s->g.N;
+    double* d;
+    if ((rc = stage(h, s, 7 * N, &d))) return rc;
+    if ((rc = h2d(h, d, gamma, N))) return rc;
+    if ((rc = h2d(h, d + N, U, 3 * N))) return rc;
+    if ((rc = fvLaplacianGammaVector(h, s, 1.0, d, gammaB, d + N, d + 4 * N))) return rc;
+    return d2h(h, out3, d + 4 * N, 3 * N);
 }
 
 // matrix coefficients arrive in LDU face order; the kernels want owner slots
@@ -244,6 +295,14 @@ int fy_fv_get(fy_handle h, const char* name, double* dst)
     if (k == "gradP") return d2h(h, dst, s->gradP, 3 * N);
     if (k == "diagU") return d2h(h, dst, s->diagU, N);
     if (k == "sourceU") return d2h(h, dst, s->srcU, 3 * N);
+    if (k == "divDev" && s->divDev) return d2h(h, dst, s->divDev, 3 * N);
+    if (k == "phicForces" && s->phicForces) {
+        const size_t nF = (size_t)s->nFi + s->nB;
+        double* d;
+        if ((rc = stage(h, s, nF, &d))) return rc;
+        if ((rc = fvSlotsToFaces(h, s, (int)nF, s->phicForces, d))) return rc;
+        return d2h(h, dst, d, nF);
+    }
     if (k == "phiHbyA" || k == "phi" || k == "upperP" || k == "upperU" || k == "lowerU") {
         const size_t nF = (k == "phiHbyA" || k == "phi") ? (size_t)s->nFi + s->nB : (size_t)s->nFi;
         double* d;

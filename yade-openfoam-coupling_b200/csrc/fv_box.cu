@@ -213,6 +213,97 @@ __global__ void __launch_bounds__(BLK) k_div_flux(BoxGeom g, const double* __res
 }
 
 // ---------------------------------------------------------------------------------------------
+// pimpleFoamYade.C:73-76: the explicit operators whose results FoamYade reads in the Gaussian branch.
+//   fvc::div(phi, U)        = surfaceIntegrate(phi_f * interpolate(U))                (gaussConvectionScheme, linear)
+//   fvc::laplacian(gamma,U) = surfaceIntegrate((interpolate(gamma)*magSf) * snGrad(U)) (gaussLaplacianScheme,
+//                             snGrad = deltaCoeffs*(U_N - U_P); gammaB = value of gamma on the patches -- alphac's are
+//                             `calculated` and hold the 1.0 FoamYade::initFields assigns field-wide, F.C:67)
+// Face order per cell as everywhere: z-, y-, x- (cell is the neighbour: -=), x+, y+, z+ (owner: +=), boundary.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLK)
+    k_div_phi_vector(BoxGeom g, const double* __restrict__ phi, const double* __restrict__ U, double* __restrict__ out)
+{
+    FV_CELL_LOOP(g, c) {
+        int i, j, k;
+        fvIJK(g, c, i, j, k);
+        const double uc[3] = {U[3 * (size_t)c], U[3 * (size_t)c + 1], U[3 * (size_t)c + 2]};
+        double a[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int d = 2; d >= 0; --d) {
+            if (fvIdx(d, i, j, k) == 0) continue;
+            const int cn = c - fvStride(g, d);
+            const double ph = phi[d * (size_t)g.N + cn];
+            const double* un = U + 3 * (size_t)cn;
+#pragma unroll
+            for (int m = 0; m < 3; ++m) a[m] -= ph * fvLerp(g.w[d], un[m], uc[m]);
+        }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            if (fvIdx(d, i, j, k) == fvN(g, d) - 1) continue;
+            const double ph = phi[d * (size_t)g.N + c];
+            const double* un = U + 3 * (size_t)(c + fvStride(g, d));
+#pragma unroll
+            for (int m = 0; m < 3; ++m) a[m] += ph * fvLerp(g.w[d], uc[m], un[m]);
+        }
+        if (!fvInterior(g, i, j, k)) {
+            for (int q = 0; q < 6; ++q) {
+                const int s = g.seq[q];
+                if (g.kindU[s] == FV_EMPTY || !fvOnSide(g, s, i, j, k)) continue;
+                const double ph = phi[fvSideSlot(g, s, c, i, j, k)];
+#pragma unroll
+                for (int m = 0; m < 3; ++m) a[m] += ph * (g.kindU[s] == FV_FIXED_VALUE ? g.valU[s][m] : uc[m]);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < 3; ++m) out[3 * (size_t)c + m] = a[m] / g.V;
+    }
+}
+
+// out = scale * fvc::laplacian(gamma, U)   (scale = 2 nu gives pimpleFoamYade's divT; 1.0 is exact)
+__global__ void __launch_bounds__(BLK)
+k_laplacian_gamma_vector(BoxGeom g, double scale, const double* __restrict__ gamma, double gammaB, const double* __restrict__ U,
+                         double* __restrict__ out)
+{
+    FV_CELL_LOOP(g, c) {
+        int i, j, k;
+        fvIJK(g, c, i, j, k);
+        const double uc[3] = {U[3 * (size_t)c], U[3 * (size_t)c + 1], U[3 * (size_t)c + 2]};
+        const double gc = gamma[c];
+        double a[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int d = 2; d >= 0; --d) {
+            if (fvIdx(d, i, j, k) == 0) continue;
+            const int cn = c - fvStride(g, d);
+            const double gm = fvLerp(g.w[d], gamma[cn], gc) * g.magSf[d];
+            const double* un = U + 3 * (size_t)cn;
+#pragma unroll
+            for (int m = 0; m < 3; ++m) a[m] -= gm * (g.dc[d] * (uc[m] - un[m]));
+        }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            if (fvIdx(d, i, j, k) == fvN(g, d) - 1) continue;
+            const int cp = c + fvStride(g, d);
+            const double gm = fvLerp(g.w[d], gc, gamma[cp]) * g.magSf[d];
+            const double* un = U + 3 * (size_t)cp;
+#pragma unroll
+            for (int m = 0; m < 3; ++m) a[m] += gm * (g.dc[d] * (un[m] - uc[m]));
+        }
+        if (!fvInterior(g, i, j, k)) {
+            for (int q = 0; q < 6; ++q) {
+                const int s = g.seq[q];
+                if (g.kindU[s] == FV_EMPTY || !fvOnSide(g, s, i, j, k)) continue;
+                const double gm = gammaB * g.bMagSf[s];
+#pragma unroll
+                for (int m = 0; m < 3; ++m)
+                    a[m] += gm * (g.kindU[s] == FV_FIXED_VALUE ? g.bDc[s] * (g.valU[s][m] - uc[m]) : 0.0);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < 3; ++m) out[3 * (size_t)c + m] = scale * (a[m] / g.V);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // UEqn = fvm::ddt(U) + fvm::div(phi,U) - fvm::laplacian(nu,U) == uSource           icoFoamYade.C:79-85
 // per cell: diag, lower/upper of its own faces, source; also rAU = 1/A() and the per-component solve
 // diagonals (diag + internalCoeffs), which depend on the matrix only.
@@ -592,6 +683,449 @@ k_correct_U(BoxGeom g, double dt, int corr, const double* __restrict__ phi, cons
 }
 
 // ---------------------------------------------------------------------------------------------
+// pimpleFoamYade: UcEqn.H + pEqn.H + continuityErrs.H on the box  (pimpleFoamYade.C:82-104, one outer corrector,
+// laminar).  Operator definitions and the boundary / old-time conventions: oracle/fv_oracle.cc (pimpleSolve).
+// alphacf = fvc::interpolate(alphac) is recomputed from alphac wherever a face needs it (its patches hold 1.0, so
+// alphacf_b*x == x bit for bit and the icoFoam boundary-coefficient helpers serve unchanged).
+// ---------------------------------------------------------------------------------------------
+constexpr double FV_ALPHA_B = 1.0;
+
+// surfaceIntegrate(alphacf*phi) of one cell -- fvc::div(alphaPhic), fvc::div(alphacf*phiHbyA), fvc::div(alphacf*phic)
+__device__ __forceinline__ double fvDivAlphaCell(const BoxGeom& g, const double* __restrict__ alpha,
+                                                 const double* __restrict__ phi, int c, int i, int j, int k)
+{
+    const double ac = alpha[c];
+    double d = 0.0;
+    if (k > 0) d -= fvLerp(g.w[2], alpha[c - g.sz], ac) * phi[2 * g.N + c - g.sz];
+    if (j > 0) d -= fvLerp(g.w[1], alpha[c - g.sy], ac) * phi[g.N + c - g.sy];
+    if (i > 0) d -= fvLerp(g.w[0], alpha[c - 1], ac) * phi[c - 1];
+    if (i < g.nx - 1) d += fvLerp(g.w[0], ac, alpha[c + 1]) * phi[c];
+    if (j < g.ny - 1) d += fvLerp(g.w[1], ac, alpha[c + g.sy]) * phi[g.N + c];
+    if (k < g.nz - 1) d += fvLerp(g.w[2], ac, alpha[c + g.sz]) * phi[2 * g.N + c];
+    if (!fvInterior(g, i, j, k)) {
+        for (int q = 0; q < 6; ++q) {
+            const int s = g.seq[q];
+            if (g.kindU[s] == FV_EMPTY || !fvOnSide(g, s, i, j, k)) continue;
+            d += FV_ALPHA_B * phi[fvSideSlot(g, s, c, i, j, k)];
+        }
+    }
+    return d / g.V;
+}
+
+// fvc::div((alpha*nuEff)*dev2(T(fvc::grad(U)))): the explicit half of the laminar divDevRhoReff.  Only row d of the
+// stress tensor meets a face normal to d; patch values of grad(U) carry gaussGrad's normal-gradient correction.
+__device__ __forceinline__ void fvDevRow(const double* __restrict__ gr, int d, double a, double* x)
+{
+    const double sph = (2.0 / 3.0) * (gr[0] + gr[4] + gr[8]);
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+        double t = gr[3 * m + d];                     // T(grad)_dm
+        if (m == d) t -= sph;
+        x[m] = a * t;
+    }
+}
+__global__ void __launch_bounds__(BLK)
+k_pim_div_dev(BoxGeom g, double nu, const double* __restrict__ alpha, const double* __restrict__ U,
+              const double* __restrict__ vGrad, double* __restrict__ out)
+{
+    FV_CELL_LOOP(g, c) {
+        int i, j, k;
+        fvIJK(g, c, i, j, k);
+        const double* gc = vGrad + 9 * (size_t)c;
+        const double ac = alpha[c] * nu;
+        double acc[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int d = 2; d >= 0; --d) {
+            if (fvIdx(d, i, j, k) == 0) continue;
+            const int cn = c - fvStride(g, d);
+            double xp[3], xn[3];
+            fvDevRow(vGrad + 9 * (size_t)cn, d, alpha[cn] * nu, xp);
+            fvDevRow(gc, d, ac, xn);
+#pragma unroll
+            for (int m = 0; m < 3; ++m) acc[m] -= g.Sf[d] * fvLerp(g.w[d], xp[m], xn[m]);
+        }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            if (fvIdx(d, i, j, k) == fvN(g, d) - 1) continue;
+            const int cp = c + fvStride(g, d);
+            double xp[3], xn[3];
+            fvDevRow(gc, d, ac, xp);
+            fvDevRow(vGrad + 9 * (size_t)cp, d, alpha[cp] * nu, xn);
+#pragma unroll
+            for (int m = 0; m < 3; ++m) acc[m] += g.Sf[d] * fvLerp(g.w[d], xp[m], xn[m]);
+        }
+        if (!fvInterior(g, i, j, k)) {
+            for (int q = 0; q < 6; ++q) {
+                const int s = g.seq[q];
+                if (g.kindU[s] == FV_EMPTY || !fvOnSide(g, s, i, j, k)) continue;
+                const int d = s >> 1;
+                const double n = g.bSf[s] / g.bMagSf[s];
+                double gb[9];
+#pragma unroll
+                for (int t = 0; t < 9; ++t) gb[t] = gc[t];
+#pragma unroll
+                for (int m = 0; m < 3; ++m) {
+                    const double sn = g.kindU[s] == FV_FIXED_VALUE ? g.bDc[s] * (g.valU[s][m] - U[3 * (size_t)c + m]) : 0.0;
+                    const double nG = n * gc[3 * d + m];
+                    gb[3 * d + m] = gc[3 * d + m] + n * (sn - nG);
+                }
+                double xb[3];
+                fvDevRow(gb, d, FV_ALPHA_B * nu, xb);
+#pragma unroll
+                for (int m = 0; m < 3; ++m) acc[m] += g.bSf[s] * xb[m];
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < 3; ++m) out[3 * (size_t)c + m] = acc[m] / g.V;
+    }
+}
+
+// UcEqn = fvm::ddt(alphac,Uc) + fvm::div(alphaPhic,Uc) - fvm::Sp(fvc::ddt(alphac) + fvc::div(alphaPhic),Uc)
+//         + divDevRhoReff(Uc) == fvm::Sp(uSourceDrag,Uc)                                        pim/UcEqn.H:3-11
+__global__ void __launch_bounds__(BLK)
+k_pim_assemble_U(BoxGeom g, double nu, double rDeltaT, const double* __restrict__ phi, const double* __restrict__ alpha,
+                 const double* __restrict__ alpha0, const double* __restrict__ U0, const double* __restrict__ uSourceDrag,
+                 const double* __restrict__ divDev, double* __restrict__ diagU, double* __restrict__ loU,
+                 double* __restrict__ upU, double* __restrict__ srcU, double* __restrict__ dgU, double* __restrict__ rAU)
+{
+    FV_CELL_LOOP(g, c) {
+        int i, j, k;
+        fvIJK(g, c, i, j, k);
+        const int N = g.N;
+        const double ac = alpha[c], a0 = alpha0[c];
+        const double diagD = (rDeltaT * ac) * g.V;
+        double diagC = 0.0, diagL = 0.0, dv = 0.0;
+#pragma unroll
+        for (int d = 2; d >= 0; --d) {
+            const int v = fvIdx(d, i, j, k), sd = fvStride(g, d);
+            if (v > 0) {
+                const double an = alpha[c - sd];
+                const double aph = fvLerp(g.w[d], an, ac) * phi[d * N + c - sd];
+                const double lowerC = -g.w[d] * aph;
+                const double upperC = lowerC + aph;
+                diagC -= upperC;
+                diagL -= g.dc[d] * (fvLerp(g.w[d], an * nu, ac * nu) * g.magSf[d]);
+                dv -= aph;
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const int v = fvIdx(d, i, j, k), nd = fvN(g, d), sd = fvStride(g, d);
+            double lo = 0.0, up = 0.0;
+            if (v < nd - 1) {
+                const double an = alpha[c + sd];
+                const double aph = fvLerp(g.w[d], ac, an) * phi[d * N + c];
+                const double lowerC = -g.w[d] * aph;
+                const double upperC = lowerC + aph;
+                const double upperL = g.dc[d] * (fvLerp(g.w[d], ac * nu, an * nu) * g.magSf[d]);
+                diagC -= lowerC;
+                diagL -= upperL;
+                dv += aph;
+                lo = lowerC + (-upperL);
+                up = upperC + (-upperL);
+            }
+            loU[d * N + c] = lo;
+            upU[d * N + c] = up;
+        }
+        double D = 0.0, dgB[3] = {0.0, 0.0, 0.0};
+        if (!fvInterior(g, i, j, k)) {
+            for (int q = 0; q < 6; ++q) {
+                const int s = g.seq[q];
+                if (g.kindU[s] == FV_EMPTY || !fvOnSide(g, s, i, j, k)) continue;
+                dv += FV_ALPHA_B * phi[fvSideSlot(g, s, c, i, j, k)];
+            }
+        }
+        const double spDiv = rDeltaT * (ac - a0) + dv / g.V;
+        const double diag = (((diagD + diagC) - g.V * spDiv) + (-diagL)) - g.V * uSourceDrag[c];
+        diagU[c] = diag;
+        D = diag;
+        dgB[0] = dgB[1] = dgB[2] = diag;
+        if (!fvInterior(g, i, j, k)) {
+            for (int q = 0; q < 6; ++q) {
+                const int s = g.seq[q];
+                if (g.kindU[s] == FV_EMPTY || !fvOnSide(g, s, i, j, k)) continue;
+                const double phib = FV_ALPHA_B * phi[fvSideSlot(g, s, c, i, j, k)];
+                double ic[3], bc;
+#pragma unroll
+                for (int m = 0; m < 3; ++m) {
+                    fvBCoefU(g, s, phib, FV_ALPHA_B * nu, m, ic[m], bc);
+                    dgB[m] += ic[m];
+                }
+                D += (ic[0] + ic[1] + ic[2]) / 3.0;
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+            dgU[m * (size_t)N + c] = dgB[m];
+            double sU = ((rDeltaT * a0) * U0[3 * (size_t)c + m]) * g.V;
+            sU -= g.V * (-divDev[3 * (size_t)c + m]);
+            srcU[3 * (size_t)c + m] = sU;
+        }
+        rAU[c] = 1.0 / (D / g.V);
+    }
+}
+
+// phicForces = fvc::flux(rAUc*uSource) + rAUcf*(g & Sf)                                        pim/UcEqn.H:17-20
+__global__ void __launch_bounds__(BLK)
+k_pim_forces(BoxGeom g, double g0, double g1, double g2, const double* __restrict__ rAU, const double* __restrict__ uSource,
+             double* __restrict__ phicForces)
+{
+    const double gv[3] = {g0, g1, g2};
+    FV_CELL_LOOP(g, c) {
+        int i, j, k;
+        fvIJK(g, c, i, j, k);
+        const double rc = rAU[c];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const int v = fvIdx(d, i, j, k), nd = fvN(g, d);
+            if (v < nd - 1) {
+                const int n = c + fvStride(g, d);
+                const double rn = rAU[n];
+                const double flux = g.Sf[d] * fvLerp(g.w[d], rc * uSource[3 * (size_t)c + d], rn * uSource[3 * (size_t)n + d]);
+                phicForces[d * g.N + c] = flux + fvLerp(g.w[d], rc, rn) * (gv[d] * g.Sf[d]);
+            } else {
+                const int s = 2 * d + 1;
+                phicForces[d * g.N + c] = g.kindU[s] == FV_EMPTY ? 0.0 : g.bSf[s] * (rc * 0.0) + rc * (gv[d] * g.bSf[s]);
+            }
+            if (v == 0) {
+                const int s = 2 * d;
+                phicForces[fvSideSlot(g, s, c, i, j, k)] =
+                    g.kindU[s] == FV_EMPTY ? 0.0 : g.bSf[s] * (rc * 0.0) + rc * (gv[d] * g.bSf[s]);
+            }
+        }
+    }
+}
+
+// fvc::reconstruct(ssf) of one cell: inv(surfaceSum(SfHat*Sf)) & surfaceSum(SfHat*ssf).  On the box the tensor is
+// diagonal; `face(d, hi)` returns the (SfHat component, ssf) pair of the cell's lower / upper face in direction d
+// (ok=false: an empty face, no contribution).  g.reconRm = directions tensorField inv() removes (no faces at all).
+template <class Face>
+__device__ __forceinline__ void fvReconstruct(const BoxGeom& g, Face face, double* out)
+{
+    double T[3], v[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        T[d] = 0.0;
+        v[d] = 0.0;
+#pragma unroll
+        for (int hi = 0; hi < 2; ++hi) {
+            double nHat, area, ssf;
+            if (!face(d, hi, nHat, area, ssf)) continue;
+            T[d] += nHat * area;
+            v[d] += nHat * ssf;
+        }
+        if (g.reconRm[d]) T[d] += 1.0;
+    }
+    const double det = T[0] * T[1] * T[2];
+    double inv[3] = {(T[1] * T[2]) / det, (T[0] * T[2]) / det, (T[0] * T[1]) / det};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        if (g.reconRm[d]) inv[d] -= 1.0;
+        out[d] = inv[d] * v[d];
+    }
+}
+
+// -fvc::reconstruct(phicForces/rAUcf - fvc::snGrad(p)*magSf): the momentum predictor's source, stored negated so the
+// icoFoam set-up kernel (source + V*(-x)) adds it                                                pim/UcEqn.H:24-32
+__global__ void __launch_bounds__(BLK)
+k_pim_predictor_source(BoxGeom g, const double* __restrict__ phicForces, const double* __restrict__ rAU,
+                       const double* __restrict__ p, double* __restrict__ negRecon)
+{
+    FV_CELL_LOOP(g, c) {
+        int i, j, k;
+        fvIJK(g, c, i, j, k);
+        const double rc = rAU[c], pc = p[c];
+        auto face = [&](int d, int hi, double& nHat, double& area, double& ssf) -> bool {
+            const int v = fvIdx(d, i, j, k), nd = fvN(g, d), sd = fvStride(g, d);
+            const bool bnd = hi ? (v == nd - 1) : (v == 0);
+            if (!bnd) {
+                const int P = hi ? c : c - sd, Nb = hi ? c + sd : c;
+                const double rf = fvLerp(g.w[d], rAU[P], rAU[Nb]);
+                nHat = g.Sf[d] / g.magSf[d];
+                area = g.Sf[d];
+                ssf = phicForces[d * g.N + P] / rf - (g.dc[d] * (p[Nb] - p[P])) * g.magSf[d];
+                return true;
+            }
+            const int s = 2 * d + hi;
+            if (g.kindU[s] == FV_EMPTY) return false;
+            const double sn = g.kindP[s] == FV_FIXED_VALUE ? g.bDc[s] * (g.valP[s] - pc) : 0.0;
+            nHat = g.bSf[s] / g.bMagSf[s];
+            area = g.bSf[s];
+            ssf = phicForces[fvSideSlot(g, s, c, i, j, k)] / rc - sn * g.bMagSf[s];
+            return true;
+        };
+        double r[3];
+        fvReconstruct(g, face, r);
+#pragma unroll
+        for (int m = 0; m < 3; ++m) negRecon[3 * (size_t)c + m] = -r[m];
+    }
+}
+
+// phiHbyA = fvc::flux(HbyA) + alphacf*rAUcf*fvc::ddtCorr(Uc, phic)  and  upper(pEqn) = deltaCoeffs*((alphacf*rAUcf)*magSf)
+//                                                                                       pim/pEqn.H:4-11, 26-31
+__global__ void __launch_bounds__(BLK)
+k_pim_phiHbyA(BoxGeom g, double rDeltaT, const double* __restrict__ HbyA, const double* __restrict__ U0,
+              const double* __restrict__ phi0, const double* __restrict__ rAU, const double* __restrict__ alpha,
+              double* __restrict__ phiHbyA, double* __restrict__ upP)
+{
+    FV_CELL_LOOP(g, c) {
+        int i, j, k;
+        fvIJK(g, c, i, j, k);
+        const int N = g.N;
+        const double rc = rAU[c], ac = alpha[c];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const int v = fvIdx(d, i, j, k), nd = fvN(g, d), sd = fvStride(g, d);
+            const double hc = HbyA[3 * (size_t)c + d], u0c = U0[3 * (size_t)c + d];
+            if (v < nd - 1) {
+                const int n = c + sd;
+                const double flux = g.Sf[d] * fvLerp(g.w[d], hc, HbyA[3 * (size_t)n + d]);
+                const double u0f = g.Sf[d] * fvLerp(g.w[d], u0c, U0[3 * (size_t)n + d]);
+                const double ph0 = phi0[d * N + c];
+                const double phiCorr = ph0 - u0f;
+                const double coeff = 1.0 - fmin(fabs(phiCorr) / (fabs(ph0) + FV_SMALL), 1.0);
+                const double arf = fvLerp(g.w[d], ac, alpha[n]) * fvLerp(g.w[d], rc, rAU[n]);
+                phiHbyA[d * N + c] = flux + arf * ((coeff * rDeltaT) * phiCorr);
+                upP[d * N + c] = g.dc[d] * (arf * g.magSf[d]);
+            } else {
+                phiHbyA[d * N + c] = fvPhiHbyAB(g, 2 * d + 1, d, rDeltaT, hc, u0c, FV_ALPHA_B * rc, phi0[d * N + c]);
+                upP[d * N + c] = 0.0;
+            }
+            if (v == 0) {
+                const int sl = fvSideSlot(g, 2 * d, c, i, j, k);
+                phiHbyA[sl] = fvPhiHbyAB(g, 2 * d, d, rDeltaT, hc, u0c, FV_ALPHA_B * rc, phi0[sl]);
+            }
+        }
+    }
+}
+
+// phiHbyA += phicForces                                                                          pim/pEqn.H:18
+__global__ void __launch_bounds__(BLK) k_pim_add_forces(int n, const double* __restrict__ phicForces, double* __restrict__ phiHbyA)
+{
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) phiHbyA[q] += phicForces[q];
+}
+
+// fvm::laplacian(alphacf*rAUcf, p) == fvc::ddt(alphac) + fvc::div(alphacf*phiHbyA); setReference    pim/pEqn.H:26-33
+__global__ void __launch_bounds__(BLK)
+k_pim_pEqn(BoxGeom g, int pRefCell, double pRefValue, double rDeltaT, const double* __restrict__ upP,
+           const double* __restrict__ phiHbyA, const double* __restrict__ rAU, const double* __restrict__ alpha,
+           const double* __restrict__ alpha0, double* __restrict__ dgP, double* __restrict__ bP)
+{
+    FV_CELL_LOOP(g, c) {
+        int i, j, k;
+        fvIJK(g, c, i, j, k);
+        const int N = g.N;
+        double diag = 0.0;
+        if (k > 0) diag -= upP[2 * N + c - g.sz];
+        if (j > 0) diag -= upP[N + c - g.sy];
+        if (i > 0) diag -= upP[c - 1];
+        if (i < g.nx - 1) diag -= upP[c];
+        if (j < g.ny - 1) diag -= upP[N + c];
+        if (k < g.nz - 1) diag -= upP[2 * N + c];
+        double src = 0.0;
+        src += g.V * (rDeltaT * (alpha[c] - alpha0[c]) + fvDivAlphaCell(g, alpha, phiHbyA, c, i, j, k));
+        if (g.pNeedRef && c == pRefCell) {
+            src += diag * pRefValue;
+            diag += diag;
+        }
+        if (!fvInterior(g, i, j, k)) {
+            const double rc = FV_ALPHA_B * rAU[c];
+            for (int q = 0; q < 6; ++q) {
+                const int s = g.seq[q];
+                if (g.kindP[s] == FV_EMPTY || !fvOnSide(g, s, i, j, k)) continue;
+                double ic, bc;
+                fvBCoefP(g, s, rc, ic, bc);
+                diag += ic;
+                src += bc;
+            }
+        }
+        dgP[c] = diag;
+        bP[c] = src;
+    }
+}
+
+// phic = phiHbyA - pEqn.flux()/alphacf                                                           pim/pEqn.H:39
+__global__ void __launch_bounds__(BLK)
+k_pim_flux_update(BoxGeom g, const double* __restrict__ upP, const double* __restrict__ phiHbyA, const double* __restrict__ p,
+                  const double* __restrict__ rAU, const double* __restrict__ alpha, double* __restrict__ phi)
+{
+    FV_CELL_LOOP(g, c) {
+        int i, j, k;
+        fvIJK(g, c, i, j, k);
+        const int N = g.N;
+        const double pc = p[c], rc = FV_ALPHA_B * rAU[c], ac = alpha[c];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const int v = fvIdx(d, i, j, k), nd = fvN(g, d), sd = fvStride(g, d);
+            if (v < nd - 1) {
+                const double u = upP[d * N + c];
+                phi[d * N + c] = phiHbyA[d * N + c] - (u * p[c + sd] - u * pc) / fvLerp(g.w[d], ac, alpha[c + sd]);
+            } else {
+                double ic, bc;
+                fvBCoefP(g, 2 * d + 1, rc, ic, bc);
+                phi[d * N + c] = phiHbyA[d * N + c] - (ic * pc - bc) / FV_ALPHA_B;
+            }
+            if (v == 0) {
+                double ic, bc;
+                fvBCoefP(g, 2 * d, rc, ic, bc);
+                const int sl = fvSideSlot(g, 2 * d, c, i, j, k);
+                phi[sl] = phiHbyA[sl] - (ic * pc - bc) / FV_ALPHA_B;
+            }
+        }
+    }
+}
+
+// continuityErrs.H (contErr = fvc::ddt(alphac) + fvc::div(alphacf*phic)) and
+// Uc = HbyA + rAUc*fvc::reconstruct((phicForces - pEqn.flux()/alphacf)/rAUcf)      pim/continuityErrs.H, pEqn.H:43-45
+__global__ void __launch_bounds__(BLK)
+k_pim_correct_U(BoxGeom g, double dt, double rDeltaT, int corr, const double* __restrict__ phi, const double* __restrict__ p,
+                const double* __restrict__ upP, const double* __restrict__ phicForces, const double* __restrict__ HbyA,
+                const double* __restrict__ rAU, const double* __restrict__ alpha, const double* __restrict__ alpha0,
+                double* __restrict__ U, FvRed red, FvStepDev* out)
+{
+    double sums[2] = {0.0, 0.0};
+    FV_CELL_LOOP(g, c) {
+        int i, j, k;
+        fvIJK(g, c, i, j, k);
+        const double e = rDeltaT * (alpha[c] - alpha0[c]) + fvDivAlphaCell(g, alpha, phi, c, i, j, k);
+        sums[0] += fabs(e) * g.V;
+        sums[1] += e * g.V;
+        const double rc = rAU[c], pc = p[c];
+        auto face = [&](int d, int hi, double& nHat, double& area, double& ssf) -> bool {
+            const int v = fvIdx(d, i, j, k), nd = fvN(g, d), sd = fvStride(g, d);
+            const bool bnd = hi ? (v == nd - 1) : (v == 0);
+            if (!bnd) {
+                const int P = hi ? c : c - sd, Nb = hi ? c + sd : c;
+                const double u = upP[d * g.N + P];
+                const double fluxByA = (u * p[Nb] - u * p[P]) / fvLerp(g.w[d], alpha[P], alpha[Nb]);
+                nHat = g.Sf[d] / g.magSf[d];
+                area = g.Sf[d];
+                ssf = (phicForces[d * g.N + P] - fluxByA) / fvLerp(g.w[d], rAU[P], rAU[Nb]);
+                return true;
+            }
+            const int s = 2 * d + hi;
+            if (g.kindU[s] == FV_EMPTY) return false;
+            double ic, bc;
+            fvBCoefP(g, s, FV_ALPHA_B * rc, ic, bc);
+            nHat = g.bSf[s] / g.bMagSf[s];
+            area = g.bSf[s];
+            ssf = (phicForces[fvSideSlot(g, s, c, i, j, k)] - (ic * pc - bc) / FV_ALPHA_B) / rc;
+            return true;
+        };
+        double r[3];
+        fvReconstruct(g, face, r);
+#pragma unroll
+        for (int m = 0; m < 3; ++m) U[3 * (size_t)c + m] = HbyA[3 * (size_t)c + m] + rc * r[m];
+    }
+    const double sumV = g.sumV;
+    fvGridReduce<2, false, BLK>(sums, red, [=](const double* t) {
+        out->sumLocal = dt * (t[0] / sumV);
+        out->global = dt * (t[1] / sumV);
+        if (corr < 8) { out->corrSumLocal[corr] = out->sumLocal; out->corrGlobal[corr] = out->global; }
+    });
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 #define FV_LAUNCH(kernel, grid, ...)                                                        \
@@ -631,6 +1165,34 @@ int fvFacesToSlots(fy_ctx* h, FvState* s, int n, const double* dFaces, double* d
 int fvSlotsToFaces(fy_ctx* h, FvState* s, int n, const double* dSlots, double* dFaces)
 {
     FV_LAUNCH(k_slots_to_faces, s->cellGrid, n, s->dSlotOfFace, dSlots, dFaces);
+    return FY_OK;
+}
+
+int fvDivPhiVector(fy_ctx* h, FvState* s, const double* dPhiSlots, const double* dU, double* dOut)
+{
+    FV_LAUNCH(k_div_phi_vector, s->cellGrid, s->g, dPhiSlots, dU, dOut);
+    return FY_OK;
+}
+int fvLaplacianGammaVector(fy_ctx* h, FvState* s, double scale, const double* dGamma, double gammaB, const double* dU,
+                           double* dOut)
+{
+    FV_LAUNCH(k_laplacian_gamma_vector, s->cellGrid, s->g, scale, dGamma, gammaB, dU, dOut);
+    return FY_OK;
+}
+
+// pimpleFoamYade.C:71-76: CourantNo, then the four fields FoamYade's Gaussian branch reads --
+//   ddtU_f = fvc::ddt(Uc) + fvc::div(phic, Uc)   gradP = fvc::grad(p)
+//   divT   = 2 nu fvc::laplacian(alphac, Uc)     vGrad = fvc::grad(Uc)
+// fvc::ddt(Uc) is taken before Uc changes in the new time step, when GeometricField::oldTime() has just stored
+// Uc.oldTime() := Uc, so the Euler term is rDeltaT*(Uc - Uc) = +0 and ddtU_f == fvc::div(phic, Uc) bit for bit.
+int fvPimplePre(fy_ctx* h, FvState* s, double dt)
+{
+    const double* U = h->dField[FY_F_U];
+    FV_LAUNCH(k_courant, s->cellGrid, s->g, s->phi, dt, s->red, s->dStep);
+    FV_LAUNCH(k_div_phi_vector, s->cellGrid, s->g, s->phi, U, h->dField[FY_F_DDTU]);
+    FV_LAUNCH(k_grad_scalar, s->cellGrid, s->g, h->dField[FY_F_P], h->dField[FY_F_GRADP]);
+    FV_LAUNCH(k_laplacian_gamma_vector, s->cellGrid, s->g, 2 * s->nu, h->dField[FY_F_ALPHA], 1.0, U, h->dField[FY_F_DIVT]);
+    FV_LAUNCH(k_grad_vector, s->cellGrid, s->g, U, h->dField[FY_F_VGRAD]);
     return FY_OK;
 }
 
@@ -708,6 +1270,104 @@ int fvIcoSolve(fy_ctx* h, FvState* s, double dt)
     h->phaseMs[6] = msMom;
     h->phaseMs[7] = msP;
     s->stats.pad_ = 0;
+    FY_CUDA(cudaMemcpyAsync(s->hStep, s->dStep, sizeof(FvStepDev), cudaMemcpyDeviceToHost, h->stream));
+    FY_CUDA(cudaStreamSynchronize(h->stream));
+    if (g.pNeedRef && s->hStep->adjustFail) {
+        h->err = "adjustPhi: continuity error cannot be removed by adjusting the outflow";
+        return FY_ERR_NOT_CONVERGED;
+    }
+    s->stats.CoNum = s->hStep->CoNum;
+    s->stats.meanCoNum = s->hStep->meanCoNum;
+    s->stats.sumLocalContErr = s->hStep->sumLocal;
+    s->stats.globalContErr = s->hStep->global;
+    for (int q = 0; q < 8; ++q) {
+        s->stats.corrSumLocal[q] = s->hStep->corrSumLocal[q];
+        s->stats.corrGlobal[q] = s->hStep->corrGlobal[q];
+    }
+    for (int q = 0; q < ctl.nCorrectors && q < 8; ++q) s->cumulativeContErr += s->hStep->corrGlobal[q];
+    s->stats.cumulativeContErr = s->cumulativeContErr;
+    s->fluidMs[0] = msMom; s->fluidMs[1] = msP; s->fluidMs[2] = msOther;
+    return FY_OK;
+}
+
+// pimpleFoamYade.C:82-104 (one outer corrector): alphacf / alphaPhic, UcEqn.H, the PISO loop over pEqn.H, continuityErrs.H.
+// Reads the coupling operator's device fields alpha, uSource, uSourceDrag; alphac.oldTime() == alphac (see the oracle).
+int fvPimpleSolve(fy_ctx* h, FvState* s, double dt, const double gvec[3])
+{
+    const BoxGeom& g = s->g;
+    const int N = g.N, G = s->cellGrid;
+    const double rDeltaT = 1.0 / dt;
+    double* U = h->dField[FY_F_U];
+    double* p = h->dField[FY_F_P];
+    const double* alpha = h->dField[FY_F_ALPHA];
+    const double* alpha0 = alpha;
+    const fy_piso_controls& ctl = s->ctl;
+    int rc;
+    cudaEvent_t* ev = h->ev;
+    float msMom = 0, msP = 0, msOther = 0, tmp = 0;
+    s->stats.nPSolves = 0;
+    for (auto& u : s->stats.U) u = fy_solver_perf{0, 0, 0, 0};
+    if (!s->phicForces) {
+        FY_CUDA(cudaMalloc((void**)&s->phicForces, (size_t)g.nSlots * sizeof(double)));
+        FY_CUDA(cudaMalloc((void**)&s->divDev, 3 * (size_t)N * sizeof(double)));
+    }
+
+    cudaEventRecord(ev[0], h->stream);
+    FY_CUDA(cudaMemcpyAsync(s->U0, U, 3 * (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    FY_CUDA(cudaMemcpyAsync(s->phi0, s->phi, (size_t)g.nSlots * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    FV_LAUNCH(k_grad_vector, G, g, U, h->dField[FY_F_VGRAD]);
+    FV_LAUNCH(k_pim_div_dev, G, g, s->nu, alpha, U, h->dField[FY_F_VGRAD], s->divDev);
+    FV_LAUNCH(k_pim_assemble_U, G, g, s->nu, rDeltaT, s->phi, alpha, alpha0, s->U0, h->dField[FY_F_USOURCEDRAG], s->divDev,
+              s->diagU, s->loU, s->upU, s->srcU, s->dgU, s->rAU);
+    FV_LAUNCH(k_pim_forces, G, g, gvec[0], gvec[1], gvec[2], s->rAU, h->dField[FY_F_USOURCE], s->phicForces);
+    if (ctl.momentumPredictor) {
+        FV_LAUNCH(k_pim_predictor_source, G, g, s->phicForces, s->rAU, p, s->gradP);
+        FV_LAUNCH(k_usolve_setup, G, g, FV_ALPHA_B * s->nu, s->phi, s->srcU, s->gradP, U, s->bU, s->psiU);
+        if ((rc = fvSmoothSetMatrix(h, s, s->loU, s->upU))) return rc;
+        for (int m = 0; m < 3; ++m) {
+            if (!g.valid[m]) continue;
+            if ((rc = fvSmoothSolve(h, s, s->dgU + (size_t)m * N, s->bU + (size_t)m * N, s->psiU + (size_t)m * N, ctl.UTol,
+                                    ctl.URelTol, ctl.maxIter, &s->stats.U[m])))
+                return rc;
+            FV_LAUNCH(k_store_component, G, N, s->psiU + (size_t)m * N, m, U);
+        }
+    }
+    cudaEventRecord(ev[1], h->stream);
+    for (int corr = 1; corr <= ctl.nCorrectors; ++corr) {
+        cudaEventRecord(ev[2], h->stream);
+        FV_LAUNCH(k_HbyA, G, g, FV_ALPHA_B * s->nu, s->phi0, s->loU, s->upU, s->srcU, U, s->rAU, s->HbyA);
+        FV_LAUNCH(k_pim_phiHbyA, G, g, rDeltaT, s->HbyA, s->U0, s->phi0, s->rAU, alpha, s->phiHbyA, s->upP);
+        if (g.pNeedRef) {
+            FV_LAUNCH(k_adjust_sum, G, g, s->phiHbyA, s->red, s->dStep);
+            FV_LAUNCH(k_adjust_scale, G, g, s->phiHbyA, s->dStep);
+        }
+        FV_LAUNCH(k_pim_add_forces, G, g.nSlots, s->phicForces, s->phiHbyA);
+        cudaEventRecord(ev[3], h->stream);
+        for (int nonOrth = 0; nonOrth <= ctl.nNonOrthogonalCorrectors; ++nonOrth) {
+            FV_LAUNCH(k_pim_pEqn, G, g, ctl.pRefCell, ctl.pRefValue, rDeltaT, s->upP, s->phiHbyA, s->rAU, alpha, alpha0, s->dgP,
+                      s->bP);
+            const bool fin = corr == ctl.nCorrectors && nonOrth == ctl.nNonOrthogonalCorrectors;
+            fy_solver_perf perf{0, 0, 0, 0};
+            if ((rc = fvPcgSolve(h, s, s->dgP, s->upP, s->bP, p, fin ? ctl.pFinalTol : ctl.pTol,
+                                 fin ? ctl.pFinalRelTol : ctl.pRelTol, ctl.maxIter, ctl.preconditioner, &perf)))
+                return rc;
+            if (s->stats.nPSolves < 8) s->stats.p[s->stats.nPSolves] = perf;
+            s->stats.nPSolves++;
+            if (nonOrth == ctl.nNonOrthogonalCorrectors)
+                FV_LAUNCH(k_pim_flux_update, G, g, s->upP, s->phiHbyA, p, s->rAU, alpha, s->phi);
+        }
+        cudaEventRecord(ev[4], h->stream);
+        FV_LAUNCH(k_pim_correct_U, G, g, dt, rDeltaT, corr - 1, s->phi, p, s->upP, s->phicForces, s->HbyA, s->rAU, alpha, alpha0,
+                  U, s->red, s->dStep);
+        cudaEventRecord(ev[5], h->stream);
+        FY_CUDA(cudaEventSynchronize(ev[5]));
+        cudaEventElapsedTime(&tmp, ev[2], ev[3]); msOther += tmp;
+        cudaEventElapsedTime(&tmp, ev[3], ev[4]); msP += tmp;
+        cudaEventElapsedTime(&tmp, ev[4], ev[5]); msOther += tmp;
+    }
+    cudaEventElapsedTime(&msMom, ev[0], ev[1]);
+    h->phaseMs[6] = msMom;
+    h->phaseMs[7] = msP;
     FY_CUDA(cudaMemcpyAsync(s->hStep, s->dStep, sizeof(FvStepDev), cudaMemcpyDeviceToHost, h->stream));
     FY_CUDA(cudaStreamSynchronize(h->stream));
     if (g.pNeedRef && s->hStep->adjustFail) {
@@ -852,6 +1512,21 @@ int fvCreate(fy_ctx* h, const fy_mesh_desc* m)
     g.pNeedRef = 1;
     for (int q = 0; q < 6; ++q)
         if (g.kindP[q] == FV_FIXED_VALUE) g.pNeedRef = 0;
+    {
+        // tensorField inv() decides from cell 0's surfaceSum(SfHat*Sf) which directions to remove [OF-6 tensorField.C]
+        double T[3], scale = 0;
+        for (int d = 0; d < 3; ++d) {
+            const int nd = d == 0 ? nx : (d == 1 ? ny : nz);
+            T[d] = 0;
+            if (nd > 1) T[d] += (g.Sf[d] / g.magSf[d]) * g.Sf[d];
+            for (int hi = 0; hi < 2; ++hi) {
+                const int sd = 2 * d + hi;
+                if ((hi == 0 || nd == 1) && g.kindU[sd] != FV_EMPTY) T[d] += (g.bSf[sd] / g.bMagSf[sd]) * g.bSf[sd];
+            }
+            scale += T[d] * T[d];
+        }
+        for (int d = 0; d < 3; ++d) g.reconRm[d] = (T[d] * T[d]) / scale < FV_SMALL ? 1 : 0;
+    }
     s->hSlotOfFace.insert(s->hSlotOfFace.end(), bslot.begin(), bslot.end());
 
     // device buffers
@@ -889,7 +1564,7 @@ void fvDestroy(fy_ctx* h)
     FvState* s = h->fv;
     if (!s) return;
     void* ptrs[] = {s->dSlotOfFace, s->phi, s->phi0, s->phiHbyA, s->U0, s->HbyA, s->rAU, s->gradP, s->diagU, s->loU, s->upU,
-                    s->srcU, s->dgU, s->bU, s->psiU, s->upP, s->dgP, s->bP, s->stage,
+                    s->srcU, s->dgU, s->bU, s->psiU, s->upP, s->dgP, s->bP, s->stage, s->phicForces, s->divDev,
                     s->red.partial, s->red.ticket, s->dSolve, s->dStep};
     for (void* p : ptrs) if (p) cudaFree(p);
     penDestroy(s);

@@ -35,6 +35,7 @@ struct BoxGeom {
     int seq[6];              // sides in boundary-list (patch) order
     int valid[3];            // solved vector components (an EMPTY side pair removes its direction)
     int pNeedRef;
+    int reconRm[3];          // fvc::reconstruct: directions tensorField inv() removes (no faces: empty patch pair)
     double sumV;             // sum of cell volumes, accumulated sequentially like the CPU loop
 };
 

@@ -71,6 +71,8 @@ struct FvState {
     double *dgU = nullptr, *bU = nullptr, *psiU = nullptr;
     // pEqn
     double *upP = nullptr, *dgP = nullptr, *bP = nullptr;
+    // pimpleFoamYade extras (allocated by the first fy_pimple_solve): phicForces [slots], explicit stress term [N][3]
+    double *phicForces = nullptr, *divDev = nullptr;
     // scratch for the parity hooks (LDU-order staging)
     double *stage = nullptr;
     size_t stageCap = 0;
@@ -109,6 +111,11 @@ int fvGradScalar(fy_ctx* h, FvState* s, const double* dP, double* dOut);
 int fvDivFlux(fy_ctx* h, FvState* s, const double* dPhiSlots, double* dOut);
 int fvFacesToSlots(fy_ctx* h, FvState* s, int n, const double* dFaces, double* dSlots);
 int fvSlotsToFaces(fy_ctx* h, FvState* s, int n, const double* dSlots, double* dFaces);
+int fvDivPhiVector(fy_ctx* h, FvState* s, const double* dPhiSlots, const double* dU, double* dOut);
+int fvLaplacianGammaVector(fy_ctx* h, FvState* s, double scale, const double* dGamma, double gammaB, const double* dU,
+                           double* dOut);
 int fvIcoPre(fy_ctx* h, FvState* s, double dt);
+int fvPimplePre(fy_ctx* h, FvState* s, double dt);
+int fvPimpleSolve(fy_ctx* h, FvState* s, double dt, const double gvec[3]);
 int fvIcoSolve(fy_ctx* h, FvState* s, double dt);
 void fvDestroy(fy_ctx* h);
