@@ -35,6 +35,8 @@ WORKLOADS = {
     "C1": (32, 32, 32, 1000, 42, "cavity", 5e-3, 0.01, "icoFoamYade lid-driven cavity 32^3 cells, 1k particles"),
     "C2": (128, 128, 128, 1000000, 7, "channel", 5e-3, 1e-6, "icoFoamYade channel 128^3 cells, 1M particles, fp64, 1xB200"),
     "C2s": (64, 64, 64, 125000, 7, "channel", 1e-2, 1e-6, "icoFoamYade channel 64^3 cells, 125k particles (reduced C2)"),
+    "C3": (256, 256, 256, 10000000, 1001, "channel", 2.5e-3, 1e-6, "pimpleFoamYade channel 256^3 cells, 10M particles, void fraction + UcEqn/pEqn, fp64, 1xB200 (use --solver pimple)"),
+    "C3s": (128, 128, 128, 1000000, 1001, "channel", 5e-3, 1e-6, "pimpleFoamYade channel 128^3 cells, 1M particles (reduced C3; use --solver pimple)"),
     "C2p": (128, 128, 128, 10000000, 7, "channel", 5e-3, 1e-6, "icoFoamYade channel 128^3 cells, 10M particles (particle-bound, for --partition particles)"),
 }
 UIN = 0.3
@@ -178,25 +180,30 @@ def run_engine(args):
     h_force = torch.empty(P, 6, dtype=torch.float64).pin_memory()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
+    pimple = args.solver == "pimple"
+    if pimple and not gaussian:
+        raise SystemExit("bench.py: pimpleFoamYade constructs the operator with gaussianInterp = true (pimpleFoamYade.C:53)")
+    fluid_pre = E.pimple_pre if pimple else E.ico_pre
+    fluid_solve = E.pimple_solve if pimple else E.ico_solve
     S = None
     if sharded:
         S = pkg.sharded.ShardedCoupling(E, dist, pkg.sharded.device_views(E), gaussian, pkg.sharded.external_stream_ctx(E))
 
     def step_device():
         if fluid:
-            E.ico_pre(dt)
+            fluid_pre(dt)
         if S is not None:
             S.step(dt, d_pd.data_ptr(), P, d_found.data_ptr(), d_force.data_ptr())
         else:
             E.coupling_begin(dt)
             E.coupling_proc_device(d_pd.data_ptr(), P, d_found.data_ptr(), d_force.data_ptr())
         if fluid:
-            E.ico_solve(dt)
+            fluid_solve(dt)
         E.set_source_zero()
 
     def step_e2e():
         if fluid:
-            E.ico_pre(dt)
+            fluid_pre(dt)
         if S is not None:
             with S.stream_ctx():
                 d_pd.copy_(h_pd, non_blocking=True)
@@ -208,7 +215,7 @@ def run_engine(args):
             L.fy_set_particle_action(E.h, dt, ctypes.c_void_p(h_pd.data_ptr()), P, ctypes.c_void_p(h_found.data_ptr()),
                                      ctypes.c_void_p(h_force.data_ptr()))
         if fluid:
-            E.ico_solve(dt)
+            fluid_solve(dt)
         E.set_source_zero()
         E.synchronize()
 
@@ -262,13 +269,13 @@ def run_engine(args):
         flush.fill_(1)
         torch.cuda.synchronize()
         if fluid:
-            E.ico_pre(dt)
+            fluid_pre(dt)
         E.coupling_begin(dt)
         L.fy_coupling_proc(E.h, ctypes.c_void_p(h_pd.data_ptr()), P, ctypes.c_void_p(h_found.data_ptr()),
                            ctypes.c_void_p(h_force.data_ptr()))
         phase += E.phase_ms()
         if fluid:
-            E.ico_solve(dt)
+            fluid_solve(dt)
             fl_ms += E.fluid_ms()
         E.set_source_zero()
     phase /= nprof
@@ -311,6 +318,7 @@ def run_engine(args):
             "config": {"workload": "%s: %s" % (wl, desc), "cells": N, "internal_faces": Fi, "particles_per_gpu": P,
                        "particles_total": P_total if sharded else P * world,
                        "coupling": args.coupling, "fluid_solve": bool(fluid), "flow": flow, "dt": dt, "nu": nu,
+                       "solver": ("pimpleFoamYade (UcEqn.H/pEqn.H, nOuterCorrectors 1, laminar)" if pimple else "icoFoamYade"),
                        "fvSolution": "PISO nCorrectors 2; p PCG/DIC 1e-06 relTol 0.05 (pFinal 0); U smoothSolver symGaussSeidel 1e-05",
                        "l2": "flushed between timed steps (256 MiB write)",
                        "partition": ("one domain, particle buffer sharded over the GPUs, NCCL all-reduce of the cell sums, fluid solve replicated"
@@ -339,9 +347,9 @@ def run_engine(args):
                 # the same step (same start fields, same particle sample) on the engine: parity at the full mesh size
                 Ps = ref_out["pd"].shape[0]
                 E.upload("U", state["U"]); E.upload("p", state["p"]); E.upload("phi", state["phi"])
-                E.ico_pre(dt)
+                fluid_pre(dt)
                 fe, Fe = E.set_particle_action(dt, ref_out["pd"])
-                E.ico_solve(dt)
+                fluid_solve(dt)
                 E.set_source_zero()
                 st = E.ico_stats()
                 line["parity_full_size"] = {
@@ -388,9 +396,14 @@ def cpu_baseline(args, state=None, steps=1, warmup=0, out=None):
             O.create_phi()
     t_cpl = t_fl = 0.0
     iters = []
+    pimple = getattr(args, "solver", "ico") == "pimple"
     for it in range(warmup + steps):
         t0 = time.time()
-        if fluid:
+        if fluid and pimple:
+            ddtU, gradP, divT, vGrad = O.pimple_pre(dt, R.field("alpha").reshape(-1))
+            for k, v in (("U", O.field("U")), ("ddtU", ddtU), ("gradP", gradP), ("divT", divT), ("vGrad", vGrad)):
+                R.field(k)[:] = v.reshape(R.field(k).shape)
+        elif fluid:
             O.pre(dt)
             R.field("U")[:] = O.field("U")
             R.field("vGrad")[:] = O.field("vGrad")
@@ -398,9 +411,13 @@ def cpu_baseline(args, state=None, steps=1, warmup=0, out=None):
         found_cpu, force_cpu = R.step(dt, pd, pieces=True, truncate12=True, dense=True)
         if fluid:
             O.field("uSource")[:] = R.field("uSource")
+        if pimple:
+            alpha_c, drag_c = R.field("alpha").reshape(-1).copy(), R.field("uSourceDrag").reshape(-1).copy()
         R.set_source_zero()
         t2 = time.time()
-        if fluid:
+        if fluid and pimple:
+            O.pimple_solve(dt, alpha_c, drag_c)
+        elif fluid:
             O.solve(dt)
         t3 = time.time()
         if it >= warmup:
@@ -443,7 +460,8 @@ def run_reference(args):
         "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": "%s: %s" % (args.workload, desc), "cells": nx * ny * nz, "particles_per_gpu": P,
-                   "coupling": args.coupling, "fluid_solve": not args.coupling_only, "flow": flow, "dt": dt, "nu": nu},
+                   "coupling": args.coupling, "fluid_solve": not args.coupling_only, "flow": flow, "dt": dt, "nu": nu,
+                   "solver": args.solver},
         "cpu_baseline": cb,
         "e2e": {"value": v, "unit": "coupled timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
@@ -456,6 +474,8 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--coupling", default="gaussian", choices=["gaussian", "point"])
+    ap.add_argument("--solver", default="ico", choices=["ico", "pimple"],
+                    help="fluid step: icoFoamYade (default, the headline) or pimpleFoamYade (UcEqn.H/pEqn.H; Gaussian coupling)")
     ap.add_argument("--coupling-only", action="store_true")
     ap.add_argument("--partition", default="replicas", choices=["replicas", "particles"],
                     help="N > 1: independent domain replicas (weak scaling, default) or one domain with the particle "
