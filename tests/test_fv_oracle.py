@@ -126,6 +126,75 @@ def test_pimple_pre_operators_are_exact_on_polynomials():
     O.close()
 
 
+def test_pimple_explicit_stress_and_reconstruct_closed_forms():
+    """fvc::div((alpha nu) dev2(T(grad U))) and fvc::reconstruct on fields the discretisation reproduces exactly two cells
+    away from the walls (the patch values of grad(U) carry the wall's fixedValue)."""
+    m = _mesh3d((9, 8, 7))
+    O = port.IcoOracle(m, nu=0.02)
+    C = m["C"]
+    N = len(C)
+    nx, ny, nz = m["n"]
+    idx = np.arange(N).reshape(nz, ny, nx)[2:-2, 2:-2, 2:-2].reshape(-1)
+    A = np.array([[0.3, -1.0, 2.0], [0.7, 0.2, -0.4], [1.5, 0.0, 0.9]])
+    assert np.abs(O.div_dev(np.ones(N), C @ A, 0.02)[idx]).max() < 1e-12          # constant stress: no divergence
+    U = np.stack([C[:, 0] * C[:, 1], np.zeros(N), np.zeros(N)], 1)             # T(grad U): xx = y, xy = x ; tr = y
+    d = O.div_dev(np.ones(N), U, 0.02)[idx]                                   # div_y = d_x(x) + d_y(-2y/3) = 1/3
+    np.testing.assert_allclose(d, np.broadcast_to([0.0, 0.02 / 3.0, 0.0], d.shape), rtol=0, atol=1e-12)
+    a = np.array([0.3, -0.2, 0.5])
+    O.field("U")[:] = a
+    O.create_phi()
+    r = O.reconstruct(np.asarray(O.field("phi")).copy())                      # reconstruct(a . Sf) = a
+    idx1 = np.arange(N).reshape(nz, ny, nx)[1:-1, 1:-1, 1:-1].reshape(-1)
+    np.testing.assert_allclose(r[idx1], np.broadcast_to(a, (idx1.size, 3)), rtol=0, atol=1e-14)
+    O.close()
+
+
+def test_pimple_step_reduces_to_icoFoam_and_conserves_mass():
+    """pimpleSolve (pim/UcEqn.H, pEqn.H) with alphac = 1 and no particle sources is icoFoam's equation in another
+    pressure-gradient form: from rest the first step is icoFoam's to round-off (the stock cavity log's numbers), later
+    steps agree at first order in h.  With a non-uniform void fraction, implicit drag and a source,
+    fvc::div(alphacf*phic) closes to the solver tolerance."""
+    one = zero = None
+    err = []
+    for n in (10, 20):
+        mc = cavity_mesh(n)
+        Oi, Op = port.IcoOracle(mc, nu=0.01), port.IcoOracle(mc, nu=0.01)
+        one, zero = np.ones(mc["nCells"]), np.zeros(mc["nCells"])
+        dt = 0.005 * 20 / n
+        for O_ in (Oi, Op):
+            O_.create_phi()
+        for it in range(int(round(0.05 / dt))):
+            Oi.pre(dt)
+            Oi.solve(dt)
+            Op.pre(dt)
+            Op.pimple_solve(dt, one, zero)
+            if it == 0:
+                assert np.linalg.norm(Oi.field("U") - Op.field("U")) <= 1e-12 * np.linalg.norm(Oi.field("U"))
+                assert np.linalg.norm(Oi.field("p") - Op.field("p")) <= 1e-11 * np.linalg.norm(Oi.field("p"))
+                if n == 20:
+                    so = Op.stats()
+                    assert (sig6(so["p"][0]["final"]), so["p"][0]["iters"]) == CAVITY_LOG[0]["p1"][1:]
+                    assert (sig6(so["p"][1]["final"]), so["p"][1]["iters"]) == CAVITY_LOG[0]["p2"][1:]
+        err.append(np.linalg.norm(Oi.field("U") - Op.field("U")) / np.linalg.norm(Oi.field("U")))
+        assert not np.any(Op.field("U")[:, 2])                                  # the empty direction stays empty
+        Oi.close()
+        Op.close()
+    assert err[1] < 0.04 and err[1] < 0.65 * err[0]
+    m = meshgen.hex_box_ldu(10, 8, 6, 1.0, 0.8, 0.6, patches=[("walls", ["xmin", "xmax", "ymin", "ymax", "zmin", "zmax"])])
+    O = port.IcoOracle(m, nu=0.01)
+    C = m["C"]
+    O.field("U")[:] = 0.1 * np.stack([np.sin(3 * C[:, 1]), np.cos(2 * C[:, 0]), 0 * C[:, 0]], 1)
+    O.create_phi()
+    alpha = 1 - 0.4 * np.exp(-((C - 0.4) ** 2).sum(1) / 0.05)
+    O.field("uSource")[:] = np.stack([0 * alpha, -0.8 * (1 - alpha), 0.2 * (1 - alpha)], 1)
+    for it in range(3):
+        O.pimple_solve(2e-3, alpha, -50.0 * (1 - alpha))
+        st = O.stats()
+        assert st["sumLocalContErr"] < 5e-9 and abs(st["globalContErr"]) < 5e-9
+        assert np.all(np.isfinite(O.field("U"))) and np.abs(O.field("U")).max() < 1.0
+    O.close()
+
+
 def _ldu_dense(m, diag, lower, upper):
     N = m["nCells"]
     A = np.zeros((N, N))
