@@ -28,6 +28,9 @@ constexpr int PEN_D = 8;                      // rows per flow-control block / h
 #ifndef PEN_DEPTH
 #define PEN_DEPTH 8
 #endif
+#ifndef PEN_YPRED
+#define PEN_YPRED 1            // re-arm the y slot with a predicated store instead of a one-lane branch (2 % on B200)
+#endif
 #ifndef PEN_FBLOCK
 #define PEN_FBLOCK 8
 #endif
@@ -61,6 +64,11 @@ __device__ __forceinline__ double ldSharedV(uint32_t p)
 __device__ __forceinline__ void stSharedV(uint32_t p, double v)
 {
     asm volatile("st.volatile.shared.f64 [%0], %1;" ::"r"(p), "d"(v));
+}
+// predicated store: no branch, so a one-lane store does not split the warp
+__device__ __forceinline__ void stSharedVIf(bool on, uint32_t p, double v)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q st.volatile.shared.f64 [%1], %2;\n\t}" ::"r"((unsigned)on), "r"(p), "d"(v));
 }
 __device__ __forceinline__ double ldPoll(const double* p)
 {
@@ -405,8 +413,15 @@ __device__ __forceinline__ void penSweep(const Op& op, const PenWarp& w, double&
         if (YIN) {
             double v = vyN;
             int spin = 0;
+#if PEN_YPRED
+            if (w.edge && isSent(v)) {                     // only the edge lane owns the slot; rare (the helper runs 32 rows ahead)
+                do { v = ldSharedV(w.yInS + ys * 8); } while (isSent(v) && ++spin < PEN_SPIN_LIMIT);
+            }
+            stSharedVIf(w.edge, w.yInS + ys * 8, sentValue());
+#else
             while (w.edge && isSent(v) && ++spin < PEN_SPIN_LIMIT) v = ldSharedV(w.yInS + ys * 8);   // only the edge lane owns the slot
             if (w.edge) stSharedV(w.yInS + ys * 8, sentValue());
+#endif
             vyN = ldSharedV(w.yInS + ysN * 8);
             vy = w.edge ? v : vy;
         }
@@ -495,7 +510,7 @@ __device__ __forceinline__ void penHelpY(const double* yRow0, uint32_t chanS, in
 }
 
 template <class Op, bool REV>
-__global__ void __launch_bounds__(32 * (2 * PEN_WMAX + 1)) k_pencil(PencilGeom g, Op op, PenCtl ctl)
+__global__ void __launch_bounds__(32 * (2 * PEN_WMAX + 1), 1) k_pencil(PencilGeom g, Op op, PenCtl ctl)
 {
     constexpr int NIN = Op::NIN, D = penDepth(Op::NIN), CD = PEN_CD;
     constexpr unsigned int FULL = 0xffffffffu;
