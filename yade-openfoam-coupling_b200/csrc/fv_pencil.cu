@@ -485,9 +485,10 @@ __device__ __forceinline__ void penHelpZ(const double* zRow0, uint32_t chanS, in
 
 // Y helpers: one warp per compute warp.  It fetches the y-neighbour of the plane's edge lane -- the last lane
 // of the neighbouring j-block's rows, another CTA's output in L2 -- 32 rows at a time: lane l polls row
-// 32b + l on its own and drops it into slot l of the plane's y channel as soon as the consumer has taken
-// the previous block's row from it.  Every lane waits independently, so a value is delivered one L2 round
-// trip after it was produced however close the two j-blocks run.
+// 32b + l and drops it into slot l of the plane's y channel as soon as the consumer has taken the previous
+// block's row from it.  Poll and hand-over are ONE loop: a lane whose row has arrived delivers it in the same
+// trip while the other lanes keep polling (two loops in a row would park the early lanes at the first loop's
+// reconvergence point until the block's last row exists, i.e. add up to 31 row times to every j-block hop).
 template <bool REV>
 __device__ __forceinline__ void penHelpY(const double* yRow0, uint32_t chanS, int Tp, int& fail, unsigned napNs)
 {
@@ -498,14 +499,17 @@ __device__ __forceinline__ void penHelpY(const double* yRow0, uint32_t chanS, in
         const double* a = yRow0 + (long long)(b0 + lane) * RS;
         double v = ldPoll(a);
         int spin = 0;
-        while (isSent(v) && !fail) {
-            if (napNs) __nanosleep(napNs);                 // the row is still being produced: do not hog the LSU
-            v = ldPoll(a);
+        bool pending = true;
+        while (pending && !fail) {
+            if (isSent(v)) {
+                if (napNs) __nanosleep(napNs);             // the row is still being produced: do not hog the LSU
+                v = ldPoll(a);
+            } else if (isSent(ldSharedV(slot))) {
+                stSharedV(slot, v);
+                pending = false;
+            }
             if (++spin > PEN_SPIN_LIMIT) fail = 1;
         }
-        spin = 0;
-        while (!isSent(ldSharedV(slot)) && ++spin < PEN_SPIN_LIMIT) { if (napNs) __nanosleep(napNs); }
-        stSharedV(slot, v);
     }
 }
 
