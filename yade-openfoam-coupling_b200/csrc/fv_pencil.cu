@@ -858,19 +858,29 @@ k_pen_amul(PencilGeom g, PenMatrix M, const double* __restrict__ pA, double* __r
     });
 }
 
-// psi += alpha pA; rA -= alpha wA; finalResidual = sum|rA|/normFactor; PCG.C's loop condition
+// psi += alpha pA; rA -= alpha wA; finalResidual = sum|rA|/normFactor; PCG.C's loop condition.
+// A pure vector update: it runs over the arrays as flat streams of double2 (the pads of every vector are zero and stay
+// zero, so they add nothing to the sum), with no cell decoding at all.
 __global__ void __launch_bounds__(BLK)
-k_pen_update(PencilGeom g, const double* __restrict__ pA, const double* __restrict__ wA, double* __restrict__ psi,
-             double* __restrict__ rA, FvRed red, FvSolveDev* st)
+k_pen_update(PencilGeom g, const double2* __restrict__ pA, const double2* __restrict__ wA, double2* __restrict__ psi,
+             double2* __restrict__ rA, FvRed red, FvSolveDev* st)
 {
     if (st->done) return;
     const double alpha = st->alpha;
     double v[1] = {0.0};
-    PEN_ROW_LOOP(g, c) {
-        psi[c.pos] += alpha * pA[c.pos];
-        const double r = rA[c.pos] - alpha * wA[c.pos];
-        rA[c.pos] = r;
-        v[0] += fabs(r);
+    const long long n2 = g.NP >> 1, stride = (long long)gridDim.x * BLK;
+#pragma unroll 2
+    for (long long q = (long long)blockIdx.x * BLK + threadIdx.x; q < n2; q += stride) {
+        const double2 p = pA[q], w = wA[q];
+        double2 x = psi[q], r = rA[q];
+        x.x += alpha * p.x;
+        x.y += alpha * p.y;
+        r.x = r.x - alpha * w.x;
+        r.y = r.y - alpha * w.y;
+        psi[q] = x;
+        rA[q] = r;
+        v[0] += fabs(r.x);
+        v[0] += fabs(r.y);
     }
     fvGridReduce<1, false, BLK>(v, red, [=](const double* t) {
         st->finalRes = t[0] / st->normFactor;
@@ -967,6 +977,7 @@ int penCreate(fy_ctx* h, FvState* s)
     g.nJB = (b.ny + 31) / 32;
     g.Tp = ((b.nx + 31 + PEN_CY - 1) / PEN_CY) * PEN_CY;
     g.nRows = (long long)b.nz * g.nJB * g.Tp;
+    if (g.nRows * 32 >= (1LL << 31)) { h->err = "pencil layout: mesh too large for 32-bit row arithmetic"; return FY_ERR_INVALID; }
     g.NP = g.nRows * 32;
     g.zStride = (long long)g.nJB * g.Tp * 32;
     int dev = 0, sms = 148;
@@ -1074,7 +1085,8 @@ int fvPcgSolve(fy_ctx* h, FvState* s, const double* dg, const double* up, const 
         if (ev) cudaEventRecord(s->pev[3], h->stream);
         PEN_LAUNCH(k_pen_amul, g, M, v[V_PA], v[V_WA], s->red, s->dSolve);
         if (ev) cudaEventRecord(s->pev[4], h->stream);
-        PEN_LAUNCH(k_pen_update, g, v[V_PA], v[V_WA], v[V_X], v[V_RA], s->red, s->dSolve);
+        PEN_LAUNCH(k_pen_update, g, (const double2*)v[V_PA], (const double2*)v[V_WA], (double2*)v[V_X], (double2*)v[V_RA], s->red,
+                   s->dSolve);
         if (ev) cudaEventRecord(s->pev[5], h->stream);
         return FY_OK;
     };

@@ -46,8 +46,9 @@ struct PenCell {
 __device__ __forceinline__ PenCell penDecode(const PencilGeom& g, long long row, int lane)
 {
     PenCell c;
-    const int sb = (int)(row / g.Tp);
-    const int m = (int)(row - (long long)sb * g.Tp);
+    const int r32 = (int)row;                              // nRows < 2^31 (checked at creation): 32-bit divisions
+    const int sb = r32 / g.Tp;
+    const int m = r32 - sb * g.Tp;
     c.k = sb / g.nJB;
     const int jb = sb - c.k * g.nJB;
     c.lane = lane;
