@@ -101,9 +101,12 @@ def test_sweeps_across_clusters_and_helpers(pkg, monkeypatch, n, cluster, warps)
     O.close()
 
 
-@pytest.mark.parametrize("pre", ["DIC", "diagonal", "none"])
-def test_pcg_matches_oracle(pkg, pre):
-    mo, mp = cases_fv.cavity3d(pkg, (24, 20, 16))
+@pytest.mark.parametrize("pre,n", [("DIC", (24, 20, 16)), ("diagonal", (24, 20, 16)), ("none", (24, 20, 16)),
+                                   ("DIC", (33, 40, 6)), ("none", (65, 33, 3)), ("diagonal", (1, 70, 5))])
+def test_pcg_matches_oracle(pkg, pre, n):
+    """(33, ..), (65, ..): nx + 31 is a multiple of 32, so a slab's last row of the pencil layout holds real cells and the
+    row-blocked Amul's x-neighbours cross into the neighbouring slabs' pads."""
+    mo, mp = cases_fv.cavity3d(pkg, n)
     rng = np.random.default_rng(4)
     N, Fi = mo["nCells"], mo["nInternalFaces"]
     upper = rng.uniform(0.5, 1.5, Fi)              # negative-definite Laplacian-like matrix, as pEqn's

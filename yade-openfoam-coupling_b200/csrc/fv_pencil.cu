@@ -28,6 +28,9 @@ constexpr int PEN_D = 8;                      // rows per flow-control block / h
 #ifndef PEN_DEPTH
 #define PEN_DEPTH 8
 #endif
+#ifndef PEN_AMUL_R
+#define PEN_AMUL_R 8           // rows of a slab per warp and trip in the PCG's Amul (1 = the cell-by-cell kernel)
+#endif
 #ifndef PEN_YPRED
 #define PEN_YPRED 1            // re-arm the y slot with a predicated store instead of a one-lane branch (2 % on B200)
 #endif
@@ -858,6 +861,66 @@ k_pen_amul(PencilGeom g, PenMatrix M, const double* __restrict__ pA, double* __r
     });
 }
 
+// The same product with R consecutive rows of a slab per warp and trip: the rows share their x-neighbours (R+2 loads of
+// pA and R+1 of up[0] instead of 3R and 2R), the row decode is paid once, and ~12 R loads are in flight per warp.
+// A missing x-neighbour is a pad (value 0) behind a zero coefficient, so the x terms need no predicate (an exact "+ 0");
+// the y / z predicates only keep the addresses inside the arrays.  Same terms in the same order as penAmulCellSym.
+template <int R>
+__global__ void __launch_bounds__(BLK)
+k_pen_amul_rows(PencilGeom g, PenMatrix M, const double* __restrict__ pA, double* __restrict__ wA, FvRed red, FvSolveDev* st)
+{
+    if (st->done) return;
+    double v[1] = {0.0};
+    const int lane = threadIdx.x & 31;
+    const int nGroups = (int)(g.nRows / R);                // Tp is a multiple of 32: a group never straddles two slabs
+    const long long dYm = lane > 0 ? -33 : -(long long)g.Tp * 32 + 31 * 32 + 31;
+    const long long dYp = lane < 31 ? 33 : (long long)g.Tp * 32 - 31 * 32 - 31;
+    const double* __restrict__ dg = M.dg;
+    const double* __restrict__ u0 = M.up[0];
+    const double* __restrict__ u1 = M.up[1];
+    const double* __restrict__ u2 = M.up[2];
+    for (int grp = blockIdx.x * (BLK / 32) + (threadIdx.x >> 5); grp < nGroups; grp += gridDim.x * (BLK / 32)) {
+        const int row0 = grp * R;
+        const int sb = row0 / g.Tp, m0 = row0 - sb * g.Tp;
+        const int k = sb / g.nJB, jb = sb - k * g.nJB;
+        const int j = jb * 32 + lane;
+        if (j >= g.ny) continue;
+        const bool hasYm = j > 0, hasYp = j < g.ny - 1, hasZm = k > 0, hasZp = k < g.nz - 1;
+        const long long p0 = (long long)row0 * 32 + lane;
+        double xr[R + 2], cr[R + 1];
+#pragma unroll
+        for (int r = 0; r < R + 2; ++r) xr[r] = pA[p0 + (r - 1) * 32];
+#pragma unroll
+        for (int r = 0; r < R + 1; ++r) cr[r] = u0[p0 + (r - 1) * 32];
+        double a[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const long long p = p0 + r * 32;
+            double t = dg[p] * xr[r + 1];
+            if (hasZm) t += u2[p - g.zStride] * pA[p - g.zStride];
+            if (hasYm) t += u1[p + dYm] * pA[p + dYm];
+            t += cr[r] * xr[r];
+            t += cr[r + 1] * xr[r + 2];
+            if (hasYp) t += u1[p] * pA[p + dYp];
+            if (hasZp) t += u2[p] * pA[p + g.zStride];
+            a[r] = t;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = m0 + r - lane;
+            if (i >= 0 && i < g.nx) {
+                wA[p0 + r * 32] = a[r];
+                v[0] += a[r] * xr[r + 1];
+            }
+        }
+    }
+    fvGridReduce<1, false, BLK>(v, red, [=](const double* t) {
+        st->wApA = t[0];
+        if (fabs(t[0]) / st->normFactor < FV_VSMALL) { st->singular = 1; st->done = 1; }
+        else st->alpha = st->wArA / t[0];
+    });
+}
+
 // psi += alpha pA; rA -= alpha wA; finalResidual = sum|rA|/normFactor; PCG.C's loop condition.
 // A pure vector update: it runs over the arrays as flat streams of double2 (the pads of every vector are zero and stay
 // zero, so they add nothing to the sum), with no cell decoding at all.
@@ -1083,7 +1146,11 @@ int fvPcgSolve(fy_ctx* h, FvState* s, const double* dg, const double* up, const 
         if (ev) cudaEventRecord(s->pev[2], h->stream);
         PEN_LAUNCH(k_pen_dir, g, v[V_ZA], v[V_PA], s->dSolve);
         if (ev) cudaEventRecord(s->pev[3], h->stream);
+#if PEN_AMUL_R > 1
+        PEN_LAUNCH(k_pen_amul_rows<PEN_AMUL_R>, g, M, v[V_PA], v[V_WA], s->red, s->dSolve);
+#else
         PEN_LAUNCH(k_pen_amul, g, M, v[V_PA], v[V_WA], s->red, s->dSolve);
+#endif
         if (ev) cudaEventRecord(s->pev[4], h->stream);
         PEN_LAUNCH(k_pen_update, g, (const double2*)v[V_PA], (const double2*)v[V_WA], (double2*)v[V_X], (double2*)v[V_RA], s->red,
                    s->dSolve);
