@@ -299,7 +299,7 @@ def run_engine(args):
             # pencil-layout kernels: algorithmic bytes = 8 B x (streams read + written) per cell (kernels)
             cand["k_pencil<OpDicFwd> (DIC forward sweep)"] = (kms["precond_fwd"], 48.0 * N, it_step)       # rD rA low[3] -> y
             cand["k_pencil<OpDicBwd> (DIC backward sweep + wA.rA)"] = (kms["precond_bwd"], 64.0 * N, it_step)  # y rD up[3] rA -> z, re-arm y
-            cand["k_pen_amul"] = (kms["amul"], 72.0 * N, it_step)                                         # dg low[3] up[3] p -> w
+            cand["k_pen_amul_rows<8>"] = (kms["amul"], 48.0 * N, it_step)                                 # dg up[3] p -> w (symmetric: lower = the neighbours' upper)
             cand["k_pen_update"] = (kms["update"], 48.0 * N, it_step)                                     # p w x r -> x r
             cand["k_pen_dir"] = (kms["direction"], 32.0 * N, it_step)                                     # z p -> p, re-arm z
         # dominant = largest share of the step

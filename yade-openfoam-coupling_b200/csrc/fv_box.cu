@@ -1252,7 +1252,8 @@ int fvIcoSolve(fy_ctx* h, FvState* s, double dt)
             const bool fin = corr == ctl.nCorrectors && nonOrth == ctl.nNonOrthogonalCorrectors;
             fy_solver_perf perf{0, 0, 0, 0};
             if ((rc = fvPcgSolve(h, s, s->dgP, s->upP, s->bP, p, fin ? ctl.pFinalTol : ctl.pTol,
-                                 fin ? ctl.pFinalRelTol : ctl.pRelTol, ctl.maxIter, ctl.preconditioner, &perf)))
+                                 fin ? ctl.pFinalRelTol : ctl.pRelTol, ctl.maxIter, ctl.preconditioner, &perf,
+                                 s->stats.nPSolves > 0)))     // 1/A() is fixed for the step: every pEqn has the same matrix
                 return rc;
             if (s->stats.nPSolves < 8) s->stats.p[s->stats.nPSolves] = perf;
             s->stats.nPSolves++;
@@ -1349,7 +1350,8 @@ int fvPimpleSolve(fy_ctx* h, FvState* s, double dt, const double gvec[3])
             const bool fin = corr == ctl.nCorrectors && nonOrth == ctl.nNonOrthogonalCorrectors;
             fy_solver_perf perf{0, 0, 0, 0};
             if ((rc = fvPcgSolve(h, s, s->dgP, s->upP, s->bP, p, fin ? ctl.pFinalTol : ctl.pTol,
-                                 fin ? ctl.pFinalRelTol : ctl.pRelTol, ctl.maxIter, ctl.preconditioner, &perf)))
+                                 fin ? ctl.pFinalRelTol : ctl.pRelTol, ctl.maxIter, ctl.preconditioner, &perf,
+                                 s->stats.nPSolves > 0)))     // 1/A() is fixed for the step: every pEqn has the same matrix
                 return rc;
             if (s->stats.nPSolves < 8) s->stats.p[s->stats.nPSolves] = perf;
             s->stats.nPSolves++;

@@ -1105,14 +1105,19 @@ enum { V_B = 0, V_X, V_RD, V_D, V_RA, V_PA, V_WA, V_YA, V_ZA, V_BPRIME = V_RA, V
 // PCG on owner-slot coefficients (device pointers, natural cell order).  Iteration kernels are queued in
 // batches and test the device-side `done` flag themselves; the host looks at the state once per batch.
 int fvPcgSolve(fy_ctx* h, FvState* s, const double* dg, const double* up, const double* b, double* psi, double tol,
-               double relTol, int maxIter, int precond, fy_solver_perf* perf)
+               double relTol, int maxIter, int precond, fy_solver_perf* perf, bool sameMatrix)
 {
     PenState& P = s->pen;
     const PencilGeom& g = P.g;
     int rc;
     PenMatrix M = penMatrixOf(P, 0);
     double** v = P.v;
-    PEN_LAUNCH(k_pen_matrix, g, dg, up, up, M);
+    // sameMatrix: the caller solved with these very coefficients last time (the PISO correctors of one time step share
+    // their pEqn matrix, only the source changes) -- the pencil-layout copy and the preconditioner's reciprocal
+    // diagonal are still in place.  OpenFOAM recomputes them for every solve; the values are the same.
+    const bool reuse = sameMatrix && P.precondOf == precond;
+    P.precondOf = -1;
+    if (!reuse) PEN_LAUNCH(k_pen_matrix, g, dg, up, up, M);
     PEN_LAUNCH(k_pen_from_nat, g, b, v[V_B]);
     PEN_LAUNCH(k_pen_from_nat, g, psi, v[V_X]);
     k_solve_begin<<<1, 1, 0, h->stream>>>(s->dSolve, tol, relTol, maxIter, precond);
@@ -1120,10 +1125,12 @@ int fvPcgSolve(fy_ctx* h, FvState* s, const double* dg, const double* up, const 
     PEN_LAUNCH(k_pen_avg, g, v[V_X], s->red, s->dSolve);
     PEN_LAUNCH(k_pen_solve_init, g, M, v[V_B], v[V_X], v[V_RA], s->red, s->dSolve);
     if (precond == FV_PRECOND_DIC) {
-        PEN_LAUNCH(k_pen_arm, g, v[V_D], v[V_YA], v[V_ZA], s->dSolve);
-        OpDicD op{{M.dg, M.low[0], M.low[1], M.low[2]}, v[V_D], v[V_RD]};
-        if ((rc = launchPencil<OpDicD, false>(h, s, op, s->dSolve))) return rc;
-    } else if (precond == FV_PRECOND_DIAGONAL) {
+        PEN_LAUNCH(k_pen_arm, g, reuse ? (double*)nullptr : v[V_D], v[V_YA], v[V_ZA], s->dSolve);
+        if (!reuse) {
+            OpDicD op{{M.dg, M.low[0], M.low[1], M.low[2]}, v[V_D], v[V_RD]};
+            if ((rc = launchPencil<OpDicD, false>(h, s, op, s->dSolve))) return rc;
+        }
+    } else if (precond == FV_PRECOND_DIAGONAL && !reuse) {
         PEN_LAUNCH(k_pen_recip, g, M.dg, v[V_RD]);
     }
     bool sampled = false;
@@ -1203,6 +1210,7 @@ int fvPcgSolve(fy_ctx* h, FvState* s, const double* dg, const double* up, const 
         perf->finalResidual = s->hSolve->finalRes;
         perf->nIterations = s->hSolve->nIter;
     }
+    P.precondOf = precond;
     return FY_OK;
 }
 
@@ -1261,6 +1269,7 @@ int fvDicPrecondition(fy_ctx* h, FvState* s, const double* dg, const double* up,
     int rc;
     PenMatrix M = penMatrixOf(P, 0);
     double** v = P.v;
+    P.precondOf = -1;
     PEN_LAUNCH(k_pen_matrix, g, dg, up, up, M);
     PEN_LAUNCH(k_pen_from_nat, g, rA, v[V_RA]);
     PEN_LAUNCH(k_pen_arm, g, v[V_D], v[V_YA], v[V_ZA], (const FvSolveDev*)nullptr);

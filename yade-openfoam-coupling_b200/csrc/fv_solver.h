@@ -45,6 +45,7 @@ struct PenState {
     int graphLaunches = 0;              // kernel launches inside one graph replay
     bool graphWarm[3] = {false, false, false};   // the iteration kernels have run eagerly at least once
     int dbg = 0;
+    int precondOf = -1;                 // preconditioner whose matrix copy + reciprocal diagonal the last PCG solve left in place
     unsigned int* ticket = nullptr;     // [2]
     int* error = nullptr;
     int* hError = nullptr;              // pinned
@@ -98,7 +99,7 @@ struct FvState {
 
 int fvCreate(fy_ctx* h, const fy_mesh_desc* m);
 int fvPcgSolve(fy_ctx* h, FvState* s, const double* dg, const double* up, const double* b, double* psi, double tol,
-               double relTol, int maxIter, int precond, fy_solver_perf* perf);
+               double relTol, int maxIter, int precond, fy_solver_perf* perf, bool sameMatrix = false);
 int fvSmoothSetMatrix(fy_ctx* h, FvState* s, const double* lo, const double* up);
 int fvSmoothSolve(fy_ctx* h, FvState* s, const double* dg, const double* b, double* psi, double tol, double relTol,
                   int maxIter, fy_solver_perf* perf);
