@@ -118,14 +118,15 @@ class ClockSampler:
 
 
 def flow_case(wl, pkg=None):
-    """(oracle mesh, product mesh, U0, p0) of the workload's flow"""
+    """(oracle mesh, product mesh, U0, p0) of the workload's flow.  With a package (the engine arm) only the product's
+    mesh is built -- nothing under oracle/ is imported there; without one (the CPU arm) only the oracle's."""
     from tests import cases_fv
     nx, ny, nz, P, seed, flow, dt, nu, _ = WORKLOADS[wl]
     if flow == "cavity":
-        mo, mp = cases_fv.cavity3d(pkg, (nx, ny, nz), (1.0, 1.0, 1.0))
+        mo, mp = cases_fv.cavity3d(pkg, (nx, ny, nz), (1.0, 1.0, 1.0), oracle=pkg is None)
         U0 = np.zeros((nx * ny * nz, 3))
     else:
-        mo, mp = cases_fv.channel(pkg, (nx, ny, nz), (1.0, 1.0, 1.0), UIN)
+        mo, mp = cases_fv.channel(pkg, (nx, ny, nz), (1.0, 1.0, 1.0), UIN, oracle=pkg is None)
         U0 = np.tile(np.array([UIN, 0.0, 0.0]), (nx * ny * nz, 1))
     return mo, mp, U0, np.zeros(nx * ny * nz)
 

@@ -13,12 +13,14 @@ def _apply(set_bc, mesh, spec):
         set_bc(mesh, name, **kw)
 
 
-def cavity2d(pkg=None, n=20):
+def cavity2d(pkg=None, n=20, oracle=True):
     """stock OpenFOAM cavity tutorial: n x n x 1 cells on 0.1 x 0.1 x 0.01, lid U = (1 0 0), empty front/back"""
-    from oracle import meshgen
     spec = dict(movingWall=dict(valueU=(1, 0, 0)), frontAndBack=dict(bcU=2, bcP=2))
-    mo = meshgen.hex_box_ldu(n, n, 1, 0.1, 0.1, 0.01, patches=CAVITY_PATCHES)
-    _apply(meshgen.set_bc, mo, spec)
+    mo = None
+    if oracle:
+        from oracle import meshgen
+        mo = meshgen.hex_box_ldu(n, n, 1, 0.1, 0.1, 0.01, patches=CAVITY_PATCHES)
+        _apply(meshgen.set_bc, mo, spec)
     mp = None
     if pkg is not None:
         mp = pkg.box_mesh(n, n, 1, 0.1, 0.1, 0.01, patches=CAVITY_PATCHES)
@@ -26,12 +28,15 @@ def cavity2d(pkg=None, n=20):
     return mo, mp
 
 
-def cavity3d(pkg=None, n=(16, 16, 16), L=(0.1, 0.1, 0.1)):
-    """lid-driven cavity box (BASELINE config C1 flow): lid = ymax moving in +x, all other walls no-slip"""
-    from oracle import meshgen
+def cavity3d(pkg=None, n=(16, 16, 16), L=(0.1, 0.1, 0.1), oracle=True):
+    """lid-driven cavity box (BASELINE config C1 flow): lid = ymax moving in +x, all other walls no-slip.
+    oracle=False builds the product's mesh only (bench.py's engine arm must not touch oracle/)."""
     spec = dict(ymax=dict(valueU=(1, 0, 0)))
-    mo = meshgen.hex_box_ldu(*n, *L)
-    _apply(meshgen.set_bc, mo, spec)
+    mo = None
+    if oracle:
+        from oracle import meshgen
+        mo = meshgen.hex_box_ldu(*n, *L)
+        _apply(meshgen.set_bc, mo, spec)
     mp = None
     if pkg is not None:
         mp = pkg.box_mesh(*n, *L)
@@ -39,12 +44,14 @@ def cavity3d(pkg=None, n=(16, 16, 16), L=(0.1, 0.1, 0.1)):
     return mo, mp
 
 
-def channel(pkg=None, n=(24, 12, 10), L=(2.0, 1.0, 1.0), Uin=0.3):
+def channel(pkg=None, n=(24, 12, 10), L=(2.0, 1.0, 1.0), Uin=0.3, oracle=True):
     """channel (BASELINE config C2 flow): xmin inlet U = (Uin 0 0), xmax outlet (zeroGradient U, p = 0), walls no-slip"""
-    from oracle import meshgen
     spec = dict(xmin=dict(valueU=(Uin, 0, 0)), xmax=dict(bcU=1, bcP=0, valueP=0.0))
-    mo = meshgen.hex_box_ldu(*n, *L)
-    _apply(meshgen.set_bc, mo, spec)
+    mo = None
+    if oracle:
+        from oracle import meshgen
+        mo = meshgen.hex_box_ldu(*n, *L)
+        _apply(meshgen.set_bc, mo, spec)
     mp = None
     if pkg is not None:
         mp = pkg.box_mesh(*n, *L)
