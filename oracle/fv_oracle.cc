@@ -30,7 +30,7 @@ namespace
 typedef std::vector<double> dvec;
 typedef std::vector<int> ivec;
 
-enum { BC_FIXED_VALUE = 0, BC_ZERO_GRADIENT = 1, BC_EMPTY = 2 };
+enum { BC_FIXED_VALUE = 0, BC_ZERO_GRADIENT = 1, BC_EMPTY = 2, BC_FIXED_FLUX_PRESSURE = 3 };   // the last one: p only, pimpleSolve only
 enum { PRECOND_DIC = 0, PRECOND_DIAGONAL = 1, PRECOND_NONE = 2 };
 
 const double SMALL = 1e-15;     // OpenFOAM `small` (double precision build)
@@ -55,6 +55,7 @@ struct Mesh
     dvec bSf, bMagSf, bDc;      // [nB][3], [nB], [nB]
     ivec ownStart;              // [N+1]
     bool validCmpt[3] = {true, true, true};   // false for the direction "empty" patches remove
+    mutable dvec bGradP;        // [nB] gradient of the fixedFluxPressure patches (set by constrainPressure), else 0
 };
 
 struct SolverPerf
@@ -259,6 +260,7 @@ inline void patchU(const Mesh& m, const Patch& p, int b, const double* U, double
 }
 inline double patchP(const Mesh& m, const Patch& p, int b, const double* P)
 {
+    if (p.bcP == BC_FIXED_FLUX_PRESSURE) return P[m.bCell[b]] + m.bGradP[b]/m.bDc[b];      // fixedGradient: p_P + gradient/deltaCoeffs
     return p.bcP == BC_FIXED_VALUE ? p.valueP : P[m.bCell[b]];
 }
 
@@ -853,6 +855,7 @@ void snGradPMagSf(const Mesh& m, const double* p, double* out)
         for (int b = pt.start; b < pt.start + pt.n; ++b) {
             double sn = 0.0;
             if (pt.bcP == BC_FIXED_VALUE) sn = m.bDc[b]*(pt.valueP - p[m.bCell[b]]);
+            if (pt.bcP == BC_FIXED_FLUX_PRESSURE) sn = m.bGradP[b];
             out[m.nFaces + b] = pt.bcP == BC_EMPTY ? 0.0 : sn*m.bMagSf[b];
         }
 }
@@ -1088,6 +1091,17 @@ int pimpleSolve(Ico& s, Pim& q, double dt, const double* alpha, const double* al
         }
         if (adjustPhi(m, s.phiHbyA.data()) != 0) return -1;                                  // pim/pEqn.H:13-16
         for (int f = 0; f < nF; ++f) s.phiHbyA[f] += q.phicForces[f];                        // pim/pEqn.H:18
+        // constrainPressure(p, Uc, phiHbyA, rAUcf)   pim/pEqn.H:21  [OF-6 constrainPressure.C: on fixedFluxPressure
+        // patches snGrad(p) = (phiHbyA_b - Sf_b & U_b)/(magSf_b rAUcf_b), so that the corrected flux equals the wall's]
+        for (const Patch& p : m.patches) {
+            if (p.bcP != BC_FIXED_FLUX_PRESSURE) continue;
+            for (int b = p.start; b < p.start + p.n; ++b) {
+                double ub[3], su = 0;
+                patchU(m, p, b, s.U.data(), ub);
+                for (int j = 0; j < 3; ++j) su += m.bSf[3*(size_t)b + j]*ub[j];
+                m.bGradP[b] = (s.phiHbyA[Fi + b] - su)/(m.bMagSf[b]*q.rAUf[Fi + b]);
+            }
+        }
         s.tOther += nowSec() - t0;
         for (int nonOrth = 0; nonOrth <= s.ctl.nNonOrthCorrectors; ++nonOrth) {
             t0 = nowSec();
@@ -1098,8 +1112,12 @@ int pimpleSolve(Ico& s, Pim& q, double dt, const double* alpha, const double* al
                 for (int b = p.start; b < p.start + p.n; ++b) {
                     icP[b] = 0.0;
                     bcP[b] = 0.0;
-                    if (p.bcP != BC_FIXED_VALUE) continue;
                     const double pGamma = (q.alphaf[Fi + b]*q.rAUf[Fi + b])*m.bMagSf[b];
+                    if (p.bcP == BC_FIXED_FLUX_PRESSURE) {                     // fixedGradient: gradientInternalCoeffs 0,
+                        icP[b] = pGamma*0.0;                                   // gradientBoundaryCoeffs = gradient
+                        bcP[b] = -pGamma*m.bGradP[b];
+                    }
+                    if (p.bcP != BC_FIXED_VALUE) continue;
                     icP[b] = pGamma*(-1.0*m.bDc[b]);
                     bcP[b] = -pGamma*(m.bDc[b]*p.valueP);
                 }
@@ -1187,6 +1205,7 @@ Mesh* buildMesh(int nCells, const double* V, int nFaces, const int* owner, const
     m.bSf.assign(bSf, bSf + 3*(size_t)o);
     m.bMagSf.assign(bMagSf, bMagSf + o);
     m.bDc.assign(bDc, bDc + o);
+    m.bGradP.assign(o, 0.0);
     m.ownStart.assign(nCells + 1, 0);
     for (int f = 0; f < nFaces; ++f) m.ownStart[owner[f] + 1]++;
     for (int c = 0; c < nCells; ++c) m.ownStart[c + 1] += m.ownStart[c];

@@ -38,6 +38,7 @@ def hex_box(nx, ny, nz, lx=1.0, ly=1.0, lz=1.0, origin=(0.0, 0.0, 0.0)):
 
 SIDES = ("xmin", "xmax", "ymin", "ymax", "zmin", "zmax")
 BC_FIXED_VALUE, BC_ZERO_GRADIENT, BC_EMPTY = 0, 1, 2
+BC_FIXED_FLUX_PRESSURE = 3          # p only; honoured by the pimpleFoamYade restatement (oracle/fv_oracle.cc pimpleSolve)
 
 
 def hex_box_ldu(nx, ny, nz, lx=1.0, ly=1.0, lz=1.0, origin=(0.0, 0.0, 0.0), patches=None):

@@ -233,6 +233,30 @@ def test_pimple_UcEqn_matrix_is_the_sum_of_its_explicit_operators():
     O.close()
 
 
+def test_pimple_hydrostatic_balance_with_fixedFluxPressure():
+    """constrainPressure on fixedFluxPressure walls (pim/pEqn.H:21; oracle only so far, the device path still refuses
+    the patch type): a closed box under gravity stays at rest, p = g.x, no flux through the walls -- with and without a
+    void-fraction blob."""
+    m = meshgen.hex_box_ldu(8, 12, 6, 0.8, 1.2, 0.6, patches=[("walls", ["xmin", "xmax", "ymin", "ymax", "zmin", "zmax"])])
+    meshgen.set_bc(m, "walls", bcP=meshgen.BC_FIXED_FLUX_PRESSURE)
+    O = port.IcoOracle(m, nu=0.01)
+    N, Fi, C = m["nCells"], m["nInternalFaces"], m["C"]
+    O.create_phi()
+    g = (0.0, -9.81, 0.0)
+    alpha = np.ones(N)
+    for it in range(4):
+        if it == 2:
+            alpha = 1 - 0.4 * np.exp(-((C - C.mean(0)) ** 2).sum(1) / 0.02)
+        O.pimple_solve(1e-3, alpha, -20.0 * (1 - alpha), g)
+        p = np.asarray(O.field("p"))
+        assert np.abs(O.field("U")).max() < 1e-6                                  # solver tolerance, not a flow
+        assert abs(np.polyfit(C[:, 1], p, 1)[0] + 9.81) < 1e-3
+        assert np.abs(p - p[0] + 9.81 * (C[:, 1] - C[0, 1])).max() < 1e-3
+        assert np.abs(np.asarray(O.field("phi"))[Fi:]).max() < 1e-15
+        assert O.stats()["sumLocalContErr"] < 1e-9
+    O.close()
+
+
 def _ldu_dense(m, diag, lower, upper):
     N = m["nCells"]
     A = np.zeros((N, N))
