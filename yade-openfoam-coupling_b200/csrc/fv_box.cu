@@ -1457,6 +1457,8 @@ int fvCreate(fy_ctx* h, const fy_mesh_desc* m)
     std::vector<int> bslot;
     for (int pI = 0; pI < m->nPatches; ++pI) {
         const fy_patch_desc& pd = m->patches[pI];
+        if (pd.bcU < FV_FIXED_VALUE || pd.bcU > FV_EMPTY || pd.bcP < FV_FIXED_VALUE || pd.bcP > FV_EMPTY)
+            return no("patch type not supported by the device FV path (fixedValue / zeroGradient / empty only)");
         for (int q = 0; q < pd.nFaces; ++q, ++b) {
             const double* sf = pd.Sf + 3 * (size_t)q;
             int d = 0;
