@@ -257,6 +257,24 @@ def test_pimple_hydrostatic_balance_with_fixedFluxPressure():
     O.close()
 
 
+@pytest.mark.parametrize("solver", ["ico", "pimple"])
+def test_fluid_restatement_reproduces_its_fixture(solver):
+    """tests/golden/fluid_*.npz (tests/golden/gen_golden_fluid.py): regression pins of the two fluid-step restatements,
+    so that an edit of the oracle cannot silently move the target the CUDA path is compared with."""
+    import importlib.util
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("gen_golden_fluid", os.path.join(here, "gen_golden_fluid.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    want = np.load(os.path.join(here, "fluid_%s_channel.npz" % solver))
+    got = gen.run(solver)
+    assert np.array_equal(got["iters"], want["iters"])
+    for k in ("U", "p", "phi"):
+        assert np.linalg.norm(got[k] - want[k]) <= 1e-12 * np.linalg.norm(want[k]), k
+    np.testing.assert_allclose(got["contErr"], want["contErr"], rtol=1e-6, atol=1e-18)
+
+
 def _ldu_dense(m, diag, lower, upper):
     N = m["nCells"]
     A = np.zeros((N, N))
