@@ -70,13 +70,17 @@ def test_dic_precondition_bit_exact(pkg, n):
     O.close()
 
 
-@pytest.mark.parametrize("n,cluster,warps", [((8, 8, 150), "16", "8"), ((6, 40, 70), "2", "4"), ((10, 33, 37), "1", "8"),
-                                             ((9, 70, 20), "4", "2"), ((5, 5, 300), "8", "1")])
-def test_sweeps_across_clusters_and_helpers(pkg, monkeypatch, n, cluster, warps):
+@pytest.mark.parametrize("n,cluster,warps,planes", [((8, 8, 150), "16", "8", "1"), ((6, 40, 70), "2", "4", "2"), ((10, 33, 37), "1", "8", "1"),
+                                                    ((9, 70, 20), "4", "2", "4"), ((5, 5, 300), "8", "1", "4"), ((7, 45, 131), "16", "3", "2"),
+                                                    ((40, 33, 19), "16", "8", "1"), ((3, 100, 9), "2", "1", "4")])
+def test_sweeps_across_clusters_and_helpers(pkg, monkeypatch, n, cluster, warps, planes):
     """every hand-off route of the pencil pipeline: shared-memory channels, DSMEM between the CTAs of a cluster,
     the L2 z-helper between clusters (nz > planes per cluster) and the y-helpers between j-blocks (ny > 32)"""
     monkeypatch.setenv("FY_PENCIL_CLUSTER", cluster)
     monkeypatch.setenv("FY_PENCIL_W", warps)
+    monkeypatch.setenv("FY_PEN2_W", warps)
+    monkeypatch.setenv("FY_PEN2_Z", planes)
+    monkeypatch.setenv("FY_PEN2_SMEM_KB", "200")
     mo, mp = cases_fv.cavity3d(pkg, n)
     rng = np.random.default_rng(7)
     N, Fi = mo["nCells"], mo["nInternalFaces"]

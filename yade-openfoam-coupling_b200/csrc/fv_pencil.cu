@@ -9,6 +9,9 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <set>
+#include <utility>
 
 #include "fv_pencil.cuh"
 #include "fv_solver.h"
@@ -450,10 +453,10 @@ __device__ __forceinline__ void penSweep(const Op& op, const PenWarp& w, double&
 
 // Z helper: streams the rows of the plane behind the group (another CTA's output, in L2) into z channel 0.
 // Eight rows are kept in flight; when the wanted row is still armed, every armed row is re-requested at once.
-template <bool REV>
+template <bool REV, int CD = PEN_CD>
 __device__ __forceinline__ void penHelpZ(const double* zRow0, uint32_t chanS, int Tp, int& fail, unsigned long long* tr, int dbg)
 {
-    constexpr int D = PEN_D, CD = PEN_CD;
+    constexpr int D = PEN_D;
     constexpr int RS = REV ? -32 : 32;
     const double* zB = zRow0;
     double r[D];
@@ -638,6 +641,8 @@ __global__ void __launch_bounds__(32 * (2 * PEN_WMAX + 1), 1) k_pencil(PencilGeo
         for (PenCell c = penDecode((g), row_, threadIdx.x & 31); c.valid; c.valid = false)
 
 __device__ __forceinline__ int penNat(const PencilGeom& g, const PenCell& c) { return c.i + g.nx * (c.j + g.ny * c.k); }
+
+#include "fv_pencil2.cuh"
 
 // matrix: dg [N], lo / up owner slots [3N] (natural) -> PenMatrix
 __global__ void __launch_bounds__(BLK)
@@ -962,6 +967,19 @@ k_pen_update(PencilGeom g, const double2* __restrict__ pA, const double2* __rest
         FY_CHECK_LAUNCH();                                                                  \
     } while (0)
 
+// cudaFuncSetAttribute is per (function, device): remember which pairs have been opted in
+int penFuncAttrs(fy_ctx* h, const void* fn)
+{
+    static std::mutex mu;
+    static std::set<std::pair<const void*, int>> done;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done.count({fn, h->device})) return FY_OK;
+    FY_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    FY_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    done.insert({fn, h->device});
+    return FY_OK;
+}
+
 template <class Op, bool REV>
 int launchPencil(fy_ctx* h, FvState* s, const Op& op, FvSolveDev* st)
 {
@@ -971,12 +989,7 @@ int launchPencil(fy_ctx* h, FvState* s, const Op& op, FvSolveDev* st)
     int W = std::max(1, std::min(std::min(P.W, PEN_WMAX), P.smemBudget / perWarp));
     W = std::min(W, P.g.nz);
     const size_t smem = (size_t)W * perWarp;
-    static bool attrDone = false;
-    if (!attrDone) {
-        FY_CUDA(cudaFuncSetAttribute((const void*)k_pencil<Op, REV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        FY_CUDA(cudaFuncSetAttribute((const void*)k_pencil<Op, REV>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        attrDone = true;
-    }
+    if (int rc = penFuncAttrs(h, (const void*)k_pencil<Op, REV>)) return rc;
     PenCtl ctl{P.ticket, P.error, P.partial, st, P.dbg, P.traceOn ? P.trace : nullptr};
     // clusters of C consecutive plane groups hand the z-neighbour over through distributed shared memory
     const int nKQ = (P.g.nz + W - 1) / W;
@@ -1007,6 +1020,77 @@ int launchPencil(fy_ctx* h, FvState* s, const Op& op, FvSolveDev* st)
     FY_CUDA(cudaLaunchKernelEx(&cfg, k_pencil<Op, REV>, P.g, op, ctl));
     h->launches++;
     return FY_OK;
+}
+
+// second-generation sweeps (fv_pencil2.cuh): Z planes per compute warp, R rows per TMA stage
+template <class Op, bool REV, int Z, int R>
+int launchPen2T(fy_ctx* h, FvState* s, const Op& op, FvSolveDev* st)
+{
+    PenState& P = s->pen;
+    const int stageBytes = Z * Op::NA * R * 256;
+    const int fixedPerWarp = P2_CD * 256 + Z * P2_YRING * 8 + 16 * P2_MAXSTAGE + 8 * 8 + 16;
+    int W = std::max(1, std::min(P.W2, Pen2Max<Z>::W));
+    W = std::min(W, (P.g.nz + Z - 1) / Z);
+    int nStage = 0;
+    for (; W >= 1; --W) {
+        nStage = std::min(std::min(P.maxStage2, P2_MAXSTAGE), (P.smemBudget2 / W - fixedPerWarp) / stageBytes);
+        if (nStage >= 2) break;
+    }
+    if (nStage < 2) {
+        W = 1;
+        nStage = std::min(P2_MAXSTAGE, (216 * 1024 - fixedPerWarp) / stageBytes);
+        if (nStage < 2) { h->err = "pencil sweep: stage does not fit shared memory"; return FY_ERR_INVALID; }
+        nStage = std::min(nStage, std::max(2, P.maxStage2));
+    }
+    const size_t smem = (size_t)W * nStage * stageBytes + (size_t)W * P2_CD * 256 + (size_t)W * Z * P2_YRING * 8 + (size_t)W * nStage * 16 +
+                        (size_t)W * 8 * 8 + (size_t)W * 4 + 16;
+    if (int rc = penFuncAttrs(h, (const void*)k_pen2<Op, REV, Z, R>)) return rc;
+    PenCtl ctl{P.ticket, P.error, P.partial, st, P.dbg, P.traceOn ? P.trace : nullptr};
+    const int PZ = W * Z, nKQ = (P.g.nz + PZ - 1) / PZ;
+    int C = 1;
+    while (C * 2 <= P.cluster && C < nKQ) C *= 2;
+    const int nCl = (nKQ + C - 1) / C;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(P.g.nJB * nCl * C));
+    cfg.blockDim = dim3(32 * (2 * W + 1 + W * Z));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (C > 8) {                                           // 16-CTA clusters are non-portable: check that one fits
+        int nClusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nClusters, k_pen2<Op, REV, Z, R>, &cfg) != cudaSuccess || nClusters < 1) {
+            cudaGetLastError();
+            C = 8;
+            attr[0].val.clusterDim.x = 8;
+            cfg.gridDim = dim3((unsigned)(P.g.nJB * ((nKQ + 7) / 8) * 8));
+        }
+    }
+    FY_CUDA(cudaLaunchKernelEx(&cfg, k_pen2<Op, REV, Z, R>, P.g, op, ctl, W, nStage));
+    h->launches++;
+    return FY_OK;
+}
+template <class Op, bool REV>
+int launchPen2(fy_ctx* h, FvState* s, const Op& op, FvSolveDev* st)
+{
+    const PenState& P = s->pen;
+    const int key = P.Z2 * 100 + P.R2;
+    switch (key) {
+    case 104: return launchPen2T<Op, REV, 1, 4>(h, s, op, st);
+    case 204: return launchPen2T<Op, REV, 2, 4>(h, s, op, st);
+#ifdef PEN2_ALL_VARIANTS
+    case 108: return launchPen2T<Op, REV, 1, 8>(h, s, op, st);
+    case 208: return launchPen2T<Op, REV, 2, 8>(h, s, op, st);
+    case 408: return launchPen2T<Op, REV, 4, 8>(h, s, op, st);
+#endif
+    case 404: return launchPen2T<Op, REV, 4, 4>(h, s, op, st);
+    default: h->err = "pencil sweep: no kernel for this FY_PEN2_Z / FY_PEN2_R"; return FY_ERR_INVALID;
+    }
 }
 
 int readSolve(fy_ctx* h, FvState* s)
@@ -1057,14 +1141,21 @@ int penCreate(fy_ctx* h, FvState* s)
     if (const char* e = std::getenv("FY_PENCIL_SMEM_KB")) { const int k = std::atoi(e); if (k >= 16 && k <= 216) P.smemBudget = k * 1024; }
     // every array carries PEN_GUARD rows of zeros in front and behind: the sweeps prefetch D rows past either end
     const size_t guard = (size_t)PEN_GUARD * 32, bytes = ((size_t)g.NP + 2 * guard) * sizeof(double);
-    auto alloc = [&](double*& p) -> int {
+    auto alloc = [&](double*& p, int mult = 1) -> int {
         double* raw = nullptr;
-        FY_CUDA(cudaMalloc((void**)&raw, bytes));
-        FY_CUDA(cudaMemsetAsync(raw, 0, bytes, h->stream));
-        p = raw + guard;
+        FY_CUDA(cudaMalloc((void**)&raw, bytes * mult));
+        FY_CUDA(cudaMemsetAsync(raw, 0, bytes * mult, h->stream));
+        p = raw + guard * mult;
         return FY_OK;
     };
     int rc;
+    if (const char* e = std::getenv("FY_PENCIL_VER")) P.ver = std::atoi(e) == 1 ? 1 : 2;
+    if (const char* e = std::getenv("FY_PEN2_Z")) P.Z2 = std::atoi(e);
+    if (const char* e = std::getenv("FY_PEN2_R")) P.R2 = std::atoi(e);
+    if (const char* e = std::getenv("FY_PEN2_W")) P.W2 = std::atoi(e);
+    if (const char* e = std::getenv("FY_PEN2_STAGES")) P.maxStage2 = std::max(2, std::atoi(e));
+    if (const char* e = std::getenv("FY_PEN2_SMEM_KB")) { const int k = std::atoi(e); if (k >= 16 && k <= 216) P.smemBudget2 = k * 1024; }
+    for (int q = 0; q < 4; ++q) if ((rc = alloc(P.pk[q], q < 3 ? 2 : 1))) return rc;
     for (auto& p : P.mP) if ((rc = alloc(p))) return rc;
     for (auto& p : P.mU) if ((rc = alloc(p))) return rc;
     for (auto& p : P.v) if ((rc = alloc(p))) return rc;
@@ -1088,6 +1179,7 @@ void penDestroy(FvState* s)
 {
     PenState& P = s->pen;
     const size_t guard = (size_t)PEN_GUARD * 32;
+    for (int q = 0; q < 4; ++q) if (P.pk[q]) cudaFree(P.pk[q] - guard * (q < 3 ? 2 : 1));
     for (auto p : P.mP) if (p) cudaFree(p - guard);
     for (auto p : P.mU) if (p) cudaFree(p - guard);
     for (auto p : P.v) if (p) cudaFree(p - guard);
@@ -1101,6 +1193,66 @@ void penDestroy(FvState* s)
 
 // vector roles inside the shared pool P.v[]
 enum { V_B = 0, V_X, V_RD, V_D, V_RA, V_PA, V_WA, V_YA, V_ZA, V_BPRIME = V_RA, V_MID = V_PA, V_EX = V_WA, V_EY = V_YA, V_EZ = V_ZA };
+
+// the five recurrences, dispatched to the pipeline generation in use
+static int sweepDicD(fy_ctx* h, FvState* s, const PenMatrix& M, FvSolveDev* st)
+{
+    PenState& P = s->pen;
+    double** v = P.v;
+    int rc;
+    if (P.ver == 1) {
+        OpDicD op{{M.dg, M.low[0], M.low[1], M.low[2]}, v[V_D], v[V_RD]};
+        return launchPencil<OpDicD, false>(h, s, op, st);
+    }
+    Op2DicD op{{M.dg, M.low[0], M.low[1], M.low[2]}, v[V_D], v[V_RD]};
+    if ((rc = launchPen2<Op2DicD, false>(h, s, op, st))) return rc;
+    PEN_LAUNCH(k_pen_pack_dic, P.g, v[V_RD], M, (double2*)P.pk[0], (double2*)P.pk[1], (double2*)P.pk[2], P.pk[3]);
+    return FY_OK;
+}
+static int sweepDicFwd(fy_ctx* h, FvState* s, const PenMatrix& M, FvSolveDev* st)
+{
+    PenState& P = s->pen;
+    double** v = P.v;
+    if (P.ver == 1) {
+        OpDicFwd f{{v[V_RD], v[V_RA], M.low[0], M.low[1], M.low[2]}, v[V_YA]};
+        return launchPencil<OpDicFwd, false>(h, s, f, st);
+    }
+    Op2DicFwd f{{P.pk[0], P.pk[1], v[V_RA]}, v[V_YA]};
+    return launchPen2<Op2DicFwd, false>(h, s, f, st);
+}
+static int sweepDicBwd(fy_ctx* h, FvState* s, const PenMatrix& M, FvSolveDev* st)
+{
+    PenState& P = s->pen;
+    double** v = P.v;
+    if (P.ver == 1) {
+        OpDicBwd bw{{v[V_YA], v[V_RD], M.up[0], M.up[1], M.up[2], v[V_RA]}, v[V_ZA], v[V_YA]};
+        return launchPencil<OpDicBwd, true>(h, s, bw, st);
+    }
+    Op2DicBwd bw{{v[V_YA], P.pk[2], P.pk[3], v[V_RA]}, v[V_ZA], v[V_YA]};
+    return launchPen2<Op2DicBwd, true>(h, s, bw, st);
+}
+static int sweepGsFwd(fy_ctx* h, FvState* s, const PenMatrix& M, FvSolveDev* st)
+{
+    PenState& P = s->pen;
+    double** v = P.v;
+    if (P.ver == 1) {
+        OpGsFwd f{{v[V_B], M.low[0], M.low[1], M.low[2], v[V_EX], v[V_EY], v[V_EZ], M.dg}, v[V_MID], v[V_BPRIME], v[V_X]};
+        return launchPencil<OpGsFwd, false>(h, s, f, st);
+    }
+    Op2GsFwd f{{v[V_B], M.low[0], M.low[1], M.low[2], v[V_EX], v[V_EY], v[V_EZ], M.dg}, v[V_MID], v[V_BPRIME], v[V_X]};
+    return launchPen2<Op2GsFwd, false>(h, s, f, st);
+}
+static int sweepGsBwd(fy_ctx* h, FvState* s, const PenMatrix& M, FvSolveDev* st)
+{
+    PenState& P = s->pen;
+    double** v = P.v;
+    if (P.ver == 1) {
+        OpGsBwd bw{{v[V_BPRIME], M.up[0], M.up[1], M.up[2], M.dg}, v[V_X], v[V_MID]};
+        return launchPencil<OpGsBwd, true>(h, s, bw, st);
+    }
+    Op2GsBwd bw{{v[V_BPRIME], M.up[0], M.up[1], M.up[2], M.dg}, v[V_X], v[V_MID]};
+    return launchPen2<Op2GsBwd, true>(h, s, bw, st);
+}
 
 // PCG on owner-slot coefficients (device pointers, natural cell order).  Iteration kernels are queued in
 // batches and test the device-side `done` flag themselves; the host looks at the state once per batch.
@@ -1126,10 +1278,7 @@ int fvPcgSolve(fy_ctx* h, FvState* s, const double* dg, const double* up, const 
     PEN_LAUNCH(k_pen_solve_init, g, M, v[V_B], v[V_X], v[V_RA], s->red, s->dSolve);
     if (precond == FV_PRECOND_DIC) {
         PEN_LAUNCH(k_pen_arm, g, reuse ? (double*)nullptr : v[V_D], v[V_YA], v[V_ZA], s->dSolve);
-        if (!reuse) {
-            OpDicD op{{M.dg, M.low[0], M.low[1], M.low[2]}, v[V_D], v[V_RD]};
-            if ((rc = launchPencil<OpDicD, false>(h, s, op, s->dSolve))) return rc;
-        }
+        if (!reuse && (rc = sweepDicD(h, s, M, s->dSolve))) return rc;
     } else if (precond == FV_PRECOND_DIAGONAL && !reuse) {
         PEN_LAUNCH(k_pen_recip, g, M.dg, v[V_RD]);
     }
@@ -1140,11 +1289,9 @@ int fvPcgSolve(fy_ctx* h, FvState* s, const double* dg, const double* up, const 
     auto enqueueIteration = [&](bool ev) -> int {
         if (ev) cudaEventRecord(s->pev[0], h->stream);
         if (precond == FV_PRECOND_DIC) {
-            OpDicFwd f{{v[V_RD], v[V_RA], M.low[0], M.low[1], M.low[2]}, v[V_YA]};
-            if ((rc = launchPencil<OpDicFwd, false>(h, s, f, s->dSolve))) return rc;
+            if ((rc = sweepDicFwd(h, s, M, s->dSolve))) return rc;
             if (ev) cudaEventRecord(s->pev[1], h->stream);
-            OpDicBwd bw{{v[V_YA], v[V_RD], M.up[0], M.up[1], M.up[2], v[V_RA]}, v[V_ZA], v[V_YA]};
-            if ((rc = launchPencil<OpDicBwd, true>(h, s, bw, s->dSolve))) return rc;
+            if ((rc = sweepDicBwd(h, s, M, s->dSolve))) return rc;
         } else {
             if (ev) cudaEventRecord(s->pev[1], h->stream);
             PEN_LAUNCH(k_pen_precond_diag, g, precond == FV_PRECOND_DIAGONAL ? v[V_RD] : (const double*)nullptr, v[V_RA],
@@ -1246,10 +1393,8 @@ int fvSmoothSolve(fy_ctx* h, FvState* s, const double* dg, const double* b, doub
         if (s->hSolve->done) break;
         for (int it = 0; it < s->gsBatch; ++it) {
             PEN_LAUNCH(k_pen_gs_upper, g, M, v[V_X], v[V_EX], v[V_EY], v[V_EZ], s->dSolve);
-            OpGsFwd f{{v[V_B], M.low[0], M.low[1], M.low[2], v[V_EX], v[V_EY], v[V_EZ], M.dg}, v[V_MID], v[V_BPRIME], v[V_X]};
-            if ((rc = launchPencil<OpGsFwd, false>(h, s, f, s->dSolve))) return rc;
-            OpGsBwd bw{{v[V_BPRIME], M.up[0], M.up[1], M.up[2], M.dg}, v[V_X], v[V_MID]};
-            if ((rc = launchPencil<OpGsBwd, true>(h, s, bw, s->dSolve))) return rc;
+            if ((rc = sweepGsFwd(h, s, M, s->dSolve))) return rc;
+            if ((rc = sweepGsBwd(h, s, M, s->dSolve))) return rc;
             PEN_LAUNCH(k_pen_residual, g, M, v[V_B], v[V_X], s->red, s->dSolve);
         }
     }
@@ -1273,12 +1418,9 @@ int fvDicPrecondition(fy_ctx* h, FvState* s, const double* dg, const double* up,
     PEN_LAUNCH(k_pen_matrix, g, dg, up, up, M);
     PEN_LAUNCH(k_pen_from_nat, g, rA, v[V_RA]);
     PEN_LAUNCH(k_pen_arm, g, v[V_D], v[V_YA], v[V_ZA], (const FvSolveDev*)nullptr);
-    OpDicD op{{M.dg, M.low[0], M.low[1], M.low[2]}, v[V_D], v[V_RD]};
-    if ((rc = launchPencil<OpDicD, false>(h, s, op, nullptr))) return rc;
-    OpDicFwd f{{v[V_RD], v[V_RA], M.low[0], M.low[1], M.low[2]}, v[V_YA]};
-    if ((rc = launchPencil<OpDicFwd, false>(h, s, f, nullptr))) return rc;
-    OpDicBwd bw{{v[V_YA], v[V_RD], M.up[0], M.up[1], M.up[2], v[V_RA]}, v[V_ZA], v[V_YA]};
-    if (!(P.dbg & 64) && (rc = launchPencil<OpDicBwd, true>(h, s, bw, nullptr))) return rc;      // dbg 64: dev probe of the forward sweep
+    if ((rc = sweepDicD(h, s, M, nullptr))) return rc;
+    if ((rc = sweepDicFwd(h, s, M, nullptr))) return rc;
+    if (!(P.dbg & 64) && (rc = sweepDicBwd(h, s, M, nullptr))) return rc;      // dbg 64: dev probe of the forward sweep
     PEN_LAUNCH(k_pen_to_nat, g, v[V_ZA], wA);
     FY_CUDA(cudaMemcpyAsync(P.hError, P.error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     FY_CUDA(cudaStreamSynchronize(h->stream));

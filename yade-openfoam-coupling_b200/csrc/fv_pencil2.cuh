@@ -1,0 +1,696 @@
+// fv_pencil2.cuh -- second generation of the warp-pencil sweeps (included by fv_pencil.cu inside its anonymous
+// namespace, after the PTX helpers).
+//
+// What changed against the first pipeline (k_pencil, one plane per warp, per-lane cp.async, 75 instructions per row):
+//   * a compute warp owns Z consecutive k-planes of its 32-lane j-block and walks them skewed by one row per plane
+//     (plane z works on row t - z at step t), so the z-neighbour is the warp's OWN previous-step result of plane
+//     z-1: it stays in a register, the Z dependent chains of a step are independent of each other (instruction-level
+//     parallelism instead of one latency-bound chain), and only every Z-th plane crosses warps;
+//   * inputs arrive by TMA: a producer warp issues one 1-D bulk copy (cp.async.bulk, SASS UBLKCP) per plane and
+//     stream for R rows at a time -- a row of the pencil layout is one contiguous 256-byte line, R rows one contiguous
+//     block -- into a shared-memory ring whose stages complete on mbarriers (complete_tx); the compute warp waits with
+//     mbarrier.try_wait once per R rows and hands the stage back through a second mbarrier.  No per-lane cp.async, no
+//     address arithmetic per stream in the compute loop;
+//   * the matrix coefficients come pre-multiplied by the reciprocal diagonal and packed two per 16-byte word
+//     (k_pen_pack_dic, once per matrix): OpenFOAM evaluates (rD[u]*upper[f])*wA[l] left to right, so the product
+//     rD*upper is the same bits whenever it is formed;
+//   * the remote flow-control check of a DSMEM channel is prefetched one block ahead, channels are 32 rows deep.
+// Cross-CTA hand-offs are the first pipeline's: sentinel-armed 8-byte slots in shared memory / distributed shared
+// memory inside a cluster, helper warps that poll the output array in L2 between clusters (z) and j-blocks (y).
+// The per-cell operation order is unchanged, so every sweep stays bit-identical to OpenFOAM's sequential loops.
+#pragma once
+
+constexpr int P2_CD = 32;                     // z channel depth (rows)
+constexpr int P2_MAXSTAGE = 8;
+constexpr int P2_SPIN_LIMIT = 1 << 22;
+
+__device__ __forceinline__ void mbarInit(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbarExpectTx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarArrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbarTry(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbarWait(uint32_t bar, uint32_t parity, int& fail)
+{
+    int spin = 0;
+    while (!mbarTry(bar, parity)) {                        // (a failed try_wait has already slept for the hardware's time limit)
+        if (++spin > (P2_SPIN_LIMIT >> 6)) { fail = 1; break; }
+    }
+}
+// 1-D TMA bulk copy global -> shared, completion on an mbarrier (bytes and addresses are multiples of 16)
+__device__ __forceinline__ void bulkLoad(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fenceBarrierInit() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void ldShared2V(uint32_t p, double& a, double& b)
+{
+    asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(p));
+}
+__device__ __forceinline__ bool isSentHi(double v) { return (unsigned)__double2hiint(v) == (unsigned)(PEN_SENT >> 32); }
+
+// ---------------------------------------------------------------------------------------------
+// the recurrences, second form.  A sweep has NS input streams; stream s carries wd(s) doubles per cell (8- or
+// 16-byte words), NA doubles per cell in all, delivered to cell() as a[pre(s)..].  cell() is the dependent chain in
+// OpenFOAM's order, post() the side outputs, fin() the global sum's consumer.
+// ---------------------------------------------------------------------------------------------
+struct Op2DicD {           // DICPreconditioner::calcReciprocalD: rD[u] -= upper^2 / rD[l]; then rD = 1/rD
+    static constexpr int NS = 4, NA = 4;
+    static constexpr bool PADS_ZERO = false;     // inactive cells (pads, lanes past ny) evaluate to exactly 0 by themselves
+    static constexpr bool DOT = false;
+    __host__ __device__ static constexpr int wd(int) { return 1; }
+    __host__ __device__ static constexpr int pre(int s) { return s; }
+    const double* in[NS];      // dg lowx lowy lowz
+    double* chain;             // D before the reciprocal
+    double* rD;
+    __device__ __forceinline__ double cell(const double (&a)[NA], double vx, double vy, double vz, double&) const
+    {
+        const double c1 = a[1] * a[1], c2 = a[2] * a[2], c3 = a[3] * a[3];
+        double r = a[0];
+        r -= c3 / (c3 == 0.0 ? 1.0 : vz);           // no such face: u*u = 0, and v may be a pad's 0
+        r -= c2 / (c2 == 0.0 ? 1.0 : vy);
+        r -= c1 / (c1 == 0.0 ? 1.0 : vx);
+        return r;
+    }
+    static constexpr int NP = 3;
+    __device__ __forceinline__ void pre(const double (&a)[NA], double vx, double vy, double (&p)[NP]) const
+    {
+        const double c1 = a[1] * a[1], c2 = a[2] * a[2];
+        p[0] = a[3] * a[3];
+        p[1] = c2 / (c2 == 0.0 ? 1.0 : vy);
+        p[2] = c1 / (c1 == 0.0 ? 1.0 : vx);
+    }
+    __device__ __forceinline__ double fin(const double (&a)[NA], const double (&p)[NP], double vz, double&) const
+    {
+        double r = a[0];
+        r -= p[0] / (p[0] == 0.0 ? 1.0 : vz);
+        r -= p[1];
+        r -= p[2];
+        return r;
+    }
+    __device__ __forceinline__ void post(double* cp, bool active, const double (&)[NA], double res, double, double&) const
+    {
+        if (active) rD[cp - chain] = 1.0 / res;
+    }
+    __device__ __forceinline__ void fin(FvSolveDev*, double) const {}
+};
+struct Op2DicFwd {         // wA = rD rA;  wA[u] -= (rD[u] upper) wA[l]   (faces ascending)
+    static constexpr int NS = 3, NA = 5;
+    static constexpr bool PADS_ZERO = true;     // inactive cells (pads, lanes past ny) evaluate to exactly 0 by themselves
+    static constexpr bool DOT = false;
+    __host__ __device__ static constexpr int wd(int s) { return s < 2 ? 2 : 1; }
+    __host__ __device__ static constexpr int pre(int s) { return 2 * s; }
+    const double* in[NS];      // {rD, rD lowx} {rD lowy, rD lowz} rA
+    double* chain;             // yA
+    __device__ __forceinline__ double cell(const double (&a)[NA], double vx, double vy, double vz, double&) const
+    {
+        double w = a[0] * a[4];
+        w -= a[3] * vz;
+        w -= a[2] * vy;
+        w -= a[1] * vx;
+        return w;
+    }
+    static constexpr int NP = 3;
+    __device__ __forceinline__ void pre(const double (&a)[NA], double vx, double vy, double (&p)[NP]) const
+    {
+        p[0] = a[0] * a[4];
+        p[1] = a[2] * vy;
+        p[2] = a[1] * vx;
+    }
+    __device__ __forceinline__ double fin(const double (&a)[NA], const double (&p)[NP], double vz, double&) const
+    {
+        double w = p[0];
+        w -= a[3] * vz;
+        w -= p[1];
+        w -= p[2];
+        return w;
+    }
+    __device__ __forceinline__ void post(double*, bool, const double (&)[NA], double, double, double&) const {}
+    __device__ __forceinline__ void fin(FvSolveDev*, double) const {}
+};
+struct Op2DicBwd {         // wA[l] -= (rD[l] upper) wA[u]   (faces descending); accumulates wA.rA; re-arms yA
+    static constexpr int NS = 4, NA = 5;
+    static constexpr bool PADS_ZERO = true;     // inactive cells (pads, lanes past ny) evaluate to exactly 0 by themselves
+    static constexpr bool DOT = true;
+    __host__ __device__ static constexpr int wd(int s) { return s == 1 ? 2 : 1; }
+    __host__ __device__ static constexpr int pre(int s) { return s == 0 ? 0 : (s == 1 ? 1 : s + 1); }
+    const double* in[NS];      // yA {rD upx, rD upy} rD upz rA
+    double* chain;             // zA
+    double* y;
+    __device__ __forceinline__ double cell(const double (&a)[NA], double vx, double vy, double vz, double&) const
+    {
+        double w = a[0];
+        w -= a[3] * vz;
+        w -= a[2] * vy;
+        w -= a[1] * vx;
+        return w;
+    }
+    static constexpr int NP = 3;
+    __device__ __forceinline__ void pre(const double (&a)[NA], double vx, double vy, double (&p)[NP]) const
+    {
+        p[0] = a[0];
+        p[1] = a[2] * vy;
+        p[2] = a[1] * vx;
+    }
+    __device__ __forceinline__ double fin(const double (&a)[NA], const double (&p)[NP], double vz, double&) const
+    {
+        double w = p[0];
+        w -= a[3] * vz;
+        w -= p[1];
+        w -= p[2];
+        return w;
+    }
+    __device__ __forceinline__ void post(double* cp, bool, const double (&a)[NA], double res, double, double& acc) const
+    {
+        acc += res * a[4];
+        y[cp - chain] = sentValue();                // pads are armed too: the next forward sweep writes every slot of the slab
+    }
+    __device__ __forceinline__ void fin(FvSolveDev* st, double tot) const
+    {
+        if (!st) return;
+        st->wArAold = st->wArA;
+        st->wArA = tot;
+        st->beta = st->wArA / st->wArAold;
+    }
+};
+struct Op2GsFwd {          // GaussSeidelSmoother forward sweep: new values below; old values above arrive pre-multiplied (e)
+    static constexpr int NS = 8, NA = 8;
+    static constexpr bool PADS_ZERO = false;     // inactive cells (pads, lanes past ny) evaluate to exactly 0 by themselves
+    static constexpr bool DOT = false;
+    __host__ __device__ static constexpr int wd(int) { return 1; }
+    __host__ __device__ static constexpr int pre(int s) { return s; }
+    const double* in[NS];      // b lowx lowy lowz ex ey ez dg
+    double* chain;             // psi after the forward sweep
+    double* bPrime;
+    double* psiOld;            // consumed by k_pen_gs_upper before the sweep: re-armed here for the backward sweep
+    __device__ __forceinline__ double cell(const double (&c)[NA], double vx, double vy, double vz, double& side) const
+    {
+        double bp = c[0];
+        bp -= c[3] * vz;
+        bp -= c[2] * vy;
+        bp -= c[1] * vx;
+        side = bp;
+        double x = bp;
+        x -= c[4];                                  // upper[x+] psi_old[c+1]   (0 when there is no such face)
+        x -= c[5];
+        x -= c[6];
+        return x / c[7];
+    }
+    static constexpr int NP = 3;
+    __device__ __forceinline__ void pre(const double (&c)[NA], double vx, double vy, double (&p)[NP]) const
+    {
+        p[0] = c[0];
+        p[1] = c[2] * vy;
+        p[2] = c[1] * vx;
+    }
+    __device__ __forceinline__ double fin(const double (&c)[NA], const double (&p)[NP], double vz, double& side) const
+    {
+        double bp = p[0];
+        bp -= c[3] * vz;
+        bp -= p[1];
+        bp -= p[2];
+        side = bp;
+        double x = bp;
+        x -= c[4];
+        x -= c[5];
+        x -= c[6];
+        return x / c[7];
+    }
+    __device__ __forceinline__ void post(double* cp, bool active, const double (&)[NA], double, double side, double&) const
+    {
+        if (active) {
+            bPrime[cp - chain] = side;
+            psiOld[cp - chain] = sentValue();
+        }
+    }
+    __device__ __forceinline__ void fin(FvSolveDev*, double) const {}
+};
+struct Op2GsBwd {          // GaussSeidelSmoother backward sweep (own faces in ascending order: x, y, z)
+    static constexpr int NS = 5, NA = 5;
+    static constexpr bool PADS_ZERO = false;     // inactive cells (pads, lanes past ny) evaluate to exactly 0 by themselves
+    static constexpr bool DOT = false;
+    __host__ __device__ static constexpr int wd(int) { return 1; }
+    __host__ __device__ static constexpr int pre(int s) { return s; }
+    const double* in[NS];      // bPrime upx upy upz dg
+    double* chain;             // psi
+    double* mid;               // forward-sweep values: dead now, re-armed for the next iteration
+    __device__ __forceinline__ double cell(const double (&c)[NA], double vx, double vy, double vz, double&) const
+    {
+        double x = c[0];
+        x -= c[1] * vx;
+        x -= c[2] * vy;
+        x -= c[3] * vz;
+        return x / c[4];
+    }
+    static constexpr int NP = 3;
+    __device__ __forceinline__ void pre(const double (&c)[NA], double vx, double vy, double (&p)[NP]) const
+    {
+        double x = c[0];
+        x -= c[1] * vx;
+        x -= c[2] * vy;
+        p[0] = x;
+        p[1] = 0.0;
+        p[2] = 0.0;
+    }
+    __device__ __forceinline__ double fin(const double (&c)[NA], const double (&p)[NP], double vz, double&) const
+    {
+        double x = p[0];
+        x -= c[3] * vz;
+        return x / c[4];
+    }
+    __device__ __forceinline__ void post(double* cp, bool active, const double (&)[NA], double, double, double&) const
+    {
+        if (active) mid[cp - chain] = sentValue();
+    }
+    __device__ __forceinline__ void fin(FvSolveDev*, double) const {}
+};
+
+struct Pen2Warp {              // per-warp constants of one sweep
+    uint32_t ringS, fullS, emptyS, zInS, zOutS, yInS, yFullS, yDoneS;
+    int s0, nx, Tp, nvalid, nStage;
+    int pos00, zoff;           // element index of (first row, this lane) of plane 0; index step from plane z to z+1 at one step
+    bool zOut, zRemote, edge;
+    int dbg;                   // timing probes (FY_PENCIL_DBG): 1 no chain stores, 16 no input loads (the ring holds whatever it holds)
+};
+
+constexpr int P2_YRING = 64;                  // y ring depth (steps) per plane
+constexpr int P2_YG = 8;                      // steps per y group (one mbarrier phase)
+
+__device__ __forceinline__ double ldSharedN(uint32_t p)            // plain (schedulable) shared loads of the input ring
+{
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(p));
+    return v;
+}
+__device__ __forceinline__ void ldShared2N(uint32_t p, double& a, double& b)
+{
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(p));
+}
+__device__ __forceinline__ unsigned ldSharedU32V(uint32_t p)
+{
+    unsigned v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(p));
+    return v;
+}
+__device__ __forceinline__ void stSharedU32V(uint32_t p, unsigned v)
+{
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(p), "r"(v));
+}
+
+// One block of R steps of the compute warp.  EDGEBLK = false is the steady state: every plane's row is inside
+// [0, Tp) for every step of the block and the warp owns Z real planes, so there are no range predicates at all.
+template <class Op, bool REV, int Z, int R, bool ZIN, bool YIN, bool EDGEBLK>
+__device__ __forceinline__ void pen2Block(const Op& op, const Pen2Warp& w, int t0, uint32_t sb, double (&prev)[Z], double& vzN,
+                                          double& zchk, double& acc, int& fail)
+{
+    constexpr int NA = Op::NA, NS = Op::NS, CD = P2_CD;
+    constexpr unsigned int FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    // chain addresses of the block's first step, one per plane (steps and planes are constant offsets from here)
+    double* cp[Z];
+#pragma unroll
+    for (int z = 0; z < Z; ++z) cp[z] = op.chain + (w.pos00 + (REV ? -32 : 32) * (t0 - z) + z * ((REV ? -32 : 32) + w.zoff));
+    if (YIN && (t0 & (P2_YG - 1)) == 0) mbarWait(w.yFullS + ((t0 >> 3) & 7) * 8, (uint32_t)((t0 >> 6) & 1), fail);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int t = t0 + r;
+        const int rr = REV ? R - 1 - r : r;
+        // (A) this step's inputs, all planes (plain loads: the scheduler may hoist them across the steps of the block)
+        double a[Z][NA];
+#pragma unroll
+        for (int z = 0; z < Z; ++z) {
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                const uint32_t ad = sb + (uint32_t)(((z * NA + Op::pre(s)) * R + rr * Op::wd(s)) * 256 + lane * 8 * Op::wd(s));
+                if (Op::wd(s) == 2) ldShared2N(ad, a[z][Op::pre(s)], a[z][Op::pre(s) + 1 < NA ? Op::pre(s) + 1 : NA - 1]);
+                else a[z][Op::pre(s)] = ldSharedN(ad);
+            }
+        }
+        // (B) flow control of the z channel this warp writes: once per R rows of its last plane
+        const int qo = t - (Z - 1);                    // row of the last plane
+        const bool zOutNow = w.zOut && (!EDGEBLK || (qo >= 0 && qo < w.Tp));
+        if (zOutNow && ((r - (Z - 1)) & (R - 1)) == 0) {
+            const uint32_t cs = (uint32_t)(qo & (CD - 1));
+            if (!isSentHi(zchk)) {
+                int spin = 0;
+                const uint32_t p = w.zOutS + ((cs + R - 1) & (CD - 1)) * 256;
+                while (!isSentHi(w.zRemote ? ldClusterV(p) : ldSharedV(p))) {
+                    if (++spin > P2_SPIN_LIMIT) { fail = 1; break; }
+                }
+            }
+            const uint32_t pn = w.zOutS + ((cs + 2 * R - 1) & (CD - 1)) * 256;
+            zchk = w.zRemote ? ldClusterV(pn) : ldSharedV(pn);
+        }
+        const uint32_t zOutP = w.zOutS + (uint32_t)(qo & (CD - 1)) * 256;
+        // (C) everything that does not wait for another warp: the y values, the shuffles, the chains of the planes whose
+        // z-neighbour is this warp's own plane behind (its OLD value), and the z-independent part of plane 0.  The hand-over
+        // of the last plane goes out as early as its value exists: the lag of the whole z chain is the time between a warp
+        // receiving a row and passing its own on.
+        double yv[Z];
+        if (YIN) {
+            const uint32_t ya = w.yInS + (uint32_t)(t & (P2_YRING - 1)) * 8;       // plane z's row t - z sits in slot t of its ring
+#pragma unroll
+            for (int z = 0; z < Z; ++z) yv[z] = ldSharedV(ya + z * (P2_YRING * 8));
+        }
+        double res[Z], side[Z], vyA[Z];
+#pragma unroll
+        for (int z = 0; z < Z; ++z) {
+            vyA[z] = REV ? __shfl_down_sync(FULL, prev[z], 1) : __shfl_up_sync(FULL, prev[z], 1);
+            if (YIN) vyA[z] = w.edge ? yv[z] : vyA[z];
+            side[z] = 0.0;
+        }
+        bool act[Z];
+#pragma unroll
+        for (int z = 0; z < Z; ++z) {
+            act[z] = true;
+            if (EDGEBLK || !Op::PADS_ZERO) act[z] = (!EDGEBLK || z < w.nvalid) && (unsigned)(t - z - w.s0) < (unsigned)w.nx;
+        }
+#pragma unroll
+        for (int z = Z - 1; z >= 1; --z) {
+            res[z] = op.cell(a[z], prev[z], vyA[z], prev[z - 1], side[z]);
+            if (EDGEBLK || !Op::PADS_ZERO) res[z] = act[z] ? res[z] : 0.0;
+        }
+        if (Z > 1 && zOutNow) {
+            if (w.zRemote) stClusterV(zOutP, res[Z - 1]);
+            else stSharedV(zOutP, res[Z - 1]);
+        }
+        double pre0[Op::NP];
+        op.pre(a[0], prev[0], vyA[0], pre0);
+        // (D) the z-neighbour of plane 0: the one value that crosses warps
+        double vz0 = 0.0;
+        if (ZIN && (!EDGEBLK || t < w.Tp)) {
+            const uint32_t cs = (uint32_t)(t & (CD - 1));
+            double v = vzN;
+            if (isSentHi(v)) {
+                int spin = 0;
+                do {
+                    v = ldSharedV(w.zInS + cs * 256);
+                    if (++spin > P2_SPIN_LIMIT) { fail = 1; v = 0.0; break; }
+                } while (isSentHi(v));
+            }
+            vz0 = v;
+        }
+        res[0] = op.fin(a[0], pre0, vz0, side[0]);
+        if (EDGEBLK || !Op::PADS_ZERO) res[0] = act[0] ? res[0] : 0.0;
+        if (Z == 1 && zOutNow) {
+            if (w.zRemote) stClusterV(zOutP, res[0]);
+            else stSharedV(zOutP, res[0]);
+        }
+        // (E) off the critical path: re-arm the consumed slot, look at the next one, the results, the side outputs
+        if (ZIN && (!EDGEBLK || t < w.Tp)) {
+            stSharedV(w.zInS + (uint32_t)(t & (CD - 1)) * 256, sentValue());
+            vzN = ldSharedV(w.zInS + (uint32_t)((t + 1) & (CD - 1)) * 256);
+        }
+#pragma unroll
+        for (int z = Z - 1; z >= 0; --z) {
+            if (!EDGEBLK || (z < w.nvalid && (unsigned)(t - z) < (unsigned)w.Tp)) {
+                if (!(w.dbg & 1)) stChain(cp[z] + (REV ? -32 : 32) * r, res[z]);
+                op.post(cp[z] + (REV ? -32 : 32) * r, act[z], a[z], res[z], side[z], acc);
+            }
+            prev[z] = res[z];
+        }
+    }
+    if (YIN && ((t0 + R) & (P2_YG - 1)) == 0) {            // the y group is consumed: its slots may be refilled
+        __syncwarp();
+        if (lane == 0) stSharedU32V(w.yDoneS, (unsigned)(t0 + R));
+    }
+}
+
+// The compute warp.  Step t: plane z (sweep order) works on row q = t - z of its slab; stage slot r of the input ring
+// holds, for EVERY plane, the row of step blk*R + r (the producer shifts plane z's copies by z rows), so all planes
+// read the same slot.  All Z cells of a step depend only on the previous step's results.
+template <class Op, bool REV, int Z, int R, bool ZIN, bool YIN>
+__device__ __forceinline__ void pen2Sweep(const Op& op, const Pen2Warp& w, double& acc, int& fail)
+{
+    constexpr int NA = Op::NA;
+    constexpr uint32_t STAGE = (uint32_t)Z * NA * R * 256;
+    const int lane = threadIdx.x & 31;
+    double prev[Z];
+#pragma unroll
+    for (int z = 0; z < Z; ++z) prev[z] = 0.0;
+    const int nBlk = (w.Tp + Z - 1 + R - 1) / R;
+    int stage = 0;
+    uint32_t phase = 0;
+    double vzN = ZIN ? ldSharedV(w.zInS) : 0.0;            // channel reads run one row ahead
+    double zchk = sentValue();                             // flow-control probe of the NEXT block, taken one block early
+    for (int blk = 0; blk < nBlk; ++blk) {
+        const int t0 = blk * R;
+        if (!(w.dbg & 16)) mbarWait(w.fullS + stage * 8, phase, fail);
+        const uint32_t sb = w.ringS + stage * STAGE;
+        const bool steady = w.nvalid == Z && t0 >= Z - 1 && t0 + R <= w.Tp && !(w.dbg & 32);
+        if (steady) pen2Block<Op, REV, Z, R, ZIN, YIN, false>(op, w, t0, sb, prev, vzN, zchk, acc, fail);
+        else pen2Block<Op, REV, Z, R, ZIN, YIN, true>(op, w, t0, sb, prev, vzN, zchk, acc, fail);
+        __syncwarp();
+        if (lane == 0 && !(w.dbg & 16)) mbarArrive(w.emptyS + stage * 8);
+        if (++stage == w.nStage) { stage = 0; phase ^= 1u; }
+    }
+}
+
+// The producer warp of one compute warp: per stage, lane c < Z*NS issues the bulk copy of (plane c / NS, stream c % NS).
+template <class Op, bool REV, int Z, int R>
+__device__ __forceinline__ void pen2Produce(const Op& op, const PencilGeom& g, uint32_t ringS, uint32_t fullS, uint32_t emptyS,
+                                            int nStage, long long slab0, long long slabStep, int nvalid, int& fail)
+{
+    constexpr int NA = Op::NA, NS = Op::NS;
+    constexpr uint32_t STAGE = (uint32_t)Z * NA * R * 256;
+    const int lane = threadIdx.x & 31;
+    const int nBlk = (g.Tp + Z - 1 + R - 1) / R;
+    const int z = lane / NS, s = lane - z * NS;
+    const bool mine = lane < Z * NS;
+    const int wds = mine ? Op::wd(s) : 1;
+    // planes past the end of the box are read from the warp's last real plane (finite values; their results are masked)
+    const int zl = z < nvalid ? z : nvalid - 1;
+    const double* src0 = nullptr;
+    uint32_t dst0 = 0;
+    if (mine) {
+        src0 = op.in[s] + (long long)wds * (slab0 + zl * slabStep);
+        dst0 = ringS + (uint32_t)((z * NA + Op::pre(s)) * R * 256);
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int blk = 0; blk < nBlk; ++blk) {
+        mbarWait(emptyS + stage * 8, phase ^ 1u, fail);
+        if (lane == 0) mbarExpectTx(fullS + stage * 8, STAGE);
+        __syncwarp();
+        if (mine) {
+            const int row0 = REV ? g.Tp - (blk + 1) * R + z : blk * R - z;     // first memory row of the block (guard rows absorb the overrun)
+            bulkLoad(dst0 + stage * STAGE, src0 + (long long)wds * row0 * 32, (uint32_t)(R * 256 * wds), fullS + stage * 8);
+        }
+        if (++stage == nStage) { stage = 0; phase ^= 1u; }
+    }
+}
+
+// Y helper of one plane (sweep-order index z inside its compute warp): fetches the y-neighbour of the plane's edge lane
+// -- the last lane of the neighbouring j-block's rows, another CTA's output in L2 -- 32 steps at a time: lane l polls
+// the row of step u = 32b + l (row q = u - z of the plane) and drops it into slot u of the plane's ring as soon as the
+// compute warp has finished step u - 64, then arrives on the mbarrier of the step's group of 8; the compute warp waits
+// once per group for all its planes.  Steps whose row lies outside [0, Tp) only arrive.  Poll and hand-over are ONE
+// loop (two loops in a row would park the early lanes at the first loop's reconvergence point).
+template <bool REV>
+__device__ __forceinline__ void pen2HelpY(const double* yRow0, uint32_t slotS, uint32_t yFullS, uint32_t yDoneS, int z, int Tp,
+                                          int nSteps, int& fail)
+{
+    constexpr int RS = REV ? -32 : 32;
+    const int lane = threadIdx.x & 31;
+    for (int u0 = 0; u0 < nSteps; u0 += 32) {
+        const int u = u0 + lane, q = u - z;
+        const bool real = q >= 0 && q < Tp;
+        const double* a = yRow0 + (long long)q * RS;
+        double v = real ? ldPoll(a) : 0.0;
+        bool pending = u < nSteps;
+        int spin = 0;
+        while (pending && !fail) {
+            if (real && isSent(v)) v = ldPoll(a);
+            else if ((int)ldSharedU32V(yDoneS) > u - P2_YRING) {
+                if (real) stSharedV(slotS + (uint32_t)(u & (P2_YRING - 1)) * 8, v);
+                mbarArrive(yFullS + ((u >> 3) & 7) * 8);
+                pending = false;
+            }
+            if (++spin > P2_SPIN_LIMIT) fail = 1;
+        }
+    }
+}
+
+template <int Z> struct Pen2Max { static constexpr int W = Z >= 8 ? 1 : (Z >= 4 ? 2 : (Z >= 2 ? 4 : 8)); static constexpr int WARPS = 2 * W + 1 + W * Z; };
+
+// One CTA per pencil group (j-block jb, plane group kq of W*Z planes).  Warps: [0,W) compute | [W,2W) producers |
+// 2W z helper | (2W, 2W + W*Z] y helpers (one per plane).  Dynamic shared memory: input rings [W][nStage][STAGE] |
+// z channels [W][CD][32] | y rings [W*Z][64] | mbarriers [W][nStage]{full, empty} | y group barriers [W][8] | y progress [W].
+template <class Op, bool REV, int Z, int R>
+__global__ void __launch_bounds__(32 * Pen2Max<Z>::WARPS, 1) k_pen2(PencilGeom g, Op op, PenCtl ctl, int W, int nStage)
+{
+    constexpr int NA = Op::NA, CD = P2_CD;
+    constexpr unsigned int FULL = 0xffffffffu;
+    constexpr uint32_t STAGE = (uint32_t)Z * NA * R * 256;
+    extern __shared__ __align__(128) unsigned char penSmem[];
+    __shared__ unsigned int shTicket;
+    if (ctl.st && ctl.st->done) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5, PZ = W * Z;
+    double* const zChan = reinterpret_cast<double*>(penSmem + (size_t)W * nStage * STAGE);
+    double* const yChan = zChan + (size_t)W * (CD * 32);
+    unsigned long long* const bars = reinterpret_cast<unsigned long long*>(yChan + (size_t)PZ * P2_YRING);
+    unsigned long long* const yBars = bars + (size_t)W * nStage * 2;
+    unsigned int* const yDone = reinterpret_cast<unsigned int*>(yBars + (size_t)W * 8);
+    // one ticket per cluster; the C CTAs of a cluster take C consecutive plane groups of one j-block
+    const int C = (int)clusterSize(), rank = (int)clusterRank();
+    if (rank == 0 && threadIdx.x == 0) shTicket = atomicAdd(ctl.ticket, 1u);
+    for (int x = threadIdx.x; x < W * CD * 32; x += blockDim.x) zChan[x] = sentValue();
+    if (threadIdx.x < W * nStage * 2) mbarInit(smemU32(bars + threadIdx.x), 1);
+    if (threadIdx.x < W) yDone[threadIdx.x] = 0u;
+    clusterSync();                                         // channels armed, ticket taken: cluster-wide
+    const unsigned int tk = ldClusterU32(mapToRank(smemU32(&shTicket), 0));
+    const int nKQ = (g.nz + PZ - 1) / PZ, nCl = (nKQ + C - 1) / C;
+    const int cl = (int)tk / g.nJB;
+    int jb = (int)tk - cl * g.nJB;
+    if (REV) jb = g.nJB - 1 - jb;
+    (void)nCl;
+    const int kq = cl * C + rank;                          // plane group in SWEEP order; may be >= nKQ: a CTA without planes
+    constexpr int KS = REV ? -1 : 1;
+    // q-th plane of the group in sweep order (backward sweeps count from the top, so that a partial group's real
+    // planes always come first)
+    auto planeOf = [&](int q) { return REV ? g.nz - 1 - (kq * PZ + q) : kq * PZ + q; };
+    auto planeOk = [&](int k) { return k >= 0 && k < g.nz; };
+    auto nValidOf = [&](int wq) {                          // real planes of compute warp wq
+        int n = 0;
+        for (int z = 0; z < Z; ++z) n += planeOk(planeOf(wq * Z + z)) ? 1 : 0;
+        return n;
+    };
+    // the y group barriers complete on 8 arrivals per real plane (the plane's y helper)
+    if (threadIdx.x < W * 8) mbarInit(smemU32(yBars + threadIdx.x), (uint32_t)(P2_YG * max(1, nValidOf(threadIdx.x >> 3))));
+    fenceBarrierInit();
+    __syncthreads();
+    const int ctaId = kq * g.nJB + jb;
+    if (ctl.trace && lane == 0) {
+        unsigned long long ts;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts));
+        ctl.trace[((size_t)ctaId * 32 + warp) * 4 + 0] = ts;
+    }
+    double acc = 0.0;
+    int fail = 0;
+    // timing probes (FY_PENCIL_DBG; results are wrong with any of them): 2 no z hand-over out, 4 no z in, 8 no y in
+    const bool yCol = (REV ? jb < g.nJB - 1 : jb > 0) && !(ctl.dbg & 8);       // this j-block has a y-producer block
+    const long long yOff = REV ? ((long long)g.Tp - 31) * 32 - 31 : -(((long long)g.Tp - 31) * 32 - 31);
+    const int row00 = REV ? (g.Tp - 1) * 32 : 0;
+    constexpr int EDGE = REV ? 31 : 0;
+    const int nBlk = (g.Tp + Z - 1 + R - 1) / R;
+    if (warp < W) {
+        const int nvalid = nValidOf(warp);
+        if (nvalid > 0) {
+            const int k0 = planeOf(warp * Z);
+            const int j = jb * 32 + lane;
+            const bool jvalid = j < g.ny;
+            Pen2Warp w;
+            w.ringS = smemU32(penSmem + (size_t)warp * nStage * STAGE);
+            w.fullS = smemU32(bars + (size_t)warp * nStage * 2);
+            w.emptyS = w.fullS + nStage * 8;
+            w.nStage = nStage;
+            w.zInS = smemU32(zChan + (size_t)warp * (CD * 32) + lane);
+            w.zOutS = w.zInS + CD * 256;
+            w.yInS = smemU32(yChan + (size_t)warp * Z * P2_YRING);
+            w.yFullS = smemU32(yBars + (size_t)warp * 8);
+            w.yDoneS = smemU32(yDone + warp);
+            w.s0 = jvalid ? (REV ? g.Tp - g.nx - lane : lane) : (1 << 30);
+            w.nx = g.nx;
+            w.Tp = g.Tp;
+            w.nvalid = nvalid;
+            w.pos00 = (int)((((long long)k0 * g.nJB + jb) * g.Tp) * 32 + lane + row00);
+            w.zoff = (int)(KS * g.zStride - (REV ? -32 : 32));
+            const int kBehind = k0 - KS, kLast = planeOf(warp * Z + Z - 1), kAhead = kLast + KS;
+            const bool zin = planeOk(kBehind) && !(ctl.dbg & 4);
+            w.dbg = ctl.dbg;
+            w.zRemote = warp == W - 1;
+            w.zOut = nvalid == Z && planeOk(kAhead) && (warp < W - 1 || rank < C - 1) && !(ctl.dbg & 2);
+            if (w.zRemote) w.zOutS = mapToRank(smemU32(zChan + lane), (uint32_t)(rank < C - 1 ? rank + 1 : rank));
+            w.edge = lane == EDGE;
+            if (zin && yCol) pen2Sweep<Op, REV, Z, R, true, true>(op, w, acc, fail);
+            else if (zin) pen2Sweep<Op, REV, Z, R, true, false>(op, w, acc, fail);
+            else if (yCol) pen2Sweep<Op, REV, Z, R, false, true>(op, w, acc, fail);
+            else pen2Sweep<Op, REV, Z, R, false, false>(op, w, acc, fail);
+        }
+    } else if (warp < 2 * W) {
+        const int wq = warp - W;
+        const int nvalid = nValidOf(wq);
+        if (nvalid > 0 && !(ctl.dbg & 16)) {
+            const int k0 = planeOf(wq * Z);
+            const uint32_t fullS = smemU32(bars + (size_t)wq * nStage * 2);
+            pen2Produce<Op, REV, Z, R>(op, g, smemU32(penSmem + (size_t)wq * nStage * STAGE), fullS, fullS + nStage * 8, nStage,
+                                       (((long long)k0 * g.nJB + jb) * g.Tp) * 32, KS * g.zStride, nvalid, fail);
+        }
+    } else if (warp == 2 * W) {
+        const int k0 = planeOf(0), kBehind = k0 - KS;
+        if (rank == 0 && planeOk(k0) && planeOk(kBehind) && !(ctl.dbg & 4))
+            penHelpZ<REV, CD>(op.chain + (((long long)kBehind * g.nJB + jb) * g.Tp) * 32 + lane + row00, smemU32(zChan + lane), g.Tp, fail, nullptr, ctl.dbg);
+    } else if (yCol) {
+        const int q = warp - 2 * W - 1;
+        const int k = planeOf(q);
+        if (q < PZ && planeOk(k)) {
+            const int wq = q / Z, z = q - wq * Z;
+            pen2HelpY<REV>(op.chain + (((long long)k * g.nJB + jb) * g.Tp) * 32 + EDGE + yOff + row00, smemU32(yChan + (size_t)q * P2_YRING),
+                           smemU32(yBars + (size_t)wq * 8), smemU32(yDone + wq), z, g.Tp, (nBlk * R + P2_YG - 1) / P2_YG * P2_YG, fail);
+        }
+    }
+
+    if (ctl.trace && lane == 0) {
+        unsigned long long ts;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts));
+        ctl.trace[((size_t)ctaId * 32 + warp) * 4 + 1] = ts;
+    }
+    const int slotId = ctaId * W + warp;
+    if (Op::DOT && warp < W) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(FULL, acc, o);
+        if (lane == 0) ctl.partial[slotId] = acc;
+    }
+    fail = __any_sync(FULL, fail);
+    unsigned int last = 0;
+    if (lane == 0) {
+        if (fail) atomicExch(ctl.error, 1);
+        __threadfence();
+        last = (atomicAdd(ctl.ticket + 1, 1u) == gridDim.x * NW - 1) ? 1u : 0u;
+    }
+    last = __shfl_sync(FULL, last, 0);
+    if (!last) return;
+    __threadfence();
+    if (Op::DOT) {
+        const volatile double* p = ctl.partial;
+        double x = 0.0;
+        for (unsigned int b = lane; b < gridDim.x * W; b += 32) x += p[b];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(FULL, x, o);
+        if (lane == 0) op.fin(ctl.st, x);
+    }
+    if (lane == 0) {
+        ctl.ticket[0] = 0u;
+        ctl.ticket[1] = 0u;
+    }
+}
+
+// {rD, rD low_x} {rD low_y, rD low_z} | {rD up_x, rD up_y} rD up_z : the premultiplied coefficient streams of the DIC
+// substitutions, written once per matrix (after calcReciprocalD).  Pads stay zero.
+__global__ void __launch_bounds__(BLK)
+k_pen_pack_dic(PencilGeom g, const double* __restrict__ rD, PenMatrix M, double2* __restrict__ f0, double2* __restrict__ f1,
+               double2* __restrict__ b0, double* __restrict__ bz)
+{
+    PEN_ROW_LOOP(g, c) {
+        const long long p = c.pos;
+        const double r = rD[p];
+        f0[p] = make_double2(r, r * M.low[0][p]);
+        f1[p] = make_double2(r * M.low[1][p], r * M.low[2][p]);
+        b0[p] = make_double2(r * M.up[0][p], r * M.up[1][p]);
+        bz[p] = r * M.up[2][p];
+    }
+}

@@ -34,6 +34,14 @@ struct PenState {
     int W = 8;                          // compute warps per pencil group (CTA)
     int cluster = 16;                   // largest thread-block cluster (plane groups chained through DSMEM)
     int smemBudget = 200 * 1024;        // bytes of shared memory per pencil group
+    // second-generation sweeps (fv_pencil2.cuh)
+    int ver = 2;                        // 1: k_pencil (one plane per warp, cp.async), 2: k_pen2 (Z planes per warp, TMA + mbarrier)
+    // planes per compute warp, rows per TMA stage, compute warps per CTA: measured best on B200 at 128^3 and 256^3
+    // (profiles/r2b_sweep_variants.txt): one plane per warp, eight warps per CTA
+    int Z2 = 1, R2 = 4, W2 = 8;
+    int maxStage2 = 5;                  // input-ring stages
+    int smemBudget2 = 200 * 1024;       // shared memory per CTA the rings may fill
+    double* pk[4] = {nullptr};          // premultiplied DIC streams: {rD, rD lowx} {rD lowy, rD lowz} {rD upx, rD upy} rD upz
     double* mP[7] = {nullptr};          // pEqn: dg, low[3], up[3]
     double* mU[7] = {nullptr};          // UEqn: dg (current component), low[3], up[3]
     double* v[9] = {nullptr};           // vectors (roles: see fv_pencil.cu)
