@@ -617,8 +617,8 @@ int adjustPhi(const Mesh& m, double* phi)
             else { if (ph < 0) massIn -= ph; else adjustableMassOut += ph; }
         }
     }
-    double totalFlux = VSMALL;
-    for (int b = 0; b < m.nB; ++b) totalFlux += std::fabs(phi[m.nFaces + b]);
+    double totalFlux = VSMALL;                                   // vSmall + sum(mag(phi)): gSum of the INTERNAL field
+    for (int f = 0; f < m.nFaces; ++f) totalFlux += std::fabs(phi[f]);
     double massCorr = 1.0;
     const double magAdj = std::fabs(adjustableMassOut);
     if (magAdj > VSMALL && magAdj/totalFlux > SMALL) massCorr = (massIn - fixedMassOut)/adjustableMassOut;

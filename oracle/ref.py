@@ -172,6 +172,11 @@ class RefFoamYade:
     def set_source_zero(self):
         self.L.ref_set_source_zero(self.h)
 
+    def realloc_fields(self):
+        """moves every solver-owned field to newly allocated storage (views taken before are stale afterwards)"""
+        self.L.ref_realloc_fields.argtypes = [C.c_void_p]
+        self.L.ref_realloc_fields(self.h)
+
     def dts(self):
         out = np.empty(2)
         self.L.ref_get_dt(_d(out), self.h)

@@ -308,6 +308,14 @@ double* ref_field(void* h, const char* name)
     return nullptr;
 }
 
+// every solver-owned field moves to new storage (as OpenFOAM's `vGrad = fvc::grad(U)` etc. do every time step)
+void ref_realloc_fields(void* h)
+{
+    Ref* r = (Ref*)h;
+    r->U.reallocate(); r->gradP.reallocate(); r->divT.reallocate(); r->ddtU.reallocate(); r->vGrad.reallocate();
+    r->uSource.reallocate(); r->uParticle.reallocate(); r->uSourceDrag.reallocate(); r->alpha.reallocate();
+}
+
 void ref_get_constants(void* h, double* out4)
 {
     FyClass* fy = ((Ref*)h)->fy;

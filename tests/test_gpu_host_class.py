@@ -11,7 +11,7 @@ pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(not (ref.available() and ref.host_available()), reason="harness libraries not built")]
 
 
-def _run(host, gaussian, n_yade, mo, pd, fields, steps=2):
+def _run(host, gaussian, n_yade, mo, pd, fields, steps=2, realloc=False):
     L = ref.host_lib() if host else ref.lib()
     L.ref_clear_trace()
     L.ref_set_logging(1)
@@ -21,10 +21,14 @@ def _run(host, gaussian, n_yade, mo, pd, fields, steps=2):
         R.field(k)[:] = v
     out = []
     for it in range(steps):
+        if realloc and it > 0:
+            R.realloc_fields()              # the solver's `field = tmp` assignments: new addresses every step
         found, force = R.step(1e-3, pd, yade_dt=2.5e-4)
         out.append(dict(found=found.copy(), force=force.copy(), uSource=R.field("uSource").copy(),
                         alpha=R.field("alpha").copy(), uSourceDrag=R.field("uSourceDrag").copy(),
                         uParticle=R.field("uParticle").copy(), dts=R.dts()))
+        if realloc:
+            R.realloc_fields()
         R.set_source_zero()
     tr = R.trace()
     L.ref_set_logging(0)
@@ -50,3 +54,21 @@ def test_host_class_is_a_drop_in(pkg, gaussian, n_yade):
         for k in ("uSource", "alpha", "uSourceDrag", "uParticle"):
             assert cases.rel_l2(b[k], a[k]) <= cases.TOL, k
         assert a["dts"] == b["dts"]
+
+
+@pytest.mark.parametrize("gaussian", [True, False])
+def test_host_class_follows_reallocated_fields(pkg, gaussian):
+    """OpenFOAM solvers reassign their fields from tmps every time step, which moves the internal field's storage;
+    the host class must hand the engine the current addresses on every call (it once cached them at construction)."""
+    n = 12
+    mo = meshgen.hex_box(n, n, n)
+    pd = cases.particles(300, 9, radius=0.1 / n, moving=True)
+    f = cases.fields_for(mo["C"])
+    fields = dict(U=f["U"], gradP=f["gradP"], divT=f["divT"], vGrad=f["vGrad"])
+    _, o_ref = _run(False, gaussian, 1, mo, pd, fields, steps=3, realloc=True)
+    _, o_host = _run(True, gaussian, 1, mo, pd, fields, steps=3, realloc=True)
+    for a, b in zip(o_ref, o_host):
+        assert np.array_equal(a["found"], b["found"])
+        assert cases.rel_l2(b["force"], a["force"]) <= cases.TOL
+        for k in ("uSource", "alpha", "uSourceDrag", "uParticle"):
+            assert cases.rel_l2(b[k], a[k]) <= cases.TOL, k

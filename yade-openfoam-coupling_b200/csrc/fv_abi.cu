@@ -47,6 +47,7 @@ extern "C" {
 
 int fy_fv_supported(fy_handle h)
 {
+    FyDeviceGuard guard_(h);
     if (!h || !h->fv) return 0;
     if (!h->fv->supported) h->err = "finite-volume path unavailable on this mesh: " + h->fv->why;
     return h->fv->supported ? 1 : 0;
@@ -63,6 +64,7 @@ int fy_piso_default_controls(fy_piso_controls* c)
 
 int fy_set_piso_controls(fy_handle h, const fy_piso_controls* c)
 {
+    FyDeviceGuard guard_(h);
     FvState* s;
     int rc = needFv(h, &s);
     if (rc) return rc;
@@ -77,6 +79,7 @@ int fy_set_piso_controls(fy_handle h, const fy_piso_controls* c)
 
 int fy_set_viscosity(fy_handle h, double nu)
 {
+    FyDeviceGuard guard_(h);
     FvState* s;
     int rc = needFv(h, &s);
     if (rc) return rc;
@@ -86,6 +89,7 @@ int fy_set_viscosity(fy_handle h, double nu)
 
 int fy_create_phi(fy_handle h)
 {
+    FyDeviceGuard guard_(h);
     FvState* s;
     int rc = needFv(h, &s);
     if (rc) return rc;
@@ -94,6 +98,7 @@ int fy_create_phi(fy_handle h)
 
 int fy_ico_pre(fy_handle h, double dt)
 {
+    FyDeviceGuard guard_(h);
     FvState* s;
     int rc = needFv(h, &s);
     if (rc) return rc;
@@ -102,6 +107,7 @@ int fy_ico_pre(fy_handle h, double dt)
 
 int fy_pimple_pre(fy_handle h, double dt)
 {
+    FyDeviceGuard guard_(h);
     FvState* s;
     int rc = needFv(h, &s);
     if (rc) return rc;
@@ -111,6 +117,7 @@ int fy_pimple_pre(fy_handle h, double dt)
 
 int fy_pimple_solve(fy_handle h, double dt, const double g[3])
 {
+    FyDeviceGuard guard_(h);
     FvState* s;
     int rc = needFv(h, &s);
     if (rc) return rc;
@@ -121,6 +128,7 @@ int fy_pimple_solve(fy_handle h, double dt, const double g[3])
 
 int fy_ico_solve(fy_handle h, double dt)
 {
+    FyDeviceGuard guard_(h);
     FvState* s;
     int rc = needFv(h, &s);
     if (rc) return rc;
@@ -130,6 +138,7 @@ int fy_ico_solve(fy_handle h, double dt)
 
 int fy_get_ico_stats(fy_handle h, fy_ico_stats* out)
 {
+    FyDeviceGuard guard_(h);
     FvState* s;
     int rc = needFv(h, &s);
     if (rc) return rc;
@@ -140,6 +149,7 @@ int fy_get_ico_stats(fy_handle h, fy_ico_stats* out)
 
 int fy_fvc_grad_vector(fy_handle h, const double* U, double* out9)
 {
+    FyDeviceGuard guard_(h);
     FvState* s;
     int rc = needFv(h, &s);
     if (rc) return rc;
@@ -154,6 +164,7 @@ int fy_fvc_grad_vector(fy_handle h, const double* U, double* out9)
 
 int fy_fvc_grad_scalar(fy_handle h, const double* p, double* out3)
 {
+    FyDeviceGuard guard_(h);
     FvState* s;
     int rc = needFv(h, &s);
     if (rc) return rc;
@@ -168,6 +179,7 @@ int fy_fvc_grad_scalar(fy_handle h, const double* p, double* out3)
 
 int fy_fvc_div_flux(fy_handle h, const double* phi, double* out)
 {
+    FyDeviceGuard guard_(h);
     FvState* s;
     int rc = needFv(h, &s);
     if (rc) return rc;
@@ -183,6 +195,7 @@ int fy_fvc_div_flux(fy_handle h, const double* phi, double* out)
 
 int fy_fvc_div_phi_vector(fy_handle h, const double* phi, const double* U, double* out3)
 {
+    FyDeviceGuard guard_(h);
     FvState* s;
     int rc = needFv(h, &s);
     if (rc) return rc;
@@ -200,6 +213,7 @@ int fy_fvc_div_phi_vector(fy_handle h, const double* phi, const double* U, doubl
 
 int fy_fvc_laplacian_gamma_vector(fy_handle h, const double* gamma, double gammaB, const double* U, double* out3)
 {
+    FyDeviceGuard guard_(h);
     FvState* s;
     int rc = needFv(h, &s);
     if (rc) return rc;
@@ -242,6 +256,7 @@ static int stageMatrix(fy_ctx* h, FvState* s, const double* diag, const double* 
 int fy_pcg_solve(fy_handle h, const double* diag, const double* upper, const double* source, double* psi, double tol,
                  double relTol, int maxIter, int preconditioner, double out3[3])
 {
+    FyDeviceGuard guard_(h);
     FvState* s;
     int rc = needFv(h, &s);
     if (rc) return rc;
@@ -257,6 +272,7 @@ int fy_pcg_solve(fy_handle h, const double* diag, const double* upper, const dou
 int fy_smooth_solve(fy_handle h, const double* diag, const double* lower, const double* upper, const double* source,
                     double* psi, double tol, double relTol, int maxIter, double out3[3])
 {
+    FyDeviceGuard guard_(h);
     FvState* s;
     int rc = needFv(h, &s);
     if (rc) return rc;
@@ -272,6 +288,7 @@ int fy_smooth_solve(fy_handle h, const double* diag, const double* lower, const 
 
 int fy_dic_precondition(fy_handle h, const double* diag, const double* upper, const double* rA, double* wA)
 {
+    FyDeviceGuard guard_(h);
     FvState* s;
     int rc = needFv(h, &s);
     if (rc) return rc;
@@ -284,6 +301,7 @@ int fy_dic_precondition(fy_handle h, const double* diag, const double* upper, co
 
 int fy_fv_get(fy_handle h, const char* name, double* dst)
 {
+    FyDeviceGuard guard_(h);
     FvState* s;
     int rc = needFv(h, &s);
     if (rc) return rc;
@@ -327,6 +345,7 @@ int fy_fv_get(fy_handle h, const char* name, double* dst)
 
 int fy_get_fluid_ms(fy_handle h, double out[4])
 {
+    FyDeviceGuard guard_(h);
     FvState* s;
     int rc = needFv(h, &s);
     if (rc) return rc;
@@ -336,6 +355,7 @@ int fy_get_fluid_ms(fy_handle h, double out[4])
 
 int fy_get_kernel_ms(fy_handle h, double out[8], int reset)
 {
+    FyDeviceGuard guard_(h);
     FvState* s;
     int rc = needFv(h, &s);
     if (rc) return rc;

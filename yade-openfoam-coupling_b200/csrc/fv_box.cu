@@ -539,10 +539,14 @@ k_phiHbyA(BoxGeom g, double rDeltaT, const double* __restrict__ HbyA, const doub
 // adjustPhi(phiHbyA, U, p): sums over the boundary faces, then the outflow scaling          icoFoamYade.C:108
 __global__ void __launch_bounds__(BLK) k_adjust_sum(BoxGeom g, const double* __restrict__ phiHbyA, FvRed red, FvStepDev* out)
 {
-    double v[4] = {0.0, 0.0, 0.0, 0.0};       // massIn fixedMassOut adjustableMassOut sum|phi_b|
+    double v[4] = {0.0, 0.0, 0.0, 0.0};       // massIn fixedMassOut adjustableMassOut sum|phi| (internal faces: OpenFOAM's
+                                              // sum(mag(phi)) of a surface field reduces the internal field only)
     FV_CELL_LOOP(g, c) {
         int i, j, k;
         fvIJK(g, c, i, j, k);
+        if (i < g.nx - 1) v[3] += fabs(phiHbyA[c]);
+        if (j < g.ny - 1) v[3] += fabs(phiHbyA[(size_t)g.N + c]);
+        if (k < g.nz - 1) v[3] += fabs(phiHbyA[2 * (size_t)g.N + c]);
         if (fvInterior(g, i, j, k)) continue;
         for (int q = 0; q < 6; ++q) {
             const int s = g.seq[q];
@@ -551,7 +555,6 @@ __global__ void __launch_bounds__(BLK) k_adjust_sum(BoxGeom g, const double* __r
             if (ph < 0) v[0] -= ph;
             else if (g.kindU[s] == FV_FIXED_VALUE) v[1] += ph;
             else v[2] += ph;
-            v[3] += fabs(ph);
         }
     }
     fvGridReduce<4, false, BLK>(v, red, [=](const double* t) {

@@ -95,7 +95,15 @@ int uploadMesh(fy_ctx* h, const fy_mesh_desc* m)
             fp.valueU[0] = pd.valueU[0]; fp.valueU[1] = pd.valueU[1]; fp.valueU[2] = pd.valueU[2];
             fp.valueP = pd.valueP;
             h->patches.push_back(fp);
+            if (pd.nFaces < 0 || (pd.nFaces > 0 && (!pd.faceCells || !pd.Sf || !pd.magSf || !pd.deltaCoeffs))) {
+                h->err = "fy_create: patch arrays missing";
+                return FY_ERR_INVALID;
+            }
             for (int i = 0; i < pd.nFaces; ++i, ++o) {
+                if (pd.faceCells[i] < 0 || (size_t)pd.faceCells[i] >= N) {
+                    h->err = "fy_create: patch faceCells entry outside [0, nCells)";
+                    return FY_ERR_INVALID;
+                }
                 fc[o] = pd.faceCells[i]; pid[o] = p;
                 sf[3 * o] = pd.Sf[3 * (size_t)i]; sf[3 * o + 1] = pd.Sf[3 * (size_t)i + 1]; sf[3 * o + 2] = pd.Sf[3 * (size_t)i + 2];
                 msf[o] = pd.magSf[i]; dc[o] = pd.deltaCoeffs[i];
@@ -197,6 +205,7 @@ int fy_create(const fy_mesh_desc* m, int device, fy_handle* out)
 
 int fy_destroy(fy_handle h)
 {
+    FyDeviceGuard guard_(h);
     if (!h) return FY_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
@@ -216,6 +225,7 @@ int fy_destroy(fy_handle h)
 
 int fy_set_properties(fy_handle h, double rhoP, double rhoF, double nu, int gaussianInterp)
 {
+    FyDeviceGuard guard_(h);
     if (!h) return FY_ERR_INVALID;
     h->rhoP = rhoP; h->rhoF = rhoF; h->nu = nu;
     h->gaussian = gaussianInterp != 0;
@@ -226,6 +236,7 @@ int fy_set_properties(fy_handle h, double rhoP, double rhoF, double nu, int gaus
 
 int fy_get_constants(fy_handle h, double out4[4])
 {
+    FyDeviceGuard guard_(h);
     if (!h || !out4) return FY_ERR_INVALID;
     out4[0] = h->interpRange; out4[1] = h->sigmaInterp; out4[2] = h->interpRangeCu; out4[3] = h->sigmaPi;
     return FY_OK;
@@ -246,6 +257,7 @@ int fy_host_free(void* p)
 int fy_bind_host_fields(fy_handle h, const double* U, const double* gradP, const double* vGrad, const double* divT,
                         const double* ddtU, double* uSourceDrag, double* alpha, double* uSource, double* uParticle)
 {
+    FyDeviceGuard guard_(h);
     if (!h) return FY_ERR_INVALID;
     h->hIn[0] = U; h->hIn[1] = gradP; h->hIn[2] = vGrad; h->hIn[3] = divT; h->hIn[4] = ddtU;
     h->hOut[0] = uSourceDrag; h->hOut[1] = alpha; h->hOut[2] = uSource; h->hOut[3] = uParticle;
@@ -254,6 +266,7 @@ int fy_bind_host_fields(fy_handle h, const double* U, const double* gradP, const
 
 int fy_upload_field(fy_handle h, int f, const double* src)
 {
+    FyDeviceGuard guard_(h);
     if (!h || f < 0 || f >= FY_F_COUNT || !src || !h->dField[f]) return FY_ERR_INVALID;
     FY_CUDA(cudaMemcpyAsync(h->dField[f], src, fieldCount(h, f) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     if (f == FY_F_PHI && h->fv && h->fv->supported) {      // OpenFOAM face order -> owner slots
@@ -265,6 +278,7 @@ int fy_upload_field(fy_handle h, int f, const double* src)
 }
 int fy_download_field(fy_handle h, int f, double* dst)
 {
+    FyDeviceGuard guard_(h);
     if (!h || f < 0 || f >= FY_F_COUNT || !dst || !h->dField[f]) return FY_ERR_INVALID;
     if (f == FY_F_PHI && h->fv && h->fv->supported) {
         int rc = fvSlotsToFaces(h, h->fv, h->fv->nFi + h->fv->nB, h->fv->phi, h->dField[f]);
@@ -276,6 +290,7 @@ int fy_download_field(fy_handle h, int f, double* dst)
 }
 int fy_device_field(fy_handle h, int f, double** d)
 {
+    FyDeviceGuard guard_(h);
     if (!h || f < 0 || f >= FY_F_COUNT || !d) return FY_ERR_INVALID;
     *d = h->dField[f];
     return FY_OK;
@@ -283,22 +298,26 @@ int fy_device_field(fy_handle h, int f, double** d)
 
 int fy_locate(fy_handle h, const double* xyz, int n, int* ids, int* counts)
 {
+    FyDeviceGuard guard_(h);
     if (!h || n < 0 || (n > 0 && (!xyz || !ids || !counts))) return FY_ERR_INVALID;
     if (n == 0) return FY_OK;
     int rc;
-    if ((rc = fyReserve(h, h->dPdata, (size_t)n * 10))) return rc;
-    if ((rc = fyReserve(h, h->dIds, (size_t)n * FY_MAXLIST))) return rc;
-    if ((rc = fyReserve(h, h->dCnt, (size_t)n))) return rc;
-    FY_CUDA(cudaMemcpyAsync(h->dPdata.p, xyz, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    if ((rc = fyLaunchLocate(h, h->dPdata.p, 3, n, h->dIds.p, h->dCnt.p))) return rc;
-    FY_CUDA(cudaMemcpyAsync(ids, h->dIds.p, (size_t)n * FY_MAXLIST * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    FY_CUDA(cudaMemcpyAsync(counts, h->dCnt.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    // scratch of its own (the staging buffers of fy_get_last_lists): the particle buffer and the cell lists of the last
+    // fy_coupling_proc stay intact
+    if ((rc = fyReserve(h, h->dListW, (size_t)n * FY_MAXLIST))) return rc;
+    if ((rc = fyReserve(h, h->dListIds, (size_t)n * FY_MAXLIST))) return rc;
+    if ((rc = fyReserve(h, h->dListCnt, (size_t)n))) return rc;
+    FY_CUDA(cudaMemcpyAsync(h->dListW.p, xyz, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if ((rc = fyLaunchLocate(h, h->dListW.p, 3, n, h->dListIds.p, h->dListCnt.p))) return rc;
+    FY_CUDA(cudaMemcpyAsync(ids, h->dListIds.p, (size_t)n * FY_MAXLIST * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    FY_CUDA(cudaMemcpyAsync(counts, h->dListCnt.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     FY_CUDA(cudaStreamSynchronize(h->stream));
     return FY_OK;
 }
 
 int fy_find_cell(fy_handle h, const double* xyz, int n, int* cell)
 {
+    FyDeviceGuard guard_(h);
     if (!h || n < 0 || (n > 0 && (!xyz || !cell))) return FY_ERR_INVALID;
     if (h->boxN[0] <= 0) { h->err = "fy_find_cell: mesh has no hex-box descriptor"; return FY_ERR_UNSUPPORTED; }
     if (n == 0) return FY_OK;
@@ -314,6 +333,7 @@ int fy_find_cell(fy_handle h, const double* xyz, int n, int* cell)
 
 int fy_coupling_begin(fy_handle h, double dt)
 {
+    FyDeviceGuard guard_(h);
     if (!h) return FY_ERR_INVALID;
     if (!h->propsSet) { h->err = "fy_set_properties must be called first"; return FY_ERR_INVALID; }
     h->deltaT = dt;
@@ -331,18 +351,21 @@ int fy_coupling_begin(fy_handle h, double dt)
 
 int fy_coupling_proc_device(fy_handle h, const double* d_pdata, int n, int* d_found, double* d_force)
 {
+    FyDeviceGuard guard_(h);
     if (!h || n < 0) return FY_ERR_INVALID;
     return fyCouplingProcDevice(h, d_pdata, n, d_found, d_force);
 }
 
 int fy_coupling_pass_device(fy_handle h, int pass, const double* d_pdata, int n, int* d_found, double* d_force)
 {
+    FyDeviceGuard guard_(h);
     if (!h || n < 0 || pass < 0 || pass > 2) return FY_ERR_INVALID;
     return fyCouplingPass(h, pass, d_pdata, n, d_found, d_force);
 }
 
 int fy_device_accumulators(fy_handle h, double** d_pvol, double** d_upAcc, int** d_stamp)
 {
+    FyDeviceGuard guard_(h);
     if (!h) return FY_ERR_INVALID;
     if (d_pvol) *d_pvol = h->dPvol;
     if (d_upAcc) *d_upAcc = h->dUpAcc;
@@ -352,6 +375,7 @@ int fy_device_accumulators(fy_handle h, double** d_pvol, double** d_upAcc, int**
 
 int fy_stream(fy_handle h, void** cuda_stream)
 {
+    FyDeviceGuard guard_(h);
     if (!h || !cuda_stream) return FY_ERR_INVALID;
     *cuda_stream = (void*)h->stream;
     return FY_OK;
@@ -359,6 +383,7 @@ int fy_stream(fy_handle h, void** cuda_stream)
 
 int fy_coupling_proc(fy_handle h, const double* pdata, int n, int* found, double* force)
 {
+    FyDeviceGuard guard_(h);
     if (!h || n < 0 || (n > 0 && (!pdata || !found || !force))) return FY_ERR_INVALID;
     if (n == 0) { h->lastN = 0; return FY_OK; }
     int rc;
@@ -384,6 +409,7 @@ int fy_coupling_proc(fy_handle h, const double* pdata, int n, int* found, double
 
 int fy_coupling_end(fy_handle h)
 {
+    FyDeviceGuard guard_(h);
     if (!h) return FY_ERR_INVALID;
     static const int outId[4] = {FY_F_USOURCEDRAG, FY_F_ALPHA, FY_F_USOURCE, FY_F_UPARTICLE};
     bool any = false;
@@ -400,6 +426,7 @@ int fy_coupling_end(fy_handle h)
 
 int fy_set_particle_action(fy_handle h, double dt, const double* pdata, int n, int* found, double* force)
 {
+    FyDeviceGuard guard_(h);
     int rc;
     if ((rc = fy_coupling_begin(h, dt))) return rc;
     if ((rc = fy_coupling_proc(h, pdata, n, found, force))) return rc;
@@ -408,6 +435,7 @@ int fy_set_particle_action(fy_handle h, double dt, const double* pdata, int n, i
 
 int fy_set_source_zero(fy_handle h)
 {
+    FyDeviceGuard guard_(h);
     if (!h) return FY_ERR_INVALID;
     int rc = fySourceZeroDevice(h);
     if (rc) return rc;
@@ -424,6 +452,7 @@ int fy_set_source_zero(fy_handle h)
 
 int fy_get_last_lists(fy_handle h, int n, int* counts, int* ids, double* weights)
 {
+    FyDeviceGuard guard_(h);
     if (!h || n < 0 || n > h->lastN) return FY_ERR_INVALID;
     if (n == 0) return FY_OK;
     if (!h->gaussian) { h->err = "fy_get_last_lists: Gaussian mode only"; return FY_ERR_INVALID; }
@@ -443,6 +472,7 @@ int fy_get_last_lists(fy_handle h, int n, int* counts, int* ids, double* weights
 
 int fy_synchronize(fy_handle h)
 {
+    FyDeviceGuard guard_(h);
     if (!h) return FY_ERR_INVALID;
     FY_CUDA(cudaStreamSynchronize(h->stream));
     return FY_OK;
@@ -450,24 +480,28 @@ int fy_synchronize(fy_handle h)
 
 int fy_set_profiling(fy_handle h, int on)
 {
+    FyDeviceGuard guard_(h);
     if (!h) return FY_ERR_INVALID;
     h->profiling = on != 0;
     return FY_OK;
 }
 int fy_get_phase_ms(fy_handle h, double out[8])
 {
+    FyDeviceGuard guard_(h);
     if (!h || !out) return FY_ERR_INVALID;
     for (int i = 0; i < 8; ++i) out[i] = h->phaseMs[i];
     return FY_OK;
 }
 int fy_timer_start(fy_handle h)
 {
+    FyDeviceGuard guard_(h);
     if (!h) return FY_ERR_INVALID;
     FY_CUDA(cudaEventRecord(h->ev[6], h->stream));
     return FY_OK;
 }
 int fy_timer_stop(fy_handle h, double* ms)
 {
+    FyDeviceGuard guard_(h);
     if (!h || !ms) return FY_ERR_INVALID;
     FY_CUDA(cudaEventRecord(h->ev[7], h->stream));
     FY_CUDA(cudaEventSynchronize(h->ev[7]));

@@ -114,6 +114,22 @@ struct fy_ctx {
     struct FvState* fv = nullptr;
 };
 
+// every extern "C" entry point runs on its handle's device whatever the caller's current device is (function
+// attributes, cudaMalloc and launches are per device); the caller's device is restored on return
+struct FyDeviceGuard {
+    int prev = -1;
+    explicit FyDeviceGuard(const fy_ctx* h)
+    {
+        if (!h) return;
+        int cur = -1;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != h->device) {
+            prev = cur;
+            cudaSetDevice(h->device);
+        }
+    }
+    ~FyDeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 #define FY_CUDA(call)                                                                       \
     do {                                                                                    \
         cudaError_t e_ = (call);                                                            \
