@@ -56,6 +56,10 @@ struct Mesh
     ivec ownStart;              // [N+1]
     bool validCmpt[3] = {true, true, true};   // false for the direction "empty" patches remove
     mutable dvec bGradP;        // [nB] gradient of the fixedFluxPressure patches (set by constrainPressure), else 0
+    // decomposed run (decomposePar): processor of every cell, empty = one domain.  The internal faces between two
+    // processors are processor-patch faces there: Amul / residual / sums still see them (Pstream halo + global sums),
+    // the DIC preconditioner does not -- it factorises each processor's own lduMatrix [OF-6 DICPreconditioner.C]
+    ivec procOf;
 };
 
 struct SolverPerf
@@ -176,11 +180,19 @@ SolverPerf pcgSolve(const Mesh& m, const dvec& diag, const dvec& upper, const dv
     sp.finalResidual = sp.initialResidual;
     if (!checkConvergence(sp, tol, relTol)) {
         dvec rD;
-        if (precond == PRECOND_DIC) dicReciprocalD(m, diag, upper, rD);
+        dvec upperPre;                                   // the coefficients the preconditioner sees
+        const dvec* upP = &upper;
+        if (precond == PRECOND_DIC && !m.procOf.empty()) {
+            upperPre = upper;
+            for (int f = 0; f < m.nFaces; ++f)
+                if (m.procOf[m.l[f]] != m.procOf[m.u[f]]) upperPre[f] = 0.0;
+            upP = &upperPre;
+        }
+        if (precond == PRECOND_DIC) dicReciprocalD(m, diag, *upP, rD);
         else if (precond == PRECOND_DIAGONAL) { rD.resize(n); for (int c = 0; c < n; ++c) rD[c] = 1.0/diag[c]; }
         do {
             wArAold = wArA;
-            if (precond == PRECOND_DIC) dicPrecondition(m, upper, rD, rA.data(), wA.data());
+            if (precond == PRECOND_DIC) dicPrecondition(m, *upP, rD, rA.data(), wA.data());
             else if (precond == PRECOND_DIAGONAL) { for (int c = 0; c < n; ++c) wA[c] = rD[c]*rA[c]; }
             else { for (int c = 0; c < n; ++c) wA[c] = rA[c]; }
             wArA = sumProd(wA.data(), rA.data(), n);
@@ -1242,6 +1254,15 @@ void* fvo_create(int nCells, const double* V, int nFaces, const int* owner, cons
     s->vGrad.assign(9*(size_t)nCells, 0.0);
     return s;
 }
+// decomposed-run semantics of the pressure preconditioner: procOf [nCells] (NULL = one domain)
+void fvo_set_partition(void* h, const int* procOf)
+{
+    Ico* s = (Ico*)h;
+    Mesh& m = s->m;
+    if (procOf) m.procOf.assign(procOf, procOf + m.nCells);
+    else m.procOf.clear();
+}
+
 void fvo_destroy(void* h)
 {
     Ico* s = (Ico*)h;

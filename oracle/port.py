@@ -55,6 +55,7 @@ def lib():
         L.fvo_smooth.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int, _dp]
         L.fvo_dic.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp]
         L.fvo_amul.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _dp]
+        L.fvo_set_partition.argtypes = [C.c_void_p, _ip]
         _lib = L
     return _lib
 
@@ -117,6 +118,19 @@ class IcoOracle:
         if self.h:
             self.L.fvo_destroy(self.h)
             self.h = None
+
+    def set_slabs(self, nslabs):
+        """Decomposed-run semantics (decomposePar `simple` along z): nslabs z slabs with the planes
+        [r nz / nslabs, (r+1) nz / nslabs); the DIC preconditioner of the pressure solve then factorises each slab's
+        own matrix, as OpenFOAM does per processor.  nslabs <= 1 restores the single domain."""
+        if nslabs <= 1:
+            self.L.fvo_set_partition(self.h, None)
+            return
+        nx, ny, nz = (int(v) for v in self.mesh["boxN"])
+        k = np.arange(self.N) // (nx * ny)
+        bounds = [(r * nz) // nslabs for r in range(nslabs + 1)]
+        proc = np.searchsorted(np.asarray(bounds[1:]), k, side="right").astype(np.int32)
+        self.L.fvo_set_partition(self.h, _i(_c(proc, np.int32)))
 
     def set_controls(self, **kw):
         self.ctl.update(kw)

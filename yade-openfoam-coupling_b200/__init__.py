@@ -14,3 +14,4 @@ from .binding import Engine, FyError, lib, lib_path, FIELD  # noqa: F401
 from .mesh import box_mesh, set_bc, BC_FIXED_VALUE, BC_ZERO_GRADIENT, BC_EMPTY  # noqa: F401
 from . import replicas  # noqa: F401,E402
 from . import sharded  # noqa: F401,E402
+from . import domain  # noqa: F401,E402

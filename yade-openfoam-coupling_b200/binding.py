@@ -313,6 +313,23 @@ class Engine:
         self._ck(self.L.fy_get_last_lists(self.h, n, _i(cnt), _i(ids), _d(w)))
         return cnt, ids, w
 
+    # ---- multi-GPU: z-slab decomposition of the pressure solve (fycuda.h, fy_dist_*)
+    @staticmethod
+    def dist_unique_id():
+        buf = C.create_string_buffer(128)
+        rc = lib().fy_dist_unique_id(buf)
+        if rc != 0:
+            raise FyError("fy_dist_unique_id failed (%d): is libnccl.so.2 on the loader path?" % rc)
+        return buf.raw
+
+    def dist_init(self, rank, nranks, uid):
+        self._ck(self.L.fy_dist_init(self.h, int(rank), int(nranks), C.c_char_p(bytes(uid))))
+
+    def dist_info(self):
+        out = (C.c_longlong * 6)()
+        self._ck(self.L.fy_dist_info(self.h, out))
+        return dict(rank=out[0], nranks=out[1], kLo=out[2], kHi=out[3], collectives=out[4], halo_bytes=out[5])
+
     def synchronize(self):
         self._ck(self.L.fy_synchronize(self.h))
 

@@ -373,4 +373,26 @@ int fy_get_kernel_ms(fy_handle h, double out[8], int reset)
     return FY_OK;
 }
 
+int fy_dist_unique_id(char id[FY_DIST_ID_BYTES])
+{
+    std::string err;
+    return fvDistUniqueId(id, err);
+}
+
+int fy_dist_init(fy_handle h, int rank, int nranks, const char id[FY_DIST_ID_BYTES])
+{
+    FyDeviceGuard guard_(h);
+    if (!h || !id) return FY_ERR_INVALID;
+    if (!h->fv || !h->fv->supported) { h->err = "fy_dist_init: the mesh did not qualify for the device FV path"; return FY_ERR_UNSUPPORTED; }
+    return fvDistInit(h, h->fv, rank, nranks, id);
+}
+
+int fy_dist_info(fy_handle h, long long out[6])
+{
+    if (!h || !out || !h->fv) return FY_ERR_INVALID;
+    const PenState& P = h->fv->pen;
+    out[0] = P.rank; out[1] = P.nranks; out[2] = P.kLo; out[3] = P.kHi; out[4] = P.distCollectives; out[5] = P.distHaloBytes;
+    return FY_OK;
+}
+
 }  // extern "C"

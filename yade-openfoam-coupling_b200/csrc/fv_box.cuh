@@ -109,6 +109,8 @@ __device__ __forceinline__ void fvBCoefP(const BoxGeom& g, int s, double gammaB,
 struct FvRed {
     double* partial;         // [NV][gridDim.x]
     unsigned int* ticket;    // zero-initialised; reset by the last block
+    double* distOut;         // decomposed solve: the totals go here (this rank's partial sums) instead of to `fin`;
+                             // the host all-reduces them over the ranks and runs the finishing kernel
 };
 
 template <int NV, bool MAXFIRST, int BLOCK, class Fin>
@@ -163,6 +165,11 @@ __device__ __forceinline__ void fvGridReduce(double (&v)[NV], const FvRed& r, Fi
     }
     if (threadIdx.x == 0) {
         *r.ticket = 0u;
-        fin(tot);
+        if (r.distOut) {
+#pragma unroll
+            for (int q = 0; q < NV; ++q) r.distOut[q] = tot[q];
+        } else {
+            fin(tot);
+        }
     }
 }

@@ -300,6 +300,7 @@ struct PenCtl {
     FvSolveDev* st;            // may be null
     int dbg;                   // debug switches (FY_PENCIL_DBG)
     unsigned long long* trace; // optional [warps][8] time stamps / wait cycles
+    double* distOut;           // decomposed solve: the sweep's global sum goes here instead of to Op::fin
 };
 
 // One CTA per pencil group (j-block jb, plane group kq): W COMPUTE warps, each owning ONE k-plane of the
@@ -636,7 +637,7 @@ __global__ void __launch_bounds__(32 * (2 * PEN_WMAX + 1), 1) k_pencil(PencilGeo
 // layout conversion (natural x-fastest cell order <-> pencil layout)
 // ---------------------------------------------------------------------------------------------
 #define PEN_ROW_LOOP(g, c)                                                                                  \
-    for (long long row_ = (long long)blockIdx.x * (BLK / 32) + (threadIdx.x >> 5); row_ < (g).nRows;        \
+    for (long long row_ = (g).rowLo + (long long)blockIdx.x * (BLK / 32) + (threadIdx.x >> 5); row_ < (g).rowHi; \
          row_ += (long long)gridDim.x * (BLK / 32))                                                         \
         for (PenCell c = penDecode((g), row_, threadIdx.x & 31); c.valid; c.valid = false)
 
@@ -709,6 +710,24 @@ __device__ __forceinline__ double penSumACell(const PencilGeom& g, const PenMatr
     return a;
 }
 
+// the same sums for a SYMMETRIC matrix from the upper coefficients alone (the coefficient towards a lower neighbour
+// is that neighbour's own upper coefficient: same values, same order) -- the `low` arrays then serve the
+// preconditioner only, whose coupling across a slab boundary is dropped in a decomposed solve
+__device__ __forceinline__ double penAmulCellSym(const PencilGeom& g, const PenMatrix& M, const double* __restrict__ x,
+                                                 const PenCell& c);
+__device__ __forceinline__ double penSumACellSym(const PencilGeom& g, const PenMatrix& M, const PenCell& c)
+{
+    const long long p = c.pos;
+    double a = M.dg[p];
+    if (c.k > 0) a += M.up[2][p - g.zStride];
+    if (c.j > 0) a += M.up[1][penYm(g, c)];
+    if (c.i > 0) a += M.up[0][p - 32];
+    if (c.i < g.nx - 1) a += M.up[0][p];
+    if (c.j < g.ny - 1) a += M.up[1][p];
+    if (c.k < g.nz - 1) a += M.up[2][p];
+    return a;
+}
+
 __global__ void k_solve_begin(FvSolveDev* st, double tol, double relTol, int maxIter, int precond)
 {
     st->tol = tol; st->relTol = relTol; st->maxIter = maxIter; st->precond = precond;
@@ -721,17 +740,60 @@ __device__ __forceinline__ bool fvConverged(const FvSolveDev* st)
     return st->finalRes < st->tol || (st->relTol > 1e-20 && st->finalRes < st->relTol * st->initRes);
 }
 
+// what the kernels' global sums feed, as functions: a decomposed solve (fv_dist.cu) all-reduces the ranks' partial sums
+// first and then runs them from k_pen_fin
+enum { PEN_FIN_AVG = 0, PEN_FIN_INIT, PEN_FIN_WARA, PEN_FIN_WAPA, PEN_FIN_UPDATE };
+__device__ __forceinline__ void penFinAvg(FvSolveDev* st, const double* t, int N) { st->avg = t[0] / N; }
+__device__ __forceinline__ void penFinInit(FvSolveDev* st, const double* t)
+{
+    st->normFactor = t[0] + 1e-20;
+    st->initRes = t[1] / st->normFactor;
+    st->finalRes = st->initRes;
+    st->done = fvConverged(st) ? 1 : 0;
+}
+__device__ __forceinline__ void penFinWArA(FvSolveDev* st, const double* t)
+{
+    st->wArAold = st->wArA;
+    st->wArA = t[0];
+    st->beta = st->wArA / st->wArAold;
+}
+__device__ __forceinline__ void penFinWApA(FvSolveDev* st, const double* t)
+{
+    st->wApA = t[0];
+    if (fabs(t[0]) / st->normFactor < FV_VSMALL) { st->singular = 1; st->done = 1; }
+    else st->alpha = st->wArA / t[0];
+}
+__device__ __forceinline__ void penFinUpdate(FvSolveDev* st, const double* t)
+{
+    st->finalRes = t[0] / st->normFactor;
+    const bool cont = st->nIter < st->maxIter;                    // nIterations++ < maxIter_
+    st->nIter += 1;
+    if (!cont || fvConverged(st)) st->done = 1;
+}
+__global__ void k_pen_fin(int which, const double* t, FvSolveDev* st, int N)
+{
+    if (st->done && which != PEN_FIN_AVG && which != PEN_FIN_INIT) return;
+    switch (which) {
+    case PEN_FIN_AVG: penFinAvg(st, t, N); break;
+    case PEN_FIN_INIT: penFinInit(st, t); break;
+    case PEN_FIN_WARA: penFinWArA(st, t); break;
+    case PEN_FIN_WAPA: penFinWApA(st, t); break;
+    default: penFinUpdate(st, t); break;
+    }
+}
+
 // gAverage(psi)
 __global__ void __launch_bounds__(BLK) k_pen_avg(PencilGeom g, const double* __restrict__ psi, FvRed red, FvSolveDev* st)
 {
     double v[1] = {0.0};
     PEN_ROW_LOOP(g, c) v[0] += psi[c.pos];
     const int N = g.N;
-    fvGridReduce<1, false, BLK>(v, red, [=](const double* t) { st->avg = t[0] / N; });
+    fvGridReduce<1, false, BLK>(v, red, [=](const double* t) { penFinAvg(st, t, N); });
 }
 
 // rA = source - A psi;  normFactor = sum(|Apsi - sumA avg| + |source - sumA avg|) + 1e-20;
 // initialResidual = sum|rA| / normFactor                              [OF-6 lduMatrix::solver::normFactor]
+template <bool SYM>
 __global__ void __launch_bounds__(BLK)
 k_pen_solve_init(PencilGeom g, PenMatrix M, const double* __restrict__ b, const double* __restrict__ psi,
                  double* __restrict__ rA, FvRed red, FvSolveDev* st)
@@ -739,19 +801,14 @@ k_pen_solve_init(PencilGeom g, PenMatrix M, const double* __restrict__ b, const 
     double v[2] = {0.0, 0.0};
     const double avg = st->avg;
     PEN_ROW_LOOP(g, c) {
-        const double Apsi = penAmulCell(g, M, psi, c);
-        const double t = penSumACell(g, M, c) * avg;
+        const double Apsi = SYM ? penAmulCellSym(g, M, psi, c) : penAmulCell(g, M, psi, c);
+        const double t = (SYM ? penSumACellSym(g, M, c) : penSumACell(g, M, c)) * avg;
         const double r = b[c.pos] - Apsi;
         if (rA) rA[c.pos] = r;
         v[0] += fabs(Apsi - t) + fabs(b[c.pos] - t);
         v[1] += fabs(r);
     }
-    fvGridReduce<2, false, BLK>(v, red, [=](const double* t) {
-        st->normFactor = t[0] + 1e-20;
-        st->initRes = t[1] / st->normFactor;
-        st->finalRes = st->initRes;
-        st->done = fvConverged(st) ? 1 : 0;
-    });
+    fvGridReduce<2, false, BLK>(v, red, [=](const double* t) { penFinInit(st, t); });
 }
 
 // lduMatrix::residual + gSumMag (smoothSolver's convergence test after each sweep)
@@ -806,11 +863,7 @@ k_pen_precond_diag(PencilGeom g, const double* __restrict__ rD, const double* __
         zA[c.pos] = w;
         v[0] += w * rA[c.pos];
     }
-    fvGridReduce<1, false, BLK>(v, red, [=](const double* t) {
-        st->wArAold = st->wArA;
-        st->wArA = t[0];
-        st->beta = st->wArA / st->wArAold;
-    });
+    fvGridReduce<1, false, BLK>(v, red, [=](const double* t) { penFinWArA(st, t); });
 }
 __global__ void __launch_bounds__(BLK) k_pen_recip(PencilGeom g, const double* __restrict__ a, double* __restrict__ out)
 {
@@ -859,11 +912,7 @@ k_pen_amul(PencilGeom g, PenMatrix M, const double* __restrict__ pA, double* __r
         wA[c.pos] = a;
         v[0] += a * pA[c.pos];
     }
-    fvGridReduce<1, false, BLK>(v, red, [=](const double* t) {
-        st->wApA = t[0];
-        if (fabs(t[0]) / st->normFactor < FV_VSMALL) { st->singular = 1; st->done = 1; }
-        else st->alpha = st->wArA / t[0];
-    });
+    fvGridReduce<1, false, BLK>(v, red, [=](const double* t) { penFinWApA(st, t); });
 }
 
 // The same product with R consecutive rows of a slab per warp and trip: the rows share their x-neighbours (R+2 loads of
@@ -877,14 +926,14 @@ k_pen_amul_rows(PencilGeom g, PenMatrix M, const double* __restrict__ pA, double
     if (st->done) return;
     double v[1] = {0.0};
     const int lane = threadIdx.x & 31;
-    const int nGroups = (int)(g.nRows / R);                // Tp is a multiple of 32: a group never straddles two slabs
+    const int grpLo = (int)(g.rowLo / R), nGroups = (int)(g.rowHi / R);   // Tp is a multiple of 32: a group never straddles two slabs
     const long long dYm = lane > 0 ? -33 : -(long long)g.Tp * 32 + 31 * 32 + 31;
     const long long dYp = lane < 31 ? 33 : (long long)g.Tp * 32 - 31 * 32 - 31;
     const double* __restrict__ dg = M.dg;
     const double* __restrict__ u0 = M.up[0];
     const double* __restrict__ u1 = M.up[1];
     const double* __restrict__ u2 = M.up[2];
-    for (int grp = blockIdx.x * (BLK / 32) + (threadIdx.x >> 5); grp < nGroups; grp += gridDim.x * (BLK / 32)) {
+    for (int grp = grpLo + blockIdx.x * (BLK / 32) + (threadIdx.x >> 5); grp < nGroups; grp += gridDim.x * (BLK / 32)) {
         const int row0 = grp * R;
         const int sb = row0 / g.Tp, m0 = row0 - sb * g.Tp;
         const int k = sb / g.nJB, jb = sb - k * g.nJB;
@@ -919,11 +968,7 @@ k_pen_amul_rows(PencilGeom g, PenMatrix M, const double* __restrict__ pA, double
             }
         }
     }
-    fvGridReduce<1, false, BLK>(v, red, [=](const double* t) {
-        st->wApA = t[0];
-        if (fabs(t[0]) / st->normFactor < FV_VSMALL) { st->singular = 1; st->done = 1; }
-        else st->alpha = st->wArA / t[0];
-    });
+    fvGridReduce<1, false, BLK>(v, red, [=](const double* t) { penFinWApA(st, t); });
 }
 
 // psi += alpha pA; rA -= alpha wA; finalResidual = sum|rA|/normFactor; PCG.C's loop condition.
@@ -936,9 +981,9 @@ k_pen_update(PencilGeom g, const double2* __restrict__ pA, const double2* __rest
     if (st->done) return;
     const double alpha = st->alpha;
     double v[1] = {0.0};
-    const long long n2 = g.NP >> 1, stride = (long long)gridDim.x * BLK;
+    const long long q0 = g.rowLo * 16, n2 = g.rowHi * 16, stride = (long long)gridDim.x * BLK;
 #pragma unroll 2
-    for (long long q = (long long)blockIdx.x * BLK + threadIdx.x; q < n2; q += stride) {
+    for (long long q = q0 + (long long)blockIdx.x * BLK + threadIdx.x; q < n2; q += stride) {
         const double2 p = pA[q], w = wA[q];
         double2 x = psi[q], r = rA[q];
         x.x += alpha * p.x;
@@ -950,12 +995,7 @@ k_pen_update(PencilGeom g, const double2* __restrict__ pA, const double2* __rest
         v[0] += fabs(r.x);
         v[0] += fabs(r.y);
     }
-    fvGridReduce<1, false, BLK>(v, red, [=](const double* t) {
-        st->finalRes = t[0] / st->normFactor;
-        const bool cont = st->nIter < st->maxIter;                    // nIterations++ < maxIter_
-        st->nIter += 1;
-        if (!cont || fvConverged(st)) st->done = 1;
-    });
+    fvGridReduce<1, false, BLK>(v, red, [=](const double* t) { penFinUpdate(st, t); });
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -990,7 +1030,7 @@ int launchPencil(fy_ctx* h, FvState* s, const Op& op, FvSolveDev* st)
     W = std::min(W, P.g.nz);
     const size_t smem = (size_t)W * perWarp;
     if (int rc = penFuncAttrs(h, (const void*)k_pencil<Op, REV>)) return rc;
-    PenCtl ctl{P.ticket, P.error, P.partial, st, P.dbg, P.traceOn ? P.trace : nullptr};
+    PenCtl ctl{P.ticket, P.error, P.partial, st, P.dbg, P.traceOn ? P.trace : nullptr, nullptr};
     // clusters of C consecutive plane groups hand the z-neighbour over through distributed shared memory
     const int nKQ = (P.g.nz + W - 1) / W;
     int C = 1;
@@ -1024,13 +1064,14 @@ int launchPencil(fy_ctx* h, FvState* s, const Op& op, FvSolveDev* st)
 
 // second-generation sweeps (fv_pencil2.cuh): Z planes per compute warp, R rows per TMA stage
 template <class Op, bool REV, int Z, int R>
-int launchPen2T(fy_ctx* h, FvState* s, const Op& op, FvSolveDev* st)
+int launchPen2T(fy_ctx* h, FvState* s, const PencilGeom& geom, const Op& op, FvSolveDev* st, double* distOut)
 {
     PenState& P = s->pen;
+    const int nzL = geom.kHi - geom.kLo;
     const int stageBytes = Z * Op::NA * R * 256;
     const int fixedPerWarp = P2_CD * 256 + Z * P2_YRING * 8 + 16 * P2_MAXSTAGE + 8 * 8 + 16;
     int W = std::max(1, std::min(P.W2, Pen2Max<Z>::W));
-    W = std::min(W, (P.g.nz + Z - 1) / Z);
+    W = std::min(W, (nzL + Z - 1) / Z);
     int nStage = 0;
     for (; W >= 1; --W) {
         nStage = std::min(std::min(P.maxStage2, P2_MAXSTAGE), (P.smemBudget2 / W - fixedPerWarp) / stageBytes);
@@ -1045,8 +1086,8 @@ int launchPen2T(fy_ctx* h, FvState* s, const Op& op, FvSolveDev* st)
     const size_t smem = (size_t)W * nStage * stageBytes + (size_t)W * P2_CD * 256 + (size_t)W * Z * P2_YRING * 8 + (size_t)W * nStage * 16 +
                         (size_t)W * 8 * 8 + (size_t)W * 4 + 16;
     if (int rc = penFuncAttrs(h, (const void*)k_pen2<Op, REV, Z, R>)) return rc;
-    PenCtl ctl{P.ticket, P.error, P.partial, st, P.dbg, P.traceOn ? P.trace : nullptr};
-    const int PZ = W * Z, nKQ = (P.g.nz + PZ - 1) / PZ;
+    PenCtl ctl{P.ticket, P.error, P.partial, st, P.dbg, P.traceOn ? P.trace : nullptr, distOut};
+    const int PZ = W * Z, nKQ = (nzL + PZ - 1) / PZ;
     int C = 1;
     while (C * 2 <= P.cluster && C < nKQ) C *= 2;
     const int nCl = (nKQ + C - 1) / C;
@@ -1071,24 +1112,24 @@ int launchPen2T(fy_ctx* h, FvState* s, const Op& op, FvSolveDev* st)
             cfg.gridDim = dim3((unsigned)(P.g.nJB * ((nKQ + 7) / 8) * 8));
         }
     }
-    FY_CUDA(cudaLaunchKernelEx(&cfg, k_pen2<Op, REV, Z, R>, P.g, op, ctl, W, nStage));
+    FY_CUDA(cudaLaunchKernelEx(&cfg, k_pen2<Op, REV, Z, R>, geom, op, ctl, W, nStage));
     h->launches++;
     return FY_OK;
 }
 template <class Op, bool REV>
-int launchPen2(fy_ctx* h, FvState* s, const Op& op, FvSolveDev* st)
+int launchPen2(fy_ctx* h, FvState* s, const PencilGeom& g, const Op& op, FvSolveDev* st, double* distOut = nullptr)
 {
     const PenState& P = s->pen;
     const int key = P.Z2 * 100 + P.R2;
     switch (key) {
-    case 104: return launchPen2T<Op, REV, 1, 4>(h, s, op, st);
-    case 204: return launchPen2T<Op, REV, 2, 4>(h, s, op, st);
+    case 104: return launchPen2T<Op, REV, 1, 4>(h, s, g, op, st, distOut);
+    case 204: return launchPen2T<Op, REV, 2, 4>(h, s, g, op, st, distOut);
 #ifdef PEN2_ALL_VARIANTS
-    case 108: return launchPen2T<Op, REV, 1, 8>(h, s, op, st);
-    case 208: return launchPen2T<Op, REV, 2, 8>(h, s, op, st);
-    case 408: return launchPen2T<Op, REV, 4, 8>(h, s, op, st);
+    case 108: return launchPen2T<Op, REV, 1, 8>(h, s, g, op, st, distOut);
+    case 208: return launchPen2T<Op, REV, 2, 8>(h, s, g, op, st, distOut);
+    case 408: return launchPen2T<Op, REV, 4, 8>(h, s, g, op, st, distOut);
 #endif
-    case 404: return launchPen2T<Op, REV, 4, 4>(h, s, op, st);
+    case 404: return launchPen2T<Op, REV, 4, 4>(h, s, g, op, st, distOut);
     default: h->err = "pencil sweep: no kernel for this FY_PEN2_Z / FY_PEN2_R"; return FY_ERR_INVALID;
     }
 }
@@ -1127,6 +1168,8 @@ int penCreate(fy_ctx* h, FvState* s)
     if (g.nRows * 32 >= (1LL << 31)) { h->err = "pencil layout: mesh too large for 32-bit row arithmetic"; return FY_ERR_INVALID; }
     g.NP = g.nRows * 32;
     g.zStride = (long long)g.nJB * g.Tp * 32;
+    g.kLo = 0; g.kHi = g.nz; g.rowLo = 0; g.rowHi = g.nRows;
+    P.gl = g; P.kLo = 0; P.kHi = g.nz;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1178,6 +1221,7 @@ int penCreate(fy_ctx* h, FvState* s)
 void penDestroy(FvState* s)
 {
     PenState& P = s->pen;
+    fvDistDestroy(s);
     const size_t guard = (size_t)PEN_GUARD * 32;
     for (int q = 0; q < 4; ++q) if (P.pk[q]) cudaFree(P.pk[q] - guard * (q < 3 ? 2 : 1));
     for (auto p : P.mP) if (p) cudaFree(p - guard);
@@ -1195,7 +1239,7 @@ void penDestroy(FvState* s)
 enum { V_B = 0, V_X, V_RD, V_D, V_RA, V_PA, V_WA, V_YA, V_ZA, V_BPRIME = V_RA, V_MID = V_PA, V_EX = V_WA, V_EY = V_YA, V_EZ = V_ZA };
 
 // the five recurrences, dispatched to the pipeline generation in use
-static int sweepDicD(fy_ctx* h, FvState* s, const PenMatrix& M, FvSolveDev* st)
+static int sweepDicD(fy_ctx* h, FvState* s, const PencilGeom& g, const PenMatrix& M, FvSolveDev* st)
 {
     PenState& P = s->pen;
     double** v = P.v;
@@ -1205,11 +1249,11 @@ static int sweepDicD(fy_ctx* h, FvState* s, const PenMatrix& M, FvSolveDev* st)
         return launchPencil<OpDicD, false>(h, s, op, st);
     }
     Op2DicD op{{M.dg, M.low[0], M.low[1], M.low[2]}, v[V_D], v[V_RD]};
-    if ((rc = launchPen2<Op2DicD, false>(h, s, op, st))) return rc;
-    PEN_LAUNCH(k_pen_pack_dic, P.g, v[V_RD], M, (double2*)P.pk[0], (double2*)P.pk[1], (double2*)P.pk[2], P.pk[3]);
+    if ((rc = launchPen2<Op2DicD, false>(h, s, g, op, st))) return rc;
+    PEN_LAUNCH(k_pen_pack_dic, g, v[V_RD], M, (double2*)P.pk[0], (double2*)P.pk[1], (double2*)P.pk[2], P.pk[3]);
     return FY_OK;
 }
-static int sweepDicFwd(fy_ctx* h, FvState* s, const PenMatrix& M, FvSolveDev* st)
+static int sweepDicFwd(fy_ctx* h, FvState* s, const PencilGeom& g, const PenMatrix& M, FvSolveDev* st)
 {
     PenState& P = s->pen;
     double** v = P.v;
@@ -1218,9 +1262,9 @@ static int sweepDicFwd(fy_ctx* h, FvState* s, const PenMatrix& M, FvSolveDev* st
         return launchPencil<OpDicFwd, false>(h, s, f, st);
     }
     Op2DicFwd f{{P.pk[0], P.pk[1], v[V_RA]}, v[V_YA]};
-    return launchPen2<Op2DicFwd, false>(h, s, f, st);
+    return launchPen2<Op2DicFwd, false>(h, s, g, f, st);
 }
-static int sweepDicBwd(fy_ctx* h, FvState* s, const PenMatrix& M, FvSolveDev* st)
+static int sweepDicBwd(fy_ctx* h, FvState* s, const PencilGeom& g, const PenMatrix& M, FvSolveDev* st, double* distOut = nullptr)
 {
     PenState& P = s->pen;
     double** v = P.v;
@@ -1229,7 +1273,7 @@ static int sweepDicBwd(fy_ctx* h, FvState* s, const PenMatrix& M, FvSolveDev* st
         return launchPencil<OpDicBwd, true>(h, s, bw, st);
     }
     Op2DicBwd bw{{v[V_YA], P.pk[2], P.pk[3], v[V_RA]}, v[V_ZA], v[V_YA]};
-    return launchPen2<Op2DicBwd, true>(h, s, bw, st);
+    return launchPen2<Op2DicBwd, true>(h, s, g, bw, st, distOut);
 }
 static int sweepGsFwd(fy_ctx* h, FvState* s, const PenMatrix& M, FvSolveDev* st)
 {
@@ -1240,7 +1284,7 @@ static int sweepGsFwd(fy_ctx* h, FvState* s, const PenMatrix& M, FvSolveDev* st)
         return launchPencil<OpGsFwd, false>(h, s, f, st);
     }
     Op2GsFwd f{{v[V_B], M.low[0], M.low[1], M.low[2], v[V_EX], v[V_EY], v[V_EZ], M.dg}, v[V_MID], v[V_BPRIME], v[V_X]};
-    return launchPen2<Op2GsFwd, false>(h, s, f, st);
+    return launchPen2<Op2GsFwd, false>(h, s, P.g, f, st);
 }
 static int sweepGsBwd(fy_ctx* h, FvState* s, const PenMatrix& M, FvSolveDev* st)
 {
@@ -1251,7 +1295,7 @@ static int sweepGsBwd(fy_ctx* h, FvState* s, const PenMatrix& M, FvSolveDev* st)
         return launchPencil<OpGsBwd, true>(h, s, bw, st);
     }
     Op2GsBwd bw{{v[V_BPRIME], M.up[0], M.up[1], M.up[2], M.dg}, v[V_X], v[V_MID]};
-    return launchPen2<Op2GsBwd, true>(h, s, bw, st);
+    return launchPen2<Op2GsBwd, true>(h, s, P.g, bw, st);
 }
 
 // PCG on owner-slot coefficients (device pointers, natural cell order).  Iteration kernels are queued in
@@ -1269,16 +1313,37 @@ int fvPcgSolve(fy_ctx* h, FvState* s, const double* dg, const double* up, const 
     // diagonal are still in place.  OpenFOAM recomputes them for every solve; the values are the same.
     const bool reuse = sameMatrix && P.precondOf == precond;
     P.precondOf = -1;
-    if (!reuse) PEN_LAUNCH(k_pen_matrix, g, dg, up, up, M);
+    // decomposed solve (fv_dist.cu): the iteration works on this rank's rows `gl`; a kernel's sum is this rank's part,
+    // all-reduced over the ranks before the finishing kernel runs what the single-domain kernel does in its last block
+    const bool dist = P.dist;
+    const PencilGeom& gl = dist ? P.gl : P.g;
+    FvRed redL = s->red;
+    if (dist) redL.distOut = P.distBuf;
+    auto finish = [&](int which, int nv) -> int {
+        if (!dist) return FY_OK;
+        if ((rc = fvDistAllReduce(h, s, P.distBuf, nv))) return rc;
+        k_pen_fin<<<1, 1, 0, h->stream>>>(which, P.distBuf, s->dSolve, g.N);
+        FY_CHECK_LAUNCH();
+        return FY_OK;
+    };
+    if (!reuse) {
+        PEN_LAUNCH(k_pen_matrix, g, dg, up, up, M);
+        // the preconditioner of a slab sees the slab's own matrix: no coupling through its bottom face (M.low serves
+        // the DIC recurrences only; Amul and the residual take every coefficient from M.up)
+        if (dist && P.kLo > 0)
+            FY_CUDA(cudaMemsetAsync(M.low[2] + (size_t)P.kLo * g.zStride, 0, (size_t)g.zStride * sizeof(double), h->stream));
+    }
     PEN_LAUNCH(k_pen_from_nat, g, b, v[V_B]);
     PEN_LAUNCH(k_pen_from_nat, g, psi, v[V_X]);
     k_solve_begin<<<1, 1, 0, h->stream>>>(s->dSolve, tol, relTol, maxIter, precond);
     FY_CHECK_LAUNCH();
-    PEN_LAUNCH(k_pen_avg, g, v[V_X], s->red, s->dSolve);
-    PEN_LAUNCH(k_pen_solve_init, g, M, v[V_B], v[V_X], v[V_RA], s->red, s->dSolve);
+    PEN_LAUNCH(k_pen_avg, gl, v[V_X], redL, s->dSolve);
+    if ((rc = finish(PEN_FIN_AVG, 1))) return rc;
+    PEN_LAUNCH(k_pen_solve_init<true>, gl, M, v[V_B], v[V_X], v[V_RA], redL, s->dSolve);
+    if ((rc = finish(PEN_FIN_INIT, 2))) return rc;
     if (precond == FV_PRECOND_DIC) {
         PEN_LAUNCH(k_pen_arm, g, reuse ? (double*)nullptr : v[V_D], v[V_YA], v[V_ZA], s->dSolve);
-        if (!reuse && (rc = sweepDicD(h, s, M, s->dSolve))) return rc;
+        if (!reuse && (rc = sweepDicD(h, s, gl, M, s->dSolve))) return rc;
     } else if (precond == FV_PRECOND_DIAGONAL && !reuse) {
         PEN_LAUNCH(k_pen_recip, g, M.dg, v[V_RD]);
     }
@@ -1289,31 +1354,35 @@ int fvPcgSolve(fy_ctx* h, FvState* s, const double* dg, const double* up, const 
     auto enqueueIteration = [&](bool ev) -> int {
         if (ev) cudaEventRecord(s->pev[0], h->stream);
         if (precond == FV_PRECOND_DIC) {
-            if ((rc = sweepDicFwd(h, s, M, s->dSolve))) return rc;
+            if ((rc = sweepDicFwd(h, s, gl, M, s->dSolve))) return rc;
             if (ev) cudaEventRecord(s->pev[1], h->stream);
-            if ((rc = sweepDicBwd(h, s, M, s->dSolve))) return rc;
+            if ((rc = sweepDicBwd(h, s, gl, M, s->dSolve, dist ? P.distBuf : nullptr))) return rc;
         } else {
             if (ev) cudaEventRecord(s->pev[1], h->stream);
-            PEN_LAUNCH(k_pen_precond_diag, g, precond == FV_PRECOND_DIAGONAL ? v[V_RD] : (const double*)nullptr, v[V_RA],
-                       v[V_ZA], s->red, s->dSolve);
+            PEN_LAUNCH(k_pen_precond_diag, gl, precond == FV_PRECOND_DIAGONAL ? v[V_RD] : (const double*)nullptr, v[V_RA],
+                       v[V_ZA], redL, s->dSolve);
         }
+        if ((rc = finish(PEN_FIN_WARA, 1))) return rc;
         if (ev) cudaEventRecord(s->pev[2], h->stream);
-        PEN_LAUNCH(k_pen_dir, g, v[V_ZA], v[V_PA], s->dSolve);
+        PEN_LAUNCH(k_pen_dir, gl, v[V_ZA], v[V_PA], s->dSolve);
+        if (dist && (rc = fvDistHalo(h, s, v[V_PA]))) return rc;      // Amul reads the neighbours' boundary planes of pA
         if (ev) cudaEventRecord(s->pev[3], h->stream);
 #if PEN_AMUL_R > 1
-        PEN_LAUNCH(k_pen_amul_rows<PEN_AMUL_R>, g, M, v[V_PA], v[V_WA], s->red, s->dSolve);
+        PEN_LAUNCH(k_pen_amul_rows<PEN_AMUL_R>, gl, M, v[V_PA], v[V_WA], redL, s->dSolve);
 #else
-        PEN_LAUNCH(k_pen_amul, g, M, v[V_PA], v[V_WA], s->red, s->dSolve);
+        PEN_LAUNCH(k_pen_amul, gl, M, v[V_PA], v[V_WA], redL, s->dSolve);
 #endif
+        if ((rc = finish(PEN_FIN_WAPA, 1))) return rc;
         if (ev) cudaEventRecord(s->pev[4], h->stream);
-        PEN_LAUNCH(k_pen_update, g, (const double2*)v[V_PA], (const double2*)v[V_WA], (double2*)v[V_X], (double2*)v[V_RA], s->red,
+        PEN_LAUNCH(k_pen_update, gl, (const double2*)v[V_PA], (const double2*)v[V_WA], (double2*)v[V_X], (double2*)v[V_RA], redL,
                    s->dSolve);
+        if ((rc = finish(PEN_FIN_UPDATE, 1))) return rc;
         if (ev) cudaEventRecord(s->pev[5], h->stream);
         return FY_OK;
     };
     const int batch = s->pcgBatch;
     cudaGraphExec_t& gexec = P.pcgGraph[precond];
-    const bool useGraph = P.useGraphs && !prof && !P.traceOn;
+    const bool useGraph = P.useGraphs && !prof && !P.traceOn && !dist;      // (the decomposed iteration holds NCCL calls: queued eagerly)
     if (useGraph && !gexec && P.graphWarm[precond]) {
         // (every kernel has run eagerly once by now: function attributes set, modules loaded)
         const long long l0 = h->launches;
@@ -1350,6 +1419,7 @@ int fvPcgSolve(fy_ctx* h, FvState* s, const double* dg, const double* up, const 
             }
         }
     }
+    if (dist && (rc = fvDistGatherPlanes(h, s, v[V_X]))) return rc;   // the assembly kernels around the solve run on the whole box
     PEN_LAUNCH(k_pen_to_nat, g, v[V_X], psi);
     s->pcgIterations += s->hSolve->nIter;
     if (perf) {
@@ -1386,7 +1456,7 @@ int fvSmoothSolve(fy_ctx* h, FvState* s, const double* dg, const double* b, doub
     k_solve_begin<<<1, 1, 0, h->stream>>>(s->dSolve, tol, relTol, maxIter, 0);
     FY_CHECK_LAUNCH();
     PEN_LAUNCH(k_pen_avg, g, v[V_X], s->red, s->dSolve);
-    PEN_LAUNCH(k_pen_solve_init, g, M, v[V_B], v[V_X], (double*)nullptr, s->red, s->dSolve);
+    PEN_LAUNCH(k_pen_solve_init<false>, g, M, v[V_B], v[V_X], (double*)nullptr, s->red, s->dSolve);
     PEN_LAUNCH(k_pen_arm, g, v[V_MID], (double*)nullptr, (double*)nullptr, s->dSolve);
     for (;;) {
         if ((rc = readSolve(h, s))) return rc;
@@ -1418,9 +1488,9 @@ int fvDicPrecondition(fy_ctx* h, FvState* s, const double* dg, const double* up,
     PEN_LAUNCH(k_pen_matrix, g, dg, up, up, M);
     PEN_LAUNCH(k_pen_from_nat, g, rA, v[V_RA]);
     PEN_LAUNCH(k_pen_arm, g, v[V_D], v[V_YA], v[V_ZA], (const FvSolveDev*)nullptr);
-    if ((rc = sweepDicD(h, s, M, nullptr))) return rc;
-    if ((rc = sweepDicFwd(h, s, M, nullptr))) return rc;
-    if (!(P.dbg & 64) && (rc = sweepDicBwd(h, s, M, nullptr))) return rc;      // dbg 64: dev probe of the forward sweep
+    if ((rc = sweepDicD(h, s, g, M, nullptr))) return rc;
+    if ((rc = sweepDicFwd(h, s, g, M, nullptr))) return rc;
+    if (!(P.dbg & 64) && (rc = sweepDicBwd(h, s, g, M, nullptr))) return rc;      // dbg 64: dev probe of the forward sweep
     PEN_LAUNCH(k_pen_to_nat, g, v[V_ZA], wA);
     FY_CUDA(cudaMemcpyAsync(P.hError, P.error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     FY_CUDA(cudaStreamSynchronize(h->stream));

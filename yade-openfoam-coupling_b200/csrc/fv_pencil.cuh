@@ -35,6 +35,9 @@ struct PencilGeom {
     long long nRows;       // nz*nJB*Tp
     long long NP;          // nRows*32 doubles per vector
     long long zStride;     // nJB*Tp*32: distance between (i,j,k) and (i,j,k+1)
+    // the part of the box this process works on (everything, unless the solve is decomposed into z slabs: fv_dist.cu)
+    int kLo, kHi;          // k-planes [kLo, kHi)
+    long long rowLo, rowHi; // rows [rowLo, rowHi) = kLo*nJB*Tp ... kHi*nJB*Tp
 };
 
 struct PenCell {

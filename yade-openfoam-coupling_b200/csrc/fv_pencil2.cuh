@@ -553,7 +553,7 @@ __global__ void __launch_bounds__(32 * Pen2Max<Z>::WARPS, 1) k_pen2(PencilGeom g
     if (threadIdx.x < W) yDone[threadIdx.x] = 0u;
     clusterSync();                                         // channels armed, ticket taken: cluster-wide
     const unsigned int tk = ldClusterU32(mapToRank(smemU32(&shTicket), 0));
-    const int nKQ = (g.nz + PZ - 1) / PZ, nCl = (nKQ + C - 1) / C;
+    const int nKQ = (g.kHi - g.kLo + PZ - 1) / PZ, nCl = (nKQ + C - 1) / C;
     const int cl = (int)tk / g.nJB;
     int jb = (int)tk - cl * g.nJB;
     if (REV) jb = g.nJB - 1 - jb;
@@ -562,8 +562,9 @@ __global__ void __launch_bounds__(32 * Pen2Max<Z>::WARPS, 1) k_pen2(PencilGeom g
     constexpr int KS = REV ? -1 : 1;
     // q-th plane of the group in sweep order (backward sweeps count from the top, so that a partial group's real
     // planes always come first)
-    auto planeOf = [&](int q) { return REV ? g.nz - 1 - (kq * PZ + q) : kq * PZ + q; };
-    auto planeOk = [&](int k) { return k >= 0 && k < g.nz; };
+    // (planes [kLo, kHi): the whole box, or this rank's slab of a decomposed solve, whose sweeps stop at the slab faces)
+    auto planeOf = [&](int q) { return REV ? g.kHi - 1 - (kq * PZ + q) : g.kLo + kq * PZ + q; };
+    auto planeOk = [&](int k) { return k >= g.kLo && k < g.kHi; };
     auto nValidOf = [&](int wq) {                          // real planes of compute warp wq
         int n = 0;
         for (int z = 0; z < Z; ++z) n += planeOk(planeOf(wq * Z + z)) ? 1 : 0;
@@ -671,7 +672,10 @@ __global__ void __launch_bounds__(32 * Pen2Max<Z>::WARPS, 1) k_pen2(PencilGeom g
         for (unsigned int b = lane; b < gridDim.x * W; b += 32) x += p[b];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(FULL, x, o);
-        if (lane == 0) op.fin(ctl.st, x);
+        if (lane == 0) {
+            if (ctl.distOut) ctl.distOut[0] = x;
+            else op.fin(ctl.st, x);
+        }
     }
     if (lane == 0) {
         ctl.ticket[0] = 0u;
@@ -688,9 +692,12 @@ k_pen_pack_dic(PencilGeom g, const double* __restrict__ rD, PenMatrix M, double2
     PEN_ROW_LOOP(g, c) {
         const long long p = c.pos;
         const double r = rD[p];
+        // a decomposed solve preconditions with the slab's own matrix: no coupling through the slab's top face (the
+        // bottom face's coefficient was dropped from M.low when the matrix was laid out)
+        const double upz = (c.k == g.kHi - 1 && g.kHi < g.nz) ? 0.0 : M.up[2][p];
         f0[p] = make_double2(r, r * M.low[0][p]);
         f1[p] = make_double2(r * M.low[1][p], r * M.low[2][p]);
         b0[p] = make_double2(r * M.up[0][p], r * M.up[1][p]);
-        bz[p] = r * M.up[2][p];
+        bz[p] = r * upz;
     }
 }

@@ -42,6 +42,14 @@ struct PenState {
     int maxStage2 = 5;                  // input-ring stages
     int smemBudget2 = 200 * 1024;       // shared memory per CTA the rings may fill
     double* pk[4] = {nullptr};          // premultiplied DIC streams: {rD, rD lowx} {rD lowy, rD lowz} {rD upx, rD upy} rD upz
+    // z-slab decomposition of the pressure solve (fv_dist.cu)
+    bool dist = false;
+    int rank = 0, nranks = 1;
+    int kLo = 0, kHi = 0;               // this rank's k-planes
+    PencilGeom gl;                      // the geometry restricted to them (rows [rowLo, rowHi), planes [kLo, kHi))
+    void* comm = nullptr;               // ncclComm_t
+    double* distBuf = nullptr;          // [8] partial sums handed to the all-reduce
+    long long distCollectives = 0, distHaloBytes = 0;
     double* mP[7] = {nullptr};          // pEqn: dg, low[3], up[3]
     double* mU[7] = {nullptr};          // UEqn: dg (current component), low[3], up[3]
     double* v[9] = {nullptr};           // vectors (roles: see fv_pencil.cu)
@@ -86,7 +94,7 @@ struct FvState {
     double *stage = nullptr;
     size_t stageCap = 0;
 
-    FvRed red{nullptr, nullptr};
+    FvRed red{nullptr, nullptr, nullptr};
     FvSolveDev* dSolve = nullptr;
     FvSolveDev* hSolve = nullptr;       // pinned
     FvStepDev* dStep = nullptr;
@@ -111,6 +119,13 @@ int fvPcgSolve(fy_ctx* h, FvState* s, const double* dg, const double* up, const 
 int fvSmoothSetMatrix(fy_ctx* h, FvState* s, const double* lo, const double* up);
 int fvSmoothSolve(fy_ctx* h, FvState* s, const double* dg, const double* b, double* psi, double tol, double relTol,
                   int maxIter, fy_solver_perf* perf);
+void fvSlabRange(int nz, int rank, int nranks, int& kLo, int& kHi);
+int fvDistUniqueId(char out[FY_DIST_ID_BYTES], std::string& err);
+int fvDistInit(fy_ctx* h, FvState* s, int rank, int nranks, const char id[FY_DIST_ID_BYTES]);
+void fvDistDestroy(FvState* s);
+int fvDistAllReduce(fy_ctx* h, FvState* s, double* d, int n);
+int fvDistHalo(fy_ctx* h, FvState* s, double* v);
+int fvDistGatherPlanes(fy_ctx* h, FvState* s, double* v);
 int penCreate(fy_ctx* h, FvState* s);
 void penDestroy(FvState* s);
 int fvDicPrecondition(fy_ctx* h, FvState* s, const double* dg, const double* up, const double* rA, double* wA);
