@@ -11,8 +11,10 @@ One "step" = one icoFoamYade time step (icoFoamYade.C:65-149) on one batch of sy
 same step through the reference-facing call fy_set_particle_action with pinned HOST wire buffers
 (80 B/particle in, 52 B/particle out inside the timed region).
 Timing: CUDA events on the engine's own stream, max over ranks; L2 is flushed between timed steps.
-N > 1: every rank owns one replica of the domain with its own particle batch (weak scaling, no collective
-on the data path; see DESIGN.md "multi-GPU").
+N > 1 (default --partition domain): ONE domain and ONE particle set on N GPUs (strong scaling): the pressure solves are
+z-slab decomposed (NCCL halo exchange + all-reduces, csrc/fv_dist.cu), the particles migrate every step to the rank that
+owns their slab (all-to-all) and the per-cell coupling sums are all-reduced; see DESIGN.md "multi-GPU".
+--partition replicas keeps round 1's N independent replicas (weak scaling, no collective on the data path).
 """
 import argparse
 import ctypes
@@ -38,6 +40,8 @@ WORKLOADS = {
     "C3": (256, 256, 256, 10000000, 1001, "channel", 2.5e-3, 1e-6, "pimpleFoamYade channel 256^3 cells, 10M particles, void fraction + UcEqn/pEqn, fp64, 1xB200 (use --solver pimple)"),
     "C3s": (128, 128, 128, 1000000, 1001, "channel", 5e-3, 1e-6, "pimpleFoamYade channel 128^3 cells, 1M particles (reduced C3; use --solver pimple)"),
     "C2p": (128, 128, 128, 10000000, 7, "channel", 5e-3, 1e-6, "icoFoamYade channel 128^3 cells, 10M particles (particle-bound, for --partition particles)"),
+    "C4": (512, 256, 256, 50000000, 1002, "channel", 1.25e-3, 1e-6, "icoFoamYade box 512x256x256 cells, 50M particles, domain-decomposed 8xB200 (BASELINE configs[3])"),
+    "C4s": (256, 128, 128, 6250000, 1002, "channel", 2.5e-3, 1e-6, "icoFoamYade box 256x128x128 cells, 6.25M particles (C4 at 1/8 size)"),
 }
 UIN = 0.3
 
@@ -53,16 +57,19 @@ def peaks():
 
 
 def ncu_traffic(kernel_label):
-    """DRAM bytes per launch (read + write) of the kernel class from the committed ncu --set full capture."""
-    p = os.path.join(ROOT, "profiles", "r1f_ncu_traffic.json")
-    try:
-        ks = json.load(open(p))["kernels"]
-    except Exception:
-        return None
-    for name, v in ks.items():
-        if kernel_label.startswith(name):
-            return (v["dram_read_MB"] + v["dram_write_MB"]) * 1e6
-    return None
+    """(DRAM bytes per launch (read + write), source file) of the kernel class from the NEWEST committed ncu --set full
+    capture that knows the kernel (profiles/r*_ncu_traffic.json, written by tools/ncu_summary.py --traffic from a
+    capture of this command); (None, None) when no capture names it -- a stale figure is not reported."""
+    import glob
+    for p in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_traffic.json")), reverse=True):
+        try:
+            ks = json.load(open(p))["kernels"]
+        except Exception:
+            continue
+        for name, v in ks.items():
+            if kernel_label.startswith(name):
+                return (v["dram_read_MB"] + v["dram_write_MB"]) * 1e6, os.path.relpath(p, ROOT)
+    return None, None
 
 
 class ClockSampler:
@@ -117,6 +124,32 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def partition_text(partition, world):
+    if world == 1:
+        return "single domain"
+    return {"domain": "one domain on %d GPUs: pressure solve z-slab decomposed (NCCL halo exchange of the PCG search direction + "
+                      "3 all-reduces per iteration, slab-local DIC), particles migrate to the owner slab's rank every step "
+                      "(all-to-all), per-cell coupling sums all-reduced, FV assembly replicated" % world,
+            "particles": "one domain, particle buffer sharded over the GPUs, NCCL all-reduce of the cell sums, fluid solve replicated",
+            "replicas": "one domain replica per GPU"}[partition]
+
+
+def config_of(args, world):
+    """The `config` of the JSON line -- the SAME dict in the engine arm and in the reference arm (the reference arm runs
+    the CPU path "on the engine arm's config")."""
+    nx, ny, nz, P, seed, flow, dt, nu, desc = WORKLOADS[args.workload]
+    N = nx * ny * nz
+    pimple = args.solver == "pimple"
+    replicas = args.partition == "replicas" and world > 1
+    return {"workload": "%s: %s" % (args.workload, desc), "cells": N, "internal_faces": 3 * N - nx * ny - ny * nz - nx * nz,
+            "particles_total": P * world if replicas else P,
+            "coupling": args.coupling, "fluid_solve": not args.coupling_only, "flow": flow, "dt": dt, "nu": nu,
+            "solver": ("pimpleFoamYade (UcEqn.H/pEqn.H, nOuterCorrectors 1, laminar)" if pimple else "icoFoamYade"),
+            "fvSolution": "PISO nCorrectors 2; p PCG/DIC 1e-06 relTol 0.05 (pFinal 0); U smoothSolver symGaussSeidel 1e-05",
+            "l2": "flushed between timed steps (256 MiB write)",
+            "partition": partition_text(args.partition, world)}
+
+
 def flow_case(wl, pkg=None):
     """(oracle mesh, product mesh, U0, p0) of the workload's flow.  With a package (the engine arm) only the product's
     mesh is built -- nothing under oracle/ is imported there; without one (the CPU arm) only the oracle's."""
@@ -151,7 +184,10 @@ def run_engine(args):
     gaussian = args.coupling == "gaussian"
     _, mp, U0, p0 = flow_case(wl, pkg)
     N = mp["nCells"]
-    sharded = args.partition == "particles" and world > 1
+    domain = args.partition == "domain" and world > 1
+    if domain and (args.solver == "pimple" or args.coupling_only):
+        raise SystemExit("bench.py: --partition domain decomposes icoFoamYade's pressure solve (use --partition particles / replicas)")
+    sharded = (args.partition == "particles" or domain) and world > 1
     if sharded:
         # ONE domain, ONE particle buffer split over the ranks (strong scaling of the coupling half; the fluid
         # solve is replicated on every rank from identical inputs)
@@ -171,6 +207,7 @@ def run_engine(args):
     E.upload("p", p0)
     E.create_phi()
     L = E.L
+    dinfo = pkg.domain.init_domain(E, dist, "cuda") if domain else None
 
     # device-resident wire buffers (value) and pinned host wire buffers (e2e)
     d_pd = torch.from_numpy(pd).cuda()
@@ -190,10 +227,31 @@ def run_engine(args):
     if sharded:
         S = pkg.sharded.ShardedCoupling(E, dist, pkg.sharded.device_views(E), gaussian, pkg.sharded.external_stream_ctx(E))
 
+    hz, bounds = 1.0 / nz, None
+    if domain:
+        bounds = torch.tensor([((r + 1) * nz) // world for r in range(world)], dtype=torch.int64, device="cuda")
+    moved = {"records": 0}
+
+    def coupling_domain(src):
+        """particle migration to the owner slab's rank, coupling there, results back to the rank Yade handed them to"""
+        k = torch.clamp(torch.floor(src[:, 2] / hz).to(torch.int64), 0, nz - 1)
+        owner = torch.searchsorted(bounds, k, right=True)
+        mine, route = pkg.domain.migrate(dist, src, owner, "cuda")
+        n = mine.shape[0]
+        fo = torch.empty(max(n, 1), dtype=torch.int32, device="cuda")
+        Fo = torch.empty(max(n, 1), 6, dtype=torch.float64, device="cuda")
+        S.step(dt, mine.data_ptr(), n, fo.data_ptr(), Fo.data_ptr())
+        E.synchronize()
+        d_force.copy_(pkg.domain.migrate_back(dist, Fo[:n], route, "cuda"))
+        d_found.copy_(pkg.domain.migrate_back(dist, fo[:n].reshape(-1, 1), route, "cuda")[:, 0])
+        moved["records"] = int((owner != rank).sum())
+
     def step_device():
         if fluid:
             fluid_pre(dt)
-        if S is not None:
+        if domain:
+            coupling_domain(d_pd)
+        elif S is not None:
             S.step(dt, d_pd.data_ptr(), P, d_found.data_ptr(), d_force.data_ptr())
         else:
             E.coupling_begin(dt)
@@ -205,7 +263,13 @@ def run_engine(args):
     def step_e2e():
         if fluid:
             fluid_pre(dt)
-        if S is not None:
+        if domain:
+            d_pd.copy_(h_pd, non_blocking=True)
+            coupling_domain(d_pd)
+            h_found.copy_(d_found, non_blocking=True)
+            h_force.copy_(d_force, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        elif S is not None:
             with S.stream_ctx():
                 d_pd.copy_(h_pd, non_blocking=True)
             S.step(dt, d_pd.data_ptr(), P, d_found.data_ptr(), d_force.data_ptr())
@@ -307,8 +371,8 @@ def run_engine(args):
         if fluid and kms and kms["samples"] > 0:
             it_step = kms["pcg_iterations"] / float(nprof)
             # pencil-layout kernels: algorithmic bytes = 8 B x (streams read + written) per cell (kernels)
-            cand["k_pencil<OpDicFwd> (DIC forward sweep)"] = (kms["precond_fwd"], 48.0 * N, it_step)       # rD rA low[3] -> y
-            cand["k_pencil<OpDicBwd> (DIC backward sweep + wA.rA)"] = (kms["precond_bwd"], 64.0 * N, it_step)  # y rD up[3] rA -> z, re-arm y
+            cand["k_pen2<Op2DicFwd> (DIC forward sweep)"] = (kms["precond_fwd"], 48.0 * N, it_step)       # {rD, rD low[3]} rA -> y
+            cand["k_pen2<Op2DicBwd> (DIC backward sweep + wA.rA)"] = (kms["precond_bwd"], 56.0 * N, it_step)  # y {rD up[3]} rA -> z, re-arm y
             cand["k_pen_amul_rows<8>"] = (kms["amul"], 48.0 * N, it_step)                                 # dg up[3] p -> w (symmetric: lower = the neighbours' upper)
             cand["k_pen_update"] = (kms["update"], 48.0 * N, it_step)                                     # p w x r -> x r
             cand["k_pen_dir"] = (kms["direction"], 32.0 * N, it_step)                                     # z p -> p, re-arm z
@@ -317,7 +381,7 @@ def run_engine(args):
             return v[0] * (v[2] if len(v) > 2 else 1.0)
         kname = max(cand, key=lambda k: share(cand[k]))
         kms_dom, kbytes = cand[kname][0], cand[kname][1]
-        traffic = ncu_traffic(kname) if wl == "C2" else None
+        traffic, traffic_src = ncu_traffic(kname) if wl == "C2" else (None, None)
         ach = kbytes / (kms_dom * 1e-3) / 1e9 if kms_dom > 0 else 0.0
         line = {
             "metric": METRIC,
@@ -325,14 +389,7 @@ def run_engine(args):
             "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": "%s: %s" % (wl, desc), "cells": N, "internal_faces": Fi, "particles_per_gpu": P,
-                       "particles_total": P_total if sharded else P * world,
-                       "coupling": args.coupling, "fluid_solve": bool(fluid), "flow": flow, "dt": dt, "nu": nu,
-                       "solver": ("pimpleFoamYade (UcEqn.H/pEqn.H, nOuterCorrectors 1, laminar)" if pimple else "icoFoamYade"),
-                       "fvSolution": "PISO nCorrectors 2; p PCG/DIC 1e-06 relTol 0.05 (pFinal 0); U smoothSolver symGaussSeidel 1e-05",
-                       "l2": "flushed between timed steps (256 MiB write)",
-                       "partition": ("one domain, particle buffer sharded over the GPUs, NCCL all-reduce of the cell sums, fluid solve replicated"
-                                     if sharded else ("one domain replica per GPU" if world > 1 else "single domain"))},
+            "config": config_of(args, world),
             "e2e": {"value": pkg.replicas.job_throughput(1 if sharded else world, args.steps, ms_e2e), "unit": "coupled timesteps/s",
                     "h2d_bytes_per_step": 80 * P, "d2h_bytes_per_step": 52 * P},
             "gpu_launches": int(launches),
@@ -347,9 +404,16 @@ def run_engine(args):
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": traffic, "peak_source": which, "kernel_ms": kms_dom,
                          "algorithmic_bytes": kbytes,
-                         "traffic_source": "profiles/r1f_ncu_traffic.json (ncu --set full, dram read+write per launch)" if traffic else None},
+                         "traffic_source": ("%s (ncu --set full, dram read+write per launch)" % traffic_src) if traffic else None},
             "clocks": clocks,
+            "particles_per_gpu": P,
         }
+        if domain:
+            di = E.dist_info()
+            line["domain"] = {"planes_rank0": [dinfo["kLo"], dinfo["kHi"]], "collectives_issued_rank0": di["collectives"],
+                              "halo_bytes_sent_rank0": di["halo_bytes"], "particles_migrated_last_step_rank0": moved["records"],
+                              "limiting_collective": "the three 1-double all-reduces + one 2-plane halo exchange of every PCG iteration "
+                                                     "(latency-bound: %d bytes per plane)" % (8 * (E.N // nz))}
         if not args.no_cpu_baseline and world == 1:
             state = dict(U=E.download("U"), p=E.download("p"), phi=E.download("phi")) if fluid else None
             ref_out = {}
@@ -443,21 +507,109 @@ def cpu_baseline(args, state=None, steps=1, warmup=0, out=None):
     if O:
         O.close()
     t_full = (t_cpl * (P / float(Ps)) + t_fl) / steps
-    return {"value": 1.0 / t_full, "unit": "coupled timesteps/s", "cores": 1, "kind": "port",
-            "sample": "%d step(s): reference coupling operator (unmodified FoamYade.C, quadratic buildCellPartList replaced by "
-                      "its order-preserving dense accumulate) on %d of %d particles scaled linearly to P, %s; "
-                      "one-time k-d build %.1f s excluded" % (
-                          steps, Ps, P,
-                          ("oracle port of the OpenFOAM-6 fluid step on the full %dx%dx%d mesh" % (nx, ny, nz)) if fluid
-                          else "no fluid solve", t_tree),
-            "coupling_seconds_scaled": t_cpl * (P / float(Ps)) / steps, "fluid_seconds": t_fl / steps,
-            "pcg_iterations_per_step": (float(np.mean(iters)) if iters else None)}
+    one = {"value": 1.0 / t_full, "coupling_seconds_scaled": t_cpl * (P / float(Ps)) / steps, "fluid_seconds": t_fl / steps}
+    cores = host_cores()
+    allc = cpu_all_cores(args, cores, state) if (cores > 1 and not args.cpu_one_core) else None
+    fluid_txt = ("oracle port of the OpenFOAM-6 fluid step on the full %dx%dx%d mesh" % (nx, ny, nz)) if fluid else "no fluid solve"
+    base = {"unit": "coupled timesteps/s", "kind": "port", "pcg_iterations_per_step": (float(np.mean(iters)) if iters else None),
+            "single_core": {"value": one["value"], "coupling_seconds_scaled": one["coupling_seconds_scaled"], "fluid_seconds": one["fluid_seconds"],
+                            "sample": "%d step(s): reference coupling operator (unmodified FoamYade.C, quadratic buildCellPartList replaced by its "
+                                      "order-preserving dense accumulate) on %d of %d particles scaled linearly to P, %s; one-time k-d build "
+                                      "%.1f s excluded" % (steps, Ps, P, fluid_txt, t_tree)}}
+    if allc is None:
+        base.update(value=one["value"], cores=1, sample=base["single_core"]["sample"],
+                    coupling_seconds_scaled=one["coupling_seconds_scaled"], fluid_seconds=one["fluid_seconds"])
+    else:
+        base.update(allc)
+    return base
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_all_cores(args, cores, state=None):
+    """The same step with the host's cores used the way the reference uses them (`mpiexec -n <cores> icoFoamYade -parallel`,
+    README.md:29): the particles are split over `cores` reference FoamYade objects (one process each, as the Foam ranks of a
+    decomposed run each take the particles in their sub-domain), and the pressure solve runs decomposed into `cores` z slabs
+    with one host thread per slab (oracle pcgSolvePar: slab-local DIC, OpenFOAM's decomposed preconditioner).  The FV assembly
+    and the momentum predictor of the oracle stay on one core (they are 10-15 % of its step) -- stated in `sample`."""
+    from oracle import port
+    wl = args.workload
+    nx, ny, nz, P, seed, flow, dt, nu, desc = WORKLOADS[wl]
+    fluid = not args.coupling_only
+    pimple = getattr(args, "solver", "ico") == "pimple"
+    Ps = min(P, max(args.cpu_particles, 20000 * cores))
+    # coupling: one process per core, each with its share of the particle sample
+    procs = []
+    for i in range(cores):
+        cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", wl, "--coupling", args.coupling,
+               "--cpl-worker", "%d,%d,%d" % (i, cores, Ps)]
+        procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, cwd=ROOT))
+    t_fl, slabs = 0.0, min(cores, nz)
+    if fluid and not pimple:
+        mo, _, U0, p0 = flow_case(wl, None)
+        O = port.IcoOracle(mo, nu=nu)
+        O.field("U")[:] = state["U"] if state else U0
+        O.field("p")[:] = state["p"] if state else p0
+        if state:
+            O.field("phi")[:] = state["phi"]
+        else:
+            O.create_phi()
+        O.set_slabs(slabs)
+        O.set_threads(slabs)
+    t_cpl = 0.0
+    for pr in procs:                                      # (the workers have the cores to themselves while they run)
+        out, _ = pr.communicate(timeout=1800)
+        for ln in out.splitlines():
+            if ln.startswith("CPLWORKER "):
+                t_cpl = max(t_cpl, float(ln.split()[1]))
+    if fluid and not pimple:
+        t0 = time.time()
+        O.pre(dt)
+        O.solve(dt)
+        t_fl = time.time() - t0
+        O.set_threads(1)
+        O.close()
+    elif fluid:
+        return None                                       # (pimpleFoamYade: single-core baseline only)
+    t_cpl_scaled = t_cpl * (P / float(Ps))
+    return {"value": 1.0 / (t_cpl_scaled + t_fl), "cores": cores, "coupling_seconds_scaled": t_cpl_scaled, "fluid_seconds": t_fl,
+            "sample": "1 step on %d host cores: %d reference FoamYade objects (unmodified FoamYade.C, dense accumulate), one process per "
+                      "core, %d of %d particles split between them and scaled linearly to P (slowest process counts); oracle fluid step "
+                      "with the pressure solve decomposed into %d z slabs, one thread per slab (slab-local DIC as in OpenFOAM -parallel); "
+                      "the oracle's FV assembly and momentum predictor run on one core" % (cores, cores, Ps, P, slabs)}
+
+
+def cpl_worker(args):
+    """one of the all-core baseline's coupling processes: `i,n,Ps` = worker i of n on its share of the first Ps particles"""
+    from oracle import ref
+    from tests import cases
+    i, n, Ps = (int(x) for x in args.cpl_worker.split(","))
+    nx, ny, nz, P, seed, flow, dt, nu, desc = WORKLOADS[args.workload]
+    gaussian = args.coupling == "gaussian"
+    mo, _, U0, p0 = flow_case(args.workload, None)
+    pd = cases.particles(P, seed, radius=0.1 / nx, moving=True)[:Ps]
+    lo, hi = (i * Ps) // n, ((i + 1) * Ps) // n
+    R = ref.RefFoamYade(mo, gaussian)
+    R.set_properties(cases.RHOP, cases.RHOF, nu)
+    R.field("U")[:] = U0
+    t0 = time.time()
+    R.step(dt, pd[lo:hi], pieces=True, truncate12=True, dense=True)
+    R.set_source_zero()
+    print("CPLWORKER %.6f" % (time.time() - t0), flush=True)
+    R.close()
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.cpl_worker:
+        return cpl_worker(args)
     # bounded: at 128^3 one CPU step is ~10-20 s
     steps = max(1, min(args.steps, 2))
     warm = max(0, min(args.warmup, 1))
@@ -468,11 +620,10 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC,
         "value": v, "unit": "coupled timesteps/s", "n_gpus": world, "steps": steps, "warmup": warm,
-        "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": 1e3 / v, "higher_is_better": True,
+        "scaling": "strong" if (world > 1 and args.partition != "replicas") else "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "%s: %s" % (args.workload, desc), "cells": nx * ny * nz, "particles_per_gpu": P,
-                   "coupling": args.coupling, "fluid_solve": not args.coupling_only, "flow": flow, "dt": dt, "nu": nu,
-                   "solver": args.solver},
+        "config": config_of(args, world),
         "cpu_baseline": cb,
         "e2e": {"value": v, "unit": "coupled timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
@@ -488,11 +639,13 @@ def main():
     ap.add_argument("--solver", default="ico", choices=["ico", "pimple"],
                     help="fluid step: icoFoamYade (default, the headline) or pimpleFoamYade (UcEqn.H/pEqn.H; Gaussian coupling)")
     ap.add_argument("--coupling-only", action="store_true")
-    ap.add_argument("--partition", default="replicas", choices=["replicas", "particles"],
-                    help="N > 1: independent domain replicas (weak scaling, default) or one domain with the particle "
-                         "buffer sharded over the GPUs (strong scaling of the coupling half)")
+    ap.add_argument("--partition", default="domain", choices=["domain", "particles", "replicas"],
+                    help="N > 1: one domain, pressure solve z-slab decomposed + particle migration (strong scaling, default); "
+                         "one domain with only the particle buffer sharded; or independent domain replicas (weak scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-particles", type=int, default=200000)
+    ap.add_argument("--cpu-one-core", action="store_true", help="CPU baseline on one core only (skip the all-core arm)")
+    ap.add_argument("--cpl-worker", default="", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -166,9 +166,129 @@ void dicPrecondition(const Mesh& m, const dvec& upper, const dvec& rD, const dou
     for (int f = m.nFaces - 1; f >= 0; --f) wA[m.l[f]] -= rD[m.l[f]]*upper[f]*wA[m.u[f]];
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same PCG with the work of a DECOMPOSED run spread over host threads (cpu baseline on all cores, bench.py): one
+// OpenMP thread per processor (slab) does what an MPI rank of `icoFoamYade -parallel` does -- its rows of Amul, its
+// part of every sum, the DIC substitutions of its own matrix -- and the faces between two slabs (the processor-patch
+// faces) are applied in a short serial pass.  Needs a partition (Mesh::procOf, non-decreasing in the cell index).  The
+// sums are associated per slab, so the last digits (not the algorithm) differ from pcgSolve's; it is a TIMING path and
+// is never the parity checker.
+// ---------------------------------------------------------------------------------------------
+int g_threads = 1;
+
+struct Slabs {
+    std::vector<int> c0, c1, f0, f1;          // cell and owned-face ranges of every slab
+    std::vector<int> cross;                   // faces between two slabs
+};
+
+Slabs slabsOf(const Mesh& m)
+{
+    Slabs S;
+    int n = 0;
+    for (int c = 0; c < m.nCells; ++c) n = std::max(n, m.procOf[c] + 1);
+    S.c0.assign(n, m.nCells); S.c1.assign(n, 0);
+    for (int c = 0; c < m.nCells; ++c) { const int r = m.procOf[c]; S.c0[r] = std::min(S.c0[r], c); S.c1[r] = std::max(S.c1[r], c + 1); }
+    S.f0.resize(n); S.f1.resize(n);
+    for (int r = 0; r < n; ++r) { S.f0[r] = m.ownStart[S.c0[r]]; S.f1[r] = m.ownStart[S.c1[r]]; }
+    for (int f = 0; f < m.nFaces; ++f) if (m.procOf[m.l[f]] != m.procOf[m.u[f]]) S.cross.push_back(f);
+    return S;
+}
+
+SolverPerf pcgSolvePar(const Mesh& m, const dvec& diag, const dvec& upper, const dvec& source, double* psi, double tol,
+                       double relTol, int maxIter, int precond)
+{
+    const int n = m.nCells;
+    const Slabs S = slabsOf(m);
+    const int R = (int)S.c0.size();
+    const int T = std::max(1, std::min(g_threads, R));
+    SolverPerf sp;
+    dvec pA(n), wA(n), rA(n), rD, part(R), part2(R);
+    auto amul = [&](const double* x, double* y) {
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+        for (int r = 0; r < R; ++r) {
+            for (int c = S.c0[r]; c < S.c1[r]; ++c) y[c] = diag[c]*x[c];
+            for (int f = S.f0[r]; f < S.f1[r]; ++f) {
+                if (m.procOf[m.u[f]] != r) continue;
+                y[m.u[f]] += upper[f]*x[m.l[f]];
+                y[m.l[f]] += upper[f]*x[m.u[f]];
+            }
+        }
+        for (int f : S.cross) { y[m.u[f]] += upper[f]*x[m.l[f]]; y[m.l[f]] += upper[f]*x[m.u[f]]; }
+    };
+    auto reduce = [&](const dvec& p) { double s = 0; for (int r = 0; r < R; ++r) s += p[r]; return s; };
+    amul(psi, wA.data());
+    // normFactor
+    dvec sA(n);
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+    for (int r = 0; r < R; ++r) {
+        double a = 0;
+        for (int c = S.c0[r]; c < S.c1[r]; ++c) { rA[c] = source[c] - wA[c]; sA[c] = diag[c]; a += psi[c]; }
+        for (int f = S.f0[r]; f < S.f1[r]; ++f) { if (m.procOf[m.u[f]] != r) continue; sA[m.u[f]] += upper[f]; sA[m.l[f]] += upper[f]; }
+        part[r] = a;
+    }
+    for (int f : S.cross) { sA[m.u[f]] += upper[f]; sA[m.l[f]] += upper[f]; }
+    const double avg = reduce(part)/n;
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+    for (int r = 0; r < R; ++r) {
+        double a = 0, b = 0;
+        for (int c = S.c0[r]; c < S.c1[r]; ++c) { const double t = sA[c]*avg; a += std::fabs(wA[c] - t) + std::fabs(source[c] - t); b += std::fabs(rA[c]); }
+        part[r] = a; part2[r] = b;
+    }
+    const double nf = reduce(part) + 1e-20;
+    sp.initialResidual = reduce(part2)/nf;
+    sp.finalResidual = sp.initialResidual;
+    double wArA = 1e20, wArAold = wArA;
+    if (!checkConvergence(sp, tol, relTol)) {
+        if (precond == PRECOND_DIC) {
+            rD = diag;
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+            for (int r = 0; r < R; ++r) {
+                for (int f = S.f0[r]; f < S.f1[r]; ++f) if (m.procOf[m.u[f]] == r) rD[m.u[f]] -= upper[f]*upper[f]/rD[m.l[f]];
+                for (int c = S.c0[r]; c < S.c1[r]; ++c) rD[c] = 1.0/rD[c];
+            }
+        } else if (precond == PRECOND_DIAGONAL) { rD.resize(n); for (int c = 0; c < n; ++c) rD[c] = 1.0/diag[c]; }
+        do {
+            wArAold = wArA;
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+            for (int r = 0; r < R; ++r) {
+                if (precond == PRECOND_DIC) {
+                    for (int c = S.c0[r]; c < S.c1[r]; ++c) wA[c] = rD[c]*rA[c];
+                    for (int f = S.f0[r]; f < S.f1[r]; ++f) if (m.procOf[m.u[f]] == r) wA[m.u[f]] -= rD[m.u[f]]*upper[f]*wA[m.l[f]];
+                    for (int f = S.f1[r] - 1; f >= S.f0[r]; --f) if (m.procOf[m.u[f]] == r) wA[m.l[f]] -= rD[m.l[f]]*upper[f]*wA[m.u[f]];
+                } else if (precond == PRECOND_DIAGONAL) { for (int c = S.c0[r]; c < S.c1[r]; ++c) wA[c] = rD[c]*rA[c]; }
+                else { for (int c = S.c0[r]; c < S.c1[r]; ++c) wA[c] = rA[c]; }
+                double a = 0;
+                for (int c = S.c0[r]; c < S.c1[r]; ++c) a += wA[c]*rA[c];
+                part[r] = a;
+            }
+            wArA = reduce(part);
+            const double beta = wArA/wArAold;
+            const bool first = sp.nIterations == 0;
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+            for (int r = 0; r < R; ++r)
+                for (int c = S.c0[r]; c < S.c1[r]; ++c) pA[c] = first ? wA[c] : wA[c] + beta*pA[c];
+            amul(pA.data(), wA.data());
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+            for (int r = 0; r < R; ++r) { double a = 0; for (int c = S.c0[r]; c < S.c1[r]; ++c) a += wA[c]*pA[c]; part[r] = a; }
+            const double wApA = reduce(part);
+            if (std::fabs(wApA)/nf < VSMALL) break;
+            const double alpha = wArA/wApA;
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+            for (int r = 0; r < R; ++r) {
+                double a = 0;
+                for (int c = S.c0[r]; c < S.c1[r]; ++c) { psi[c] += alpha*pA[c]; rA[c] -= alpha*wA[c]; a += std::fabs(rA[c]); }
+                part[r] = a;
+            }
+            sp.finalResidual = reduce(part)/nf;
+        } while (sp.nIterations++ < maxIter && !checkConvergence(sp, tol, relTol));
+    }
+    return sp;
+}
+
 SolverPerf pcgSolve(const Mesh& m, const dvec& diag, const dvec& upper, const dvec& source, double* psi, double tol,
                     double relTol, int maxIter, int precond)
 {
+    if (g_threads > 1 && !m.procOf.empty()) return pcgSolvePar(m, diag, upper, source, psi, tol, relTol, maxIter, precond);
     const int n = m.nCells;
     SolverPerf sp;
     dvec pA(n), wA(n), rA(n);
@@ -1262,6 +1382,9 @@ void fvo_set_partition(void* h, const int* procOf)
     if (procOf) m.procOf.assign(procOf, procOf + m.nCells);
     else m.procOf.clear();
 }
+
+// host threads of the timing path (pcgSolvePar); 1 = the sequential checker
+void fvo_set_threads(int n) { g_threads = n < 1 ? 1 : n; }
 
 void fvo_destroy(void* h)
 {

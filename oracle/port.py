@@ -56,6 +56,7 @@ def lib():
         L.fvo_dic.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp]
         L.fvo_amul.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _dp]
         L.fvo_set_partition.argtypes = [C.c_void_p, _ip]
+        L.fvo_set_threads.argtypes = [C.c_int]
         _lib = L
     return _lib
 
@@ -131,6 +132,11 @@ class IcoOracle:
         bounds = [(r * nz) // nslabs for r in range(nslabs + 1)]
         proc = np.searchsorted(np.asarray(bounds[1:]), k, side="right").astype(np.int32)
         self.L.fvo_set_partition(self.h, _i(_c(proc, np.int32)))
+
+    def set_threads(self, n):
+        """host threads of the decomposed PCG's TIMING path (bench.py's all-core CPU baseline); needs set_slabs(>1).
+        Process-wide; 1 restores the sequential checker."""
+        self.L.fvo_set_threads(int(n))
 
     def set_controls(self, **kw):
         self.ctl.update(kw)
