@@ -48,7 +48,9 @@ enum {
 enum {
     FY_BC_FIXED_VALUE = 0,    /* fixedValue / noSlip / movingWall: value given per patch */
     FY_BC_ZERO_GRADIENT = 1,
-    FY_BC_EMPTY = 2           /* OpenFOAM `empty` (2-D cases): the faces take part in nothing */
+    FY_BC_EMPTY = 2,          /* OpenFOAM `empty` (2-D cases): the faces take part in nothing */
+    FY_BC_FIXED_FLUX_PRESSURE = 3   /* p only: fixedFluxPressure, its gradient set by constrainPressure (pimpleFoamYade/pEqn.H:21;
+                                       createFields.H of both solvers declares p so that walls under gravity can carry it) */
 };
 
 /* A patch: nFaces boundary faces that all belong to one boundary-condition group.

@@ -411,6 +411,70 @@ def test_coupled_pimpleFoamYade_step(pkg, case):
     O.close()
 
 
+def test_pimple_closed_box_with_gravity_fixedFluxPressure_on_gpu(pkg):
+    """constrainPressure on fixedFluxPressure walls (pimpleFoamYade/pEqn.H:21) on the device: a closed box under gravity --
+    the case SURVEY.md 8(d) prescribes for C3 / C5 -- with a void-fraction blob, implicit drag and a momentum source that
+    set the fluid in motion.  Assembly bit-exact, fields within 1e-10, identical iteration counts against the oracle; and
+    with no forcing the box stays at rest with p = g.x (the hydrostatic balance of tests/test_fv_oracle.py on the GPU).
+    grad(p) of the NEXT step's pre-coupling block sees the patch's gradient too (fvc::grad(p), pimpleFoamYade.C:74)."""
+    from oracle import meshgen
+    n, L = (10, 12, 8), (0.8, 1.2, 0.6)
+    patches = [("walls", ["xmin", "xmax", "ymin", "ymax", "zmin", "zmax"])]
+    mo = meshgen.hex_box_ldu(*n, *L, patches=patches)
+    meshgen.set_bc(mo, "walls", bcP=meshgen.BC_FIXED_FLUX_PRESSURE)
+    mp = pkg.box_mesh(*n, *L, patches=patches)
+    pkg.set_bc(mp, "walls", bcP=pkg.BC_FIXED_FLUX_PRESSURE)
+    N, Fi, C = mo["nCells"], mo["nInternalFaces"], mo["C"]
+    g = (0.0, -9.81, 0.0)
+    nu, dt = 0.01, 1e-3
+    for forced in (False, True):
+        O = port.IcoOracle(mo, nu=nu)
+        O.create_phi()
+        E = pkg.Engine(mp)
+        assert E.fv_supported(), E.L.fy_last_error(E.h).decode()
+        E.set_properties(cases.RHOP, cases.RHOF, nu, True)
+        E.set_piso_controls(nu=nu)
+        E.create_phi()
+        with pytest.raises(pkg.FyError):
+            E.ico_solve(dt)                               # icoFoamYade's step has no fixedFluxPressure path
+        for it in range(4):
+            if forced:
+                alpha, drag, src = _pimple_drive(mo, it)
+            else:
+                alpha = np.ones(N) if it < 2 else 1 - 0.4 * np.exp(-((C - C.mean(0)) ** 2).sum(1) / 0.02)
+                drag, src = -20.0 * (1 - alpha), np.zeros((N, 3))
+            O.field("uSource")[:] = src
+            O.pimple_solve(dt, alpha, drag, g)
+            E.upload("alpha", alpha)
+            E.upload("uSourceDrag", drag)
+            E.upload("uSource", src)
+            E.pimple_solve(dt, g)
+            if it == 0:
+                for k in ("diagU", "sourceU", "rAU"):
+                    assert np.array_equal(E.fv_get(k), O.field(k)), k
+                assert np.array_equal(E.fv_get("phicForces"), O.pimple_field("phicForces"))
+            so, se = O.stats(), E.ico_stats()
+            assert [q["iters"] for q in so["p"]] == [q["iters"] for q in se["p"]], (forced, it)
+            # (at rest U and phi are solver-tolerance noise around zero: the scale of the comparison is then the velocity
+            # / flux gravity alone would produce in one time step)
+            floor = dict(U=np.sqrt(N) * 9.81 * dt, p=0.0, phi=np.sqrt(Fi) * mo["magSf"].max() * 9.81 * dt)
+            for k in ("U", "p", "phi"):
+                a, b = E.download(k), O.field(k)
+                assert np.linalg.norm(a - b) <= TOL * max(np.linalg.norm(b), floor[k]), (k, forced, it)
+            assert np.abs(E.download("phi")[Fi:]).max() < 1e-14               # no flux through the walls
+            if not forced:
+                p = E.download("p")
+                assert np.abs(E.download("U")).max() < 1e-6                   # solver tolerance, not a flow
+                assert np.abs(p - p[0] + 9.81 * (C[:, 1] - C[0, 1])).max() < 1e-3
+            # the next step's pre-coupling block: gradP with the patch gradient in the boundary cells
+            E.upload("alpha", np.ones(N))
+            E.pimple_pre(dt)
+            want = O.pimple_pre(dt, np.ones(N))[1]
+            assert cases.rel_l2(E.download("gradP").reshape(want.shape), want) <= TOL
+        E.close()
+        O.close()
+
+
 def test_unsupported_mesh_is_refused(pkg):
     mp = pkg.box_mesh(6, 6, 6)
     mp["V"] = mp["V"].copy()

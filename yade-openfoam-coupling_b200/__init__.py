@@ -11,7 +11,7 @@ The directory name contains '-', so load it with
 (see __graft_entry__.load_package()).
 """
 from .binding import Engine, FyError, lib, lib_path, FIELD  # noqa: F401
-from .mesh import box_mesh, set_bc, BC_FIXED_VALUE, BC_ZERO_GRADIENT, BC_EMPTY  # noqa: F401
+from .mesh import box_mesh, set_bc, BC_FIXED_VALUE, BC_ZERO_GRADIENT, BC_EMPTY, BC_FIXED_FLUX_PRESSURE  # noqa: F401
 from . import replicas  # noqa: F401,E402
 from . import sharded  # noqa: F401,E402
 from . import domain  # noqa: F401,E402

@@ -111,8 +111,9 @@ __global__ void __launch_bounds__(BLK) k_courant(BoxGeom g, const double* __rest
 // ---------------------------------------------------------------------------------------------
 // fvc::grad (Gauss linear).  Vector -> tensor [N][9] (T_ij = Sf_i U_j), scalar -> vector [N][3].
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double fvPatchP(const BoxGeom& g, int s, double pc)
+__device__ __forceinline__ double fvPatchP(const BoxGeom& g, int s, double pc, double gradP = 0.0)
 {
+    if (g.kindP[s] == FV_FIXED_FLUX_PRESSURE) return pc + gradP / g.bDc[s];       // fixedGradient: p_P + gradient/deltaCoeffs
     return g.kindP[s] == FV_FIXED_VALUE ? g.valP[s] : pc;
 }
 
@@ -129,7 +130,7 @@ __device__ __forceinline__ void fvGradP(const BoxGeom& g, const double* __restri
             for (int q = 0; q < 6; ++q) {
                 const int s = g.seq[q];
                 if ((s >> 1) != d || g.kindP[s] == FV_EMPTY || !fvOnSide(g, s, i, j, k)) continue;
-                a += g.bSf[s] * fvPatchP(g, s, pc);
+                a += g.bSf[s] * fvPatchP(g, s, pc, fvFluxGradP(g, s, c, i, j, k));
             }
         }
         gp[d] = a / g.V;
@@ -951,7 +952,7 @@ k_pim_predictor_source(BoxGeom g, const double* __restrict__ phicForces, const d
             }
             const int s = 2 * d + hi;
             if (g.kindU[s] == FV_EMPTY) return false;
-            const double sn = g.kindP[s] == FV_FIXED_VALUE ? g.bDc[s] * (g.valP[s] - pc) : 0.0;
+            const double sn = g.kindP[s] == FV_FIXED_VALUE ? g.bDc[s] * (g.valP[s] - pc) : fvFluxGradP(g, s, c, i, j, k);
             nHat = g.bSf[s] / g.bMagSf[s];
             area = g.bSf[s];
             ssf = phicForces[fvSideSlot(g, s, c, i, j, k)] / rc - sn * g.bMagSf[s];
@@ -1008,6 +1009,32 @@ __global__ void __launch_bounds__(BLK) k_pim_add_forces(int n, const double* __r
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) phiHbyA[q] += phicForces[q];
 }
 
+// constrainPressure(p, Uc, phiHbyA, rAUcf)  pim/pEqn.H:21  [OF-6 constrainPressure.C]: on fixedFluxPressure patches
+// snGrad(p) = (phiHbyA_b - Sf_b & U_b)/(magSf_b rAUcf_b), so that the corrected flux through the face equals the wall's
+__global__ void __launch_bounds__(BLK)
+k_pim_constrain_pressure(BoxGeom g, const double* __restrict__ phiHbyA, const double* __restrict__ U,
+                         const double* __restrict__ rAU, double* __restrict__ bGradP)
+{
+    FV_CELL_LOOP(g, c) {
+        int i, j, k;
+        fvIJK(g, c, i, j, k);
+        if (fvInterior(g, i, j, k)) continue;
+        for (int s = 0; s < 6; ++s) {
+            if (g.kindP[s] != FV_FIXED_FLUX_PRESSURE || !fvOnSide(g, s, i, j, k)) continue;
+            const int d = s >> 1, sl = fvSideSlot(g, s, c, i, j, k);
+            const double ub = g.kindU[s] == FV_FIXED_VALUE ? g.valU[s][d] : U[3 * (size_t)c + d];
+            double su = 0.0;                     // Sf_b & U_b, summed over the three components like the CPU loop (two are 0*u)
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                const double um = g.kindU[s] == FV_FIXED_VALUE ? g.valU[s][m] : U[3 * (size_t)c + m];
+                su += (m == d ? g.bSf[s] : 0.0) * um;
+            }
+            (void)ub;
+            bGradP[sl] = (phiHbyA[sl] - su) / (g.bMagSf[s] * rAU[c]);
+        }
+    }
+}
+
 // fvm::laplacian(alphacf*rAUcf, p) == fvc::ddt(alphac) + fvc::div(alphacf*phiHbyA); setReference    pim/pEqn.H:26-33
 __global__ void __launch_bounds__(BLK)
 k_pim_pEqn(BoxGeom g, int pRefCell, double pRefValue, double rDeltaT, const double* __restrict__ upP,
@@ -1037,7 +1064,7 @@ k_pim_pEqn(BoxGeom g, int pRefCell, double pRefValue, double rDeltaT, const doub
                 const int s = g.seq[q];
                 if (g.kindP[s] == FV_EMPTY || !fvOnSide(g, s, i, j, k)) continue;
                 double ic, bc;
-                fvBCoefP(g, s, rc, ic, bc);
+                fvBCoefP(g, s, rc, ic, bc, fvFluxGradP(g, s, c, i, j, k));
                 diag += ic;
                 src += bc;
             }
@@ -1065,12 +1092,12 @@ k_pim_flux_update(BoxGeom g, const double* __restrict__ upP, const double* __res
                 phi[d * N + c] = phiHbyA[d * N + c] - (u * p[c + sd] - u * pc) / fvLerp(g.w[d], ac, alpha[c + sd]);
             } else {
                 double ic, bc;
-                fvBCoefP(g, 2 * d + 1, rc, ic, bc);
+                fvBCoefP(g, 2 * d + 1, rc, ic, bc, fvFluxGradP(g, 2 * d + 1, c, i, j, k));
                 phi[d * N + c] = phiHbyA[d * N + c] - (ic * pc - bc) / FV_ALPHA_B;
             }
             if (v == 0) {
                 double ic, bc;
-                fvBCoefP(g, 2 * d, rc, ic, bc);
+                fvBCoefP(g, 2 * d, rc, ic, bc, fvFluxGradP(g, 2 * d, c, i, j, k));
                 const int sl = fvSideSlot(g, 2 * d, c, i, j, k);
                 phi[sl] = phiHbyA[sl] - (ic * pc - bc) / FV_ALPHA_B;
             }
@@ -1109,7 +1136,7 @@ k_pim_correct_U(BoxGeom g, double dt, double rDeltaT, int corr, const double* __
             const int s = 2 * d + hi;
             if (g.kindU[s] == FV_EMPTY) return false;
             double ic, bc;
-            fvBCoefP(g, s, FV_ALPHA_B * rc, ic, bc);
+            fvBCoefP(g, s, FV_ALPHA_B * rc, ic, bc, fvFluxGradP(g, s, c, i, j, k));
             nHat = g.bSf[s] / g.bMagSf[s];
             area = g.bSf[s];
             ssf = (phicForces[fvSideSlot(g, s, c, i, j, k)] - (ic * pc - bc) / FV_ALPHA_B) / rc;
@@ -1210,6 +1237,7 @@ int fvIcoPre(fy_ctx* h, FvState* s, double dt)
 // icoFoamYade.C:79-140
 int fvIcoSolve(fy_ctx* h, FvState* s, double dt)
 {
+    if (s->hasFluxP) { h->err = "fy_ico_solve: fixedFluxPressure patches are served by fy_pimple_solve only"; return FY_ERR_UNSUPPORTED; }
     const BoxGeom& g = s->g;
     const int N = g.N, G = s->cellGrid;
     const double rDeltaT = 1.0 / dt;
@@ -1346,6 +1374,7 @@ int fvPimpleSolve(fy_ctx* h, FvState* s, double dt, const double gvec[3])
             FV_LAUNCH(k_adjust_scale, G, g, s->phiHbyA, s->dStep);
         }
         FV_LAUNCH(k_pim_add_forces, G, g.nSlots, s->phicForces, s->phiHbyA);
+        if (s->bGradP) FV_LAUNCH(k_pim_constrain_pressure, G, g, s->phiHbyA, U, s->rAU, s->bGradP);
         cudaEventRecord(ev[3], h->stream);
         for (int nonOrth = 0; nonOrth <= ctl.nNonOrthogonalCorrectors; ++nonOrth) {
             FV_LAUNCH(k_pim_pEqn, G, g, ctl.pRefCell, ctl.pRefValue, rDeltaT, s->upP, s->phiHbyA, s->rAU, alpha, alpha0, s->dgP,
@@ -1460,8 +1489,8 @@ int fvCreate(fy_ctx* h, const fy_mesh_desc* m)
     std::vector<int> bslot;
     for (int pI = 0; pI < m->nPatches; ++pI) {
         const fy_patch_desc& pd = m->patches[pI];
-        if (pd.bcU < FV_FIXED_VALUE || pd.bcU > FV_EMPTY || pd.bcP < FV_FIXED_VALUE || pd.bcP > FV_EMPTY)
-            return no("patch type not supported by the device FV path (fixedValue / zeroGradient / empty only)");
+        if (pd.bcU < FV_FIXED_VALUE || pd.bcU > FV_EMPTY || pd.bcP < FV_FIXED_VALUE || pd.bcP > FV_FIXED_FLUX_PRESSURE)
+            return no("patch type not supported by the device FV path (U: fixedValue / zeroGradient / empty; p: those or fixedFluxPressure)");
         for (int q = 0; q < pd.nFaces; ++q, ++b) {
             const double* sf = pd.Sf + 3 * (size_t)q;
             int d = 0;
@@ -1548,6 +1577,13 @@ int fvCreate(fy_ctx* h, const fy_mesh_desc* m)
     for (auto pp : b3) if ((rc = devAlloc(h, pp, N3))) return rc;
     double** b1[] = {&s->rAU, &s->diagU, &s->dgP, &s->bP};
     for (auto pp : b1) if ((rc = devAlloc(h, pp, (size_t)N))) return rc;
+    g.bGradP = nullptr;
+    for (int q = 0; q < 6; ++q) s->hasFluxP = s->hasFluxP || g.kindP[q] == FV_FIXED_FLUX_PRESSURE;
+    if (s->hasFluxP) {                                     // fixedFluxPressure: the patch's gradient, one value per boundary face
+        if ((rc = devAlloc(h, &s->bGradP, NS))) return rc;
+        FY_CUDA(cudaMemsetAsync(s->bGradP, 0, NS * sizeof(double), h->stream));
+        g.bGradP = s->bGradP;
+    }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1571,7 +1607,7 @@ void fvDestroy(fy_ctx* h)
     FvState* s = h->fv;
     if (!s) return;
     void* ptrs[] = {s->dSlotOfFace, s->phi, s->phi0, s->phiHbyA, s->U0, s->HbyA, s->rAU, s->gradP, s->diagU, s->loU, s->upU,
-                    s->srcU, s->dgU, s->bU, s->psiU, s->upP, s->dgP, s->bP, s->stage, s->phicForces, s->divDev,
+                    s->srcU, s->dgU, s->bU, s->psiU, s->upP, s->dgP, s->bP, s->stage, s->phicForces, s->divDev, s->bGradP,
                     s->red.partial, s->red.ticket, s->dSolve, s->dStep};
     for (void* p : ptrs) if (p) cudaFree(p);
     penDestroy(s);

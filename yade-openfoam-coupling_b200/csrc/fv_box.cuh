@@ -19,7 +19,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
-enum { FV_FIXED_VALUE = 0, FV_ZERO_GRADIENT = 1, FV_EMPTY = 2 };
+enum { FV_FIXED_VALUE = 0, FV_ZERO_GRADIENT = 1, FV_EMPTY = 2, FV_FIXED_FLUX_PRESSURE = 3 };   // the last one: p only (pimpleFoamYade/pEqn.H:21)
 enum { FV_PRECOND_DIC = 0, FV_PRECOND_DIAGONAL = 1, FV_PRECOND_NONE = 2 };
 
 struct BoxGeom {
@@ -37,6 +37,8 @@ struct BoxGeom {
     int pNeedRef;
     int reconRm[3];          // fvc::reconstruct: directions tensorField inv() removes (no faces: empty patch pair)
     double sumV;             // sum of cell volumes, accumulated sequentially like the CPU loop
+    // fixedFluxPressure sides: snGrad(p) of every boundary face, set by constrainPressure (owner-slot layout); else null
+    const double* bGradP;
 };
 
 __device__ __forceinline__ void fvIJK(const BoxGeom& g, int c, int& i, int& j, int& k)
@@ -90,11 +92,24 @@ __device__ __forceinline__ void fvBCoefU(const BoxGeom& g, int s, double phib, d
     bc = bcC - bcL;
 }
 
-// pEqn boundary coefficients (fvm::laplacian(gamma, p)) of one boundary face; gammaB = boundary value of gamma
-__device__ __forceinline__ void fvBCoefP(const BoxGeom& g, int s, double gammaB, double& ic, double& bc)
+// snGrad(p) the fixedFluxPressure patch holds on the boundary face of cell c on side s (0 for every other patch type)
+__device__ __forceinline__ double fvFluxGradP(const BoxGeom& g, int s, int c, int i, int j, int k)
+{
+    return g.kindP[s] == FV_FIXED_FLUX_PRESSURE ? g.bGradP[fvSideSlot(g, s, c, i, j, k)] : 0.0;
+}
+
+// pEqn boundary coefficients (fvm::laplacian(gamma, p)) of one boundary face; gammaB = boundary value of gamma;
+// gradP = the face's fixedFluxPressure gradient (fixedGradient: gradientInternalCoeffs 0, gradientBoundaryCoeffs = gradient)
+__device__ __forceinline__ void fvBCoefP(const BoxGeom& g, int s, double gammaB, double& ic, double& bc, double gradP = 0.0)
 {
     ic = 0.0;
     bc = 0.0;
+    if (g.kindP[s] == FV_FIXED_FLUX_PRESSURE) {
+        const double pGamma = gammaB * g.bMagSf[s];
+        ic = pGamma * 0.0;
+        bc = -pGamma * gradP;
+        return;
+    }
     if (g.kindP[s] != FV_FIXED_VALUE) return;
     const double pGamma = gammaB * g.bMagSf[s];
     ic = pGamma * (-1.0 * g.bDc[s]);

@@ -90,6 +90,8 @@ struct FvState {
     double *upP = nullptr, *dgP = nullptr, *bP = nullptr;
     // pimpleFoamYade extras (allocated by the first fy_pimple_solve): phicForces [slots], explicit stress term [N][3]
     double *phicForces = nullptr, *divDev = nullptr;
+    double *bGradP = nullptr;           // [slots] snGrad(p) of the fixedFluxPressure faces (constrainPressure), else null
+    bool hasFluxP = false;
     // scratch for the parity hooks (LDU-order staging)
     double *stage = nullptr;
     size_t stageCap = 0;

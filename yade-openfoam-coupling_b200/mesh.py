@@ -11,6 +11,7 @@ PATCH_NAMES = ("xmin", "xmax", "ymin", "ymax", "zmin", "zmax")
 BC_FIXED_VALUE = 0
 BC_ZERO_GRADIENT = 1
 BC_EMPTY = 2
+BC_FIXED_FLUX_PRESSURE = 3      # p only: gradient set by constrainPressure (pimpleFoamYade/pEqn.H:21)
 
 
 def box_mesh(nx, ny, nz, lx=1.0, ly=1.0, lz=1.0, origin=(0.0, 0.0, 0.0), faces=True, patches=None):
