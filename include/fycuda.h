@@ -173,6 +173,18 @@ int fy_coupling_proc(fy_handle h, const double* h_pdata, int n, int* h_found, do
 int fy_coupling_end(fy_handle h);
 int fy_set_particle_action(fy_handle h, double dt, const double* h_pdata, int n, int* h_found, double* h_force);
 
+/* Overlapped wire transfers for a solver that runs its fluid step on the device (fy_ico_* / fy_pimple_*): the particle
+ * records of the step (caller-owned PINNED host memory, see fy_host_alloc) come up on a second stream while the
+ * pre-coupling block (fy_ico_pre: CourantNo, grad(U); icoFoamYade.C:68-71) runs, and found / force go down while the
+ * pressure-velocity solve (fy_ico_solve) runs.  Same arithmetic as fy_coupling_proc (FoamYade.C:612-628):
+ *   fy_particles_upload_async(h, h_pdata, n)    starts the upload, returns at once
+ *   fy_coupling_proc_staged(h, h_found, h_force) the coupling operator on the staged records (after fy_coupling_begin);
+ *                                                queues the download, returns without waiting
+ *   fy_results_wait(h)                           h_found / h_force are valid after it returns (before the reply to Yade)  */
+int fy_particles_upload_async(fy_handle h, const double* h_pdata, int n);
+int fy_coupling_proc_staged(fy_handle h, int* h_found, double* h_force);
+int fy_results_wait(fy_handle h);
+
 /* Device-resident variant of fy_coupling_proc: all three buffers are device pointers; no PCIe traffic,
  * no host synchronisation.                                                                            */
 int fy_coupling_proc_device(fy_handle h, const double* d_pdata, int n, int* d_found, double* d_force);

@@ -154,7 +154,7 @@ class IcoOracle:
         if not p or n.value == 0:
             raise KeyError(name)
         a = np.ctypeslib.as_array(p, shape=(n.value,))
-        if name in ("U", "uSource", "HbyA", "gradP", "sourceU"):
+        if name in ("U", "uSource", "HbyA", "gradP", "sourceU", "icU", "bcU"):
             return a.reshape(-1, 3)
         if name == "vGrad":
             return a.reshape(-1, 9)

@@ -102,7 +102,7 @@ def mt19937_64_uniform(seed, n):
     return out
 
 
-FIELD_WIDTH = dict(U=3, gradP=3, divT=3, ddtU=3, uSource=3, uParticle=3, vGrad=9, uSourceDrag=1, alpha=1)
+FIELD_WIDTH = dict(U=3, gradP=3, divT=3, ddtU=3, uSource=3, uParticle=3, vGrad=9, uSourceDrag=1, alpha=1, p=1)
 
 
 class RefFoamYade:
@@ -171,6 +171,50 @@ class RefFoamYade:
 
     def set_source_zero(self):
         self.L.ref_set_source_zero(self.h)
+
+    # ---- host-class build only: the solver's loop body with the fluid step on the device (icoFoamYadeB200.H)
+    def set_fv_mesh(self, mo):
+        """LDU addressing, face geometry, patches and the patch types of U / p from an oracle.meshgen.hex_box_ldu() dict;
+        call before set_properties (the engine is created there)."""
+        L = self.L
+        L.ref_set_fv_mesh.argtypes = [C.c_void_p, C.c_int, _ip, _ip, _dp, _dp, _dp, _dp, C.c_int, _ip, _ip, _dp, _dp, _dp, _ip, _dp, _ip, _dp]
+        pl = mo["patches"]
+        c = lambda a, dt=np.float64: np.ascontiguousarray(a, dtype=dt)
+        sizes = c([p["faceCells"].size for p in pl], np.int32)
+        keep = [c(mo["owner"], np.int32), c(mo["neighbour"], np.int32), c(mo["Sf"]), c(mo["magSf"]), c(mo["weights"]),
+                c(mo["deltaCoeffs"]), sizes, c(np.concatenate([p["faceCells"] for p in pl]), np.int32),
+                c(np.concatenate([p["Sf"] for p in pl])), c(np.concatenate([p["magSf"] for p in pl])),
+                c(np.concatenate([p["deltaCoeffs"] for p in pl])), c([p["bcU"] for p in pl], np.int32),
+                c([p["valueU"] for p in pl]).reshape(-1), c([p["bcP"] for p in pl], np.int32), c([p["valueP"] for p in pl])]
+        L.ref_set_fv_mesh(self.h, int(mo["nInternalFaces"]), _i(keep[0]), _i(keep[1]), _d(keep[2]), _d(keep[3]), _d(keep[4]),
+                          _d(keep[5]), len(pl), _i(keep[6]), _i(keep[7]), _d(keep[8]), _d(keep[9]), _d(keep[10]), _i(keep[11]),
+                          _d(keep[12]), _i(keep[13]), _d(keep[14]))
+
+    def set_piso(self, nCorrectors=2, nNonOrthogonalCorrectors=0, momentumPredictor=1):
+        self.L.ref_set_piso.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        self.L.ref_set_piso(self.h, nCorrectors, nNonOrthogonalCorrectors, momentumPredictor)
+
+    def fluid_step(self, solver, dt, pdata, g=(0.0, 0.0, 0.0), yade_dt=0.0):
+        """one pass of the solver's loop body on the device: 'ico' (icoFoamYade.C:65-149) or 'pimple'"""
+        L = self.L
+        L.ref_fluid_step.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, _dp, C.c_int, _ip, _dp, _ip, _dp, _dp]
+        pdata = np.ascontiguousarray(pdata, dtype=np.float64)
+        n = pdata.shape[0]
+        found = np.empty(max(n, 1), dtype=np.int32)
+        force = np.empty((max(n, 1), 6), dtype=np.float64)
+        out = np.zeros(10)
+        gv = np.ascontiguousarray(g, dtype=np.float64)
+        L.ref_fluid_step(self.h, 0 if solver == "ico" else 1, dt, yade_dt, _d(pdata), n, None, _d(gv), _i(found), _d(force), _d(out))
+        return found[:n], force[:n], dict(p_iters=[int(x) for x in out[:int(out[8])]], CoNum=out[9])
+
+    def download_fluid(self):
+        self.L.ref_download_fluid.argtypes = [C.c_void_p]
+        self.L.ref_download_fluid(self.h)
+
+    def set_batched_wire(self, on=True):
+        """host-class build only: one message per direction and step (F1)"""
+        self.L.ref_set_batched_wire.argtypes = [C.c_void_p, C.c_int]
+        self.L.ref_set_batched_wire(self.h, int(on))
 
     def realloc_fields(self):
         """moves every solver-owned field to newly allocated storage (views taken before are stale afterwards)"""

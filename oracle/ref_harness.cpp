@@ -30,7 +30,7 @@
 // second build of this harness (oracle/_build/libhost_harness.so): the SAME fake Yade peer and fields drive
 // the product's OpenFOAM-side host class (yade-openfoam-coupling_b200/host/FoamYadeB200.H) instead of the
 // reference, so a GPU test can compare wire traces and replies message for message.
-#include "FoamYadeB200.H"
+#include "icoFoamYadeB200.H"
 typedef Foam::FoamYadeB200 FyClass;
 #else
 #include "FoamYade.H"
@@ -154,8 +154,10 @@ int MPI_Allreduce(const void* in, void* out, int cnt, MPI_Datatype t, MPI_Op, MP
 {
     g_peer.nAllreduce++;
     g_peer.log("Allreduce", tyName(t), cnt, -1, -1, commName(c));
-    if (t == MPI_INT) { *(int*)out = *(const int*)in; g_peer.ownerRank.push_back(*(const int*)in); }  // F.C:228
-    else { *(double*)out = *(const double*)in; g_peer.sumForce.push_back(*(const double*)in); }       // F.C:514
+    // (cnt == 1: the reference's per-particle / per-component collectives, F.C:228, 514; cnt > 1: the product's batched
+    // wire mode, one message per direction and step)
+    if (t == MPI_INT) { for (int i = 0; i < cnt; ++i) { ((int*)out)[i] = ((const int*)in)[i]; g_peer.ownerRank.push_back(((const int*)in)[i]); } }
+    else { for (int i = 0; i < cnt; ++i) { ((double*)out)[i] = ((const double*)in)[i]; g_peer.sumForce.push_back(((const double*)in)[i]); } }
     return 0;
 }
 int MPI_Finalize(void) { return 0; }
@@ -185,7 +187,7 @@ struct Ref
     Foam::fvMesh mesh;
     Foam::volVectorField U, gradP, divT, ddtU, uSource, uParticle;
     Foam::volTensorField vGrad;
-    Foam::volScalarField uSourceDrag, alpha;
+    Foam::volScalarField uSourceDrag, alpha, p;
     Foam::uniformDimensionedVectorField g;
     FyClass* fy = nullptr;
     void* fyStorage = nullptr;
@@ -208,6 +210,9 @@ void collectOutputs(Ref* r, int n, int* found, double* force6)
         for (int i = 0; i < n && i < (int)P.ownerRank.size(); ++i) found[i] = (P.ownerRank[i] > 0) ? 1 : -1;
         if (r->gaussian) {
             for (size_t i = 0; i < P.sumForce.size() && i < 6*(size_t)n; ++i) force6[i] = P.sumForce[i];
+        } else if (P.p2pForce.size() == 6*(size_t)n && P.nSend <= 2) {
+            // batched wire mode: ONE message with all 6n doubles (zeros for particles this rank did not find)
+            for (size_t i = 0; i < 6*(size_t)n; ++i) force6[i] = P.p2pForce[i];
         } else {
             size_t m = 0;     // one 6-double message per found particle, in index order (F.C:519-531)
             for (int i = 0; i < n; ++i) {
@@ -260,7 +265,7 @@ void* ref_create(int nCells, const double* C, const double* V, int nPoints, cons
     r->mesh.findCellFn_ = boxFindCell; r->mesh.findCellCtx_ = &r->box;
     r->U.setSize(nCells); r->gradP.setSize(nCells); r->divT.setSize(nCells); r->ddtU.setSize(nCells);
     r->uSource.setSize(nCells); r->uParticle.setSize(nCells); r->vGrad.setSize(nCells);
-    r->uSourceDrag.setSize(nCells); r->alpha.setSize(nCells);
+    r->uSourceDrag.setSize(nCells); r->alpha.setSize(nCells); r->p.setSize(nCells);
 
     const bool keepLogging = g_peer.logging;     // ref_set_logging(1) before ref_create records the ctor's sends
     g_peer = Peer();
@@ -305,6 +310,7 @@ double* ref_field(void* h, const char* name)
     if (s == "vGrad") return (double*)r->vGrad.data();
     if (s == "uSourceDrag") return r->uSourceDrag.data();
     if (s == "alpha") return r->alpha.data();
+    if (s == "p") return r->p.data();
     return nullptr;
 }
 
@@ -364,6 +370,78 @@ int ref_find_cell(void* h, const double* xyz)
     Ref* r = (Ref*)h;
     return r->mesh.findCell(Foam::point(xyz[0], xyz[1], xyz[2]));
 }
+
+#ifdef FY_HOST_CLASS
+// ---- the fluid step on the device, driven through the host class and the C++ loop bodies of icoFoamYadeB200.H.
+// The harness fills the shim fvMesh's LDU addressing / face geometry / patches and the patch types of U and p, which
+// the host class reads through the OpenFOAM accessors (owner(), Sf().boundaryField()[patchi], U.boundaryField()[patchi].type()).
+void ref_set_fv_mesh(void* h, int nF, const int* owner, const int* neigh, const double* Sf, const double* magSf,
+                     const double* w, const double* dc, int nPatches, const int* sizes, const int* faceCells,
+                     const double* bSf, const double* bMagSf, const double* bDc, const int* bcU, const double* valU,
+                     const int* bcP, const double* valP)
+{
+    Ref* r = (Ref*)h;
+    Foam::fvMesh& m = r->mesh;
+    m.owner_.setSize(nF); m.neighbour_.setSize(nF); m.Sf_.setSize(nF); m.magSf_.setSize(nF); m.weights_.setSize(nF);
+    m.deltaCoeffs_.setSize(nF);
+    for (int f = 0; f < nF; ++f) {
+        m.owner_[f] = owner[f]; m.neighbour_[f] = neigh[f];
+        m.Sf_[f] = Foam::vector(Sf[3*(size_t)f], Sf[3*(size_t)f + 1], Sf[3*(size_t)f + 2]);
+        m.magSf_[f] = magSf[f]; m.weights_[f] = w[f]; m.deltaCoeffs_[f] = dc[f];
+    }
+    static const char* typeOf[] = {"fixedValue", "zeroGradient", "empty", "fixedFluxPressure"};
+    m.boundary_.assign(nPatches, Foam::fvPatch());
+    m.Sf_.bf_.resize(nPatches); m.magSf_.bf_.resize(nPatches); m.deltaCoeffs_.bf_.resize(nPatches);
+    r->U.bf_.resize(nPatches); r->p.bf_.resize(nPatches);
+    size_t o = 0;
+    for (int pI = 0; pI < nPatches; ++pI) {
+        const int n = sizes[pI];
+        m.boundary_[pI].name_ = "patch" + std::to_string(pI);
+        m.boundary_[pI].faceCells_.setSize(n);
+        r->U.bf_[pI].type_ = typeOf[bcU[pI]];
+        r->p.bf_[pI].type_ = typeOf[bcP[pI]];
+        for (int q = 0; q < n; ++q, ++o) {
+            m.boundary_[pI].faceCells_[q] = faceCells[o];
+            m.Sf_.bf_[pI].v_.push_back(Foam::vector(bSf[3*o], bSf[3*o + 1], bSf[3*o + 2]));
+            m.magSf_.bf_[pI].v_.push_back(bMagSf[o]);
+            m.deltaCoeffs_.bf_[pI].v_.push_back(bDc[o]);
+            r->U.bf_[pI].v_.push_back(Foam::vector(valU[3*pI], valU[3*pI + 1], valU[3*pI + 2]));
+            r->p.bf_[pI].v_.push_back(valP[pI]);
+        }
+    }
+    r->fy->enableFluidSolve(r->U, r->p);
+}
+
+// F1: one message per direction and step instead of 7n collectives (needs the matching Yade-side change)
+void ref_set_batched_wire(void* h, int on) { ((Ref*)h)->fy->batchedWire = on != 0; }
+
+// PISO controls of the device fluid step (defaults: the stock cavity set)
+void ref_set_piso(void* h, int nCorrectors, int nNonOrth, int momentumPredictor)
+{
+    Ref* r = (Ref*)h;
+    fy_piso_controls c;
+    fy_piso_default_controls(&c);
+    c.nCorrectors = nCorrectors; c.nNonOrthogonalCorrectors = nNonOrth; c.momentumPredictor = momentumPredictor;
+    fy_set_piso_controls(r->fy->engine(), &c);
+}
+
+// one pass of the solver's loop body (solver 0: icoFoamYade.C:65-149, 1: pimpleFoamYade.C:65-110) with the fake Yade
+// peer on the wire; out: pressure-solve iteration counts (up to 8), their number, the Courant number
+void ref_fluid_step(void* h, int solver, double dt, double yadeDT, const double* pdata, int n, const int* split,
+                    const double* g3, int* found, double* force6, double* out10)
+{
+    Ref* r = (Ref*)h;
+    setupStep(r, yadeDT, pdata, n, split);
+    Foam::FluidStepLog lg = solver == 0 ? Foam::icoFoamYadeTimeStep(*r->fy, dt)
+                                        : Foam::pimpleFoamYadeTimeStep(*r->fy, dt, Foam::vector(g3[0], g3[1], g3[2]));
+    collectOutputs(r, n, found, force6);
+    for (int q = 0; q < 8; ++q) out10[q] = lg.stats.p[q].nIterations;
+    out10[8] = lg.stats.nPSolves;
+    out10[9] = lg.stats.CoNum;
+}
+
+void ref_download_fluid(void* h) { ((Ref*)h)->fy->downloadFluid(); }
+#endif
 
 // the unmodified driver, F.C:605-632
 void ref_step(void* h, double dt, double yadeDT, const double* pdata, int n, const int* split, int* found, double* force6)

@@ -340,3 +340,106 @@ def test_channel_step_is_divergence_free_and_bounded():
     assert inflow < 0 and abs(inflow + outflow) < 1e-7 * abs(inflow)
     assert np.all(np.isfinite(O.field("U"))) and np.abs(O.field("U")).max() < 1.0
     O.close()
+
+
+def _bcells(m):
+    return np.concatenate([p["faceCells"] for p in m["patches"]])
+
+
+def test_ico_channel_UEqn_and_pEqn_against_independent_routes():
+    """An independent pin of the icoFoamYade restatement on a 3-D case with an inlet, an outlet and walls -- what the
+    2-D cavity log cannot reach (no reference test exists for the fluid half).
+    (1) UEqn (icoFoamYade.C:79-84): the assembled LDU matrix INCLUDING its boundary coefficients, applied to an arbitrary
+        field W, equals V ((W - U0)/dt + div(phi, W) - nu laplacian(W)) evaluated with the separately written explicit
+        fvc operators, in EVERY cell (boundary cells too: a fixedValue patch contributes its value through the
+        boundary coefficients on one side and through the patch value of the fvc operator on the other).
+    (2) pEqn (icoFoamYade.C:118-125): the assembled matrix solved by dense LU gives the p the PCG returned (to solver
+        tolerance), and div(phi) after the corrector is the pEqn residual (continuity closes to tolerance).
+    (3) adjustPhi does not fire with a fixed-value outlet pressure; mass flux in == mass flux out after the step."""
+    from tests import cases_fv
+    mo, _ = cases_fv.channel(None, (10, 7, 6))
+    nu, dt = 0.01, 5e-3
+    O = port.IcoOracle(mo, nu=nu, momentumPredictor=1, nCorrectors=2, pTol=1e-12, pRelTol=0.0, pFinalTol=1e-12)
+    N, Fi = mo["nCells"], mo["nInternalFaces"]
+    U0, p0 = cases_fv.channel_init(mo["C"])
+    O.field("U")[:] = U0
+    O.field("p")[:] = p0
+    O.create_phi()
+    phi0 = np.asarray(O.field("phi")).copy()
+    O.pre(dt)
+    O.solve(dt)
+    diag, lower, upper = (np.asarray(O.field(k)).copy() for k in ("diagU", "lowerU", "upperU"))
+    source, ic, bc = (np.asarray(O.field(k)).copy() for k in ("sourceU", "icU", "bcU"))
+    rng = np.random.default_rng(11)
+    W = rng.standard_normal((N, 3))
+    AW = diag[:, None] * W
+    np.add.at(AW, mo["owner"], upper[:, None] * W[mo["neighbour"]])
+    np.add.at(AW, mo["neighbour"], lower[:, None] * W[mo["owner"]])
+    bcell = _bcells(mo)
+    np.add.at(AW, bcell, ic * W[bcell])
+    rhs = source.copy()
+    np.add.at(rhs, bcell, bc)
+    V = mo["V"][:, None]
+    want = V * ((W - U0) / dt + O.div_phi_vector(phi0, W) - O.laplacian_gamma_vector(np.full(N, nu), W, gammaB=nu))
+    got = AW - rhs
+    assert np.abs(got - want).max() <= 1e-10 * np.abs(want).max()
+    assert len(np.unique(bcell)) > N // 3                                   # the boundary layer is a large part of this mesh
+    # (2) pEqn by dense algebra
+    dP, uP, sP = (np.asarray(O.field(k)).copy() for k in ("diagP", "upperP", "sourceP"))
+    A = _ldu_dense(mo, dP, uP, uP)
+    bP = sP.copy()
+    # the fixed-value outlet enters through the boundary coefficients: rebuild them from the definition
+    rAU = np.asarray(O.field("rAU"))
+    off = 0
+    for pt in mo["patches"]:
+        nf = pt["faceCells"].size
+        if pt["bcP"] == meshgen.BC_FIXED_VALUE:
+            g = rAU[pt["faceCells"]] * pt["magSf"]
+            A[pt["faceCells"], pt["faceCells"]] += g * (-1.0 * pt["deltaCoeffs"])
+            np.add.at(bP, pt["faceCells"], -g * (pt["deltaCoeffs"] * pt["valueP"]))
+        off += nf
+    p_dense = np.linalg.solve(A, bP)
+    p = np.asarray(O.field("p"))
+    assert np.linalg.norm(p - p_dense) <= 1e-8 * np.linalg.norm(p_dense)
+    st = O.stats()
+    assert st["sumLocalContErr"] < 1e-12 and abs(st["globalContErr"]) < 1e-13
+    # (3) mass balance over the patches
+    phi = np.asarray(O.field("phi"))
+    assert abs(phi[Fi:].sum()) < 1e-12 * np.abs(phi[Fi:]).sum()
+    O.close()
+
+
+def test_pimple_UcEqn_matrix_with_boundary_cells():
+    """The term-by-term check of the assembled UcEqn (above) extended to EVERY cell: the boundary coefficients of the
+    restatement's matrix (fixedValue walls: value through the implicit laplacian and the convection; alphac's patches
+    hold 1) against the explicit operators with the patch values."""
+    m = _mesh3d((9, 8, 7))
+    nu, dt = 0.02, 0.01
+    O = port.IcoOracle(m, nu=nu, momentumPredictor=0, nCorrectors=1)
+    C = m["C"]
+    N = m["nCells"]
+    rng = np.random.default_rng(5)
+    U0 = 0.3 * np.stack([np.sin(3 * C[:, 1]) + C[:, 0] ** 2, np.cos(2 * C[:, 0]) * C[:, 2], C[:, 0] * C[:, 1]], 1)
+    O.field("U")[:] = U0
+    O.create_phi()
+    phi0 = np.asarray(O.field("phi")).copy()
+    alpha = 1 - 0.4 * np.exp(-((C - C.mean(0)) ** 2).sum(1) / (0.05 * np.ptp(C[:, 0]) ** 2))
+    drag = -30.0 * (1 - alpha)
+    O.field("uSource")[:] = 0.0
+    O.pimple_solve(dt, alpha, drag)
+    diag, lower, upper = (np.asarray(O.field(k)).copy() for k in ("diagU", "lowerU", "upperU"))
+    source, ic, bc = (np.asarray(O.field(k)).copy() for k in ("sourceU", "icU", "bcU"))
+    alphaf, spDiv, divDev = (np.asarray(O.pimple_field(k)).copy() for k in ("alphaf", "spDiv", "divDev"))
+    W = rng.standard_normal((N, 3))
+    AW = diag[:, None] * W
+    np.add.at(AW, m["owner"], upper[:, None] * W[m["neighbour"]])
+    np.add.at(AW, m["neighbour"], lower[:, None] * W[m["owner"]])
+    bcell = _bcells(m)
+    np.add.at(AW, bcell, ic * W[bcell])
+    rhs = source.copy()
+    np.add.at(rhs, bcell, bc)
+    V = m["V"][:, None]
+    want = V * (alpha[:, None] * (W - U0) / dt + O.div_phi_vector(alphaf * phi0, W) - spDiv[:, None] * W
+                - O.laplacian_gamma_vector(alpha * nu, W, gammaB=nu) - divDev - drag[:, None] * W)
+    got = AW - rhs
+    assert np.abs(got - want).max() <= 1e-10 * np.abs(want).max()

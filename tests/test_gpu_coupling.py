@@ -5,6 +5,8 @@ Bar: cell lists / found flags bit-exact; forces and source fields within 1e-10 r
 the only difference is the order of the atomic per-cell additions)."""
 import os
 
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -159,6 +161,40 @@ def test_device_resident_path_and_repeatability(pkg):
         assert cases.rel_l2(d_force.cpu().numpy(), F0) <= 1e-14
         assert cases.rel_l2(E.download("uSource"), src0) <= TOL
         E.set_source_zero()
+    E.close()
+
+
+def test_overlapped_wire_transfers_equal_the_blocking_call(pkg):
+    """fy_particles_upload_async + fy_coupling_proc_staged + fy_results_wait (copies on the engine's second stream) give
+    what fy_set_particle_action gives, step after step, with pinned host buffers that are refilled in between."""
+    import torch
+    n, P = 24, 4000
+    mp = pkg.box_mesh(n, n, n, faces=False)
+    flds = cases.fields_for(mp["C"])
+    E = pkg.Engine(mp)
+    L = E.L
+    for gaussian in (True, False):
+        E.set_properties(cases.RHOP, cases.RHOF, cases.NU, gaussian)
+        for k in ("U", "gradP", "divT", "vGrad"):
+            E.upload(k, flds[k])
+        h_pd = torch.empty(P, 10, dtype=torch.float64).pin_memory()
+        h_found = torch.zeros(P, dtype=torch.int32).pin_memory()
+        h_force = torch.zeros(P, 6, dtype=torch.float64).pin_memory()
+        for it in range(3):
+            pd = cases.particles(P, 50 + it, radius=0.1 / n, moving=True)
+            f0, F0 = E.set_particle_action(1e-3, pd)
+            src0 = E.download("uSource")
+            E.set_source_zero()
+            h_pd.copy_(torch.from_numpy(pd))
+            E._ck(L.fy_particles_upload_async(E.h, C.c_void_p(h_pd.data_ptr()), P))
+            E.coupling_begin(1e-3)
+            E._ck(L.fy_coupling_proc_staged(E.h, C.c_void_p(h_found.data_ptr()), C.c_void_p(h_force.data_ptr())))
+            src1 = E.download("uSource")
+            E.set_source_zero()
+            E._ck(L.fy_results_wait(E.h))
+            assert np.array_equal(h_found.numpy(), f0)
+            assert cases.rel_l2(h_force.numpy(), F0) <= 1e-14
+            assert cases.rel_l2(src1, src0) <= TOL
     E.close()
 
 

@@ -91,6 +91,11 @@ def test_survey_known_answers_c1():
     assert ids[0, :3].tolist() == [25240, 25272, 25241] and cnt[0] == 3
     assert ids[1, :2].tolist() == [3972, 4967] and cnt[1] == 2
     assert ids[2, :4].tolist() == [8562, 8594, 8595, 7507] and cnt[2] == 4
+    # the whole cell-id stream as one number (FNV-1a-64 over the ids as u32 words, 0xffffffff after each particle).  The
+    # survey quotes 3010d9a434ff91c7 for its own hashing code, which it does not give and the stated recipe does not
+    # reproduce (every other known answer of SURVEY.md 8(c) -- pair count, lists, weights, forces, field sums -- does);
+    # the value below is this recipe on the reference's lists and pins them all at once.
+    assert ref.fnv1a_lists(cnt, ids) == 0xcb6dab77c8744071
     np.testing.assert_allclose(F[0, :3], [-2.7627465786243748e-05, 5.1855587194777599e-07, 1.7114769700056499e-06], rtol=1e-14)
     np.testing.assert_allclose(F[1, :3], [-1.8041716856012765e-05, 1.6363090206990569e-06, 1.3900794444619142e-06], rtol=1e-14)
     np.testing.assert_allclose(np.linalg.norm(R.field("uSource"), axis=1).sum(), 0.00041887902047863922, rtol=1e-12)

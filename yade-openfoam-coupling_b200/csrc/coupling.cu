@@ -17,6 +17,9 @@
 #include <cmath>
 #include <cstdio>
 
+#include <mutex>
+#include <set>
+#include <utility>
 #include <cub/device/device_radix_sort.cuh>
 
 #include "fy_ctx.h"
@@ -57,14 +60,24 @@ struct Trail {
     int nImp;
 };
 
+// The stack of pending "other" subtrees: 16 bytes per entry (the range [lo, hi) with the depth in the top 5 bits of hi,
+// and the squared plane distance), per-thread local memory.  A subtree whose plane distance is not below the best
+// distance AT PUSH TIME is never pushed: the reference tests it after the near side returned (MT.C:225), when `best`
+// can only be smaller, so it would be rejected then anyway.  (Measured on B200: keeping the stack in shared memory
+// instead -- 61 KB per 128-thread block, 12 warps per SM -- costs more in lost latency hiding than the local-memory
+// traffic it removes: 2.39 ms against 1.39 ms at C2.)
+constexpr int KD_STACK = 30;                  // >= tree depth (2^26 nodes: 27 levels)
+constexpr int KD_BLOCK = 128;
+constexpr int KD_SMEM = 0;
+
 __device__ __forceinline__ void kdDescend(const FyKdNode* __restrict__ tree, int nTree, double px, double py,
                                           double pz, double maxDist, Trail& tr)
 {
     tr.nImp = 0;
     if (nTree <= 0) return;
-    int slo[40], shi[40];
-    double sdf2[40];
-    unsigned char sdep[40];
+    constexpr int T = 1, me = 0;
+    int2 sRange[KD_STACK];
+    double sDf2[KD_STACK];
     int sp = 0;
 
     int lo = 0, hi = nTree, depth = 0;
@@ -92,16 +105,18 @@ __device__ __forceinline__ void kdDescend(const FyKdNode* __restrict__ tree, int
             if (df > 0.0) { olo = md + 1; ohi = hi; hi = md; }      // next = left, other = right (MT.C:206-212)
             else          { olo = lo; ohi = md; lo = md + 1; }
             depth++;
-            if (olo < ohi) {
-                slo[sp] = olo; shi[sp] = ohi; sdf2[sp] = df2; sdep[sp] = (unsigned char)depth;
+            if (olo < ohi && df2 < best && sp < KD_STACK) {
+                sRange[sp * T + me] = make_int2(olo, ohi | (depth << 26));
+                sDf2[sp * T + me] = df2;
                 sp++;
             }
         } else {
             bool got = false;
             while (sp > 0) {
                 --sp;
-                if (sdf2[sp] < best) {                              // MT.C:225, tested after the near side returned
-                    lo = slo[sp]; hi = shi[sp]; depth = sdep[sp];
+                if (sDf2[sp * T + me] < best) {                     // MT.C:225, tested after the near side returned
+                    const int2 r = sRange[sp * T + me];
+                    lo = r.x; hi = r.y & ((1 << 26) - 1); depth = (int)((unsigned)r.y >> 26);
                     got = true;
                     break;
                 }
@@ -180,14 +195,11 @@ k_locate_gauss(const FyKdNode* __restrict__ tree, int nTree, const double* __res
     }
     // weights (F.C:301-314): the squared distance is the same number the descent computed
     // ((C-p)^2 == (p-C)^2 term by term, same summation order), so no cell-centre gather is needed.
-    double w[FY_MAXLIST];
-    int id[FY_MAXLIST];
     double allwt = 0.0;
     for (int j = 0; j < k; ++j) {
         const int s = (tr.nImp - 1 - j) % FY_MAXLIST;
-        id[j] = tr.id[s];
         const double wj = exp(-tr.d2[s] / gc.twoSigmaSq) * gc.interpRangeCu * gc.sigmaPi;
-        w[j] = wj;
+        tr.d2[s] = wj;                                               // (the weight takes the distance's place: no second array)
         allwt += wj;
     }
     const double vx = rec[3], vy = rec[4], vz = rec[5];
@@ -195,10 +207,11 @@ k_locate_gauss(const FyKdNode* __restrict__ tree, int nTree, const double* __res
     const double vol = M_PI * pow(dia, 3.0) / 6.0;                   // F.H:36
     for (int j = 0; j < FY_MAXLIST; ++j) {
         if (j < k) {
-            const double wj = w[j] / allwt;                          // F.C:313
-            ids[(size_t)j * n + t] = id[j];
+            const int s = (tr.nImp - 1 - j) % FY_MAXLIST;
+            const double wj = tr.d2[s] / allwt;                      // F.C:313
+            const int c = tr.id[s];
+            ids[(size_t)j * n + t] = c;
             wts[(size_t)j * n + t] = wj;
-            const int c = id[j];
             // F.C:271-272 / 278-279: pVol*weight ; (linearVelocity*weight)*pVol
             atomicAdd(&pvolAcc[c], vol * wj);
             atomicAdd(&upAcc[3 * (size_t)c], vx * wj * vol);
@@ -392,10 +405,18 @@ __global__ void k_fill(double* __restrict__ a, size_t n, double v)
 
 }  // namespace
 
+// the packed stack entries hold the subtree depth in 5 bits next to a 26-bit node index
+static int kdFuncAttrs(fy_ctx* h, const void*)
+{
+    if (h->nTree >= (1 << 26)) { h->err = "k-d descent: more than 2^26 cells"; return FY_ERR_UNSUPPORTED; }
+    return FY_OK;
+}
+
 int fyLaunchLocate(fy_ctx* h, const double* d_xyz, int stride, int n, int* d_ids, int* d_cnt)
 {
     if (n <= 0) return FY_OK;
-    k_locate<<<fyGrid(n, 128), 128, 0, h->stream>>>(h->dTree, h->nTree, d_xyz, stride, n, h->maxDist, d_ids, d_cnt);
+    if (int rc = kdFuncAttrs(h, (const void*)k_locate)) return rc;
+    k_locate<<<fyGrid(n, KD_BLOCK), KD_BLOCK, KD_SMEM, h->stream>>>(h->dTree, h->nTree, d_xyz, stride, n, h->maxDist, d_ids, d_cnt);
     FY_CHECK_LAUNCH();
     return FY_OK;
 }
@@ -412,17 +433,19 @@ int fyLaunchFindCell(fy_ctx* h, const double* d_xyz, int stride, int n, int* d_c
 
 // One YadeProc's worth of FoamYade.C:612-628 on device-resident buffers.
 namespace {
-// sort key: the particle's cell on a 128^3 grid over the mesh bounding box, x fastest like the cells
+// sort key: the particle's cell on a gx x gy x gz grid over the mesh bounding box, x fastest like the cells (the mesh's
+// own hex box when it has one, up to 256 per direction; 128^3 otherwise)
 __global__ void k_particle_keys(const double* __restrict__ pdata, int n, double x0, double y0, double z0, double sx,
-                                double sy, double sz, unsigned int* __restrict__ key, int* __restrict__ idx)
+                                double sy, double sz, int gx, int gy, int gz, unsigned int* __restrict__ key,
+                                int* __restrict__ idx)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     const double* r = pdata + (size_t)p * 10;
-    const int ix = min(127, max(0, (int)((r[0] - x0) * sx)));
-    const int iy = min(127, max(0, (int)((r[1] - y0) * sy)));
-    const int iz = min(127, max(0, (int)((r[2] - z0) * sz)));
-    key[p] = (unsigned int)(ix + 128 * (iy + 128 * iz));
+    const int ix = min(gx - 1, max(0, (int)((r[0] - x0) * sx)));
+    const int iy = min(gy - 1, max(0, (int)((r[1] - y0) * sy)));
+    const int iz = min(gz - 1, max(0, (int)((r[2] - z0) * sz)));
+    key[p] = (unsigned int)(ix + gx * (iy + gy * iz));
     idx[p] = p;
 }
 // lists of the last buffer back in wire order, array-of-structures (parity hook fy_get_last_lists)
@@ -451,14 +474,19 @@ int fySortParticles(fy_ctx* h, const double* d_pdata, int n)
     if ((rc = fyReserve(h, h->dIdx, (size_t)n))) return rc;
     if ((rc = fyReserve(h, h->dPerm, (size_t)n))) return rc;
     const double ex = h->bbox[3] - h->bbox[0], ey = h->bbox[4] - h->bbox[1], ez = h->bbox[5] - h->bbox[2];
+    int gq[3] = {128, 128, 128};
+    if (h->boxN[0] > 0)
+        for (int q = 0; q < 3; ++q) gq[q] = std::max(1, std::min(h->boxN[q], 256));
+    int bits = 1;
+    while ((1LL << bits) < (long long)gq[0] * gq[1] * gq[2]) ++bits;
     k_particle_keys<<<fyGrid(n, 256), 256, 0, h->stream>>>(d_pdata, n, h->bbox[0], h->bbox[1], h->bbox[2],
-                                                          ex > 0 ? 128.0 / ex : 0.0, ey > 0 ? 128.0 / ey : 0.0,
-                                                          ez > 0 ? 128.0 / ez : 0.0, h->dKey.p, h->dIdx.p);
+                                                          ex > 0 ? gq[0] / ex : 0.0, ey > 0 ? gq[1] / ey : 0.0,
+                                                          ez > 0 ? gq[2] / ez : 0.0, gq[0], gq[1], gq[2], h->dKey.p, h->dIdx.p);
     FY_CHECK_LAUNCH();
     size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, h->dKey.p, h->dKey2.p, h->dIdx.p, h->dPerm.p, n, 0, 21, h->stream);
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, h->dKey.p, h->dKey2.p, h->dIdx.p, h->dPerm.p, n, 0, bits, h->stream);
     if ((rc = fyReserve(h, h->dSortTmp, bytes))) return rc;
-    FY_CUDA(cub::DeviceRadixSort::SortPairs(h->dSortTmp.p, bytes, h->dKey.p, h->dKey2.p, h->dIdx.p, h->dPerm.p, n, 0, 21,
+    FY_CUDA(cub::DeviceRadixSort::SortPairs(h->dSortTmp.p, bytes, h->dKey.p, h->dKey2.p, h->dIdx.p, h->dPerm.p, n, 0, bits,
                                             h->stream));
     h->launches += 4;
     return FY_OK;
@@ -487,7 +515,8 @@ int fyCouplingProcDevice(fy_ctx* h, const double* d_pdata, int n, int* d_found, 
         const GaussConst gc{h->maxDist, 2 * std::pow(h->sigmaInterp, 2), h->interpRangeCu, h->sigmaPi};
         if (prof) cudaEventRecord(h->ev[1], h->stream);
         if ((rc = fySortParticles(h, d_pdata, n))) return rc;
-        k_locate_gauss<<<fyGrid(n, 128), 128, 0, h->stream>>>(h->dTree, h->nTree, d_pdata, n, h->dPerm.p, gc, h->procSerial,
+        if ((rc = kdFuncAttrs(h, (const void*)k_locate_gauss))) return rc;
+        k_locate_gauss<<<fyGrid(n, KD_BLOCK), KD_BLOCK, KD_SMEM, h->stream>>>(h->dTree, h->nTree, d_pdata, n, h->dPerm.p, gc, h->procSerial,
                                                               h->dIds.p, h->dCnt.p, h->dW.p, d_found, h->dPvol,
                                                               h->dUpAcc, h->dStamp);
         FY_CHECK_LAUNCH();
@@ -538,7 +567,8 @@ int fyCouplingPass(fy_ctx* h, int pass, const double* d_pdata, int n, int* d_fou
         if ((rc = fyReserve(h, h->dW, (size_t)n * FY_MAXLIST))) return rc;
         const GaussConst gc{h->maxDist, 2 * std::pow(h->sigmaInterp, 2), h->interpRangeCu, h->sigmaPi};
         if ((rc = fySortParticles(h, d_pdata, n))) return rc;
-        k_locate_gauss<<<fyGrid(n, 128), 128, 0, h->stream>>>(h->dTree, h->nTree, d_pdata, n, h->dPerm.p, gc, h->procSerial,
+        if ((rc = kdFuncAttrs(h, (const void*)k_locate_gauss))) return rc;
+        k_locate_gauss<<<fyGrid(n, KD_BLOCK), KD_BLOCK, KD_SMEM, h->stream>>>(h->dTree, h->nTree, d_pdata, n, h->dPerm.p, gc, h->procSerial,
                                                               h->dIds.p, h->dCnt.p, h->dW.p, d_found, h->dPvol, h->dUpAcc,
                                                               h->dStamp);
         FY_CHECK_LAUNCH();

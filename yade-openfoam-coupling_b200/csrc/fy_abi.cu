@@ -218,6 +218,11 @@ int fy_destroy(fy_handle h)
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& f : h->dField) if (f) cudaFree(f);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->copyStream) {
+        cudaStreamSynchronize(h->copyStream);
+        cudaEventDestroy(h->evUp); cudaEventDestroy(h->evProc); cudaEventDestroy(h->evDown);
+        cudaStreamDestroy(h->copyStream);
+    }
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return FY_OK;
@@ -404,6 +409,61 @@ int fy_coupling_proc(fy_handle h, const double* pdata, int n, int* found, double
             h->phaseMs[i] = ms;
         }
     }
+    return FY_OK;
+}
+
+// ---- overlapped wire transfers (second stream + events): the records come up while the solver's pre-coupling block
+// runs, the forces go down while the pressure-velocity solve runs
+static int copyStream(fy_ctx* h)
+{
+    if (h->copyStream) return FY_OK;
+    FY_CUDA(cudaStreamCreateWithFlags(&h->copyStream, cudaStreamNonBlocking));
+    FY_CUDA(cudaEventCreateWithFlags(&h->evUp, cudaEventDisableTiming));
+    FY_CUDA(cudaEventCreateWithFlags(&h->evProc, cudaEventDisableTiming));
+    FY_CUDA(cudaEventCreateWithFlags(&h->evDown, cudaEventDisableTiming));
+    return FY_OK;
+}
+
+int fy_particles_upload_async(fy_handle h, const double* pdata, int n)
+{
+    FyDeviceGuard guard_(h);
+    if (!h || n < 0 || (n > 0 && !pdata)) return FY_ERR_INVALID;
+    int rc;
+    if ((rc = copyStream(h))) return rc;
+    h->stagedN = n;
+    if (n == 0) return FY_OK;
+    if ((rc = fyReserve(h, h->dPdata, (size_t)n * 10))) return rc;
+    if ((rc = fyReserve(h, h->dFound, (size_t)n))) return rc;
+    if ((rc = fyReserve(h, h->dForce, (size_t)n * 6))) return rc;
+    // (the previous step's kernels that read dPdata are long done: fy_results_wait has returned)
+    FY_CUDA(cudaMemcpyAsync(h->dPdata.p, pdata, (size_t)n * 10 * sizeof(double), cudaMemcpyHostToDevice, h->copyStream));
+    FY_CUDA(cudaEventRecord(h->evUp, h->copyStream));
+    return FY_OK;
+}
+
+int fy_coupling_proc_staged(fy_handle h, int* found, double* force)
+{
+    FyDeviceGuard guard_(h);
+    if (!h || !h->copyStream) return FY_ERR_INVALID;
+    const int n = h->stagedN;
+    if (n > 0 && (!found || !force)) return FY_ERR_INVALID;
+    if (n == 0) { h->lastN = 0; return FY_OK; }
+    int rc;
+    FY_CUDA(cudaStreamWaitEvent(h->stream, h->evUp, 0));
+    if ((rc = fyCouplingProcDevice(h, h->dPdata.p, n, h->dFound.p, h->dForce.p))) return rc;
+    FY_CUDA(cudaEventRecord(h->evProc, h->stream));
+    FY_CUDA(cudaStreamWaitEvent(h->copyStream, h->evProc, 0));
+    FY_CUDA(cudaMemcpyAsync(found, h->dFound.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->copyStream));
+    FY_CUDA(cudaMemcpyAsync(force, h->dForce.p, (size_t)n * 6 * sizeof(double), cudaMemcpyDeviceToHost, h->copyStream));
+    FY_CUDA(cudaEventRecord(h->evDown, h->copyStream));
+    return FY_OK;
+}
+
+int fy_results_wait(fy_handle h)
+{
+    FyDeviceGuard guard_(h);
+    if (!h || !h->copyStream) return FY_ERR_INVALID;
+    FY_CUDA(cudaEventSynchronize(h->evDown));
     return FY_OK;
 }
 

@@ -40,6 +40,10 @@ struct FvMatrixDev;          // fv_solver.h
 struct fy_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    // overlapped wire transfers (fy_particles_upload_async / fy_coupling_proc_staged / fy_results_wait)
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t evUp = nullptr, evProc = nullptr, evDown = nullptr;
+    int stagedN = 0;
     std::string err;
     long long launches = 0;
 
