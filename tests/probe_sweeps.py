@@ -21,7 +21,8 @@ def child(n):
     from tests import cases_fv
     pkg = g.load_package()
     check = os.environ.get("PROBE_CHECK", "1") == "1"
-    mo, mp = cases_fv.cavity3d(pkg, (n, n, n), oracle=check)
+    dims = tuple(int(x) for x in os.environ["PROBE_DIMS"].split(",")) if os.environ.get("PROBE_DIMS") else (n, n, n)
+    mo, mp = cases_fv.cavity3d(pkg, dims, oracle=check)
     rng = np.random.default_rng(2)
     N, Fi = mp["nCells"], mp["nInternalFaces"]
     upper = -rng.uniform(0.5, 1.5, Fi)
@@ -64,7 +65,8 @@ def child(n):
         tr = np.empty((nJB * (n + 16 * 8 + 64) * 4 + 64) * 32)
         E._ck(E.L.fy_fv_get(E.h, b"pencilTrace", tr.ctypes.data_as(C.POINTER(C.c_double))))
         nKQ = (n + W * Z - 1) // (W * Z)
-        tr = tr[: nKQ * nJB * 32 * 4].reshape(nKQ, nJB, 32, 4)
+        raw = tr.copy()
+        tr = tr[: nKQ * nJB * 32 * 8].reshape(nKQ, nJB, 32, 8)
         lines = []
         rev = not (int(os.environ.get("FY_PENCIL_DBG", "0")) & 64)
         for jb in range(nJB):
@@ -76,6 +78,19 @@ def child(n):
                 row.append("%.1f-%.1f" % (c[0] / 1e3, c[1] / 1e3))
             lines.append("jb%d: " % jj + " ".join(row))
         out["trace_us(start-end of compute warp 0 per kq, sweep order)"] = lines
+        if os.environ.get("PROBE_TSEC"):
+            # PEN2_TIMING build: cycles per section of a step (A loads+flow control, C y/shuffle/pre, D z wait + finish + hand-over, E stores),
+            # per block of R steps, for the head warp and a mid-chain consumer of the first column
+            jj = nJB - 1 if rev else 0
+            sec = {}
+            raw = np.empty_like(raw)
+            E._ck(E.L.fy_fv_get(E.h, b"pencilTraceRaw", raw.ctypes.data_as(C.POINTER(C.c_double))))
+            for name, kq, wv in (("head", 0, 0), ("consumer_kq0_w3", 0, 3), ("consumer_kq5_w0", min(5, nKQ - 1), 0)):
+                c = raw[: nKQ * nJB * 32 * 8].reshape(nKQ, nJB, 32, 8)[kq, jj, wv]
+                # the stored values are offsets from the earliest stamp (fy_fv_get), counters start at 0: undo by differences
+                nb = max(c[6], 1.0)
+                sec[name] = dict(blocks=int(c[6]), cycles_per_step=[round(float(x) / nb / 4, 1) for x in c[2:6]])
+            out["tsec_raw"] = sec
     E.close()
     print("PROBE " + json.dumps(out), flush=True)
 

@@ -329,6 +329,14 @@ int fy_fv_get(fy_handle h, const char* name, double* dst)
         if ((rc = fvSlotsToFaces(h, s, (int)nF, src, d))) return rc;
         return d2h(h, dst, d, nF);
     }
+    if (k == "pencilTraceRaw") {     // debug: the same buffer, raw 64-bit values as doubles (section counters of a PEN2_TIMING build)
+        const size_t n = ((size_t)s->pen.g.nJB * (s->pen.g.nz + 16 * 8 + 64) * 4 + 64) * 32;
+        std::vector<unsigned long long> t(n);
+        FY_CUDA(cudaStreamSynchronize(h->stream));
+        FY_CUDA(cudaMemcpy(t.data(), s->pen.trace, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        for (size_t q = 0; q < n; ++q) dst[q] = (double)t[q];
+        return FY_OK;
+    }
     if (k == "pencilTrace") {        // debug: [nJB*nz][4] time stamps (ns, relative to the earliest) of the last pencil launch
         const size_t n = ((size_t)s->pen.g.nJB * (s->pen.g.nz + 16 * 8 + 64) * 4 + 64) * 32;
         std::vector<unsigned long long> t(n);
