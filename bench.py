@@ -124,12 +124,22 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def partition_text(partition, world):
+def solve_grid(ny, world, py=0):
+    """(Py, Pz) of the decomposed pressure solve -- yade-openfoam-coupling_b200/domain.py solve_grid, restated here so that
+    the reference arm (no package import needed) prints the same config."""
+    njb = (int(ny) + 31) // 32
+    if py == 0:
+        py = max(c for c in range(1, world + 1) if world % c == 0 and c <= njb)
+    return py, world // py
+
+
+def partition_text(partition, world, ny=0, py=0):
     if world == 1:
         return "single domain"
-    return {"domain": "one domain on %d GPUs: pressure solve z-slab decomposed (NCCL halo exchange of the PCG search direction + "
-                      "3 all-reduces per iteration, slab-local DIC), particles migrate to the owner slab's rank every step "
-                      "(all-to-all), per-cell coupling sums all-reduced, FV assembly replicated" % world,
+    gy, gz = solve_grid(ny, world, py) if partition == "domain" else (1, world)
+    return {"domain": "one domain on %d GPUs: pressure solve decomposed on a %d (y) x %d (z) grid of ranks (NCCL halo exchange of the "
+                      "PCG search direction + 3 all-reduces per iteration, rank-local DIC), particles migrate to the owner z slab's "
+                      "rank every step (all-to-all), per-cell coupling sums all-reduced, FV assembly replicated" % (world, gy, gz),
             "particles": "one domain, particle buffer sharded over the GPUs, NCCL all-reduce of the cell sums, fluid solve replicated",
             "replicas": "one domain replica per GPU"}[partition]
 
@@ -147,7 +157,7 @@ def config_of(args, world):
             "solver": ("pimpleFoamYade (UcEqn.H/pEqn.H, nOuterCorrectors 1, laminar)" if pimple else "icoFoamYade"),
             "fvSolution": "PISO nCorrectors 2; p PCG/DIC 1e-06 relTol 0.05 (pFinal 0); U smoothSolver symGaussSeidel 1e-05",
             "l2": "flushed between timed steps (256 MiB write)",
-            "partition": partition_text(args.partition, world)}
+            "partition": partition_text(args.partition, world, ny, args.py)}
 
 
 def flow_case(wl, pkg=None):
@@ -207,7 +217,7 @@ def run_engine(args):
     E.upload("p", p0)
     E.create_phi()
     L = E.L
-    dinfo = pkg.domain.init_domain(E, dist, "cuda") if domain else None
+    dinfo = pkg.domain.init_domain(E, dist, "cuda", args.py) if domain else None
 
     # device-resident wire buffers (value) and pinned host wire buffers (e2e)
     d_pd = torch.from_numpy(pd).cuda()
@@ -387,11 +397,16 @@ def run_engine(args):
         if fluid and kms and kms["samples"] > 0:
             it_step = kms["pcg_iterations"] / float(nprof)
             # pencil-layout kernels: algorithmic bytes = 8 B x (streams read + written) per cell (kernels)
-            cand["k_pen2<Op2DicFwd> (DIC forward sweep)"] = (kms["precond_fwd"], 48.0 * N, it_step)       # {rD, rD low[3]} rA -> y
-            cand["k_pen2<Op2DicBwd> (DIC backward sweep + wA.rA)"] = (kms["precond_bwd"], 56.0 * N, it_step)  # y {rD up[3]} rA -> z, re-arm y
-            cand["k_pen_amul_rows<8>"] = (kms["amul"], 48.0 * N, it_step)                                 # dg up[3] p -> w (symmetric: lower = the neighbours' upper)
-            cand["k_pen_update"] = (kms["update"], 48.0 * N, it_step)                                     # p w x r -> x r
-            cand["k_pen_dir"] = (kms["direction"], 32.0 * N, it_step)                                     # z p -> p, re-arm z
+            Nl = N / float(world) if domain else N          # cells of this rank's part of the decomposed solve
+            cand["k_pen2<Op2DicFwd> (DIC forward sweep)"] = (kms["precond_fwd"], 48.0 * Nl, it_step)       # {rD, rD low[3]} rA -> y
+            cand["k_pen2<Op2DicBwd> (DIC backward sweep + wA.rA)"] = (kms["precond_bwd"], 56.0 * Nl, it_step)  # y {rD up[3]} rA -> z, re-arm y
+            if kms["fused_tail"]:
+                # z p -> p, re-arm z | dg up[3] p -> w | p w x r -> x r, in one cooperative launch
+                cand["k_pen_tail<8> (direction + Amul + update)"] = (kms["direction"], 128.0 * Nl, it_step)
+            else:
+                cand["k_pen_amul_rows<8>"] = (kms["amul"], 48.0 * Nl, it_step)                             # dg up[3] p -> w (symmetric: lower = the neighbours' upper)
+                cand["k_pen_update"] = (kms["update"], 48.0 * Nl, it_step)                                 # p w x r -> x r
+                cand["k_pen_dir"] = (kms["direction"], 32.0 * Nl, it_step)                                 # z p -> p, re-arm z
         # dominant = largest share of the step
         def share(v):
             return v[0] * (v[2] if len(v) > 2 else 1.0)
@@ -429,10 +444,13 @@ def run_engine(args):
         }
         if domain:
             di = E.dist_info()
-            line["domain"] = {"planes_rank0": [dinfo["kLo"], dinfo["kHi"]], "collectives_issued_rank0": di["collectives"],
+            line["domain"] = {"grid_y_z": [dinfo["Py"], dinfo["Pz"]],
+                              "iteration_collectives": ("inside the iteration's kernels over NVLink peer memory (CUDA IPC), CUDA-graph replayed"
+                                                        if dinfo["peer"] else "NCCL calls between the kernels"), "rows_rank0": [dinfo["jLo"], dinfo["jHi"]],
+                              "planes_rank0": [dinfo["kLo"], dinfo["kHi"]], "collectives_issued_rank0": di["collectives"],
                               "halo_bytes_sent_rank0": di["halo_bytes"], "particles_migrated_last_step_rank0": moved["records"],
-                              "limiting_collective": "the three 1-double all-reduces + one 2-plane halo exchange of every PCG iteration "
-                                                     "(latency-bound: %d bytes per plane)" % (8 * (E.N // nz))}
+                              "limiting_collective": "the three 1-double all-reduces + one halo exchange of every PCG iteration "
+                                                     "(latency-bound: a few hundred KB per exchange at most)"}
         if not args.no_cpu_baseline and world == 1:
             state = dict(U=E.download("U"), p=E.download("p"), phi=E.download("phi")) if fluid else None
             ref_out = {}
@@ -661,6 +679,8 @@ def main():
     ap.add_argument("--partition", default="domain", choices=["domain", "particles", "replicas"],
                     help="N > 1: one domain, pressure solve z-slab decomposed + particle migration (strong scaling, default); "
                          "one domain with only the particle buffer sharded; or independent domain replicas (weak scaling)")
+    ap.add_argument("--py", type=int, default=0,
+                    help="--partition domain: y slabs of the rank grid (0: the library's choice, y first; 1: z slabs only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-blocking", action="store_true", help="e2e through the blocking fy_set_particle_action instead of the overlapped calls")
     ap.add_argument("--cpu-particles", type=int, default=200000)

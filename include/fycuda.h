@@ -316,23 +316,34 @@ int fy_get_fluid_ms(fy_handle h, double out[4]);
 int fy_get_kernel_ms(fy_handle h, double out[8], int reset);
 
 /* ---------------------------------------------------------------------------------------------
- * multi-GPU: z-slab decomposition of the pressure solve over the ranks of one job (one process per GPU)
+ * multi-GPU: decomposition of the pressure solve over the ranks of one job (one process per GPU)
  *
  * The reference runs its fluid side decomposed (`mpiexec ... -n 2 icoFoamYade -parallel`, README.md:29; the bbox routing
  * of FoamYade.C:77-155 exists for that); OpenFOAM's Pstream does the halo exchange and the global sums of the linear
- * solvers.  Here rank r of `nranks` owns the k-planes [r nz / nranks, (r+1) nz / nranks) of the hex box in the PCG
- * solve of the pressure equation: per iteration one halo exchange of the search direction (ncclSend / ncclRecv of the
- * slab's boundary planes) and three 1-double all-reduces; the DIC preconditioner is slab-local, which is what
- * OpenFOAM's decomposed runs do (DICPreconditioner sees a processor's own lduMatrix).  The FV assembly kernels around
- * the solve run on the whole box on every rank, so the solution's planes are gathered at the end of each solve.
+ * solvers.  Here the ranks form a Py x Pz grid over the hex box (decomposePar `simple`, n (1 Py Pz)): rank rz*Py + ry
+ * owns rows [32 jbLo, 32 jbHi) of the k-planes [kLo, kHi) in the PCG solve of the pressure equation (the y cuts fall on
+ * multiples of 32 rows, the unit of the solver's memory layout).  Per iteration: one halo exchange of the search
+ * direction (ncclSend / ncclRecv of the region's boundary rows) and three 1-double all-reduces; the DIC preconditioner
+ * is rank-local, which is what OpenFOAM's decomposed runs do (DICPreconditioner sees a processor's own lduMatrix).  The
+ * FV assembly kernels around the solve run on the whole box on every rank, so the solution is gathered at the end of
+ * each solve.
  *   fy_dist_unique_id : rank 0 creates the NCCL id (FY_DIST_ID_BYTES bytes) and hands it to the others (any transport)
- *   fy_dist_init      : every rank, with the same id; call once, after fy_create and before the first solve
+ *   fy_dist_init      : every rank, with the same id; call once, after fy_create and before the first solve.  The grid
+ *                       is chosen by the library: Py = the largest divisor of nranks that is <= ceil(ny / 32)  (cutting
+ *                       in y shortens the critical path of the wavefront preconditioner sweeps, cutting in z does not;
+ *                       DESIGN.md section 6), Pz = nranks / Py.  Environment FY_DIST_PY overrides Py.
+ *   fy_dist_init_grid : the same with Py given (py = 1: z slabs only)
  *   fy_dist_info      : out[0] rank [1] nranks [2] kLo [3] kHi [4] collectives issued [5] halo bytes sent
+ *   fy_dist_grid      : out[0] Py [1] Pz [2] ry [3] rz [4] jLo [5] jHi (rows of y) [6] kLo [7] kHi
+ *                       [8] 1: the iteration's collectives run inside its kernels over NVLink peer memory (CUDA IPC
+ *                       mappings made at fy_dist_init; environment FY_DIST_PEER=0 or an IPC failure: 0, NCCL calls) [9] 0
  * ------------------------------------------------------------------------------------------- */
 #define FY_DIST_ID_BYTES 128
 int fy_dist_unique_id(char id[FY_DIST_ID_BYTES]);
 int fy_dist_init(fy_handle h, int rank, int nranks, const char id[FY_DIST_ID_BYTES]);
+int fy_dist_init_grid(fy_handle h, int rank, int nranks, int py, const char id[FY_DIST_ID_BYTES]);
 int fy_dist_info(fy_handle h, long long out[6]);
+int fy_dist_grid(fy_handle h, long long out[10]);
 
 /* Blocks until all work queued on the handle's stream is complete. */
 int fy_synchronize(fy_handle h);

@@ -133,6 +133,22 @@ class IcoOracle:
         proc = np.searchsorted(np.asarray(bounds[1:]), k, side="right").astype(np.int32)
         self.L.fvo_set_partition(self.h, _i(_c(proc, np.int32)))
 
+    def set_grid(self, py, pz):
+        """Decomposed-run semantics on a Py x Pz grid of processors (decomposePar `simple`, n (1 Py Pz), with the y cuts
+        on multiples of 32 rows as csrc/fv_dist.cu places them): processor rz*Py + ry owns the 32-row blocks
+        [ry nJB / Py, (ry+1) nJB / Py) of the planes [rz nz / Pz, (rz+1) nz / Pz)."""
+        if py * pz <= 1:
+            self.L.fvo_set_partition(self.h, None)
+            return
+        nx, ny, nz = (int(v) for v in self.mesh["boxN"])
+        c = np.arange(self.N)
+        k, jb = c // (nx * ny), ((c // nx) % ny) // 32
+        njb = (ny + 31) // 32
+        kb = np.asarray([((r + 1) * nz) // pz for r in range(pz)])
+        jbb = np.asarray([((r + 1) * njb) // py for r in range(py)])
+        proc = (np.searchsorted(kb, k, side="right") * py + np.searchsorted(jbb, jb, side="right")).astype(np.int32)
+        self.L.fvo_set_partition(self.h, _i(_c(proc, np.int32)))
+
     def set_threads(self, n):
         """host threads of the decomposed PCG's TIMING path (bench.py's all-core CPU baseline); needs set_slabs(>1).
         Process-wide; 1 restores the sequential checker."""

@@ -73,3 +73,50 @@ def test_id_handover_and_particle_migration_gloo(pkg):
     for rank, id_ok, ok_owner, ok_back, tot in out:
         assert id_ok and ok_owner and ok_back
         assert tot == 50 + 63                              # no record lost or duplicated
+
+
+def test_solve_grid_prefers_y_cuts(pkg):
+    d = pkg.domain
+    assert d.solve_grid(128, 1) == (1, 1)
+    assert d.solve_grid(128, 2) == (2, 1)
+    assert d.solve_grid(128, 4) == (4, 1)
+    assert d.solve_grid(128, 8) == (4, 2)             # four 32-row blocks: the rest of the ranks cut z
+    assert d.solve_grid(14, 2) == (1, 2)              # one block: z slabs
+    assert d.solve_grid(70, 4) == (2, 2)              # three blocks: the largest divisor of 4 that fits
+    assert d.solve_grid(128, 8, py=1) == (1, 8)
+
+
+def test_oracle_grid_partition_semantics(pkg):
+    """The oracle's decomposed DIC (the checker of tests/test_gpu_domain.py): a 1 x Pz grid IS the z-slab partition; a y
+    cut changes the preconditioner (other iteration count) but not the converged solution."""
+    from oracle import port
+    from tests import cases_fv
+    mo, _ = cases_fv.channel(pkg, (10, 70, 6))
+    rng = np.random.default_rng(4)
+    N, Fi = mo["nCells"], mo["nInternalFaces"]
+    upper = rng.uniform(0.5, 1.5, Fi)
+    diag = np.zeros(N)
+    np.subtract.at(diag, mo["owner"], upper)
+    np.subtract.at(diag, mo["neighbour"], upper)
+    diag -= rng.uniform(0.001, 0.01, N)
+    b = rng.standard_normal(N)
+    O = port.IcoOracle(mo, nu=1e-3)
+    run = lambda: O.pcg(diag, upper, b, np.zeros(N), tol=1e-10, relTol=0.0, preconditioner="DIC")
+    x1, p1 = run()
+    O.set_slabs(2)
+    xs, ps = run()
+    O.set_grid(1, 2)
+    xg, pg = run()
+    assert np.array_equal(xs, xg) and ps["iters"] == pg["iters"]
+    O.set_grid(2, 1)
+    xy, py_ = run()
+    O.set_grid(3, 2)
+    xyz, pyz = run()
+    O.set_grid(1, 1)
+    x0, p0 = run()
+    assert np.array_equal(x0, x1) and p0["iters"] == p1["iters"]
+    assert py_["iters"] >= p1["iters"] and pyz["iters"] >= py_["iters"]
+    assert not np.array_equal(xy, x1)
+    for x in (xs, xy, xyz):
+        assert np.linalg.norm(x - x1) <= 1e-7 * np.linalg.norm(x1)
+    O.close()

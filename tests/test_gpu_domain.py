@@ -1,4 +1,4 @@
-"""GPU x2 (NCCL): the z-slab decomposed pressure solve and the domain-decomposed coupled icoFoamYade step
+"""GPU x2 (NCCL): the decomposed (z slabs, and y slabs of 32-row blocks) pressure solve and the domain-decomposed coupled icoFoamYade step
 (csrc/fv_dist.cu, domain.py) against the oracle run with the SAME partition (OpenFOAM's decomposed semantics: the DIC
 preconditioner factorises each processor's own matrix) -- identical iteration counts, fields within 1e-10 -- and against
 the single-domain run at solver tolerance.  Needs two devices; the round-end single-GPU run skips it
@@ -14,7 +14,7 @@ from tests import cases, cases_fv
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-NBOX = (20, 14, 12)
+BOXES = {"z": (20, 14, 12), "y": (24, 70, 12)}      # ny = 70: three 32-row blocks, split 1 + 2 over two ranks
 P = 6000
 
 
@@ -29,13 +29,15 @@ def _matrix(mo):
     return diag, upper, rng.standard_normal(N)
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, NBOX, peer):
     import torch
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
     import __graft_entry__ as g
     pkg = g.load_package()
     torch.cuda.set_device(rank)
+    if not peer:
+        os.environ["FY_DIST_PEER"] = "0"              # the iteration's collectives as NCCL calls (the fallback path)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     _, mp_ = cases_fv.channel(pkg, NBOX, oracle=False)
@@ -88,36 +90,45 @@ def _worker(rank, world, port, q):
     q.put((rank, out))
 
 
-def test_two_gpu_domain_decomposed_solve_and_step(pkg):
+@pytest.mark.parametrize("cut,peer", [("z", True), ("y", True), ("y", False)])
+def test_two_gpu_domain_decomposed_solve_and_step(pkg, cut, peer):
     import torch
     import torch.multiprocessing as mp
     from oracle import port, ref
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
+    NBOX = BOXES[cut]
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port_no = s.getsockname()[1]
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    ps = [ctx.Process(target=_worker, args=(r, 2, port_no, q)) for r in range(2)]
+    ps = [ctx.Process(target=_worker, args=(r, 2, port_no, q, NBOX, peer)) for r in range(2)]
     for p in ps:
         p.start()
     out = dict(q.get(timeout=600) for _ in ps)
     for p in ps:
         p.join(timeout=60)
         assert p.exitcode == 0
-    assert [out[r]["info"]["kLo"] for r in range(2)] == [0, 6] and [out[r]["info"]["kHi"] for r in range(2)] == [6, 12]
-    assert out[0]["info_end"]["collectives"] > 0 and out[0]["info_end"]["halo_bytes"] > 0
+    if cut == "z":
+        assert [(out[r]["info"]["Py"], out[r]["info"]["kLo"], out[r]["info"]["kHi"]) for r in range(2)] == [(1, 0, 6), (1, 6, 12)]
+    else:
+        assert [(out[r]["info"]["Py"], out[r]["info"]["jLo"], out[r]["info"]["jHi"]) for r in range(2)] == [(2, 0, 32), (2, 32, 70)]
+        assert all(out[r]["info"]["kLo"] == 0 and out[r]["info"]["kHi"] == NBOX[2] for r in range(2))
+    grid = (1, 2) if cut == "z" else (2, 1)
+    # the collectives of the PCG iteration ran inside its kernels over peer memory (or, asked so, as NCCL calls)
+    assert all(out[r]["info"]["peer"] == peer for r in range(2)), out[0]["info"]
+    assert out[0]["info_end"]["collectives"] > 0 and (out[0]["info_end"]["halo_bytes"] > 0) == (not peer)   # (NCCL calls only)
 
     mo, mp_ = cases_fv.channel(pkg, NBOX)
     nu = 1e-3
     # (1) PCG: decomposed == the oracle with the same partition; both ranks hold the same solution
     diag, upper, b = _matrix(mo)
     O = port.IcoOracle(mo, nu=nu)
-    O.set_slabs(2)
+    O.set_grid(*grid)
     xo, po = O.pcg(diag, upper, b, np.zeros(mo["nCells"]), tol=1e-10, relTol=0.0, preconditioner="DIC")
-    O.set_slabs(1)
+    O.set_grid(1, 1)
     x1, p1 = O.pcg(diag, upper, b, np.zeros(mo["nCells"]), tol=1e-10, relTol=0.0, preconditioner="DIC")
     assert po["iters"] != p1["iters"] or not np.array_equal(xo, x1)      # the partition really changes the preconditioner
     for r in range(2):
@@ -131,7 +142,7 @@ def test_two_gpu_domain_decomposed_solve_and_step(pkg):
         assert out[r]["pcg_diag"][1]["iters"] == pd_["iters"] and cases.rel_l2(out[r]["pcg_diag"][0], xd) <= cases.TOL
 
     # (2) coupled steps against (unmodified reference coupling + oracle fluid step with the same partition)
-    O.set_slabs(2)
+    O.set_grid(*grid)
     U0, p0 = cases_fv.channel_init(mo["C"])
     O.field("U")[:] = U0
     O.field("p")[:] = p0

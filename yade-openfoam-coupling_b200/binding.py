@@ -313,7 +313,7 @@ class Engine:
         self._ck(self.L.fy_get_last_lists(self.h, n, _i(cnt), _i(ids), _d(w)))
         return cnt, ids, w
 
-    # ---- multi-GPU: z-slab decomposition of the pressure solve (fycuda.h, fy_dist_*)
+    # ---- multi-GPU: Py x Pz decomposition of the pressure solve (fycuda.h, fy_dist_*)
     @staticmethod
     def dist_unique_id():
         buf = C.create_string_buffer(128)
@@ -322,13 +322,17 @@ class Engine:
             raise FyError("fy_dist_unique_id failed (%d): is libnccl.so.2 on the loader path?" % rc)
         return buf.raw
 
-    def dist_init(self, rank, nranks, uid):
-        self._ck(self.L.fy_dist_init(self.h, int(rank), int(nranks), C.c_char_p(bytes(uid))))
+    def dist_init(self, rank, nranks, uid, py=0):
+        """py = 0: the library picks the Py x Pz grid of ranks (y first); py = 1: z slabs only."""
+        self._ck(self.L.fy_dist_init_grid(self.h, int(rank), int(nranks), int(py), C.c_char_p(bytes(uid))))
 
     def dist_info(self):
         out = (C.c_longlong * 6)()
         self._ck(self.L.fy_dist_info(self.h, out))
-        return dict(rank=out[0], nranks=out[1], kLo=out[2], kHi=out[3], collectives=out[4], halo_bytes=out[5])
+        g = (C.c_longlong * 10)()
+        self._ck(self.L.fy_dist_grid(self.h, g))
+        return dict(rank=out[0], nranks=out[1], kLo=out[2], kHi=out[3], collectives=out[4], halo_bytes=out[5],
+                    Py=g[0], Pz=g[1], ry=g[2], rz=g[3], jLo=g[4], jHi=g[5], peer=bool(g[8]))
 
     def synchronize(self):
         self._ck(self.L.fy_synchronize(self.h))
@@ -465,4 +469,4 @@ class Engine:
         out = np.zeros(8)
         self._ck(self.L.fy_get_kernel_ms(self.h, _d(out), int(reset)))
         return dict(precond_fwd=out[0], precond_bwd=out[1], direction=out[2], amul=out[3], update=out[4],
-                    samples=int(out[5]), pcg_iterations=int(out[6]))
+                    samples=int(out[5]), pcg_iterations=int(out[6]), fused_tail=bool(out[7]))

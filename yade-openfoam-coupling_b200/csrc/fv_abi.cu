@@ -372,7 +372,7 @@ int fy_get_kernel_ms(fy_handle h, double out[8], int reset)
     for (int q = 0; q < 5; ++q) out[q] = s->kernelMs[q] / n;
     out[5] = (double)s->kernelSamples;
     out[6] = (double)s->pcgIterations;
-    out[7] = 0;
+    out[7] = s->pen.fusedTail && (!s->pen.dist || s->pen.peer) ? 1.0 : 0.0;      // 1: out[2] is the fused direction + Amul + update kernel, out[3] = out[4] = 0
     if (reset) {
         for (int q = 0; q < 5; ++q) s->kernelMs[q] = 0;
         s->kernelSamples = 0;
@@ -392,7 +392,25 @@ int fy_dist_init(fy_handle h, int rank, int nranks, const char id[FY_DIST_ID_BYT
     FyDeviceGuard guard_(h);
     if (!h || !id) return FY_ERR_INVALID;
     if (!h->fv || !h->fv->supported) { h->err = "fy_dist_init: the mesh did not qualify for the device FV path"; return FY_ERR_UNSUPPORTED; }
-    return fvDistInit(h, h->fv, rank, nranks, id);
+    return fvDistInit(h, h->fv, rank, nranks, 0, id);
+}
+
+int fy_dist_init_grid(fy_handle h, int rank, int nranks, int py, const char id[FY_DIST_ID_BYTES])
+{
+    FyDeviceGuard guard_(h);
+    if (!h || !id) return FY_ERR_INVALID;
+    if (!h->fv || !h->fv->supported) { h->err = "fy_dist_init_grid: the mesh did not qualify for the device FV path"; return FY_ERR_UNSUPPORTED; }
+    return fvDistInit(h, h->fv, rank, nranks, py, id);
+}
+
+int fy_dist_grid(fy_handle h, long long out[10])
+{
+    if (!h || !out || !h->fv) return FY_ERR_INVALID;
+    const PenState& P = h->fv->pen;
+    out[0] = P.Py; out[1] = P.Pz; out[2] = P.ry; out[3] = P.rz;
+    out[4] = P.gl.jbLo * 32; out[5] = std::min(P.gl.jbHi * 32, P.g.ny); out[6] = P.gl.kLo; out[7] = P.gl.kHi;
+    out[8] = P.peer ? 1 : 0; out[9] = 0;
+    return FY_OK;
 }
 
 int fy_dist_info(fy_handle h, long long out[6])

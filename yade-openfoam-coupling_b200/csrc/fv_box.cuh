@@ -19,6 +19,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "fv_peer.cuh"
+
 enum { FV_FIXED_VALUE = 0, FV_ZERO_GRADIENT = 1, FV_EMPTY = 2, FV_FIXED_FLUX_PRESSURE = 3 };   // the last one: p only (pimpleFoamYade/pEqn.H:21)
 enum { FV_PRECOND_DIC = 0, FV_PRECOND_DIAGONAL = 1, FV_PRECOND_NONE = 2 };
 
@@ -124,8 +126,10 @@ __device__ __forceinline__ void fvBCoefP(const BoxGeom& g, int s, double gammaB,
 struct FvRed {
     double* partial;         // [NV][gridDim.x]
     unsigned int* ticket;    // zero-initialised; reset by the last block
-    double* distOut;         // decomposed solve: the totals go here (this rank's partial sums) instead of to `fin`;
-                             // the host all-reduces them over the ranks and runs the finishing kernel
+    double* distOut;         // decomposed solve, NCCL path: the totals go here (this rank's partial sums) instead of to
+                             // `fin`; the host all-reduces them over the ranks and runs the finishing kernel
+    PeerDev* peer;           // decomposed solve, peer-memory path (fv_peer.cuh): the last block all-reduces the totals over
+                             // the ranks itself and then runs `fin`
 };
 
 template <int NV, bool MAXFIRST, int BLOCK, class Fin>
@@ -178,6 +182,8 @@ __device__ __forceinline__ void fvGridReduce(double (&v)[NV], const FvRed& r, Fi
         for (int w = 1; w < BLOCK / 32; ++w) x = mx ? fmax(x, sh[q][w]) : x + sh[q][w];
         tot[q] = x;
     }
+    if constexpr (NV <= 2 && !MAXFIRST)
+        if (r.peer && threadIdx.x < 32) peerAllReduce<NV>(r.peer, tot);      // (warp 0; `tot` of thread 0 counts)
     if (threadIdx.x == 0) {
         *r.ticket = 0u;
         if (r.distOut) {

@@ -300,7 +300,8 @@ struct PenCtl {
     FvSolveDev* st;            // may be null
     int dbg;                   // debug switches (FY_PENCIL_DBG)
     unsigned long long* trace; // optional [warps][8] time stamps / wait cycles
-    double* distOut;           // decomposed solve: the sweep's global sum goes here instead of to Op::fin
+    double* distOut;           // decomposed solve (NCCL path): the sweep's global sum goes here instead of to Op::fin
+    PeerDev* peer;             // decomposed solve (peer-memory path): the sum is all-reduced over the ranks before Op::fin
 };
 
 // One CTA per pencil group (j-block jb, plane group kq): W COMPUTE warps, each owning ONE k-plane of the
@@ -637,9 +638,9 @@ __global__ void __launch_bounds__(32 * (2 * PEN_WMAX + 1), 1) k_pencil(PencilGeo
 // layout conversion (natural x-fastest cell order <-> pencil layout)
 // ---------------------------------------------------------------------------------------------
 #define PEN_ROW_LOOP(g, c)                                                                                  \
-    for (long long row_ = (g).rowLo + (long long)blockIdx.x * (BLK / 32) + (threadIdx.x >> 5); row_ < (g).rowHi; \
-         row_ += (long long)gridDim.x * (BLK / 32))                                                         \
-        for (PenCell c = penDecode((g), row_, threadIdx.x & 31); c.valid; c.valid = false)
+    for (long long l_ = (long long)blockIdx.x * (BLK / 32) + (threadIdx.x >> 5); l_ < (g).nLoc;            \
+         l_ += (long long)gridDim.x * (BLK / 32))                                                           \
+        for (PenCell c = penDecode((g), penGlobalRow((g), l_), threadIdx.x & 31); c.valid; c.valid = false)
 
 __device__ __forceinline__ int penNat(const PencilGeom& g, const PenCell& c) { return c.i + g.nx * (c.j + g.ny * c.k); }
 
@@ -872,17 +873,39 @@ __global__ void __launch_bounds__(BLK) k_pen_recip(PencilGeom g, const double* _
 
 // pA = zA (first iteration) | zA + beta pA;  re-arms zA for the next backward sweep
 __global__ void __launch_bounds__(BLK)
-k_pen_dir(PencilGeom g, double* __restrict__ zA, double* __restrict__ pA, const FvSolveDev* st)
+k_pen_dir(PencilGeom g, double* __restrict__ zA, double* __restrict__ pA, const FvSolveDev* st, PeerDev* peer)
 {
     if (st->done) return;
     const bool first = st->nIter == 0;
     const double beta = st->beta;
     const double sv = sentValue();
+    if (!peer) {
+        PEN_ROW_LOOP(g, c) {
+            const double z = zA[c.pos];
+            pA[c.pos] = first ? z : z + beta * pA[c.pos];
+            zA[c.pos] = sv;
+        }
+        return;
+    }
+    // decomposed solve: the boundary cells of this rank's region go into the neighbours' ghost cells as well (same
+    // offset: every rank keeps the global layout), then the neighbours are told (fv_peer.cuh)
+    double* const zlo = peer->pa[0];
+    double* const zhi = peer->pa[1];
+    double* const ylo = peer->pa[2];
+    double* const yhi = peer->pa[3];
+    const int jLo = g.jbLo * 32, jHi = g.jbHi * 32 - 1;
+    bool wrote = false;
     PEN_ROW_LOOP(g, c) {
         const double z = zA[c.pos];
-        pA[c.pos] = first ? z : z + beta * pA[c.pos];
+        const double v = first ? z : z + beta * pA[c.pos];
+        pA[c.pos] = v;
         zA[c.pos] = sv;
+        if (zlo && c.k == g.kLo) { zlo[c.pos] = v; wrote = true; }
+        if (zhi && c.k == g.kHi - 1) { zhi[c.pos] = v; wrote = true; }
+        if (ylo && c.j == jLo) { ylo[c.pos] = v; wrote = true; }
+        if (yhi && c.j == jHi) { yhi[c.pos] = v; wrote = true; }
     }
+    peerHaloPublish(peer, wrote);
 }
 
 // Amul of a SYMMETRIC matrix: the coefficient towards a lower neighbour is that neighbour's own upper coefficient,
@@ -906,6 +929,7 @@ __global__ void __launch_bounds__(BLK)
 k_pen_amul(PencilGeom g, PenMatrix M, const double* __restrict__ pA, double* __restrict__ wA, FvRed red, FvSolveDev* st)
 {
     if (st->done) return;
+    if (red.peer) peerHaloWait(red.peer);                  // the neighbours' boundary cells of pA have arrived
     double v[1] = {0.0};
     PEN_ROW_LOOP(g, c) {
         const double a = penAmulCellSym(g, M, pA, c);
@@ -924,17 +948,18 @@ __global__ void __launch_bounds__(BLK)
 k_pen_amul_rows(PencilGeom g, PenMatrix M, const double* __restrict__ pA, double* __restrict__ wA, FvRed red, FvSolveDev* st)
 {
     if (st->done) return;
+    if (red.peer) peerHaloWait(red.peer);                  // the neighbours' boundary cells of pA have arrived
     double v[1] = {0.0};
     const int lane = threadIdx.x & 31;
-    const int grpLo = (int)(g.rowLo / R), nGroups = (int)(g.rowHi / R);   // Tp is a multiple of 32: a group never straddles two slabs
+    const int nGroups = (int)(g.nLoc / R);                 // Tp is a multiple of 32: a group never straddles two slabs
     const long long dYm = lane > 0 ? -33 : -(long long)g.Tp * 32 + 31 * 32 + 31;
     const long long dYp = lane < 31 ? 33 : (long long)g.Tp * 32 - 31 * 32 - 31;
     const double* __restrict__ dg = M.dg;
     const double* __restrict__ u0 = M.up[0];
     const double* __restrict__ u1 = M.up[1];
     const double* __restrict__ u2 = M.up[2];
-    for (int grp = grpLo + blockIdx.x * (BLK / 32) + (threadIdx.x >> 5); grp < nGroups; grp += gridDim.x * (BLK / 32)) {
-        const int row0 = grp * R;
+    for (int grp = blockIdx.x * (BLK / 32) + (threadIdx.x >> 5); grp < nGroups; grp += gridDim.x * (BLK / 32)) {
+        const int row0 = (int)penGlobalRow(g, (long long)grp * R);
         const int sb = row0 / g.Tp, m0 = row0 - sb * g.Tp;
         const int k = sb / g.nJB, jb = sb - k * g.nJB;
         const int j = jb * 32 + lane;
@@ -981,7 +1006,9 @@ k_pen_update(PencilGeom g, const double2* __restrict__ pA, const double2* __rest
     if (st->done) return;
     const double alpha = st->alpha;
     double v[1] = {0.0};
-    const long long q0 = g.rowLo * 16, n2 = g.rowHi * 16, stride = (long long)gridDim.x * BLK;
+    // (the local rows are ONE contiguous range here: every j-block of the planes [kLo, kHi); a y-decomposed solve uses
+    // k_pen_update_rows)
+    const long long q0 = (long long)g.kLo * g.nJB * g.Tp * 16, n2 = (long long)g.kHi * g.nJB * g.Tp * 16, stride = (long long)gridDim.x * BLK;
 #pragma unroll 2
     for (long long q = q0 + (long long)blockIdx.x * BLK + threadIdx.x; q < n2; q += stride) {
         const double2 p = pA[q], w = wA[q];
@@ -996,6 +1023,303 @@ k_pen_update(PencilGeom g, const double2* __restrict__ pA, const double2* __rest
         v[0] += fabs(r.y);
     }
     fvGridReduce<1, false, BLK>(v, red, [=](const double* t) { penFinUpdate(st, t); });
+}
+
+// the same update over an arbitrary set of local rows (y-decomposed solve: the rows of a rank are not contiguous)
+__global__ void __launch_bounds__(BLK)
+k_pen_update_rows(PencilGeom g, const double* __restrict__ pA, const double* __restrict__ wA, double* __restrict__ psi,
+                  double* __restrict__ rA, FvRed red, FvSolveDev* st)
+{
+    if (st->done) return;
+    const double alpha = st->alpha;
+    double v[1] = {0.0};
+    PEN_ROW_LOOP(g, c) {
+        const long long p = c.pos;
+        psi[p] += alpha * pA[p];
+        const double r = rA[p] - alpha * wA[p];
+        rA[p] = r;
+        v[0] += fabs(r);
+    }
+    fvGridReduce<1, false, BLK>(v, red, [=](const double* t) { penFinUpdate(st, t); });
+}
+
+// ---------------------------------------------------------------------------------------------
+// The tail of a PCG iteration as ONE kernel: direction (pA = zA + beta pA), Amul (wA = A pA, wA.pA -> alpha) and update
+// (psi += alpha pA, rA -= alpha wA, sum|rA| -> convergence test).  The three steps are separated by two global sums, so
+// as three launches each pays a launch, a drain and a reduction tail for a few microseconds of memory traffic -- and on
+// a decomposed solve, where a rank's part of the arrays shrinks with the number of ranks, that fixed cost is all that
+// is left of them.  Here the grid is launched cooperatively (every block resident) and the steps are separated by grid
+// barriers on a device counter:
+//   step 1 | barrier: every block's pA is written (decomposed: boundary cells also into the neighbours' ghost cells, block
+//          |   0 then raises the neighbours' halo flags, and every block waits for its own rank's flags)
+//   step 2 | block partial sums, arrive; block 0 waits for all, adds the partials in block order (decomposed: all-reduce
+//          |   over the ranks, fv_peer.cuh), computes alpha, releases the others
+//   step 3 | the usual last-block reduction (decomposed: + all-reduce) and the loop test; the last block re-arms the barrier
+// A warp works on groups of R consecutive rows, the same groups in every step.
+// Loads of values another block wrote earlier in this launch bypass L1 (__ldcg / volatile).
+// ---------------------------------------------------------------------------------------------
+struct PenTailCtl {
+    unsigned int* bar;         // [0] arrivals after step 1  [1] arrivals after step 2  [2] release (alpha is ready)
+    int* error;
+};
+
+__device__ __forceinline__ void penGridArrive(unsigned int* c)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(c, 1u);
+    }
+}
+__device__ __forceinline__ void penSpinUntil(const unsigned int* c, unsigned int n, int* error)     // one thread
+{
+    unsigned int spin = 0;
+    while (*(const volatile unsigned int*)c < n)
+        if (++spin > FY_PEER_SPIN_LIMIT) { atomicExch(error, 1); break; }
+    __threadfence();
+}
+
+template <int R>
+__global__ void __launch_bounds__(BLK, 3)
+k_pen_tail(PencilGeom g, PenMatrix M, double* __restrict__ zA, double* pA, double* wA, double* __restrict__ psi,
+           double* __restrict__ rA, FvRed red, PenTailCtl tc, FvSolveDev* st, PeerDev* peer)
+{
+    if (st->done) return;
+    __shared__ double shSum[BLK / 32];
+    const bool first = st->nIter == 0;
+    const double beta = st->beta;
+    const double sv = sentValue();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nGroups = (int)(g.nLoc / R);                 // Tp is a multiple of 32: a group never straddles two slabs
+    const int w0 = blockIdx.x * (BLK / 32) + warp, nW = gridDim.x * (BLK / 32);
+    const unsigned long long haloTarget = peer ? peer->haloSeq + 1 : 0ull;
+    // ---- step 1: the search direction
+    {
+        double* const zlo = peer ? peer->pa[0] : nullptr;
+        double* const zhi = peer ? peer->pa[1] : nullptr;
+        double* const ylo = peer ? peer->pa[2] : nullptr;
+        double* const yhi = peer ? peer->pa[3] : nullptr;
+        const int jLo = g.jbLo * 32, jHi = g.jbHi * 32 - 1;
+        bool wrote = false;
+        for (int grp = w0; grp < nGroups; grp += nW) {
+            const int row0 = (int)penGlobalRow(g, (long long)grp * R);
+            const int sb = row0 / g.Tp, m0 = row0 - sb * g.Tp;
+            const int k = sb / g.nJB, jb = sb - k * g.nJB;
+            const int j = jb * 32 + lane;
+            if (j >= g.ny) continue;
+            const long long p0 = (long long)row0 * 32 + lane;
+            double z[R], o[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int i = m0 + r - lane;
+                const bool act = i >= 0 && i < g.nx;
+                z[r] = act ? zA[p0 + r * 32] : 0.0;
+                o[r] = (act && !first) ? pA[p0 + r * 32] : 0.0;
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int i = m0 + r - lane;
+                if (i < 0 || i >= g.nx) continue;
+                const long long p = p0 + r * 32;
+                const double v = first ? z[r] : z[r] + beta * o[r];
+                pA[p] = v;
+                zA[p] = sv;
+                if (zlo && k == g.kLo) { zlo[p] = v; wrote = true; }
+                if (zhi && k == g.kHi - 1) { zhi[p] = v; wrote = true; }
+                if (ylo && j == jLo) { ylo[p] = v; wrote = true; }
+                if (yhi && j == jHi) { yhi[p] = v; wrote = true; }
+            }
+        }
+        if (wrote) __threadfence_system();                 // remote stores performed before this block reports
+    }
+    penGridArrive(tc.bar + 0);
+    if (threadIdx.x == 0) {
+        penSpinUntil(tc.bar + 0, gridDim.x, tc.error);
+        if (peer) {
+            if (blockIdx.x == 0) {
+                __threadfence_system();
+                for (int d = 0; d < 4; ++d)
+                    if (peer->nbr[d] >= 0) peerSt(&peer->box[peer->nbr[d]]->halo[d ^ 1], haloTarget);
+                peer->haloSeq = haloTarget;
+            }
+            const unsigned long long* f = peer->box[peer->rank]->halo;
+            for (int d = 0; d < 4; ++d) {
+                if (peer->nbr[d] < 0) continue;
+                unsigned int spin = 0;
+                while (peerLd(f + d) < haloTarget)
+                    if (++spin > FY_PEER_SPIN_LIMIT) { atomicExch(tc.error, 1); break; }
+            }
+            __threadfence();
+        }
+    }
+    __syncthreads();
+    // ---- step 2: wA = A pA, wA.pA
+    double acc = 0.0;
+    {
+        const long long dYm = lane > 0 ? -33 : -(long long)g.Tp * 32 + 31 * 32 + 31;
+        const long long dYp = lane < 31 ? 33 : (long long)g.Tp * 32 - 31 * 32 - 31;
+        const double* __restrict__ dg = M.dg;
+        const double* __restrict__ u0 = M.up[0];
+        const double* __restrict__ u1 = M.up[1];
+        const double* __restrict__ u2 = M.up[2];
+        for (int grp = w0; grp < nGroups; grp += nW) {
+            const int row0 = (int)penGlobalRow(g, (long long)grp * R);
+            const int sb = row0 / g.Tp, m0 = row0 - sb * g.Tp;
+            const int k = sb / g.nJB, jb = sb - k * g.nJB;
+            const int j = jb * 32 + lane;
+            if (j >= g.ny) continue;
+            const bool hasYm = j > 0, hasYp = j < g.ny - 1, hasZm = k > 0, hasZp = k < g.nz - 1;
+            const long long p0 = (long long)row0 * 32 + lane;
+            double xr[R + 2], cr[R + 1];
+#pragma unroll
+            for (int r = 0; r < R + 2; ++r) xr[r] = __ldcg(pA + p0 + (r - 1) * 32);
+#pragma unroll
+            for (int r = 0; r < R + 1; ++r) cr[r] = u0[p0 + (r - 1) * 32];
+            double a[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const long long p = p0 + r * 32;
+                double t = dg[p] * xr[r + 1];
+                if (hasZm) t += u2[p - g.zStride] * __ldcg(pA + p - g.zStride);
+                if (hasYm) t += u1[p + dYm] * __ldcg(pA + p + dYm);
+                t += cr[r] * xr[r];
+                t += cr[r + 1] * xr[r + 2];
+                if (hasYp) t += u1[p] * __ldcg(pA + p + dYp);
+                if (hasZp) t += u2[p] * __ldcg(pA + p + g.zStride);
+                a[r] = t;
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int i = m0 + r - lane;
+                if (i >= 0 && i < g.nx) {
+                    wA[p0 + r * 32] = a[r];
+                    acc += a[r] * xr[r + 1];
+                }
+            }
+        }
+    }
+    {   // block sum -> partial[block]; block 0 finishes the sum for everybody
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        if (lane == 0) shSum[warp] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double x = shSum[0];
+            for (int w = 1; w < BLK / 32; ++w) x += shSum[w];
+            red.partial[blockIdx.x] = x;
+        }
+        penGridArrive(tc.bar + 1);
+        if (blockIdx.x == 0) {
+            if (threadIdx.x == 0) penSpinUntil(tc.bar + 1, gridDim.x, tc.error);
+            __syncthreads();
+            const volatile double* p = red.partial;
+            double x = 0.0;
+            for (unsigned int b = threadIdx.x; b < gridDim.x; b += BLK) x += p[b];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+            __syncthreads();
+            if (lane == 0) shSum[warp] = x;
+            __syncthreads();
+            double tot[1];
+            tot[0] = shSum[0];
+            for (int w = 1; w < BLK / 32; ++w) tot[0] += shSum[w];
+            if (peer && threadIdx.x < 32) peerAllReduce<1>(peer, tot);
+            if (threadIdx.x == 0) {
+                penFinWApA(st, tot);
+                __threadfence();
+                *(volatile unsigned int*)(tc.bar + 2) = 1u;
+            }
+        }
+        if (threadIdx.x == 0) penSpinUntil(tc.bar + 2, 1u, tc.error);
+        __syncthreads();
+    }
+    // ---- step 3: the update and the loop test
+    const double alpha = *(const volatile double*)&st->alpha;
+    double v[1] = {0.0};
+    for (int grp = w0; grp < nGroups; grp += nW) {
+        const int row0 = (int)penGlobalRow(g, (long long)grp * R);
+        const int sb = row0 / g.Tp, m0 = row0 - sb * g.Tp;
+        const int jb = sb % g.nJB;
+        const int j = jb * 32 + lane;
+        if (j >= g.ny) continue;
+        const long long p0 = (long long)row0 * 32 + lane;
+        double pp[R], ww[R], xx[R], rr[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = m0 + r - lane;
+            const bool act = i >= 0 && i < g.nx;
+            const long long p = p0 + r * 32;
+            pp[r] = act ? pA[p] : 0.0;
+            ww[r] = act ? wA[p] : 0.0;
+            xx[r] = act ? psi[p] : 0.0;
+            rr[r] = act ? rA[p] : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = m0 + r - lane;
+            if (i < 0 || i >= g.nx) continue;
+            const long long p = p0 + r * 32;
+            psi[p] = xx[r] + alpha * pp[r];
+            const double q = rr[r] - alpha * ww[r];
+            rA[p] = q;
+            v[0] += fabs(q);
+        }
+    }
+    unsigned int* const bar = tc.bar;
+    fvGridReduce<1, false, BLK>(v, red, [=](const double* t) {
+        penFinUpdate(st, t);
+        bar[0] = 0u;                                       // every block is past the barriers: re-arm them
+        bar[1] = 0u;
+        bar[2] = 0u;
+    });
+}
+
+// y-decomposed solve: the edge lanes of a rank's j-block range, packed for the halo exchange of the search direction.
+// buf[0 .. n) = lane 0 of the first j-block (goes to the rank below in y), buf[n .. 2n) = lane 31 of the last one (goes up);
+// n = (kHi-kLo)*Tp.  Unpacking writes the received values into the neighbours' edge lanes next to the range (the ghosts).
+__global__ void __launch_bounds__(BLK) k_pen_pack_yedge(PencilGeom g, const double* __restrict__ v, double* __restrict__ buf)
+{
+    const long long n = (long long)(g.kHi - g.kLo) * g.Tp;
+    for (long long q = (long long)blockIdx.x * BLK + threadIdx.x; q < 2 * n; q += (long long)gridDim.x * BLK) {
+        const bool hi = q >= n;
+        const long long e = hi ? q - n : q;
+        const int kk = (int)(e / g.Tp), m = (int)(e - (long long)kk * g.Tp);
+        const int jb = hi ? g.jbHi - 1 : g.jbLo;
+        buf[q] = v[(((long long)(g.kLo + kk) * g.nJB + jb) * g.Tp + m) * 32 + (hi ? 31 : 0)];
+    }
+}
+__global__ void __launch_bounds__(BLK) k_pen_unpack_yedge(PencilGeom g, const double* __restrict__ buf, double* __restrict__ v)
+{
+    // buf[0 .. n) = received from below: lane 31 of j-block jbLo-1 ; buf[n .. 2n) = received from above: lane 0 of j-block jbHi
+    const long long n = (long long)(g.kHi - g.kLo) * g.Tp;
+    for (long long q = (long long)blockIdx.x * BLK + threadIdx.x; q < 2 * n; q += (long long)gridDim.x * BLK) {
+        const bool hi = q >= n;
+        if ((hi && g.jbHi >= g.nJB) || (!hi && g.jbLo <= 0)) continue;
+        const long long e = hi ? q - n : q;
+        const int kk = (int)(e / g.Tp), m = (int)(e - (long long)kk * g.Tp);
+        const int jb = hi ? g.jbHi : g.jbLo - 1;
+        v[(((long long)(g.kLo + kk) * g.nJB + jb) * g.Tp + m) * 32 + (hi ? 0 : 31)] = buf[q];
+    }
+}
+// the owned region (planes x j-blocks) of a vector as one contiguous buffer, and back from the buffers of all ranks
+__global__ void __launch_bounds__(BLK) k_pen_pack_region(PencilGeom g, const double* __restrict__ v, double* __restrict__ buf)
+{
+    for (long long l_ = (long long)blockIdx.x * (BLK / 32) + (threadIdx.x >> 5); l_ < g.nLoc; l_ += (long long)gridDim.x * (BLK / 32))
+        buf[l_ * 32 + (threadIdx.x & 31)] = v[penGlobalRow(g, l_) * 32 + (threadIdx.x & 31)];
+}
+__global__ void __launch_bounds__(BLK) k_pen_unpack_region(PencilGeom g, const double* __restrict__ buf, double* __restrict__ v)
+{
+    for (long long l_ = (long long)blockIdx.x * (BLK / 32) + (threadIdx.x >> 5); l_ < g.nLoc; l_ += (long long)gridDim.x * (BLK / 32))
+        v[penGlobalRow(g, l_) * 32 + (threadIdx.x & 31)] = buf[l_ * 32 + (threadIdx.x & 31)];
+}
+// drops a coefficient array's entries on one lane of one j-block's rows (the y face of a slab), owned planes only
+__global__ void __launch_bounds__(BLK) k_pen_zero_lane(PencilGeom g, double* __restrict__ a, int jb, int lane)
+{
+    const long long n = (long long)(g.kHi - g.kLo) * g.Tp;
+    for (long long e = (long long)blockIdx.x * BLK + threadIdx.x; e < n; e += (long long)gridDim.x * BLK) {
+        const int kk = (int)(e / g.Tp), m = (int)(e - (long long)kk * g.Tp);
+        a[(((long long)(g.kLo + kk) * g.nJB + jb) * g.Tp + m) * 32 + lane] = 0.0;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1064,7 +1388,7 @@ int launchPencil(fy_ctx* h, FvState* s, const Op& op, FvSolveDev* st)
 
 // second-generation sweeps (fv_pencil2.cuh): Z planes per compute warp, R rows per TMA stage
 template <class Op, bool REV, int Z, int R>
-int launchPen2T(fy_ctx* h, FvState* s, const PencilGeom& geom, const Op& op, FvSolveDev* st, double* distOut)
+int launchPen2T(fy_ctx* h, FvState* s, const PencilGeom& geom, const Op& op, FvSolveDev* st, double* distOut, PeerDev* peer)
 {
     PenState& P = s->pen;
     const int nzL = geom.kHi - geom.kLo;
@@ -1086,13 +1410,14 @@ int launchPen2T(fy_ctx* h, FvState* s, const PencilGeom& geom, const Op& op, FvS
     const size_t smem = (size_t)W * nStage * stageBytes + (size_t)W * P2_CD * 256 + (size_t)W * Z * P2_YRING * 8 + (size_t)W * nStage * 16 +
                         (size_t)W * 8 * 8 + (size_t)W * 4 + 16;
     if (int rc = penFuncAttrs(h, (const void*)k_pen2<Op, REV, Z, R>)) return rc;
-    PenCtl ctl{P.ticket, P.error, P.partial, st, P.dbg, P.traceOn ? P.trace : nullptr, distOut};
+    PenCtl ctl{P.ticket, P.error, P.partial, st, P.dbg, P.traceOn ? P.trace : nullptr, distOut, peer};
     const int PZ = W * Z, nKQ = (nzL + PZ - 1) / PZ;
     int C = 1;
     while (C * 2 <= P.cluster && C < nKQ) C *= 2;
     const int nCl = (nKQ + C - 1) / C;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(P.g.nJB * nCl * C));
+    const int nJl = geom.jbHi - geom.jbLo;
+    cfg.gridDim = dim3((unsigned)(nJl * nCl * C));
     cfg.blockDim = dim3(32 * (2 * W + 1 + W * Z));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = h->stream;
@@ -1109,7 +1434,7 @@ int launchPen2T(fy_ctx* h, FvState* s, const PencilGeom& geom, const Op& op, FvS
             cudaGetLastError();
             C = 8;
             attr[0].val.clusterDim.x = 8;
-            cfg.gridDim = dim3((unsigned)(P.g.nJB * ((nKQ + 7) / 8) * 8));
+            cfg.gridDim = dim3((unsigned)(nJl * ((nKQ + 7) / 8) * 8));
         }
     }
     FY_CUDA(cudaLaunchKernelEx(&cfg, k_pen2<Op, REV, Z, R>, geom, op, ctl, W, nStage));
@@ -1117,19 +1442,19 @@ int launchPen2T(fy_ctx* h, FvState* s, const PencilGeom& geom, const Op& op, FvS
     return FY_OK;
 }
 template <class Op, bool REV>
-int launchPen2(fy_ctx* h, FvState* s, const PencilGeom& g, const Op& op, FvSolveDev* st, double* distOut = nullptr)
+int launchPen2(fy_ctx* h, FvState* s, const PencilGeom& g, const Op& op, FvSolveDev* st, double* distOut = nullptr, PeerDev* peer = nullptr)
 {
     const PenState& P = s->pen;
     const int key = P.Z2 * 100 + P.R2;
     switch (key) {
-    case 104: return launchPen2T<Op, REV, 1, 4>(h, s, g, op, st, distOut);
-    case 204: return launchPen2T<Op, REV, 2, 4>(h, s, g, op, st, distOut);
+    case 104: return launchPen2T<Op, REV, 1, 4>(h, s, g, op, st, distOut, peer);
+    case 204: return launchPen2T<Op, REV, 2, 4>(h, s, g, op, st, distOut, peer);
 #ifdef PEN2_ALL_VARIANTS
-    case 108: return launchPen2T<Op, REV, 1, 8>(h, s, g, op, st, distOut);
-    case 208: return launchPen2T<Op, REV, 2, 8>(h, s, g, op, st, distOut);
-    case 408: return launchPen2T<Op, REV, 4, 8>(h, s, g, op, st, distOut);
+    case 108: return launchPen2T<Op, REV, 1, 8>(h, s, g, op, st, distOut, peer);
+    case 208: return launchPen2T<Op, REV, 2, 8>(h, s, g, op, st, distOut, peer);
+    case 408: return launchPen2T<Op, REV, 4, 8>(h, s, g, op, st, distOut, peer);
 #endif
-    case 404: return launchPen2T<Op, REV, 4, 4>(h, s, g, op, st, distOut);
+    case 404: return launchPen2T<Op, REV, 4, 4>(h, s, g, op, st, distOut, peer);
     default: h->err = "pencil sweep: no kernel for this FY_PEN2_Z / FY_PEN2_R"; return FY_ERR_INVALID;
     }
 }
@@ -1156,6 +1481,31 @@ PenMatrix penMatrixOf(PenState& P, int which)      // 0: p (symmetric: low built
 }
 }  // namespace
 
+int penPackYEdge(fy_ctx* h, FvState* s, const PencilGeom& g, const double* v, double* buf)
+{
+    const long long n = 2LL * (g.kHi - g.kLo) * g.Tp;
+    k_pen_pack_yedge<<<(unsigned)std::min<long long>((n + BLK - 1) / BLK, 4096), BLK, 0, h->stream>>>(g, v, buf);
+    FY_CHECK_LAUNCH();
+    return FY_OK;
+}
+int penUnpackYEdge(fy_ctx* h, FvState* s, const PencilGeom& g, const double* buf, double* v)
+{
+    const long long n = 2LL * (g.kHi - g.kLo) * g.Tp;
+    k_pen_unpack_yedge<<<(unsigned)std::min<long long>((n + BLK - 1) / BLK, 4096), BLK, 0, h->stream>>>(g, buf, v);
+    FY_CHECK_LAUNCH();
+    return FY_OK;
+}
+int penPackRegion(fy_ctx* h, FvState* s, const PencilGeom& g, const double* v, double* buf)
+{
+    PEN_LAUNCH(k_pen_pack_region, g, v, buf);
+    return FY_OK;
+}
+int penUnpackRegion(fy_ctx* h, FvState* s, const PencilGeom& g, const double* buf, double* v)
+{
+    PEN_LAUNCH(k_pen_unpack_region, g, buf, v);
+    return FY_OK;
+}
+
 int penCreate(fy_ctx* h, FvState* s)
 {
     PenState& P = s->pen;
@@ -1168,7 +1518,7 @@ int penCreate(fy_ctx* h, FvState* s)
     if (g.nRows * 32 >= (1LL << 31)) { h->err = "pencil layout: mesh too large for 32-bit row arithmetic"; return FY_ERR_INVALID; }
     g.NP = g.nRows * 32;
     g.zStride = (long long)g.nJB * g.Tp * 32;
-    g.kLo = 0; g.kHi = g.nz; g.rowLo = 0; g.rowHi = g.nRows;
+    g.kLo = 0; g.kHi = g.nz; g.jbLo = 0; g.jbHi = g.nJB; g.nLoc = g.nRows;
     P.gl = g; P.kLo = 0; P.kHi = g.nz;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -1209,6 +1559,9 @@ int penCreate(fy_ctx* h, FvState* s)
     P.traceOn = std::getenv("FY_PENCIL_TRACE") != nullptr;
     if (const char* e = std::getenv("FY_PCG_GRAPH")) P.useGraphs = std::atoi(e) != 0;
     if (const char* e = std::getenv("FY_PENCIL_DBG")) P.dbg = std::atoi(e);
+    FY_CUDA(cudaMalloc((void**)&P.tailBar, 4 * sizeof(unsigned int)));
+    FY_CUDA(cudaMemsetAsync(P.tailBar, 0, 4 * sizeof(unsigned int), h->stream));
+    if (const char* e = std::getenv("FY_PCG_FUSED")) P.fusedTail = std::atoi(e) != 0;
     FY_CUDA(cudaMalloc((void**)&P.ticket, 2 * sizeof(unsigned int)));
     FY_CUDA(cudaMemsetAsync(P.ticket, 0, 2 * sizeof(unsigned int), h->stream));
     FY_CUDA(cudaMalloc((void**)&P.error, sizeof(int)));
@@ -1230,6 +1583,8 @@ void penDestroy(FvState* s)
     for (auto& ge : P.pcgGraph) if (ge) { cudaGraphExecDestroy(ge); ge = nullptr; }
     if (P.partial) cudaFree(P.partial);
     if (P.trace) cudaFree(P.trace);
+    if (P.tailBar) cudaFree(P.tailBar);
+    P.tailBar = nullptr;
     if (P.ticket) cudaFree(P.ticket);
     if (P.error) cudaFree(P.error);
     if (P.hError) cudaFreeHost(P.hError);
@@ -1237,6 +1592,12 @@ void penDestroy(FvState* s)
 
 // vector roles inside the shared pool P.v[]
 enum { V_B = 0, V_X, V_RD, V_D, V_RA, V_PA, V_WA, V_YA, V_ZA, V_BPRIME = V_RA, V_MID = V_PA, V_EX = V_WA, V_EY = V_YA, V_EZ = V_ZA };
+
+double* penSearchDir(PenState& P, size_t* guardElems)
+{
+    *guardElems = (size_t)PEN_GUARD * 32;
+    return P.v[V_PA];
+}
 
 // the five recurrences, dispatched to the pipeline generation in use
 static int sweepDicD(fy_ctx* h, FvState* s, const PencilGeom& g, const PenMatrix& M, FvSolveDev* st)
@@ -1264,7 +1625,8 @@ static int sweepDicFwd(fy_ctx* h, FvState* s, const PencilGeom& g, const PenMatr
     Op2DicFwd f{{P.pk[0], P.pk[1], v[V_RA]}, v[V_YA]};
     return launchPen2<Op2DicFwd, false>(h, s, g, f, st);
 }
-static int sweepDicBwd(fy_ctx* h, FvState* s, const PencilGeom& g, const PenMatrix& M, FvSolveDev* st, double* distOut = nullptr)
+static int sweepDicBwd(fy_ctx* h, FvState* s, const PencilGeom& g, const PenMatrix& M, FvSolveDev* st, double* distOut = nullptr,
+                       PeerDev* peer = nullptr)
 {
     PenState& P = s->pen;
     double** v = P.v;
@@ -1273,7 +1635,7 @@ static int sweepDicBwd(fy_ctx* h, FvState* s, const PencilGeom& g, const PenMatr
         return launchPencil<OpDicBwd, true>(h, s, bw, st);
     }
     Op2DicBwd bw{{v[V_YA], P.pk[2], P.pk[3], v[V_RA]}, v[V_ZA], v[V_YA]};
-    return launchPen2<Op2DicBwd, true>(h, s, g, bw, st, distOut);
+    return launchPen2<Op2DicBwd, true>(h, s, g, bw, st, distOut, peer);
 }
 static int sweepGsFwd(fy_ctx* h, FvState* s, const PenMatrix& M, FvSolveDev* st)
 {
@@ -1298,6 +1660,36 @@ static int sweepGsBwd(fy_ctx* h, FvState* s, const PenMatrix& M, FvSolveDev* st)
     return launchPen2<Op2GsBwd, true>(h, s, P.g, bw, st);
 }
 
+static int launchTail(fy_ctx* h, FvState* s, const PencilGeom& gl, const PenMatrix& M, const FvRed& red, PeerDev* peer)
+{
+    PenState& P = s->pen;
+    double** v = P.v;
+    if (P.tailBlocksPerSm == 0) {
+        int nb = 0;
+        FY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pen_tail<PEN_AMUL_R>, BLK, 0));
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        P.tailBlocksPerSm = std::max(1, nb);
+        P.tailMaxGrid = sms * P.tailBlocksPerSm;
+    }
+    const long long nGroups = gl.nLoc / PEN_AMUL_R;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((nGroups + BLK / 32 - 1) / (BLK / 32), P.tailMaxGrid));
+    PenTailCtl tc{P.tailBar, P.error};
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(BLK);
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;           // every block resident: the kernel holds grid barriers
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    FY_CUDA(cudaLaunchKernelEx(&cfg, k_pen_tail<PEN_AMUL_R>, gl, M, v[V_ZA], v[V_PA], v[V_WA], v[V_X], v[V_RA], red, tc, s->dSolve, peer));
+    h->launches++;
+    return FY_OK;
+}
+
 // PCG on owner-slot coefficients (device pointers, natural cell order).  Iteration kernels are queued in
 // batches and test the device-side `done` flag themselves; the host looks at the state once per batch.
 int fvPcgSolve(fy_ctx* h, FvState* s, const double* dg, const double* up, const double* b, double* psi, double tol,
@@ -1317,10 +1709,13 @@ int fvPcgSolve(fy_ctx* h, FvState* s, const double* dg, const double* up, const 
     // all-reduced over the ranks before the finishing kernel runs what the single-domain kernel does in its last block
     const bool dist = P.dist;
     const PencilGeom& gl = dist ? P.gl : P.g;
+    // the collectives of the iteration: inside its kernels over peer memory (fv_peer.cuh), else as NCCL calls between them
+    PeerDev* const peer = dist ? P.peer : nullptr;
     FvRed redL = s->red;
-    if (dist) redL.distOut = P.distBuf;
+    if (dist && !peer) redL.distOut = P.distBuf;
+    redL.peer = peer;
     auto finish = [&](int which, int nv) -> int {
-        if (!dist) return FY_OK;
+        if (!dist || peer) return FY_OK;
         if ((rc = fvDistAllReduce(h, s, P.distBuf, nv))) return rc;
         k_pen_fin<<<1, 1, 0, h->stream>>>(which, P.distBuf, s->dSolve, g.N);
         FY_CHECK_LAUNCH();
@@ -1332,6 +1727,10 @@ int fvPcgSolve(fy_ctx* h, FvState* s, const double* dg, const double* up, const 
         // the DIC recurrences only; Amul and the residual take every coefficient from M.up)
         if (dist && P.kLo > 0)
             FY_CUDA(cudaMemsetAsync(M.low[2] + (size_t)P.kLo * g.zStride, 0, (size_t)g.zStride * sizeof(double), h->stream));
+        if (dist && gl.jbLo > 0) {
+            k_pen_zero_lane<<<std::max(1, (int)(((long long)(gl.kHi - gl.kLo) * g.Tp + BLK - 1) / BLK)), BLK, 0, h->stream>>>(gl, M.low[1], gl.jbLo, 0);
+            FY_CHECK_LAUNCH();
+        }
     }
     PEN_LAUNCH(k_pen_from_nat, g, b, v[V_B]);
     PEN_LAUNCH(k_pen_from_nat, g, psi, v[V_X]);
@@ -1349,6 +1748,8 @@ int fvPcgSolve(fy_ctx* h, FvState* s, const double* dg, const double* up, const 
     }
     bool sampled = false;
     const bool prof = h->profiling && s->pev[0];
+    // direction + Amul + update as one cooperative kernel (k_pen_tail); the NCCL path needs host calls between them
+    const bool fusedTail = P.fusedTail && (!dist || peer);
     // one PCG iteration = 5 launches whose arguments never change (the vector pool and the matrix arrays are fixed
     // for the engine's life): a batch of iterations is captured once into a CUDA graph and replayed
     auto enqueueIteration = [&](bool ev) -> int {
@@ -1356,7 +1757,7 @@ int fvPcgSolve(fy_ctx* h, FvState* s, const double* dg, const double* up, const 
         if (precond == FV_PRECOND_DIC) {
             if ((rc = sweepDicFwd(h, s, gl, M, s->dSolve))) return rc;
             if (ev) cudaEventRecord(s->pev[1], h->stream);
-            if ((rc = sweepDicBwd(h, s, gl, M, s->dSolve, dist ? P.distBuf : nullptr))) return rc;
+            if ((rc = sweepDicBwd(h, s, gl, M, s->dSolve, dist && !peer ? P.distBuf : nullptr, peer))) return rc;
         } else {
             if (ev) cudaEventRecord(s->pev[1], h->stream);
             PEN_LAUNCH(k_pen_precond_diag, gl, precond == FV_PRECOND_DIAGONAL ? v[V_RD] : (const double*)nullptr, v[V_RA],
@@ -1364,8 +1765,13 @@ int fvPcgSolve(fy_ctx* h, FvState* s, const double* dg, const double* up, const 
         }
         if ((rc = finish(PEN_FIN_WARA, 1))) return rc;
         if (ev) cudaEventRecord(s->pev[2], h->stream);
-        PEN_LAUNCH(k_pen_dir, gl, v[V_ZA], v[V_PA], s->dSolve);
-        if (dist && (rc = fvDistHalo(h, s, v[V_PA]))) return rc;      // Amul reads the neighbours' boundary planes of pA
+        if (fusedTail) {
+            if ((rc = launchTail(h, s, gl, M, redL, peer))) return rc;
+            if (ev) { cudaEventRecord(s->pev[3], h->stream); cudaEventRecord(s->pev[4], h->stream); cudaEventRecord(s->pev[5], h->stream); }
+            return FY_OK;
+        }
+        PEN_LAUNCH(k_pen_dir, gl, v[V_ZA], v[V_PA], s->dSolve, peer);
+        if (dist && !peer && (rc = fvDistHalo(h, s, v[V_PA]))) return rc;      // Amul reads the neighbours' boundary planes of pA
         if (ev) cudaEventRecord(s->pev[3], h->stream);
 #if PEN_AMUL_R > 1
         PEN_LAUNCH(k_pen_amul_rows<PEN_AMUL_R>, gl, M, v[V_PA], v[V_WA], redL, s->dSolve);
@@ -1374,15 +1780,19 @@ int fvPcgSolve(fy_ctx* h, FvState* s, const double* dg, const double* up, const 
 #endif
         if ((rc = finish(PEN_FIN_WAPA, 1))) return rc;
         if (ev) cudaEventRecord(s->pev[4], h->stream);
-        PEN_LAUNCH(k_pen_update, gl, (const double2*)v[V_PA], (const double2*)v[V_WA], (double2*)v[V_X], (double2*)v[V_RA], redL,
-                   s->dSolve);
+        if (gl.jbHi - gl.jbLo == g.nJB) {
+            PEN_LAUNCH(k_pen_update, gl, (const double2*)v[V_PA], (const double2*)v[V_WA], (double2*)v[V_X], (double2*)v[V_RA], redL,
+                       s->dSolve);
+        } else {
+            PEN_LAUNCH(k_pen_update_rows, gl, v[V_PA], v[V_WA], v[V_X], v[V_RA], redL, s->dSolve);
+        }
         if ((rc = finish(PEN_FIN_UPDATE, 1))) return rc;
         if (ev) cudaEventRecord(s->pev[5], h->stream);
         return FY_OK;
     };
     const int batch = s->pcgBatch;
     cudaGraphExec_t& gexec = P.pcgGraph[precond];
-    const bool useGraph = P.useGraphs && !prof && !P.traceOn && !dist;      // (the decomposed iteration holds NCCL calls: queued eagerly)
+    const bool useGraph = P.useGraphs && !prof && !P.traceOn && (!dist || peer);      // (NCCL calls inside the iteration: queued eagerly)
     if (useGraph && !gexec && P.graphWarm[precond]) {
         // (every kernel has run eagerly once by now: function attributes set, modules loaded)
         const long long l0 = h->launches;

@@ -37,8 +37,18 @@ struct PencilGeom {
     long long zStride;     // nJB*Tp*32: distance between (i,j,k) and (i,j,k+1)
     // the part of the box this process works on (everything, unless the solve is decomposed into z slabs: fv_dist.cu)
     int kLo, kHi;          // k-planes [kLo, kHi)
-    long long rowLo, rowHi; // rows [rowLo, rowHi) = kLo*nJB*Tp ... kHi*nJB*Tp
+    int jbLo, jbHi;        // j-blocks [jbLo, jbHi)
+    long long nLoc;        // local rows: (kHi-kLo) * (jbHi-jbLo) * Tp, enumerated plane by plane, j-block by j-block
 };
+
+// local row l -> row of the global layout
+__host__ __device__ __forceinline__ long long penGlobalRow(const PencilGeom& g, long long l)
+{
+    const int nJl = g.jbHi - g.jbLo;
+    const int q = (int)(l / g.Tp), m = (int)(l - (long long)q * g.Tp);
+    const int kk = q / nJl, jj = q - kk * nJl;
+    return ((long long)(g.kLo + kk) * g.nJB + g.jbLo + jj) * g.Tp + m;
+}
 
 struct PenCell {
     bool valid;

@@ -606,9 +606,12 @@ __global__ void __launch_bounds__(32 * Pen2Max<Z>::WARPS, 1) k_pen2(PencilGeom g
     clusterSync();                                         // channels armed, ticket taken: cluster-wide
     const unsigned int tk = ldClusterU32(mapToRank(smemU32(&shTicket), 0));
     const int nKQ = (g.kHi - g.kLo + PZ - 1) / PZ, nCl = (nKQ + C - 1) / C;
-    const int cl = (int)tk / g.nJB;
-    int jb = (int)tk - cl * g.nJB;
-    if (REV) jb = g.nJB - 1 - jb;
+    // (j-blocks [jbLo, jbHi): all of them, or this rank's part of a y-decomposed solve, whose sweeps stop at its y faces too)
+    const int nJl = g.jbHi - g.jbLo;
+    const int cl = (int)tk / nJl;
+    int jbl = (int)tk - cl * nJl;
+    if (REV) jbl = nJl - 1 - jbl;
+    const int jb = g.jbLo + jbl;
     (void)nCl;
     const int kq = cl * C + rank;                          // plane group in SWEEP order; may be >= nKQ: a CTA without planes
     constexpr int KS = REV ? -1 : 1;
@@ -626,7 +629,7 @@ __global__ void __launch_bounds__(32 * Pen2Max<Z>::WARPS, 1) k_pen2(PencilGeom g
     if (threadIdx.x < W * 8) mbarInit(smemU32(yBars + threadIdx.x), (uint32_t)(P2_YG * max(1, nValidOf(threadIdx.x >> 3))));
     fenceBarrierInit();
     __syncthreads();
-    const int ctaId = kq * g.nJB + jb;
+    const int ctaId = kq * nJl + jbl;
     if (ctl.trace && lane == 0) {
         unsigned long long ts;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts));
@@ -636,7 +639,7 @@ __global__ void __launch_bounds__(32 * Pen2Max<Z>::WARPS, 1) k_pen2(PencilGeom g
     double acc = 0.0;
     int fail = 0;
     // timing probes (FY_PENCIL_DBG; results are wrong with any of them): 2 no z hand-over out, 4 no z in, 8 no y in
-    const bool yCol = (REV ? jb < g.nJB - 1 : jb > 0) && !(ctl.dbg & 8);       // this j-block has a y-producer block
+    const bool yCol = (REV ? jb < g.jbHi - 1 : jb > g.jbLo) && !(ctl.dbg & 8);       // this j-block has a y-producer block
     const long long yOff = REV ? ((long long)g.Tp - 31) * 32 - 31 : -(((long long)g.Tp - 31) * 32 - 31);
     const int row00 = REV ? (g.Tp - 1) * 32 : 0;
     constexpr int EDGE = REV ? 31 : 0;
@@ -727,6 +730,11 @@ __global__ void __launch_bounds__(32 * Pen2Max<Z>::WARPS, 1) k_pen2(PencilGeom g
         for (unsigned int b = lane; b < gridDim.x * W; b += 32) x += p[b];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(FULL, x, o);
+        if (ctl.peer) {                                    // decomposed solve: the sum over the ranks (warp-collective)
+            double t[1] = {x};
+            peerAllReduce<1>(ctl.peer, t);
+            x = t[0];
+        }
         if (lane == 0) {
             if (ctl.distOut) ctl.distOut[0] = x;
             else op.fin(ctl.st, x);
@@ -747,12 +755,13 @@ k_pen_pack_dic(PencilGeom g, const double* __restrict__ rD, PenMatrix M, double2
     PEN_ROW_LOOP(g, c) {
         const long long p = c.pos;
         const double r = rD[p];
-        // a decomposed solve preconditions with the slab's own matrix: no coupling through the slab's top face (the
-        // bottom face's coefficient was dropped from M.low when the matrix was laid out)
+        // a decomposed solve preconditions with the rank's own matrix: no coupling through its top z face and its upper
+        // y face (the coefficients of the lower faces were dropped from M.low when the matrix was laid out)
         const double upz = (c.k == g.kHi - 1 && g.kHi < g.nz) ? 0.0 : M.up[2][p];
+        const double upy = (c.j == g.jbHi * 32 - 1 && g.jbHi < g.nJB) ? 0.0 : M.up[1][p];
         f0[p] = make_double2(r, r * M.low[0][p]);
         f1[p] = make_double2(r * M.low[1][p], r * M.low[2][p]);
-        b0[p] = make_double2(r * M.up[0][p], r * M.up[1][p]);
+        b0[p] = make_double2(r * M.up[0][p], r * upy);
         bz[p] = r * upz;
     }
 }

@@ -41,12 +41,24 @@ struct PenState {
     int Z2 = 1, R2 = 4, W2 = 8;
     int maxStage2 = 5;                  // input-ring stages
     int smemBudget2 = 200 * 1024;       // shared memory per CTA the rings may fill
+    bool fusedTail = true;              // direction + Amul + update of a PCG iteration as one cooperative kernel (FY_PCG_FUSED=0: three)
+    unsigned int* tailBar = nullptr;    // [4] its grid-barrier counters
+    int tailBlocksPerSm = 0, tailMaxGrid = 0;
     double* pk[4] = {nullptr};          // premultiplied DIC streams: {rD, rD lowx} {rD lowy, rD lowz} {rD upx, rD upy} rD upz
-    // z-slab decomposition of the pressure solve (fv_dist.cu)
+    // decomposition of the pressure solve over a Py x Pz grid of ranks (fv_dist.cu): rank = rz * Py + ry
     bool dist = false;
     int rank = 0, nranks = 1;
+    int Py = 1, Pz = 1, ry = 0, rz = 0;
     int kLo = 0, kHi = 0;               // this rank's k-planes
-    PencilGeom gl;                      // the geometry restricted to them (rows [rowLo, rowHi), planes [kLo, kHi))
+    PencilGeom gl;                      // the geometry restricted to this rank: planes [kLo, kHi), j-blocks [jbLo, jbHi)
+    // the iteration's collectives over NVLink peer memory (fv_peer.cuh; FY_DIST_PEER=0 keeps them on NCCL)
+    PeerDev* peer = nullptr;            // device copy of this rank's peer table; null: NCCL path
+    PeerMail* peerMail = nullptr;       // this rank's mailbox
+    void* peerOpened[2 * FY_PEER_MAXR] = {nullptr};   // IPC mappings to close
+    int nPeerOpened = 0;
+    std::string peerWhy;                // why the peer path is off, if it is
+    double* yBuf = nullptr;             // y-edge halo staging: send[2n] | recv[2n], n = (kHi-kLo)*Tp
+    double* gatherBuf = nullptr;        // [NP] the ranks' regions back to back (solution gather of a y-decomposed solve)
     void* comm = nullptr;               // ncclComm_t
     double* distBuf = nullptr;          // [8] partial sums handed to the all-reduce
     long long distCollectives = 0, distHaloBytes = 0;
@@ -96,7 +108,7 @@ struct FvState {
     double *stage = nullptr;
     size_t stageCap = 0;
 
-    FvRed red{nullptr, nullptr, nullptr};
+    FvRed red{nullptr, nullptr, nullptr, nullptr};
     FvSolveDev* dSolve = nullptr;
     FvSolveDev* hSolve = nullptr;       // pinned
     FvStepDev* dStep = nullptr;
@@ -123,7 +135,13 @@ int fvSmoothSolve(fy_ctx* h, FvState* s, const double* dg, const double* b, doub
                   int maxIter, fy_solver_perf* perf);
 void fvSlabRange(int nz, int rank, int nranks, int& kLo, int& kHi);
 int fvDistUniqueId(char out[FY_DIST_ID_BYTES], std::string& err);
-int fvDistInit(fy_ctx* h, FvState* s, int rank, int nranks, const char id[FY_DIST_ID_BYTES]);
+int fvDistInit(fy_ctx* h, FvState* s, int rank, int nranks, int py, const char id[FY_DIST_ID_BYTES]);
+PencilGeom fvDistGeomOf(const PenState& P, int rank);
+double* penSearchDir(PenState& P, size_t* guardElems);   // the search-direction vector pA and the guard in front of its allocation
+int penPackYEdge(fy_ctx* h, FvState* s, const PencilGeom& g, const double* v, double* buf);
+int penUnpackYEdge(fy_ctx* h, FvState* s, const PencilGeom& g, const double* buf, double* v);
+int penPackRegion(fy_ctx* h, FvState* s, const PencilGeom& g, const double* v, double* buf);
+int penUnpackRegion(fy_ctx* h, FvState* s, const PencilGeom& g, const double* buf, double* v);
 void fvDistDestroy(FvState* s);
 int fvDistAllReduce(fy_ctx* h, FvState* s, double* d, int n);
 int fvDistHalo(fy_ctx* h, FvState* s, double* v);

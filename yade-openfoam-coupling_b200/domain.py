@@ -39,13 +39,22 @@ def broadcast_id(dist, uid, device=None):
     return bytes(t.cpu().numpy().tobytes())
 
 
-def init_domain(engine, dist, device=None):
-    """Decomposes the engine's pressure solve over the ranks of `dist` (initialised torch.distributed)."""
+def init_domain(engine, dist, device=None, py=0):
+    """Decomposes the engine's pressure solve over the ranks of `dist` (initialised torch.distributed) as a Py x Pz grid
+    (py = 0: the library's choice, y first; py = 1: z slabs).  The particles' owners stay the z slabs of slab_range."""
     world, rank = dist.get_world_size(), dist.get_rank()
     uid = engine.dist_unique_id() if rank == 0 else b"\0" * 128
     uid = broadcast_id(dist, uid, device)
-    engine.dist_init(rank, world, uid)
+    engine.dist_init(rank, world, uid, py)
     return engine.dist_info()
+
+
+def solve_grid(ny, world, py=0):
+    """(Py, Pz) the library picks for `world` ranks on a box with ny rows -- the arithmetic of csrc/fv_dist.cu."""
+    njb = (int(ny) + 31) // 32
+    if py == 0:
+        py = max(c for c in range(1, world + 1) if world % c == 0 and c <= njb)
+    return py, world // py
 
 
 def _all_to_all(dist, recv, send, rc, sc):
