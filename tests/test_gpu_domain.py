@@ -81,7 +81,8 @@ def _worker(rank, world, port, q, NBOX, peer):
         E.ico_solve(dt)
         E.set_source_zero()
         steps.append(dict(U=E.download("U"), p=E.download("p"), force=force.cpu().numpy(), found=found.cpu().numpy(),
-                          iters=[qq["iters"] for qq in E.ico_stats()["p"]], owned=n))
+                          iters=[qq["iters"] for qq in E.ico_stats()["p"]], uiters=[qq["iters"] for qq in E.ico_stats()["U"]],
+                          owned=n))
     out["steps"] = steps
     out["info_end"] = E.dist_info()
     dist.barrier()
@@ -170,6 +171,8 @@ def test_two_gpu_domain_decomposed_solve_and_step(pkg, cut, peer):
         for r in range(2):
             st = out[r]["steps"][it]
             assert st["iters"] == [qq["iters"] for qq in so["p"]], (it, r, st["iters"], so["p"])
+            # (the momentum components are solved one per rank and travel with their solver statistics)
+            assert st["uiters"] == [qq["iters"] for qq in so["U"]], (it, r, st["uiters"], so["U"])
             assert cases.rel_l2(st["U"], O.field("U")) <= cases.TOL
             assert cases.rel_l2(st["p"], O.field("p")) <= cases.TOL
         assert np.array_equal(out[0]["steps"][it]["U"], out[1]["steps"][it]["U"])

@@ -1260,13 +1260,41 @@ int fvIcoSolve(fy_ctx* h, FvState* s, double dt)
         FV_LAUNCH(k_grad_scalar, G, g, p, s->gradP);
         FV_LAUNCH(k_usolve_setup, G, g, s->nu, s->phi, s->srcU, s->gradP, U, s->bU, s->psiU);
         if ((rc = fvSmoothSetMatrix(h, s, s->loU, s->upU))) return rc;
+        // decomposed run: the momentum components are independent solves with one matrix -- each goes to one rank
+        // (component m to rank m mod min(ranks, 3)) and travels to the others afterwards; same arithmetic as one rank
+        // solving all three
+        const PenState& P = s->pen;
+        const int nOwners = P.dist ? std::min(P.nranks, 3) : 1;
         for (int m = 0; m < 3; ++m) {
-            if (!g.valid[m]) continue;
+            if (!g.valid[m] || (P.dist && m % nOwners != P.rank)) continue;
             if ((rc = fvSmoothSolve(h, s, s->dgU + (size_t)m * N, s->bU + (size_t)m * N, s->psiU + (size_t)m * N, ctl.UTol,
                                     ctl.URelTol, ctl.maxIter, &s->stats.U[m])))
                 return rc;
-            FV_LAUNCH(k_store_component, G, N, s->psiU + (size_t)m * N, m, U);
         }
+        if (P.dist) {
+            double* ptr[6];
+            size_t cnt[6];
+            int root[6], nb = 0;
+            double hp[12];
+            for (int m = 0; m < 3; ++m) {
+                const fy_solver_perf& u = s->stats.U[m];
+                hp[4 * m] = u.initialResidual; hp[4 * m + 1] = u.finalResidual; hp[4 * m + 2] = u.nIterations; hp[4 * m + 3] = 0;
+                if (!g.valid[m]) continue;
+                if (m % nOwners == P.rank)
+                    FY_CUDA(cudaMemcpyAsync(P.perfBuf + 4 * m, hp + 4 * m, 4 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+                ptr[nb] = s->psiU + (size_t)m * N; cnt[nb] = (size_t)N; root[nb++] = m % nOwners;
+                ptr[nb] = P.perfBuf + 4 * m; cnt[nb] = 4; root[nb++] = m % nOwners;
+            }
+            if ((rc = fvDistBroadcastMany(h, s, nb, ptr, cnt, root))) return rc;
+            FY_CUDA(cudaMemcpyAsync(hp, P.perfBuf, sizeof(hp), cudaMemcpyDeviceToHost, h->stream));
+            FY_CUDA(cudaStreamSynchronize(h->stream));
+            for (int m = 0; m < 3; ++m) {
+                if (!g.valid[m]) continue;
+                s->stats.U[m].initialResidual = hp[4 * m]; s->stats.U[m].finalResidual = hp[4 * m + 1]; s->stats.U[m].nIterations = (int)hp[4 * m + 2];
+            }
+        }
+        for (int m = 0; m < 3; ++m)
+            if (g.valid[m]) FV_LAUNCH(k_store_component, G, N, s->psiU + (size_t)m * N, m, U);
     }
     cudaEventRecord(ev[1], h->stream);
     for (int corr = 1; corr <= ctl.nCorrectors; ++corr) {

@@ -228,6 +228,7 @@ int fvDistInit(fy_ctx* h, FvState* s, int rank, int nranks, int py, const char i
     P.kLo = P.gl.kLo;
     P.kHi = P.gl.kHi;
     FY_CUDA(cudaMalloc((void**)&P.distBuf, 8 * sizeof(double)));
+    FY_CUDA(cudaMalloc((void**)&P.perfBuf, 12 * sizeof(double)));
     if (py > 1) {
         int nzMax = 0;
         for (int r = 0; r < pz; ++r) { int lo, hi; fvSlabRange(P.g.nz, r, pz, lo, hi); nzMax = std::max(nzMax, hi - lo); }
@@ -256,6 +257,8 @@ void fvDistDestroy(FvState* s)
     P.peer = nullptr;
     P.peerMail = nullptr;
     if (P.distBuf) cudaFree(P.distBuf);
+    if (P.perfBuf) cudaFree(P.perfBuf);
+    P.perfBuf = nullptr;
     if (P.yBuf) cudaFree(P.yBuf);
     if (P.gatherBuf) cudaFree(P.gatherBuf);
     P.distBuf = P.yBuf = P.gatherBuf = nullptr;
@@ -339,6 +342,18 @@ int fvDistGatherPlanes(fy_ctx* h, FvState* s, double* v)
     FY_NCCL(g_nccl.GroupEnd());
     for (int r = 0; r < P.nranks; ++r)
         if (r != P.rank && (rc = penUnpackRegion(h, s, fvDistGeomOf(P, r), P.gatherBuf + off[r], v))) return rc;
+    P.distCollectives++;
+    return FY_OK;
+}
+
+// cnt buffers, buffer q from rank root[q] to everybody (one NCCL group, on the handle's stream)
+int fvDistBroadcastMany(fy_ctx* h, FvState* s, int cnt, double* const* ptr, const size_t* n, const int* root)
+{
+    PenState& P = s->pen;
+    ncclComm_t comm = (ncclComm_t)P.comm;
+    FY_NCCL(g_nccl.GroupStart());
+    for (int q = 0; q < cnt; ++q) FY_NCCL(g_nccl.Broadcast(ptr[q], ptr[q], n[q], ncclDouble, root[q], comm, h->stream));
+    FY_NCCL(g_nccl.GroupEnd());
     P.distCollectives++;
     return FY_OK;
 }

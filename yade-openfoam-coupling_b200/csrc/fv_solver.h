@@ -58,7 +58,8 @@ struct PenState {
     int nPeerOpened = 0;
     std::string peerWhy;                // why the peer path is off, if it is
     double* yBuf = nullptr;             // y-edge halo staging: send[2n] | recv[2n], n = (kHi-kLo)*Tp
-    double* gatherBuf = nullptr;        // [NP] the ranks' regions back to back (solution gather of a y-decomposed solve)
+    double* gatherBuf = nullptr;
+    double* perfBuf = nullptr;          // [3][4] solver statistics of the momentum components travelling with them        // [NP] the ranks' regions back to back (solution gather of a y-decomposed solve)
     void* comm = nullptr;               // ncclComm_t
     double* distBuf = nullptr;          // [8] partial sums handed to the all-reduce
     long long distCollectives = 0, distHaloBytes = 0;
@@ -146,6 +147,7 @@ void fvDistDestroy(FvState* s);
 int fvDistAllReduce(fy_ctx* h, FvState* s, double* d, int n);
 int fvDistHalo(fy_ctx* h, FvState* s, double* v);
 int fvDistGatherPlanes(fy_ctx* h, FvState* s, double* v);
+int fvDistBroadcastMany(fy_ctx* h, FvState* s, int cnt, double* const* ptr, const size_t* n, const int* root);
 int penCreate(fy_ctx* h, FvState* s);
 void penDestroy(FvState* s);
 int fvDicPrecondition(fy_ctx* h, FvState* s, const double* dg, const double* up, const double* rA, double* wA);
