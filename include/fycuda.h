@@ -260,6 +260,16 @@ int fy_fv_supported(fy_handle h);
 /* defaults = the stock cavity set above */
 int fy_piso_default_controls(fy_piso_controls* c);
 int fy_set_piso_controls(fy_handle h, const fy_piso_controls* c);
+/* pimpleFoamYade's PIMPLE sub-dictionary and relaxationFactors (fy_pimple_solve only):
+ *   nOuterCorrectors   `while (pimple.loop())`, pimpleFoamYade/pimpleFoamYade.C:91-105: UcEqn.H + the PISO loop are repeated;
+ *                      alphaPhic stays the one built before the loop (pimpleFoamYade.C:85); the pFinal solver entry is used in
+ *                      the last PISO corrector of the LAST outer corrector only (pimple.finalInnerIter(), pEqn.H:35)
+ *   relaxU / relaxUFinal   equations { U; UFinal }: UcEqn.relax(), pimpleFoamYade/UcEqn.H:13 (OpenFOAM-6 fvMatrix::relax(alpha))
+ *   relaxP / relaxPFinal   fields { p; pFinal }:    p.relax(),     pimpleFoamYade/pEqn.H:41  (p = prevIter + alpha (p - prevIter))
+ * A factor <= 0 means "no entry in fvSolution" (the call is a no-op, the default); the ...Final factor applies on the last
+ * outer corrector when given.  As in OpenFOAM, prevIter fields exist only when nOuterCorrectors > 1: a p factor < 1 with
+ * one outer corrector is refused by fy_pimple_solve.  nOuterCorrectors x nCorrectors <= 8 (fy_ico_stats slots).          */
+int fy_set_pimple_controls(fy_handle h, int nOuterCorrectors, double relaxU, double relaxUFinal, double relaxP, double relaxPFinal);
 /* transportProperties nu of the fluid solve (fy_set_properties sets it too) */
 int fy_set_viscosity(fy_handle h, double nu);
 /* phi = linearInterpolate(U) & Sf   (createPhi.H, icoFoamYade/createFields.H:152) from the U on the device */

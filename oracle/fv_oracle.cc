@@ -568,6 +568,10 @@ struct Ctl
     double UTol = 1e-5, URelTol = 0.0;
     int maxIter = 1000;
     int precond = PRECOND_DIC;
+    // PIMPLE sub-dictionary + relaxationFactors (pimpleFoamYade only).  A factor <= 0 means "no entry in fvSolution":
+    // fvMatrix::relax() / GeometricField::relax() are then no-ops [OF-6 fvMatrix.C relax(), GeometricField.C relax()]
+    int nOuterCorrectors = 1;
+    double relaxU = 0, relaxUFinal = 0, relaxP = 0, relaxPFinal = 0;
 };
 
 struct Stats
@@ -1044,8 +1048,8 @@ void divDevTerm(const Mesh& m, const double* alpha, double alphaB, double nu, co
 }
 
 // UcEqn  (pim/UcEqn.H:3-11)
-void assembleUcEqn(Ico& s, Pim& q, double dt, const dvec& U0, const double* alpha, const double* alpha0, double alphaB,
-                   const double* uSourceDrag)
+void assembleUcEqn(Ico& s, Pim& q, double dt, const dvec& U0, const dvec& phiA, const double* alpha, const double* alpha0,
+                   double alphaB, const double* uSourceDrag)
 {
     const Mesh& m = s.m;
     const int N = m.nCells, Fi = m.nFaces, nB = m.nB;
@@ -1055,7 +1059,7 @@ void assembleUcEqn(Ico& s, Pim& q, double dt, const dvec& U0, const double* alph
     q.alphaPhi.resize((size_t)Fi + nB);
     for (int f = 0; f < Fi; ++f) q.alphaf[f] = lerp(m.w[f], alpha[m.l[f]], alpha[m.u[f]]);
     for (int b = 0; b < nB; ++b) q.alphaf[Fi + b] = alphaB;
-    for (int f = 0; f < Fi + nB; ++f) q.alphaPhi[f] = q.alphaf[f]*s.phi[f];
+    for (int f = 0; f < Fi + nB; ++f) q.alphaPhi[f] = q.alphaf[f]*phiA[f];   // phiA: phic as it stood at pim.C:85
     // fvm::ddt(alphac, Uc)   [OF-6 EulerDdtScheme::fvmDdt(alpha, vf)]
     dvec diagD(N), lowerC(Fi), upperC(Fi), diagC, upperL(Fi), diagL;
     s.sourceU.assign(3*(size_t)N, 0.0);
@@ -1118,6 +1122,42 @@ void assembleUcEqn(Ico& s, Pim& q, double dt, const dvec& U0, const double* alph
         for (int j = 0; j < 3; ++j) s.sourceU[3*(size_t)c + j] -= m.V[c]*(-q.divDev[3*(size_t)c + j]);
 }
 
+// UcEqn.relax()   pim/UcEqn.H:13  [OF-6 fvMatrix.C relax(const scalar alpha)]: make the matrix diagonally dominant, divide the
+// diagonal by alpha and move the difference, times the CURRENT field, to the source.  The non-coupled patches' internal
+// coefficients count with their largest-magnitude component while dominance is enforced and are taken out again with
+// their smallest component.  alpha <= 0: no relaxation factor in fvSolution -> not called at all.
+void relaxUcEqn(Ico& s, double alpha)
+{
+    if (alpha <= 0) return;
+    const Mesh& m = s.m;
+    const int N = m.nCells, Fi = m.nFaces;
+    dvec& D = s.diagU;
+    const dvec D0(D);
+    dvec sumOff(N, 0.0);
+    for (int f = 0; f < Fi; ++f) {                                  // lduMatrix::sumMagOffDiag
+        sumOff[m.u[f]] += std::fabs(s.lowerU[f]);
+        sumOff[m.l[f]] += std::fabs(s.upperU[f]);
+    }
+    for (const Patch& p : m.patches) {
+        if (p.bcU == BC_EMPTY) continue;                            // (an empty patch field has size 0)
+        for (int b = p.start; b < p.start + p.n; ++b) {
+            const double* ic = &s.icU[3*(size_t)b];
+            D[m.bCell[b]] += std::max(std::max(std::fabs(ic[0]), std::fabs(ic[1])), std::fabs(ic[2]));   // cmptMax(cmptMag(iCoeffs))
+        }
+    }
+    for (int c = 0; c < N; ++c) D[c] = std::max(std::fabs(D[c]), sumOff[c]);
+    for (int c = 0; c < N; ++c) D[c] /= alpha;
+    for (const Patch& p : m.patches) {
+        if (p.bcU == BC_EMPTY) continue;
+        for (int b = p.start; b < p.start + p.n; ++b) {
+            const double* ic = &s.icU[3*(size_t)b];
+            D[m.bCell[b]] -= std::min(std::min(ic[0], ic[1]), ic[2]);                                     // cmptMin(iCoeffs)
+        }
+    }
+    for (int c = 0; c < N; ++c)
+        for (int j = 0; j < 3; ++j) s.sourceU[3*(size_t)c + j] += (D[c] - D0[c])*s.U[3*(size_t)c + j];
+}
+
 int pimpleSolve(Ico& s, Pim& q, double dt, const double* alpha, const double* alpha0, const double* uSourceDrag,
                 const double* gvec)
 {
@@ -1128,7 +1168,22 @@ int pimpleSolve(Ico& s, Pim& q, double dt, const double* alpha, const double* al
     const dvec U0(s.U), phi0(s.phi);
     s.st.nPSolves = 0;
     if (q.invT.size() != 9*(size_t)N) reconstructTensor(m, q.invT);
-    assembleUcEqn(s, q, dt, U0, alpha, alpha0, alphaB, uSourceDrag);
+    const int nOuter = std::max(1, s.ctl.nOuterCorrectors);
+    dvec pPrev;
+    int corrTotal = 0;
+    // --- Pressure-velocity PIMPLE corrector loop   pim.C:91-105  [OF-6 pimpleControl::loop(): corr = 1..nOuterCorrectors;
+    // on the last one data::finalIteration is set (-> the ...Final relaxation factors and, in the last PISO corrector, the
+    // pFinal solver); prevIter fields are stored only when nOuterCorrectors != 1]
+    for (int outer = 1; outer <= nOuter; ++outer) {
+    const bool finalOuter = outer == nOuter;
+    const double fU = (finalOuter && s.ctl.relaxUFinal > 0) ? s.ctl.relaxUFinal : s.ctl.relaxU;
+    const double fP = (finalOuter && s.ctl.relaxPFinal > 0) ? s.ctl.relaxPFinal : s.ctl.relaxP;
+    if (nOuter != 1) pPrev = s.p;                                   // storePrevIterFields()
+    else if (fP > 0 && fP < 1) return -2;                           // p.relax() without a stored prevIter: FatalError in OpenFOAM
+    t0 = nowSec();
+    // alphaPhic is built ONCE per time step, before the loop (pim.C:85): every outer corrector convects with the old phic
+    assembleUcEqn(s, q, dt, U0, phi0, alpha, alpha0, alphaB, uSourceDrag);
+    relaxUcEqn(s, fU);                                              // UcEqn.relax()   pim/UcEqn.H:13
 
     // rAUc = 1/UcEqn.A(); rAUcf = fvc::interpolate(rAUc)       (A() does not depend on Uc: computed once)
     dvec H;
@@ -1265,7 +1320,7 @@ int pimpleSolve(Ico& s, Pim& q, double dt, const double* alpha, const double* al
             dg = s.diagP;
             totalSource = s.sourceP;
             for (int b = 0; b < nB; ++b) { dg[m.bCell[b]] += icP[b]; totalSource[m.bCell[b]] += bcP[b]; }
-            const bool fin = (corr == s.ctl.nCorrectors) && (nonOrth == s.ctl.nNonOrthCorrectors);
+            const bool fin = finalOuter && (corr == s.ctl.nCorrectors) && (nonOrth == s.ctl.nNonOrthCorrectors);   // pimple.finalInnerIter()
             SolverPerf sp = pcgSolve(m, dg, s.upperP, totalSource, s.p.data(), fin ? s.ctl.pFinalTol : s.ctl.pTol,
                                      fin ? s.ctl.pFinalRelTol : s.ctl.pRelTol, s.ctl.maxIter, s.ctl.precond);
             if (s.st.nPSolves < 8) s.st.p[s.st.nPSolves] = sp;
@@ -1277,6 +1332,13 @@ int pimpleSolve(Ico& s, Pim& q, double dt, const double* alpha, const double* al
                 for (int f = 0; f < Fi; ++f) fluxByA[f] = (s.upperP[f]*s.p[m.u[f]] - s.upperP[f]*s.p[m.l[f]])/q.alphaf[f];
                 for (int b = 0; b < nB; ++b) fluxByA[Fi + b] = (icP[b]*s.p[m.bCell[b]] - bcP[b])/q.alphaf[Fi + b];
                 for (int f = 0; f < nF; ++f) s.phi[f] = s.phiHbyA[f] - fluxByA[f];
+                // p.relax()   pim/pEqn.H:41  [OF-6 GeometricField::relax(alpha): if (alpha < 1) p == prevIter + alpha*(p - prevIter)];
+                // the pEqn.flux() of the Uc correction below is evaluated with the RELAXED p (fvMatrix::flux() reads psi)
+                if (fP > 0 && fP < 1) {
+                    for (int c = 0; c < N; ++c) s.p[c] = pPrev[c] + fP*(s.p[c] - pPrev[c]);
+                    for (int f = 0; f < Fi; ++f) fluxByA[f] = (s.upperP[f]*s.p[m.u[f]] - s.upperP[f]*s.p[m.l[f]])/q.alphaf[f];
+                    for (int b = 0; b < nB; ++b) fluxByA[Fi + b] = (icP[b]*s.p[m.bCell[b]] - bcP[b])/q.alphaf[Fi + b];
+                }
                 // Uc = HbyA + rAUc*fvc::reconstruct((phicForces - pEqn.flux()/alphacf)/rAUcf)  pim/pEqn.H:43-45
                 for (int f = 0; f < nF; ++f) ssf[f] = (q.phicForces[f] - fluxByA[f])/q.rAUf[f];
                 reconstruct(m, q.invT, ssf.data(), q.recon.data());
@@ -1299,9 +1361,11 @@ int pimpleSolve(Ico& s, Pim& q, double dt, const double* alpha, const double* al
         s.st.globalContErr = dt*(sg/sv);
         s.cumulativeContErr += s.st.globalContErr;
         s.st.cumulativeContErr = s.cumulativeContErr;
-        if (corr <= 8) { s.st.corrSumLocal[corr - 1] = s.st.sumLocalContErr; s.st.corrGlobal[corr - 1] = s.st.globalContErr; }
+        if (corrTotal < 8) { s.st.corrSumLocal[corrTotal] = s.st.sumLocalContErr; s.st.corrGlobal[corrTotal] = s.st.globalContErr; }
+        corrTotal++;
         s.tOther += nowSec() - t0;
     }
+    }   // outer corrector
     return 0;
 }
 
@@ -1401,6 +1465,14 @@ void fvo_set_controls(void* h, const int* ic6, const double* dc8)
     s->ctl.pRefCell = ic6[3]; s->ctl.maxIter = ic6[4]; s->ctl.precond = ic6[5];
     s->ctl.pRefValue = dc8[0]; s->ctl.pTol = dc8[1]; s->ctl.pRelTol = dc8[2]; s->ctl.pFinalTol = dc8[3];
     s->ctl.pFinalRelTol = dc8[4]; s->ctl.UTol = dc8[5]; s->ctl.URelTol = dc8[6]; s->nu = dc8[7];
+}
+
+// PIMPLE nOuterCorrectors + relaxationFactors { equations { U, UFinal } fields { p, pFinal } }; a factor <= 0 = no entry
+void fvo_set_pimple_controls(void* h, int nOuter, const double* r4)
+{
+    Ico* s = (Ico*)h;
+    s->ctl.nOuterCorrectors = nOuter;
+    s->ctl.relaxU = r4[0]; s->ctl.relaxUFinal = r4[1]; s->ctl.relaxP = r4[2]; s->ctl.relaxPFinal = r4[3];
 }
 
 // name: U p phi uSource vGrad rAU HbyA phiHbyA gradP diagU upperU lowerU sourceU diagP upperP sourceP

@@ -31,6 +31,7 @@ def lib():
                                  _ip, _dp, _ip, _dp]
         L.fvo_destroy.argtypes = [C.c_void_p]
         L.fvo_set_controls.argtypes = [C.c_void_p, _ip, _dp]
+        L.fvo_set_pimple_controls.argtypes = [C.c_void_p, C.c_int, _dp]
         L.fvo_field.restype = _dp
         L.fvo_field.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_long)]
         L.fvo_create_phi.argtypes = [C.c_void_p]
@@ -163,6 +164,11 @@ class IcoOracle:
                  c["nu"]])
         self.L.fvo_set_controls(self.h, _i(ic), _d(dc))
 
+    def set_pimple_controls(self, nOuterCorrectors=1, relaxU=0.0, relaxUFinal=0.0, relaxP=0.0, relaxPFinal=0.0):
+        """PIMPLE nOuterCorrectors (pimpleFoamYade.C:91 `while (pimple.loop())`) and fvSolution relaxationFactors
+        (UcEqn.relax() pim/UcEqn.H:13, p.relax() pim/pEqn.H:41); a factor <= 0 means `no entry` (no-op)."""
+        self.L.fvo_set_pimple_controls(self.h, int(nOuterCorrectors), _d(_c([relaxU, relaxUFinal, relaxP, relaxPFinal])))
+
     def field(self, name):
         """numpy VIEW of a state / intermediate field (shape by name)."""
         n = C.c_long()
@@ -239,6 +245,8 @@ class IcoOracle:
         a = _c(alpha).reshape(-1)
         a0 = a if alpha0 is None else _c(alpha0).reshape(-1)
         rc = self.L.fvo_pimple_solve(self.h, dt, _d(a), _d(a0), _d(_c(uSourceDrag).reshape(-1)), _d(_c(g)))
+        if rc == -2:
+            raise RuntimeError("p.relax(): previous-iteration field not stored (nOuterCorrectors 1 with a p relaxation factor < 1)")
         if rc != 0:
             raise RuntimeError("adjustPhi: continuity error cannot be removed by adjusting the outflow")
 

@@ -195,6 +195,74 @@ def test_pimple_step_reduces_to_icoFoam_and_conserves_mass():
     O.close()
 
 
+def test_pimple_outer_correctors_and_relaxation():
+    """PIMPLE outer correctors (pimpleFoamYade.C:91-105) and relaxationFactors (UcEqn.relax() UcEqn.H:13, p.relax() pEqn.H:41)
+    of the restatement: (a) the relaxed matrix equals OpenFOAM-6's fvMatrix::relax(alpha) definition written independently
+    in numpy from the unrelaxed coefficients; (b) factor 1 on the (diagonally dominant) Euler matrix changes nothing;
+    (c) the outer loop converges: successive outer correctors change the fields less and less, and the result does not
+    depend on relaxing the intermediate iterations when the final one is unrelaxed and the loop has converged;
+    (d) a p factor < 1 with one outer corrector is refused (OpenFOAM: prevIter not stored)."""
+    m = meshgen.hex_box_ldu(10, 8, 6, 1.0, 0.8, 0.6, patches=[("inlet", ["xmin"]), ("outlet", ["xmax"]),
+                                                                ("walls", ["ymin", "ymax", "zmin", "zmax"])])
+    meshgen.set_bc(m, "inlet", bcU=meshgen.BC_FIXED_VALUE, valueU=(0.3, 0, 0), bcP=meshgen.BC_ZERO_GRADIENT)
+    meshgen.set_bc(m, "outlet", bcU=meshgen.BC_ZERO_GRADIENT, bcP=meshgen.BC_FIXED_VALUE, valueP=0.0)
+    C, N = m["C"], m["nCells"]
+    alpha = 1 - 0.4 * np.exp(-((C - 0.4) ** 2).sum(1) / 0.05)
+    drag = -50.0 * (1 - alpha)
+    src = np.stack([0 * alpha, -0.8 * (1 - alpha), 0.2 * (1 - alpha)], 1)
+    U0 = np.tile([0.3, 0.0, 0.0], (N, 1)) + 0.05 * np.stack([np.sin(3 * C[:, 1]), np.cos(2 * C[:, 0]), np.sin(4 * C[:, 2])], 1)
+    dt = 5e-3
+
+    def run(steps=1, tight=False, **pc):
+        kw = dict(pTol=1e-13, pFinalTol=1e-13, pRelTol=0.0, UTol=1e-13) if tight else {}
+        O = port.IcoOracle(m, nu=0.01, **kw)
+        O.field("U")[:] = U0
+        O.create_phi()
+        O.set_pimple_controls(**pc)
+        O.field("uSource")[:] = src
+        for _ in range(steps):
+            O.pimple_solve(dt, alpha, drag, (0.0, -0.5, 0.0))
+        out = {k: O.field(k).copy() for k in ("U", "p", "phi", "diagU", "lowerU", "upperU", "sourceU", "icU", "rAU")}
+        out["stats"] = O.stats()
+        O.close()
+        return out
+
+    base = run()
+    # (a) fvMatrix::relax(0.7), independently: D = max(|D0 + sum_b max|ic||, sumMagOffDiag)/alpha - sum_b min(ic); S += (D - D0) psi
+    rel = run(relaxU=0.7)
+    lo, up = m["owner"], m["neighbour"]
+    bC = m["bCell"] if "bCell" in m else np.concatenate([np.asarray(pp["faceCells"]) for pp in m["patches"]])
+    ic = base["icU"].reshape(-1, 3)
+    D0 = base["diagU"]
+    sumOff = np.zeros(N)
+    np.add.at(sumOff, up, np.abs(base["lowerU"]))
+    np.add.at(sumOff, lo, np.abs(base["upperU"]))
+    D = D0.copy()
+    np.add.at(D, bC, np.abs(ic).max(1))
+    D = np.maximum(np.abs(D), sumOff) / 0.7
+    np.subtract.at(D, bC, ic.min(1))
+    assert np.allclose(rel["diagU"], D, rtol=1e-14, atol=0)
+    assert np.allclose(rel["sourceU"], base["sourceU"] + (D - D0)[:, None] * U0, rtol=1e-13, atol=1e-18)
+    assert np.array_equal(rel["lowerU"], base["lowerU"]) and np.array_equal(rel["upperU"], base["upperU"])
+    assert np.linalg.norm(rel["U"] - base["U"]) > 1e-6 * np.linalg.norm(base["U"])       # (it does something)
+    # (b) alpha = 1 on a dominant matrix: D + max|ic| - min(ic) = D for the fixedValue / zeroGradient coefficients
+    one = run(relaxU=1.0)
+    for k in ("U", "p", "phi"):
+        assert np.linalg.norm(one[k] - base[k]) <= 1e-11 * np.linalg.norm(base[k]), k
+    # (c) convergence of the outer loop
+    seq = [run(tight=True, nOuterCorrectors=n) for n in (1, 2, 3, 6, 7)]
+    d = [np.linalg.norm(seq[i + 1]["U"] - seq[i]["U"]) / np.linalg.norm(seq[i]["U"]) for i in range(4)]
+    assert d[0] > d[1] and d[3] < 0.05 * d[0], d
+    relaxed = run(tight=True, nOuterCorrectors=12, relaxU=0.8, relaxUFinal=1.0, relaxP=0.6, relaxPFinal=1.0)
+    plain = run(tight=True, nOuterCorrectors=12)
+    for k in ("U", "p"):
+        assert np.linalg.norm(relaxed[k] - plain[k]) <= 2e-3 * np.linalg.norm(plain[k]), k
+    assert relaxed["stats"]["nPSolves"] == 12 * 2
+    # (d)
+    with pytest.raises(RuntimeError):
+        run(relaxP=0.5)
+
+
 def test_pimple_UcEqn_matrix_is_the_sum_of_its_explicit_operators():
     """The assembled UcEqn (pim/UcEqn.H:3-11; diag / lower / upper / source of the restatement) applied to an arbitrary
     field W must equal, away from the patches, V times the same terms evaluated with the separately written fvc

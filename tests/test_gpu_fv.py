@@ -339,6 +339,64 @@ def test_pimpleFoamYade_steps_match_oracle(pkg, case):
     O.close()
 
 
+@pytest.mark.parametrize("mode", ["outer2", "outer3_relaxed", "relaxU_only"])
+def test_pimple_outer_correctors_and_relaxation_on_gpu(pkg, mode):
+    """`while (pimple.loop())` (pimpleFoamYade.C:91-105) with nOuterCorrectors > 1, UcEqn.relax() (UcEqn.H:13) and p.relax()
+    (pEqn.H:41) on the device against the oracle's restatement of OpenFOAM-6's pimpleControl / fvMatrix::relax /
+    GeometricField::relax: the relaxed UcEqn (diagonal, source, 1/A) of the last outer corrector bit-exact, fields within
+    1e-10, identical iteration counts in every pressure solve of every outer corrector."""
+    pc = {"outer2": dict(nOuterCorrectors=2),
+          "outer3_relaxed": dict(nOuterCorrectors=3, relaxU=0.7, relaxUFinal=1.0, relaxP=0.3, relaxPFinal=1.0),
+          "relaxU_only": dict(nOuterCorrectors=1, relaxU=0.8)}[mode]
+    mo, mp = cases_fv.channel(pkg, (28, 14, 12))
+    U, p = cases_fv.channel_init(mo["C"])
+    dt, nu, ctl, g = 0.02, 0.005, dict(nCorrectors=2), (0.0, -0.2, 0.05)
+    O = port.IcoOracle(mo, nu=nu, **ctl)
+    O.set_pimple_controls(**pc)
+    O.field("U")[:] = U
+    O.field("p")[:] = p
+    O.create_phi()
+    E = pkg.Engine(mp)
+    assert E.fv_supported(), E.L.fy_last_error(E.h).decode()
+    E.set_piso_controls(nu=nu, **ctl)
+    E.set_pimple_controls(**pc)
+    E.upload("U", U)
+    E.upload("p", p)
+    E.create_phi()
+    for it in range(3):
+        alpha, drag, src = _pimple_drive(mo, it)
+        O.field("uSource")[:] = src
+        O.pimple_solve(dt, alpha, drag, g)
+        E.upload("alpha", alpha)
+        E.upload("uSourceDrag", drag)
+        E.upload("uSource", src)
+        E.pimple_solve(dt, g)
+        if it == 0 and mode != "outer3_relaxed":
+            # (the last outer corrector starts from the same U on both sides only up to solver round-off once a linear
+            # solve lies in between: bit-exact assembly is asserted where no solve precedes it or U enters nowhere)
+            assert np.array_equal(E.fv_get("diagU"), O.field("diagU"))
+            assert np.array_equal(E.fv_get("rAU"), O.field("rAU"))
+        if it == 0 and mode == "relaxU_only":
+            assert np.array_equal(E.fv_get("sourceU"), O.field("sourceU"))
+        if it == 0 and mode == "outer3_relaxed":
+            assert np.array_equal(E.fv_get("diagU"), O.field("diagU"))      # the diagonal does not depend on U
+        so, se = O.stats(), E.ico_stats()
+        assert so["nPSolves"] == se["nPSolves"] == pc["nOuterCorrectors"] * 2
+        assert [q["iters"] for q in so["p"]] == [q["iters"] for q in se["p"]], it
+        assert [q["iters"] for q in so["U"]] == [q["iters"] for q in se["U"]], it
+        for k in ("U", "p", "phi"):
+            assert cases.rel_l2(E.download(k), O.field(k)) <= TOL, (k, it)
+        assert abs(se["cumulativeContErr"] - so["cumulativeContErr"]) <= 1e-9 * abs(so["cumulativeContErr"]) + 1e-16
+    with pytest.raises(pkg.FyError):
+        E.set_pimple_controls(nOuterCorrectors=1, relaxP=0.5)
+        E.pimple_solve(dt, g)                              # p.relax() without a stored prevIter
+    with pytest.raises(pkg.FyError):
+        E.set_pimple_controls(nOuterCorrectors=5)          # 5 x 2 correctors > the 8 statistics slots
+        E.pimple_solve(dt, g)
+    E.close()
+    O.close()
+
+
 @pytest.mark.parametrize("case", ["cavity3d", "channel"])
 def test_coupled_pimpleFoamYade_step(pkg, case):
     """The whole pimpleFoamYade time step with every field resident on the device (pimpleFoamYade.C:71-108): CourantNo,

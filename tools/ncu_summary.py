@@ -71,5 +71,21 @@ def launch(path):
         print("%s,%d,%.3f,%.4f" % (k, cnt[k], tot[k], tot[k] / s))
 
 
+def traffic(*csvs):
+    """profiles/rNN_ncu_traffic.json (what bench.py reads for roofline.traffic) from `full` summaries:
+       python tools/ncu_summary.py traffic profiles/rNN_ncu_full_a.csv [profiles/rNN_ncu_full_b.csv ...] > profiles/rNN_ncu_traffic.json"""
+    import json
+    ks = OrderedDict()
+    for path in csvs:
+        for r in csv.DictReader(open(path)):
+            name = re.sub(r"<(Op2?\w+);.*>", r"<\1>", r["kernel"])       # k_pen2<Op2DicBwd; 1; 1; 4> -> k_pen2<Op2DicBwd>
+            ks[name] = {"dram_read_MB": float(r["dram__bytes_read.sum [Gbyte]"]) * 1e3,
+                        "dram_write_MB": float(r["dram__bytes_write.sum [Gbyte]"]) * 1e3,
+                        "duration_us_under_ncu": float(r["gpu__time_duration.sum [ms]"]) * 1e3}
+    print(json.dumps({"source": "ncu --set full --clock-control none on `python bench.py --steps 1 --warmup 3 --no-cpu-baseline` (C2, 128^3 cells "
+                                "/ 1M particles), per launch, mid-solve; summaries: " + ", ".join(csvs),
+                      "workload": "C2", "kernels": ks}, indent=1))
+
+
 if __name__ == "__main__":
-    {"full": full, "launch": launch}[sys.argv[1]](sys.argv[2])
+    {"full": full, "launch": launch, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])

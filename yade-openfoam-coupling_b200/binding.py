@@ -106,6 +106,7 @@ def lib():
     L.fy_piso_default_controls.argtypes = [C.POINTER(PisoControls)]
     L.fy_set_piso_controls.argtypes = [H, C.POINTER(PisoControls)]
     L.fy_set_viscosity.argtypes = [H, C.c_double]
+    L.fy_set_pimple_controls.argtypes = [H, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]
     L.fy_create_phi.argtypes = [H]
     L.fy_ico_pre.argtypes = [H, C.c_double]
     L.fy_ico_solve.argtypes = [H, C.c_double]
@@ -373,6 +374,11 @@ class Engine:
                 raise KeyError(k)
             setattr(c, k, v)
         self._ck(self.L.fy_set_piso_controls(self.h, C.byref(c)))
+
+    def set_pimple_controls(self, nOuterCorrectors=1, relaxU=0.0, relaxUFinal=0.0, relaxP=0.0, relaxPFinal=0.0):
+        """PIMPLE nOuterCorrectors (pimpleFoamYade.C:91) and relaxationFactors (UcEqn.H:13, pEqn.H:41); <= 0: no entry"""
+        self._ck(self.L.fy_set_pimple_controls(self.h, int(nOuterCorrectors), float(relaxU), float(relaxUFinal), float(relaxP),
+                                               float(relaxPFinal)))
 
     def create_phi(self):
         self._ck(self.L.fy_create_phi(self.h))

@@ -77,6 +77,21 @@ int fy_set_piso_controls(fy_handle h, const fy_piso_controls* c)
     return FY_OK;
 }
 
+int fy_set_pimple_controls(fy_handle h, int nOuterCorrectors, double relaxU, double relaxUFinal, double relaxP, double relaxPFinal)
+{
+    FyDeviceGuard guard_(h);
+    FvState* s;
+    int rc = needFv(h, &s);
+    if (rc) return rc;
+    if (nOuterCorrectors < 1 || relaxU > 1 || relaxUFinal > 1 || relaxP > 1 || relaxPFinal > 1) {
+        h->err = "fy_set_pimple_controls: nOuterCorrectors >= 1 and relaxation factors <= 1 (<= 0: none)";
+        return FY_ERR_INVALID;
+    }
+    s->nOuter = nOuterCorrectors;
+    s->relaxU = relaxU; s->relaxUFinal = relaxUFinal; s->relaxP = relaxP; s->relaxPFinal = relaxPFinal;
+    return FY_OK;
+}
+
 int fy_set_viscosity(fy_handle h, double nu)
 {
     FyDeviceGuard guard_(h);

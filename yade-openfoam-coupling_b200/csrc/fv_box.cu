@@ -789,8 +789,9 @@ k_pim_div_dev(BoxGeom g, double nu, const double* __restrict__ alpha, const doub
 __global__ void __launch_bounds__(BLK)
 k_pim_assemble_U(BoxGeom g, double nu, double rDeltaT, const double* __restrict__ phi, const double* __restrict__ alpha,
                  const double* __restrict__ alpha0, const double* __restrict__ U0, const double* __restrict__ uSourceDrag,
-                 const double* __restrict__ divDev, double* __restrict__ diagU, double* __restrict__ loU,
-                 double* __restrict__ upU, double* __restrict__ srcU, double* __restrict__ dgU, double* __restrict__ rAU)
+                 const double* __restrict__ divDev, double relax, const double* __restrict__ Ucur, double* __restrict__ diagU,
+                 double* __restrict__ loU, double* __restrict__ upU, double* __restrict__ srcU, double* __restrict__ dgU,
+                 double* __restrict__ rAU)
 {
     FV_CELL_LOOP(g, c) {
         int i, j, k;
@@ -799,6 +800,7 @@ k_pim_assemble_U(BoxGeom g, double nu, double rDeltaT, const double* __restrict_
         const double ac = alpha[c], a0 = alpha0[c];
         const double diagD = (rDeltaT * ac) * g.V;
         double diagC = 0.0, diagL = 0.0, dv = 0.0;
+        double sumOff = 0.0;                          // lduMatrix::sumMagOffDiag of this row, in face order (UcEqn.relax())
 #pragma unroll
         for (int d = 2; d >= 0; --d) {
             const int v = fvIdx(d, i, j, k), sd = fvStride(g, d);
@@ -807,9 +809,11 @@ k_pim_assemble_U(BoxGeom g, double nu, double rDeltaT, const double* __restrict_
                 const double aph = fvLerp(g.w[d], an, ac) * phi[d * N + c - sd];
                 const double lowerC = -g.w[d] * aph;
                 const double upperC = lowerC + aph;
+                const double upperL = g.dc[d] * (fvLerp(g.w[d], an * nu, ac * nu) * g.magSf[d]);
                 diagC -= upperC;
-                diagL -= g.dc[d] * (fvLerp(g.w[d], an * nu, ac * nu) * g.magSf[d]);
+                diagL -= upperL;
                 dv -= aph;
+                sumOff += fabs(lowerC + (-upperL));   // this cell is the face's neighbour: |Lower[face]|
             }
         }
 #pragma unroll
@@ -827,6 +831,7 @@ k_pim_assemble_U(BoxGeom g, double nu, double rDeltaT, const double* __restrict_
                 dv += aph;
                 lo = lowerC + (-upperL);
                 up = upperC + (-upperL);
+                sumOff += fabs(up);                   // this cell is the face's owner: |Upper[face]|
             }
             loU[d * N + c] = lo;
             upU[d * N + c] = up;
@@ -840,7 +845,39 @@ k_pim_assemble_U(BoxGeom g, double nu, double rDeltaT, const double* __restrict_
             }
         }
         const double spDiv = rDeltaT * (ac - a0) + dv / g.V;
-        const double diag = (((diagD + diagC) - g.V * spDiv) + (-diagL)) - g.V * uSourceDrag[c];
+        double diag = (((diagD + diagC) - g.V * spDiv) + (-diagL)) - g.V * uSourceDrag[c];
+        double relaxSrc = 0.0;                        // D - D0 of fvMatrix::relax: the source gets (D - D0)*psi
+        if (relax > 0.0) {
+            // UcEqn.relax()   pim/UcEqn.H:13  [OF-6 fvMatrix.C relax(alpha)]: boundary internal coefficients count with
+            // their largest-magnitude component while dominance is enforced, and leave with their smallest component
+            const double D0 = diag;
+            const bool bnd = !fvInterior(g, i, j, k);
+            if (bnd) {
+                for (int q = 0; q < 6; ++q) {
+                    const int s = g.seq[q];
+                    if (g.kindU[s] == FV_EMPTY || !fvOnSide(g, s, i, j, k)) continue;
+                    const double phib = FV_ALPHA_B * phi[fvSideSlot(g, s, c, i, j, k)];
+                    double ic[3], bc;
+#pragma unroll
+                    for (int m = 0; m < 3; ++m) fvBCoefU(g, s, phib, FV_ALPHA_B * nu, m, ic[m], bc);
+                    diag += fmax(fmax(fabs(ic[0]), fabs(ic[1])), fabs(ic[2]));
+                }
+            }
+            diag = fmax(fabs(diag), sumOff);
+            diag /= relax;
+            if (bnd) {
+                for (int q = 0; q < 6; ++q) {
+                    const int s = g.seq[q];
+                    if (g.kindU[s] == FV_EMPTY || !fvOnSide(g, s, i, j, k)) continue;
+                    const double phib = FV_ALPHA_B * phi[fvSideSlot(g, s, c, i, j, k)];
+                    double ic[3], bc;
+#pragma unroll
+                    for (int m = 0; m < 3; ++m) fvBCoefU(g, s, phib, FV_ALPHA_B * nu, m, ic[m], bc);
+                    diag -= fmin(fmin(ic[0], ic[1]), ic[2]);
+                }
+            }
+            relaxSrc = diag - D0;
+        }
         diagU[c] = diag;
         D = diag;
         dgB[0] = dgB[1] = dgB[2] = diag;
@@ -863,6 +900,7 @@ k_pim_assemble_U(BoxGeom g, double nu, double rDeltaT, const double* __restrict_
             dgU[m * (size_t)N + c] = dgB[m];
             double sU = ((rDeltaT * a0) * U0[3 * (size_t)c + m]) * g.V;
             sU -= g.V * (-divDev[3 * (size_t)c + m]);
+            if (relax > 0.0) sU += relaxSrc * Ucur[3 * (size_t)c + m];
             srcU[3 * (size_t)c + m] = sU;
         }
         rAU[c] = 1.0 / (D / g.V);
@@ -1106,6 +1144,13 @@ k_pim_flux_update(BoxGeom g, const double* __restrict__ upP, const double* __res
 }
 
 // continuityErrs.H (contErr = fvc::ddt(alphac) + fvc::div(alphacf*phic)) and
+// p.relax()   pim/pEqn.H:41  [OF-6 GeometricField::relax(alpha)]: p = prevIter + alpha*(p - prevIter)
+__global__ void __launch_bounds__(BLK)
+k_relax_field(int n, double a, const double* __restrict__ prev, double* __restrict__ x)
+{
+    for (int c = blockIdx.x * BLK + threadIdx.x; c < n; c += gridDim.x * BLK) x[c] = prev[c] + a * (x[c] - prev[c]);
+}
+
 // Uc = HbyA + rAUc*fvc::reconstruct((phicForces - pEqn.flux()/alphacf)/rAUcf)      pim/continuityErrs.H, pEqn.H:43-45
 __global__ void __launch_bounds__(BLK)
 k_pim_correct_U(BoxGeom g, double dt, double rDeltaT, int corr, const double* __restrict__ phi, const double* __restrict__ p,
@@ -1350,7 +1395,8 @@ int fvIcoSolve(fy_ctx* h, FvState* s, double dt)
     return FY_OK;
 }
 
-// pimpleFoamYade.C:82-104 (one outer corrector): alphacf / alphaPhic, UcEqn.H, the PISO loop over pEqn.H, continuityErrs.H.
+// pimpleFoamYade.C:82-104: alphacf / alphaPhic, then nOuterCorrectors x { UcEqn.H (+ relax), the PISO loop over pEqn.H (+ p.relax()),
+// continuityErrs.H }.
 // Reads the coupling operator's device fields alpha, uSource, uSourceDrag; alphac.oldTime() == alphac (see the oracle).
 int fvPimpleSolve(fy_ctx* h, FvState* s, double dt, const double gvec[3])
 {
@@ -1372,17 +1418,39 @@ int fvPimpleSolve(fy_ctx* h, FvState* s, double dt, const double gvec[3])
         FY_CUDA(cudaMalloc((void**)&s->divDev, 3 * (size_t)N * sizeof(double)));
     }
 
+    const int nOuter = s->nOuter < 1 ? 1 : s->nOuter;
+    if (nOuter * ctl.nCorrectors > 8) { h->err = "fy_pimple_solve: nOuterCorrectors x nCorrectors > 8 (fy_ico_stats slots)"; return FY_ERR_INVALID; }
+    if (nOuter > 1 && !s->pPrev) FY_CUDA(cudaMalloc((void**)&s->pPrev, (size_t)N * sizeof(double)));
+    int corrTotal = 0;
+    bool pMatrixValid = false;          // the pencil copy of the pEqn matrix + its DIC diagonal belong to the current 1/A()
+    double lastFU = 0.0;
+
     cudaEventRecord(ev[0], h->stream);
     FY_CUDA(cudaMemcpyAsync(s->U0, U, 3 * (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     FY_CUDA(cudaMemcpyAsync(s->phi0, s->phi, (size_t)g.nSlots * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    // --- Pressure-velocity PIMPLE corrector loop   pim.C:91-105  ([OF-6 pimpleControl::loop()]: the last outer corrector is
+    // the "final iteration": ...Final relaxation factors, and the pFinal solver in its last PISO corrector)
+    for (int outer = 1; outer <= nOuter; ++outer) {
+    const bool finalOuter = outer == nOuter;
+    const double fU = (finalOuter && s->relaxUFinal > 0) ? s->relaxUFinal : s->relaxU;
+    const double fP = (finalOuter && s->relaxPFinal > 0) ? s->relaxPFinal : s->relaxP;
+    if (nOuter != 1) {                                   // storePrevIterFields()
+        FY_CUDA(cudaMemcpyAsync(s->pPrev, p, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    } else if (fP > 0 && fP < 1) {
+        h->err = "fy_pimple_solve: p.relax() needs the previous-iteration field, which PIMPLE stores only when nOuterCorrectors > 1";
+        return FY_ERR_INVALID;
+    }
+    if (outer == 1 || fU != lastFU) pMatrixValid = false; // UcEqn.relax() changes A(), hence the pEqn matrix
+    lastFU = fU;
     FV_LAUNCH(k_grad_vector, G, g, U, h->dField[FY_F_VGRAD]);
     FV_LAUNCH(k_pim_div_dev, G, g, s->nu, alpha, U, h->dField[FY_F_VGRAD], s->divDev);
-    FV_LAUNCH(k_pim_assemble_U, G, g, s->nu, rDeltaT, s->phi, alpha, alpha0, s->U0, h->dField[FY_F_USOURCEDRAG], s->divDev,
-              s->diagU, s->loU, s->upU, s->srcU, s->dgU, s->rAU);
+    // alphaPhic = alphacf*phic is built once per time step, before the loop (pim.C:85): phi0 in every outer corrector
+    FV_LAUNCH(k_pim_assemble_U, G, g, s->nu, rDeltaT, s->phi0, alpha, alpha0, s->U0, h->dField[FY_F_USOURCEDRAG], s->divDev,
+              fU, U, s->diagU, s->loU, s->upU, s->srcU, s->dgU, s->rAU);
     FV_LAUNCH(k_pim_forces, G, g, gvec[0], gvec[1], gvec[2], s->rAU, h->dField[FY_F_USOURCE], s->phicForces);
     if (ctl.momentumPredictor) {
         FV_LAUNCH(k_pim_predictor_source, G, g, s->phicForces, s->rAU, p, s->gradP);
-        FV_LAUNCH(k_usolve_setup, G, g, FV_ALPHA_B * s->nu, s->phi, s->srcU, s->gradP, U, s->bU, s->psiU);
+        FV_LAUNCH(k_usolve_setup, G, g, FV_ALPHA_B * s->nu, s->phi0, s->srcU, s->gradP, U, s->bU, s->psiU);
         if ((rc = fvSmoothSetMatrix(h, s, s->loU, s->upU))) return rc;
         for (int m = 0; m < 3; ++m) {
             if (!g.valid[m]) continue;
@@ -1392,7 +1460,7 @@ int fvPimpleSolve(fy_ctx* h, FvState* s, double dt, const double gvec[3])
             FV_LAUNCH(k_store_component, G, N, s->psiU + (size_t)m * N, m, U);
         }
     }
-    cudaEventRecord(ev[1], h->stream);
+    if (outer == 1) cudaEventRecord(ev[1], h->stream);
     for (int corr = 1; corr <= ctl.nCorrectors; ++corr) {
         cudaEventRecord(ev[2], h->stream);
         FV_LAUNCH(k_HbyA, G, g, FV_ALPHA_B * s->nu, s->phi0, s->loU, s->upU, s->srcU, U, s->rAU, s->HbyA);
@@ -1407,19 +1475,23 @@ int fvPimpleSolve(fy_ctx* h, FvState* s, double dt, const double gvec[3])
         for (int nonOrth = 0; nonOrth <= ctl.nNonOrthogonalCorrectors; ++nonOrth) {
             FV_LAUNCH(k_pim_pEqn, G, g, ctl.pRefCell, ctl.pRefValue, rDeltaT, s->upP, s->phiHbyA, s->rAU, alpha, alpha0, s->dgP,
                       s->bP);
-            const bool fin = corr == ctl.nCorrectors && nonOrth == ctl.nNonOrthogonalCorrectors;
+            const bool fin = finalOuter && corr == ctl.nCorrectors && nonOrth == ctl.nNonOrthogonalCorrectors;   // pimple.finalInnerIter()
             fy_solver_perf perf{0, 0, 0, 0};
             if ((rc = fvPcgSolve(h, s, s->dgP, s->upP, s->bP, p, fin ? ctl.pFinalTol : ctl.pTol,
                                  fin ? ctl.pFinalRelTol : ctl.pRelTol, ctl.maxIter, ctl.preconditioner, &perf,
-                                 s->stats.nPSolves > 0)))     // 1/A() is fixed for the step: every pEqn has the same matrix
+                                 pMatrixValid)))              // 1/A() is fixed while the relaxation factor is: same pEqn matrix
                 return rc;
+            pMatrixValid = true;
             if (s->stats.nPSolves < 8) s->stats.p[s->stats.nPSolves] = perf;
             s->stats.nPSolves++;
-            if (nonOrth == ctl.nNonOrthogonalCorrectors)
+            if (nonOrth == ctl.nNonOrthogonalCorrectors) {
                 FV_LAUNCH(k_pim_flux_update, G, g, s->upP, s->phiHbyA, p, s->rAU, alpha, s->phi);
+                // p.relax()   pim/pEqn.H:41 -- after phic, before the Uc correction (whose pEqn.flux() sees the relaxed p)
+                if (fP > 0 && fP < 1) FV_LAUNCH(k_relax_field, G, N, fP, s->pPrev, p);
+            }
         }
         cudaEventRecord(ev[4], h->stream);
-        FV_LAUNCH(k_pim_correct_U, G, g, dt, rDeltaT, corr - 1, s->phi, p, s->upP, s->phicForces, s->HbyA, s->rAU, alpha, alpha0,
+        FV_LAUNCH(k_pim_correct_U, G, g, dt, rDeltaT, corrTotal++, s->phi, p, s->upP, s->phicForces, s->HbyA, s->rAU, alpha, alpha0,
                   U, s->red, s->dStep);
         cudaEventRecord(ev[5], h->stream);
         FY_CUDA(cudaEventSynchronize(ev[5]));
@@ -1427,6 +1499,7 @@ int fvPimpleSolve(fy_ctx* h, FvState* s, double dt, const double gvec[3])
         cudaEventElapsedTime(&tmp, ev[3], ev[4]); msP += tmp;
         cudaEventElapsedTime(&tmp, ev[4], ev[5]); msOther += tmp;
     }
+    }   // outer corrector
     cudaEventElapsedTime(&msMom, ev[0], ev[1]);
     h->phaseMs[6] = msMom;
     h->phaseMs[7] = msP;
@@ -1444,7 +1517,7 @@ int fvPimpleSolve(fy_ctx* h, FvState* s, double dt, const double gvec[3])
         s->stats.corrSumLocal[q] = s->hStep->corrSumLocal[q];
         s->stats.corrGlobal[q] = s->hStep->corrGlobal[q];
     }
-    for (int q = 0; q < ctl.nCorrectors && q < 8; ++q) s->cumulativeContErr += s->hStep->corrGlobal[q];
+    for (int q = 0; q < corrTotal && q < 8; ++q) s->cumulativeContErr += s->hStep->corrGlobal[q];
     s->stats.cumulativeContErr = s->cumulativeContErr;
     s->fluidMs[0] = msMom; s->fluidMs[1] = msP; s->fluidMs[2] = msOther;
     return FY_OK;

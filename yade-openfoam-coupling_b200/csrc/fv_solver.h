@@ -103,6 +103,10 @@ struct FvState {
     double *upP = nullptr, *dgP = nullptr, *bP = nullptr;
     // pimpleFoamYade extras (allocated by the first fy_pimple_solve): phicForces [slots], explicit stress term [N][3]
     double *phicForces = nullptr, *divDev = nullptr;
+    // PIMPLE outer correctors + relaxationFactors (fy_set_pimple_controls; a factor <= 0 = no entry in fvSolution)
+    int nOuter = 1;
+    double relaxU = 0, relaxUFinal = 0, relaxP = 0, relaxPFinal = 0;
+    double *pPrev = nullptr;            // [N] p.prevIter() (allocated when nOuter > 1)
     double *bGradP = nullptr;           // [slots] snGrad(p) of the fixedFluxPressure faces (constrainPressure), else null
     bool hasFluxP = false;
     // scratch for the parity hooks (LDU-order staging)
