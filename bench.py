@@ -37,13 +37,20 @@ WORKLOADS = {
     "C1": (32, 32, 32, 1000, 42, "cavity", 5e-3, 0.01, "icoFoamYade lid-driven cavity 32^3 cells, 1k particles"),
     "C2": (128, 128, 128, 1000000, 7, "channel", 5e-3, 1e-6, "icoFoamYade channel 128^3 cells, 1M particles, fp64, 1xB200"),
     "C2s": (64, 64, 64, 125000, 7, "channel", 1e-2, 1e-6, "icoFoamYade channel 64^3 cells, 125k particles (reduced C2)"),
-    "C3": (256, 256, 256, 10000000, 1001, "channel", 2.5e-3, 1e-6, "pimpleFoamYade channel 256^3 cells, 10M particles, void fraction + UcEqn/pEqn, fp64, 1xB200 (use --solver pimple)"),
-    "C3s": (128, 128, 128, 1000000, 1001, "channel", 5e-3, 1e-6, "pimpleFoamYade channel 128^3 cells, 1M particles (reduced C3; use --solver pimple)"),
+    "C3": (256, 256, 256, 10000000, 1001, "closedbox", 2.5e-3, 1e-6, "pimpleFoamYade 4-way coupling, closed box under gravity, 256^3 cells, 10M particles, void fraction + UcEqn/pEqn, fp64, 1xB200 (use --solver pimple)"),
+    "C3s": (128, 128, 128, 1000000, 1001, "closedbox", 5e-3, 1e-6, "pimpleFoamYade closed box under gravity, 128^3 cells, 1M particles (reduced C3; use --solver pimple)"),
+    "C3c": (256, 256, 256, 10000000, 1001, "channel", 2.5e-3, 1e-6, "pimpleFoamYade channel 256^3 cells, 10M particles (round 1's C3 flow; use --solver pimple)"),
+    "C5": (256, 256, 256, 100000000, 1003, "closedbox", 2.5e-3, 1e-6, "pimpleFoamYade settling suspension, closed box under gravity, 256^3 cells, 100M particles (use --solver pimple)"),
     "C2p": (128, 128, 128, 10000000, 7, "channel", 5e-3, 1e-6, "icoFoamYade channel 128^3 cells, 10M particles (particle-bound, for --partition particles)"),
     "C4": (512, 256, 256, 50000000, 1002, "channel", 1.25e-3, 1e-6, "icoFoamYade box 512x256x256 cells, 50M particles, domain-decomposed 8xB200 (BASELINE configs[3])"),
     "C4s": (256, 128, 128, 6250000, 1002, "channel", 2.5e-3, 1e-6, "icoFoamYade box 256x128x128 cells, 6.25M particles (C4 at 1/8 size)"),
 }
 UIN = 0.3
+GRAVITY = (0.0, 0.0, -9.81)          # closed-box workloads (pimpleFoamYade's g, pimpleFoamYade/createFields.H readGravitationalAcceleration)
+
+
+def gravity_of(wl):
+    return GRAVITY if WORKLOADS[wl][5] == "closedbox" else (0.0, 0.0, 0.0)
 
 
 def peaks():
@@ -153,7 +160,8 @@ def config_of(args, world):
     replicas = args.partition == "replicas" and world > 1
     return {"workload": "%s: %s" % (args.workload, desc), "cells": N, "internal_faces": 3 * N - nx * ny - ny * nz - nx * nz,
             "particles_total": P * world if replicas else P,
-            "coupling": args.coupling, "fluid_solve": not args.coupling_only, "flow": flow, "dt": dt, "nu": nu,
+            "coupling": args.coupling, "fluid_solve": not args.coupling_only, "flow": flow, "gravity": list(gravity_of(args.workload)),
+            "dt": dt, "nu": nu,
             "solver": ("pimpleFoamYade (UcEqn.H/pEqn.H, nOuterCorrectors 1, laminar)" if pimple else "icoFoamYade"),
             "fvSolution": "PISO nCorrectors 2; p PCG/DIC 1e-06 relTol 0.05 (pFinal 0); U smoothSolver symGaussSeidel 1e-05",
             "l2": "flushed between timed steps (256 MiB write)",
@@ -167,6 +175,9 @@ def flow_case(wl, pkg=None):
     nx, ny, nz, P, seed, flow, dt, nu, _ = WORKLOADS[wl]
     if flow == "cavity":
         mo, mp = cases_fv.cavity3d(pkg, (nx, ny, nz), (1.0, 1.0, 1.0), oracle=pkg is None)
+        U0 = np.zeros((nx * ny * nz, 3))
+    elif flow == "closedbox":
+        mo, mp = cases_fv.closed_box(pkg, (nx, ny, nz), (1.0, 1.0, 1.0), oracle=pkg is None)
         U0 = np.zeros((nx * ny * nz, 3))
     else:
         mo, mp = cases_fv.channel(pkg, (nx, ny, nz), (1.0, 1.0, 1.0), UIN, oracle=pkg is None)
@@ -232,7 +243,10 @@ def run_engine(args):
     if pimple and not gaussian:
         raise SystemExit("bench.py: pimpleFoamYade constructs the operator with gaussianInterp = true (pimpleFoamYade.C:53)")
     fluid_pre = E.pimple_pre if pimple else E.ico_pre
-    fluid_solve = E.pimple_solve if pimple else E.ico_solve
+    if flow == "closedbox" and not pimple:
+        raise SystemExit("bench.py: the closed-box workloads have fixedFluxPressure walls (pimpleFoamYade/pEqn.H:21): use --solver pimple")
+    grav = gravity_of(wl)
+    fluid_solve = (lambda dt_: E.pimple_solve(dt_, grav)) if pimple else E.ico_solve
     S = None
     if sharded:
         S = pkg.sharded.ShardedCoupling(E, dist, pkg.sharded.device_views(E), gaussian, pkg.sharded.external_stream_ctx(E))
@@ -528,7 +542,7 @@ def cpu_baseline(args, state=None, steps=1, warmup=0, out=None):
         R.set_source_zero()
         t2 = time.time()
         if fluid and pimple:
-            O.pimple_solve(dt, alpha_c, drag_c)
+            O.pimple_solve(dt, alpha_c, drag_c, gravity_of(wl))
         elif fluid:
             O.solve(dt)
         t3 = time.time()

@@ -207,7 +207,22 @@ int fy_stream(fy_handle h, void** cuda_stream);
  * uParticle = 0.  Host-bound output fields are reset too.                                          */
 int fy_set_source_zero(fy_handle h);
 
-/* Cell lists + normalised Gaussian weights of the last fy_coupling_proc (parity hooks):
+/* Options of the Gaussian branch beyond what the reference's loop runs; defaults = the reference:
+ *   support    FY_SUPPORT_TRAIL  the <= 12 cells of meshTree::nnearestCellsRange's improvement trail (meshTree.C:148-238), or
+ *              FY_SUPPORT_FULL   "range based search" (README.md:5): EVERY cell whose centre lies within the same bound
+ *                                (d^2 < 1.25 interpRange^2, meshTree.C:155) carries a Gaussian weight -- ~370 cells per
+ *                                particle; one warp per particle, warp-shuffle reductions over the support; hex-box meshes.
+ *                                A particle is found when at least one cell lies inside the bound (the trail mode inherits
+ *                                meshTree's quirk that the tree's root cell is never reported, meshTree.C:156,192)
+ *   addedMass  also apply addedMassForce (FoamYade.C:392-413: defined, never called by the reference) after archimedesForce
+ *   torque     also apply calcHydroTorque's Gaussian branch (FoamYade.C:467-478, commented out at FoamYade.C:618): the
+ *              torque slots of the force record are then filled in Gaussian mode too
+ * Parity: the unmodified reference's own weight / force functions fed with the full cell sets, and its own
+ * addedMassForce / calcHydroTorque (oracle/ref_harness.cpp ref_set_gaussian_options).                                   */
+enum { FY_SUPPORT_TRAIL = 0, FY_SUPPORT_FULL = 1 };
+int fy_set_gaussian_options(fy_handle h, int support, int addedMass, int torque);
+
+/* Cell lists + normalised Gaussian weights of the last fy_coupling_proc (parity hooks; FY_SUPPORT_FULL: counts only):
  * h_counts [n], h_ids [n][12], h_weights [n][12] (FoamYade.C:293-316). Any pointer may be NULL.     */
 int fy_get_last_lists(fy_handle h, int n, int* h_counts, int* h_ids, double* h_weights);
 

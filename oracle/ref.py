@@ -46,6 +46,7 @@ def lib():
         L.ref_find_cell.argtypes = [C.c_void_p, _dp]
         L.ref_step.argtypes = [C.c_void_p, C.c_double, C.c_double, _dp, C.c_int, _ip, _ip, _dp]
         L.ref_step_pieces.argtypes = [C.c_void_p, C.c_double, C.c_double, _dp, C.c_int, _ip, C.c_int, C.c_int, _ip, _dp]
+        L.ref_set_gaussian_options.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.ref_get_lists.argtypes = [C.c_void_p, C.c_int, _ip, _ip]
         L.ref_get_times.argtypes = [C.c_void_p, _dp]
         L.ref_set_source_zero.argtypes = [C.c_void_p]
@@ -157,6 +158,11 @@ class RefFoamYade:
         else:
             self.L.ref_step(self.h, dt, yade_dt, _d(pdata), n, spp, _i(found), _d(force))
         return found[:n], force[:n]
+
+    def set_gaussian_options(self, support_full=False, added_mass=False, torque=False):
+        """SURVEY 8(f)3 options for step(pieces=True): full-support cell lists (every cell within the search bound, fed to
+        the reference's own weight / force code), addedMassForce (FoamYade.C:392-413), Gaussian torque (FoamYade.C:467-478)"""
+        self.L.ref_set_gaussian_options(self.h, int(support_full), int(added_mass), int(torque))
 
     def lists(self, n):
         cnt = np.empty(n, dtype=np.int32)

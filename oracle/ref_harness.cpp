@@ -195,7 +195,41 @@ struct Ref
     // captured cell lists of the last step (after canonical truncation when applied)
     std::vector<int> listCount, listIds;   // [n], [n][16]
     double tLocate = 0, tWeights = 0, tAccum = 0, tForce = 0, tSend = 0;
+    // SURVEY 8(f)3 options of the Gaussian branch (ref_set_gaussian_options): full-support cell lists instead of the
+    // k-d descent's improvement trail; the forces the class defines but never calls
+    bool supportFull = false, addedMass = false, gaussTorque = false;
 };
+
+// every cell whose centre lies within the search bound of meshTree::nnearestCellsRange (MT.C:155: d^2 < range^2 +
+// 0.25 range^2), ascending by distance (ties by id) -- "range based search" (README.md:5).  Box arithmetic only bounds the
+// candidates; the test uses the mesh's own centres in meshTree::distance's operation order.
+void fullSupportList(const Ref* r, const Foam::vector& pos, double range, std::vector<int>& ids)
+{
+    const Box& b = r->box;
+    const double maxDist = (range*range) + (0.25*range*range);
+    const double R = std::sqrt(maxDist);
+    int lo[3], hi[3];
+    const double pp[3] = {pos.x(), pos.y(), pos.z()}, x0[3] = {b.x0, b.y0, b.z0}, hh[3] = {b.hx, b.hy, b.hz};
+    const int nn[3] = {b.nx, b.ny, b.nz};
+    for (int d = 0; d < 3; ++d) {
+        lo[d] = std::max(0, (int)std::floor((pp[d] - R - x0[d])/hh[d]) - 1);
+        hi[d] = std::min(nn[d] - 1, (int)std::floor((pp[d] + R - x0[d])/hh[d]) + 1);
+    }
+    std::vector<std::pair<double, int> > hit;
+    for (int k = lo[2]; k <= hi[2]; ++k)
+        for (int j = lo[1]; j <= hi[1]; ++j)
+            for (int i = lo[0]; i <= hi[0]; ++i) {
+                const int c = i + b.nx*(j + b.ny*k);
+                const Foam::vector& C = r->mesh.C()[c];
+                double dist = 0;
+                const double d0 = C.x() - pos.x(), d1 = C.y() - pos.y(), d2 = C.z() - pos.z();
+                dist += d0*d0; dist += d1*d1; dist += d2*d2;                     // MT.C:54-64
+                if (dist < maxDist) hit.push_back(std::make_pair(dist, c));
+            }
+    std::sort(hit.begin(), hit.end());
+    ids.clear();
+    for (const auto& q : hit) ids.push_back(q.second);
+}
 
 double nowSec()
 {
@@ -453,6 +487,16 @@ void ref_step(void* h, double dt, double yadeDT, const double* pdata, int n, con
 }
 
 #ifndef FY_HOST_CLASS
+// Gaussian-branch options, used by ref_step_pieces: supportFull = cell lists hold every cell within the
+// search bound (fullSupportList) and are fed to the reference's OWN calcInterpWeightGaussian / hydroDragForce /
+// archimedesForce; addedMass = addedMassForce (F.C:392-413) after archimedesForce for every found particle; torque =
+// calcHydroTorque's Gaussian branch (F.C:467-478, commented out at F.C:618) after the forces.
+void ref_set_gaussian_options(void* h, int supportFull, int addedMass, int torque)
+{
+    Ref* r = (Ref*)h;
+    r->supportFull = supportFull != 0; r->addedMass = addedMass != 0; r->gaussTorque = torque != 0;
+}
+
 // same sequence through the public pieces (see header comment). truncate12: canonical list form;
 // dense: order-preserving dense accumulate instead of the quadratic scan. Records cell lists and phase times.
 void ref_step_pieces(void* h, double dt, double yadeDT, const double* pdata, int n, const int* split,
@@ -476,7 +520,8 @@ void ref_step_pieces(void* h, double dt, double yadeDT, const double* pdata, int
         int base = 0;
         if (!fy->serialYade) base = g_peer.split[yProc->yRank - 1];
         for (auto& prt : yProc->foundParticles) {
-            if (truncate12 && prt->cellIds.size() > 12) prt->cellIds.resize(12);
+            if (r->gaussian && r->supportFull) fullSupportList(r, prt->pos, fy->interpRange, prt->cellIds);
+            else if (truncate12 && prt->cellIds.size() > 12) prt->cellIds.resize(12);
             const int gi = base + prt->indx;
             r->listCount[gi] = (int)prt->cellIds.size();
             for (size_t j = 0; j < prt->cellIds.size() && j < 16; ++j) r->listIds[(size_t)gi*16 + j] = prt->cellIds[j];
@@ -512,7 +557,17 @@ void ref_step_pieces(void* h, double dt, double yadeDT, const double* pdata, int
                 r->tAccum += nowSec() - t0;
             }
             t0 = nowSec();
-            fy->calcHydroForce(yProc.get());
+            if (r->addedMass || r->gaussTorque) {
+                for (const auto& prt : yProc->foundParticles) {              // calcHydroForce's loop (F.C:331-344) + the dormant force
+                    fy->initParticleForce(prt.get());
+                    fy->hydroDragForce(prt.get());
+                    fy->archimedesForce(prt.get());
+                    if (r->addedMass) fy->addedMassForce(prt.get());
+                }
+                if (r->gaussTorque) fy->calcHydroTorque(yProc.get());
+            } else {
+                fy->calcHydroForce(yProc.get());
+            }
             r->tForce += nowSec() - t0;
         } else {
             t0 = nowSec();

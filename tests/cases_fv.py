@@ -59,6 +59,22 @@ def channel(pkg=None, n=(24, 12, 10), L=(2.0, 1.0, 1.0), Uin=0.3, oracle=True):
     return mo, mp
 
 
+def closed_box(pkg=None, n=(16, 16, 16), L=(1.0, 1.0, 1.0), oracle=True):
+    """closed box at rest under gravity (the C3 / C5 flow): no-slip walls all round, p fixedFluxPressure
+    (constrainPressure, pimpleFoamYade/pEqn.H:21) -- the suspension's drag and buoyancy set the fluid in motion"""
+    patches = [("walls", ["xmin", "xmax", "ymin", "ymax", "zmin", "zmax"])]
+    mo = None
+    if oracle:
+        from oracle import meshgen
+        mo = meshgen.hex_box_ldu(*n, *L, patches=patches)
+        meshgen.set_bc(mo, "walls", bcP=meshgen.BC_FIXED_FLUX_PRESSURE)
+    mp = None
+    if pkg is not None:
+        mp = pkg.box_mesh(*n, *L, patches=patches)
+        pkg.set_bc(mp, "walls", bcP=pkg.BC_FIXED_FLUX_PRESSURE)
+    return mo, mp
+
+
 def channel_init(C, Uin=0.3):
     """smooth, divergence-bearing start field so that every operator has work to do"""
     N = C.shape[0]

@@ -198,6 +198,70 @@ def test_overlapped_wire_transfers_equal_the_blocking_call(pkg):
     E.close()
 
 
+def _ddtU(C):
+    return np.stack([0.4 * np.sin(2.0 * C[:, 2]), -0.3 * np.cos(3.0 * C[:, 1]), 0.2 + 0.1 * C[:, 0]], 1)
+
+
+@pytest.mark.parametrize("n,P,seed,full,added_mass,torque", [(32, 1000, 42, True, False, False), (32, 1000, 42, False, True, True),
+                                                             (24, 3000, 9, True, True, True), (48, 6000, 7, True, False, True)])
+def test_full_support_and_dormant_forces_match_reference(pkg, n, P, seed, full, added_mass, torque):
+    """the full-support Gaussian mode (every cell within the k-d search bound, one warp per particle with
+    warp-shuffle reductions) and the forces the reference defines but never calls (addedMassForce F.C:392-413, Gaussian
+    torque F.C:467-478) against the UNMODIFIED reference: its own calcInterpWeightGaussian / hydroDragForce /
+    archimedesForce / addedMassForce / calcHydroTorque, fed with the full cell sets by the harness.  Cell counts
+    bit-exact (the in-range test is evaluated in meshTree::distance's operation order), forces, torques and all four
+    per-cell fields within 1e-10; particles near and outside the walls included."""
+    mo = meshgen.hex_box(n, n, n)
+    mp = pkg.box_mesh(n, n, n, faces=False)
+    flds = cases.fields_for(mo["C"])
+    flds["ddtU"] = _ddtU(mo["C"])
+    pd = cases.particles(P, seed, radius=0.1 / n, moving=True)
+    pd[:40, 0:3] = pd[:40, 0:3] * 1.3 - 0.15            # some particles outside the box, some within reach of it
+    dt = 1e-3
+    R = ref.RefFoamYade(mo, True)
+    R.set_properties(cases.RHOP, cases.RHOF, cases.NU)
+    R.set_gaussian_options(full, added_mass, torque)
+    if full:
+        # meshTree's descent never reports the tree's ROOT cell (MT.C:156,192), so the reference does not "find" a particle
+        # whose nearest cell is the root although it lies inside the mesh; the full-support mode finds every particle with
+        # a cell inside the bound.  Such particles (about P/N of them) are moved off the root cell for this comparison.
+        cnt0, ids0 = R.locate(pd[:, 0:3])
+        maxDist = 1.25 * R.constants()["interpRange"] ** 2
+        for q in np.nonzero(cnt0 == 0)[0]:
+            if ((mo["C"] - pd[q, 0:3]) ** 2).sum(1).min() < maxDist and np.all((pd[q, 0:3] > 0) & (pd[q, 0:3] < 1)):
+                pd[q, 0:3] = pd[(q + 57) % P, 0:3] + 1e-3
+    E = pkg.Engine(mp)
+    E.set_properties(cases.RHOP, cases.RHOF, cases.NU, True)
+    E.set_gaussian_options(full, added_mass, torque)
+    for k in ("U", "gradP", "divT", "vGrad", "ddtU"):
+        R.field(k)[:] = flds[k].reshape(R.field(k).shape)
+        E.upload(k, flds[k])
+    for step in range(2):                                # (the second step starts from setSourceZero's state)
+        fr, Fr = R.step(dt, pd, yade_dt=0.5 * dt, pieces=True, truncate12=True, dense=True)
+        cr, _ = R.lists(P)
+        fe, Fe = E.set_particle_action(dt, pd)
+        ce = E.last_counts(P)
+        assert np.array_equal(fr, fe)
+        assert np.array_equal(cr, ce)
+        if full:
+            inside = np.all((pd[:, 0:3] > 0.2) & (pd[:, 0:3] < 0.8), axis=1)
+            assert 340 <= ce[inside].min() and ce[inside].max() <= 410     # 4/3 pi (sqrt(1.25) 4)^3 = 374.6 cells
+            with pytest.raises(pkg.FyError):
+                E.last_lists(P)
+        assert cases.rel_l2(Fe[:, 0:3], Fr[:, 0:3]) <= TOL
+        if torque:
+            assert np.any(Fr[:, 3:6]) and cases.rel_l2(Fe[:, 3:6], Fr[:, 3:6]) <= TOL
+        else:
+            assert not np.any(Fe[:, 3:6]) and not np.any(Fr[:, 3:6])
+        for k in ("uSource", "uSourceDrag", "alpha", "uParticle"):
+            assert cases.rel_l2(E.download(k), R.field(k).reshape(E.download(k).shape)) <= TOL, (k, step)
+        R.set_source_zero()
+        E.set_source_zero()
+        pd[:, 0:3] += dt * pd[:, 3:6]
+    R.close()
+    E.close()
+
+
 def test_empty_and_all_outside(pkg):
     mp = pkg.box_mesh(8, 8, 8, faces=False)
     E = pkg.Engine(mp)

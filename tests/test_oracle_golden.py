@@ -175,3 +175,50 @@ def test_hex_mesh_first_cell_is_containing_cell():
     assert np.array_equal(ids[ok, 0], cid[ok])
     assert (~ok).sum() < 10           # particles whose nearest centre is the tree root are lost (H4)
     R.close()
+
+
+def test_full_support_lists_and_dormant_forces_of_the_harness():
+    """SURVEY 8(f)3 oracle: the harness feeds the reference's OWN weight / force functions with every cell inside the k-d
+    search bound (ref_set_gaussian_options).  Checked here without a GPU: (a) an interior particle's support is the
+    4/3 pi (sqrt(1.25) 4 h)^3 = 374.6-cell ball and contains the trail list; (b) the void fraction conserves the particle
+    volume (the normalised weights sum to one); (c) addedMassForce / the Gaussian torque equal their closed forms
+    (FoamYade.C:392-413, 467-478) on uniform fields, where every weighted average is the field value itself."""
+    from oracle import meshgen, ref
+    from tests import cases
+    n, P = 24, 400
+    mo = meshgen.hex_box(n, n, n)
+    C, V = mo["C"], mo["V"]
+    pd = cases.particles(P, 5, radius=0.1 / n, moving=True)
+    pd[:, 0:3] = 0.25 + 0.5 * pd[:, 0:3]                  # supports fully inside the box
+    N = C.shape[0]
+    dt, nu = 1e-3, cases.NU
+    ddtU0, vg = np.array([0.3, -0.2, 0.5]), np.array([0.0, 0.1, 0.2, 0.3, 0.0, 0.4, 0.5, 0.6, 0.0])
+    out = {}
+    for full in (False, True):
+        R = ref.RefFoamYade(mo, True)
+        R.set_properties(cases.RHOP, cases.RHOF, nu)
+        R.set_gaussian_options(full, True, True)
+        R.field("U")[:] = np.tile([0.1, 0.0, 0.0], (N, 1))
+        R.field("ddtU")[:] = np.tile(ddtU0, (N, 1))
+        R.field("vGrad")[:] = np.tile(vg, (N, 1)).reshape(R.field("vGrad").shape)
+        f, F = R.step(dt, pd, pieces=True)
+        cnt, ids = R.lists(P)
+        alpha = R.field("alpha").reshape(N).copy()
+        # the same step without the dormant forces: their contribution is the difference
+        R.set_source_zero()
+        R.set_gaussian_options(full, False, False)
+        f0, F0 = R.step(dt, pd, pieces=True)
+        out[full] = dict(cnt=cnt, ids=ids, F=F, F0=F0, alpha=alpha)
+        R.close()
+        vol = np.pi * (2 * pd[:, 9]) ** 3 / 6
+        assert abs(((1 - alpha) * V).sum() - vol.sum()) <= 1e-12 * vol.sum()            # (b)
+        # (c) f = (vol/k) (ddtU - u_p/dt) rhoP ; T = pi d^3 (w_f - w_p) nu rhoF, w_f = (yz-zy, zx-xz, yx-xy)
+        k = cnt.astype(float)
+        am = (vol / k)[:, None] * (ddtU0[None, :] - pd[:, 3:6] / dt) * cases.RHOP
+        assert np.allclose(F[:, 0:3] - F0[:, 0:3], am, rtol=1e-9, atol=1e-9 * np.abs(am).max())
+        wf = np.array([vg[5] - vg[7], vg[6] - vg[2], vg[3] - vg[1]])
+        T = np.pi * (2 * pd[:, 9:10]) ** 3 * (wf[None, :] - pd[:, 6:9]) * nu * cases.RHOF
+        assert np.allclose(F[:, 3:6], T, rtol=1e-10, atol=0) and not np.any(F0[:, 3:6])
+    cf = out[True]["cnt"]
+    assert cf.min() >= 340 and cf.max() <= 410 and abs(cf.mean() - 374.6) < 6                       # (a)
+    assert np.all(out[False]["cnt"] <= 12)

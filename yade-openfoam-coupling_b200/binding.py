@@ -106,6 +106,7 @@ def lib():
     L.fy_piso_default_controls.argtypes = [C.POINTER(PisoControls)]
     L.fy_set_piso_controls.argtypes = [H, C.POINTER(PisoControls)]
     L.fy_set_viscosity.argtypes = [H, C.c_double]
+    L.fy_set_gaussian_options.argtypes = [H, C.c_int, C.c_int, C.c_int]
     L.fy_set_pimple_controls.argtypes = [H, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]
     L.fy_create_phi.argtypes = [H]
     L.fy_ico_pre.argtypes = [H, C.c_double]
@@ -314,6 +315,12 @@ class Engine:
         self._ck(self.L.fy_get_last_lists(self.h, n, _i(cnt), _i(ids), _d(w)))
         return cnt, ids, w
 
+    def last_counts(self, n):
+        """cells per particle of the last Gaussian pass (the only list data the full-support mode keeps)"""
+        cnt = np.empty(n, dtype=np.int32)
+        self._ck(self.L.fy_get_last_lists(self.h, n, _i(cnt), None, None))
+        return cnt
+
     # ---- multi-GPU: Py x Pz decomposition of the pressure solve (fycuda.h, fy_dist_*)
     @staticmethod
     def dist_unique_id():
@@ -353,6 +360,10 @@ class Engine:
         ms = C.c_double()
         self._ck(self.L.fy_timer_stop(self.h, C.byref(ms)))
         return ms.value
+
+    def set_gaussian_options(self, support_full=False, added_mass=False, torque=False):
+        """full-support Gaussian cell sets (range-based search) and the reference's dormant forces (fycuda.h)"""
+        self._ck(self.L.fy_set_gaussian_options(self.h, 1 if support_full else 0, int(added_mass), int(torque)))
 
     def launch_count(self):
         return int(self.L.fy_launch_count(self.h))

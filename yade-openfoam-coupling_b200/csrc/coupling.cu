@@ -249,13 +249,37 @@ __global__ void k_void_fraction(int nCells, int serial, const int* __restrict__ 
 // pass 3: hydroDragForce + archimedesForce per particle, reaction scattered to the cells.
 struct ForceConst {
     double rhoF, nu, small;
+    // the forces the reference defines but never calls (EXTRA instantiations only)
+    double rhoP, deltaT;
+    int addedMass, torque;          // addedMassForce F.C:392-413; calcHydroTorque's Gaussian branch F.C:467-478
 };
 
+// addedMassForce (F.C:392-413) from the gathered sums: pv = (sum vol*w)/listSize (the reference divides by the list length),
+// f = pv*(ddtUf - linearVelocity/deltaT)*rhoP
+__device__ __forceinline__ void addedMassOf(const ForceConst& fc, double pvSum, int listSize, const double* ddtUf, double vx,
+                                            double vy, double vz, double* f)
+{
+    const double pv = pvSum / listSize;
+    f[0] = pv * (ddtUf[0] - (vx / fc.deltaT)) * fc.rhoP;
+    f[1] = pv * (ddtUf[1] - (vy / fc.deltaT)) * fc.rhoP;
+    f[2] = pv * (ddtUf[2] - (vz / fc.deltaT)) * fc.rhoP;
+}
+// hydroTorque += M_PI*(pow(dia,3))*(wfluid - rotationalVelocity)*nu*rhoF   (F.C:478)
+__device__ __forceinline__ void gaussTorqueOf(const ForceConst& fc, double dia, const double* wf, const double* rec, double* T)
+{
+    const double c = M_PI * (pow(dia, 3.0));
+    T[0] = c * (wf[0] - rec[6]) * fc.nu * fc.rhoF;
+    T[1] = c * (wf[1] - rec[7]) * fc.nu * fc.rhoF;
+    T[2] = c * (wf[2] - rec[8]) * fc.nu * fc.rhoF;
+}
+
+template <bool EXTRA>
 __global__ void __launch_bounds__(128)
 k_force_gauss(const double* __restrict__ pdata, int n, const int* __restrict__ perm, const int* __restrict__ ids,
               const int* __restrict__ cnt, const double* __restrict__ wts, ForceConst fc, const double* __restrict__ U,
               const double* __restrict__ alpha, const double* __restrict__ uParticle,
               const double* __restrict__ gradP, const double* __restrict__ divT, const double* __restrict__ V,
+              const double* __restrict__ ddtU, const double* __restrict__ vGrad,
               double* __restrict__ uSourceDrag, double* __restrict__ uSource, double* __restrict__ force)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -278,12 +302,23 @@ k_force_gauss(const double* __restrict__ pdata, int n, const int* __restrict__ p
     // ---- hydroDragForce gather (F.C:358-365) and archimedesForce gather (F.C:416-424)
     double ufx = 0, ufy = 0, ufz = 0, alpha_f = 0, pv = 0;
     double dtx = 0, dty = 0, dtz = 0, pgx = 0, pgy = 0, pgz = 0;
+    double ddtUf[3] = {0, 0, 0}, wf[3] = {0, 0, 0};
     const double twoNu = 2.0 * nu;
     for (int j = 0; j < k; ++j) {
         const int c = ids[(size_t)j * n + t];
         const double wj = wts[(size_t)j * n + t];
         id[j] = c;
         w[j] = wj;
+        if (EXTRA) {
+            if (fc.addedMass)
+                for (int m = 0; m < 3; ++m) ddtUf[m] = ddtUf[m] + (ddtU[3 * (size_t)c + m] * wj);              // F.C:400
+            if (fc.torque) {
+                const double* g = vGrad + 9 * (size_t)c;                                                       // F.C:471-473
+                wf[0] += ((g[5] - g[7]) * wj);
+                wf[1] += ((g[6] - g[2]) * wj);
+                wf[2] += ((g[3] - g[1]) * wj);
+            }
+        }
         ufx += U[3 * (size_t)c] * wj;
         ufy += U[3 * (size_t)c + 1] * wj;
         ufz += U[3 * (size_t)c + 2] * wj;
@@ -314,8 +349,16 @@ k_force_gauss(const double* __restrict__ pdata, int n, const int* __restrict__ p
     // archimedes (F.C:426): f = pv*(-pg + divt)
     const double ax = pv * (-pgx + dtx), ay = pv * (-pgy + dty), az = pv * (-pgz + dtz);
     Fx += ax; Fy += ay; Fz += az;
+    double am[3] = {0, 0, 0}, T[3] = {0.0, 0.0, 0.0};
+    if (EXTRA) {
+        if (fc.addedMass) {
+            addedMassOf(fc, pv, k, ddtUf, vx, vy, vz, am);
+            Fx += am[0]; Fy += am[1]; Fz += am[2];
+        }
+        if (fc.torque) gaussTorqueOf(fc, dia, wf, rec, T);
+    }
     F[0] = Fx; F[1] = Fy; F[2] = Fz;
-    F[3] = 0.0; F[4] = 0.0; F[5] = 0.0;                              // torque disabled on this branch (F.C:618)
+    F[3] = T[0]; F[4] = T[1]; F[5] = T[2];                           // zero unless enabled: torque is disabled on this branch (F.C:618)
 
     // ---- scatter (F.C:384-387 and 429-434); the two uSource contributions of a pair are summed
     //      before the atomic so that each cell component sees one RED per pair
@@ -326,13 +369,242 @@ k_force_gauss(const double* __restrict__ pdata, int n, const int* __restrict__ p
         const double mcw = -coeff * wj;
         atomicAdd(&uSourceDrag[c], mcw * oorho);
         const double ooCellVol = 1. / (V[c] * rhoF);
-        const double sx = (mcw * uParticle[3 * (size_t)c]) / rhoF + (-ax * wj * ooCellVol);
-        const double sy = (mcw * uParticle[3 * (size_t)c + 1]) / rhoF + (-ay * wj * ooCellVol);
-        const double sz = (mcw * uParticle[3 * (size_t)c + 2]) / rhoF + (-az * wj * ooCellVol);
+        double sx = (mcw * uParticle[3 * (size_t)c]) / rhoF + (-ax * wj * ooCellVol);
+        double sy = (mcw * uParticle[3 * (size_t)c + 1]) / rhoF + (-ay * wj * ooCellVol);
+        double sz = (mcw * uParticle[3 * (size_t)c + 2]) / rhoF + (-az * wj * ooCellVol);
+        if (EXTRA && fc.addedMass) {                                 // F.C:410
+            sx += (-am[0] * wj * ooCellVol);
+            sy += (-am[1] * wj * ooCellVol);
+            sz += (-am[2] * wj * ooCellVol);
+        }
         atomicAdd(&uSource[3 * (size_t)c], sx);
         atomicAdd(&uSource[3 * (size_t)c + 1], sy);
         atomicAdd(&uSource[3 * (size_t)c + 2], sz);
     }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Full-support Gaussian mode ("range based search", README.md:5): EVERY cell whose centre lies within the
+// search bound of meshTree::nnearestCellsRange (d^2 < range^2 + 0.25 range^2, MT.C:155) carries a weight -- ~370 cells
+// per particle on a uniform mesh (range = 4 h) instead of the <= 12 cells of the k-d descent's improvement trail.
+// One WARP per particle: the lanes stride over the candidate cells of the particle's index box (the hex box's own
+// tensor-product centre coordinates, verified against mesh.C() at fy_create), the normaliser and the eleven gathered
+// sums of hydroDragForce / archimedesForce are warp-shuffle reductions, the reaction is scattered with one RED per
+// cell and component.  The weights are never stored (a 370-entry list per particle would be 4.4 KB): both passes
+// recompute exp(-d^2/2 sigma^2) from the same d^2, bit for bit.  Oracle: the unmodified reference's own
+// calcInterpWeightGaussian / hydroDragForce / archimedesForce fed with the full cell lists (oracle/ref_harness.cpp).
+// ---------------------------------------------------------------------------------------------
+struct RangeBox {
+    int nx, ny, nz;
+    double x0, y0, z0, hx, hy, hz;
+    const double* ax;      // centre coordinates: xs[nx] | ys[ny] | zs[nz]
+    double R;              // sqrt(maxDist)
+};
+
+__device__ __forceinline__ void rangeSpan(double p, double R, double x0, double h, int n, int& lo, int& cnt)
+{
+    // indices whose centre x0 + (i + 1/2) h can lie within R of p, one index of slack each side (the exact test decides)
+    double a = floor((p - R - x0) / h - 0.5), b = floor((p + R - x0) / h - 0.5) + 1.0;
+    a = a < 0.0 ? 0.0 : a;
+    b = b > (double)(n - 1) ? (double)(n - 1) : b;
+    lo = a > (double)n ? n : (int)a;
+    const int hi = b < -1.0 ? -1 : (int)b;
+    cnt = hi >= lo ? hi - lo + 1 : 0;
+}
+
+__device__ __forceinline__ double warpSum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+struct RangeIter {
+    int lo[3], ni, nj, ncand;
+    double px, py, pz;
+    __device__ __forceinline__ void init(const RangeBox& b, double x, double y, double z)
+    {
+        px = x; py = y; pz = z;
+        int nk;
+        rangeSpan(x, b.R, b.x0, b.hx, b.nx, lo[0], ni);
+        rangeSpan(y, b.R, b.y0, b.hy, b.ny, lo[1], nj);
+        rangeSpan(z, b.R, b.z0, b.hz, b.nz, lo[2], nk);
+        ncand = ni * nj * nk;
+    }
+    // candidate q -> cell index and squared distance (meshTree::distance's order, MT.C:54-64)
+    __device__ __forceinline__ int cell(const RangeBox& b, int q, double& d2) const
+    {
+        const int di = q % ni, r = q / ni, dj = r % nj, dk = r / nj;
+        const int i = lo[0] + di, j = lo[1] + dj, k = lo[2] + dk;
+        const double dx = __dsub_rn(b.ax[i], px), dy = __dsub_rn(b.ax[b.nx + j], py), dz = __dsub_rn(b.ax[b.nx + b.ny + k], pz);
+        d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+        return i + b.nx * (j + b.ny * k);
+    }
+};
+
+constexpr int RANGE_WARPS = 8;
+
+// pass 1: count + normaliser + per-cell accumulate (locateAllParticles + calcInterpWeightGaussian + buildCellPartList)
+__global__ void __launch_bounds__(RANGE_WARPS * 32)
+k_range_accumulate(RangeBox b, const double* __restrict__ pdata, int n, const int* __restrict__ perm, GaussConst gc,
+                   int serial, int* __restrict__ cnt, double* __restrict__ allwtOut, int* __restrict__ found,
+                   double* __restrict__ pvolAcc, double* __restrict__ upAcc, int* __restrict__ stamp)
+{
+    const int t = blockIdx.x * RANGE_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (t >= n) return;
+    const int p = perm[t];
+    const double* rec = pdata + (size_t)p * 10;
+    RangeIter it;
+    it.init(b, rec[0], rec[1], rec[2]);
+    double sw = 0.0;
+    int hits = 0;
+    for (int q = lane; q < it.ncand; q += 32) {
+        double d2;
+        it.cell(b, q, d2);
+        if (d2 < gc.maxDist) {
+            sw += exp(-d2 / gc.twoSigmaSq) * gc.interpRangeCu * gc.sigmaPi;      // F.C:308
+            ++hits;
+        }
+    }
+    sw = warpSum(sw);
+    hits = __reduce_add_sync(0xffffffffu, hits);
+    if (lane == 0) {
+        cnt[t] = hits;
+        allwtOut[t] = sw;
+        found[p] = hits > 0 ? 1 : -1;
+    }
+    if (hits == 0) return;
+    const double vx = rec[3], vy = rec[4], vz = rec[5];
+    const double dia = 2 * rec[9];
+    const double vol = M_PI * pow(dia, 3.0) / 6.0;
+    for (int q = lane; q < it.ncand; q += 32) {
+        double d2;
+        const int c = it.cell(b, q, d2);
+        if (!(d2 < gc.maxDist)) continue;
+        const double wj = (exp(-d2 / gc.twoSigmaSq) * gc.interpRangeCu * gc.sigmaPi) / sw;   // F.C:313
+        atomicAdd(&pvolAcc[c], vol * wj);
+        atomicAdd(&upAcc[3 * (size_t)c], vx * wj * vol);
+        atomicAdd(&upAcc[3 * (size_t)c + 1], vy * wj * vol);
+        atomicAdd(&upAcc[3 * (size_t)c + 2], vz * wj * vol);
+        stamp[c] = serial;
+    }
+}
+
+// pass 3: hydroDragForce + archimedesForce (+ addedMassForce, Gaussian torque) over the full support
+template <bool EXTRA>
+__global__ void __launch_bounds__(RANGE_WARPS * 32)
+k_range_force(RangeBox b, const double* __restrict__ pdata, int n, const int* __restrict__ perm, const int* __restrict__ cnt,
+              const double* __restrict__ allwt, GaussConst gc, ForceConst fc, const double* __restrict__ U,
+              const double* __restrict__ alpha, const double* __restrict__ uParticle, const double* __restrict__ gradP,
+              const double* __restrict__ divT, const double* __restrict__ V, const double* __restrict__ ddtU,
+              const double* __restrict__ vGrad, double* __restrict__ uSourceDrag, double* __restrict__ uSource,
+              double* __restrict__ force)
+{
+    const int t = blockIdx.x * RANGE_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (t >= n) return;
+    const int p = perm[t];
+    double* F = force + (size_t)p * 6;
+    const int k = cnt[t];
+    if (k <= 0) {
+        if (lane < 6) F[lane] = 0.0;
+        return;
+    }
+    const double* rec = pdata + (size_t)p * 10;
+    const double vx = rec[3], vy = rec[4], vz = rec[5];
+    const double dia = 2 * rec[9];
+    const double vol = M_PI * pow(dia, 3.0) / 6.0;
+    const double rhoF = fc.rhoF, nu = fc.nu, sw = allwt[t];
+    const double twoNu = 2.0 * nu;
+    RangeIter it;
+    it.init(b, rec[0], rec[1], rec[2]);
+    // gathers: uf[3] alpha_f pv divt[3] pg[3] | ddtUf[3] wfluid[3]
+    double g[EXTRA ? 17 : 11];
+#pragma unroll
+    for (int m = 0; m < (EXTRA ? 17 : 11); ++m) g[m] = 0.0;
+    for (int q = lane; q < it.ncand; q += 32) {
+        double d2;
+        const int c = it.cell(b, q, d2);
+        if (!(d2 < gc.maxDist)) continue;
+        const double wj = (exp(-d2 / gc.twoSigmaSq) * gc.interpRangeCu * gc.sigmaPi) / sw;
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+            g[m] += U[3 * (size_t)c + m] * wj;                                            // F.C:360
+            g[5 + m] = g[5 + m] + (twoNu * divT[3 * (size_t)c + m] * wj * rhoF);          // F.C:422
+            g[8 + m] = g[8 + m] + (gradP[3 * (size_t)c + m] * wj);                        // F.C:423
+        }
+        g[3] += alpha[c] * wj;
+        g[4] += vol * wj;
+        if (EXTRA) {
+            if (fc.addedMass)
+                for (int m = 0; m < 3; ++m) g[11 + m] = g[11 + m] + (ddtU[3 * (size_t)c + m] * wj);
+            if (fc.torque) {
+                const double* vg = vGrad + 9 * (size_t)c;
+                g[14] += ((vg[5] - vg[7]) * wj);
+                g[15] += ((vg[6] - vg[2]) * wj);
+                g[16] += ((vg[3] - vg[1]) * wj);
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < (EXTRA ? 17 : 11); ++m) g[m] = warpSum(g[m]);
+    const double alpha_f = g[3], pv = g[4];
+    const double alpha_p = 1 - alpha_f;
+    const double urx = g[0] - vx, ury = g[1] - vy, urz = g[2] - vz;
+    const double magUR = sqrt(urx * urx + ury * ury + urz * urz);
+    const double Re = fc.small + ((magUR * dia) / nu);                                     // F.C:370
+    const double cd = Re < 1000 ? (24 / (Re)) * (1 + (0.15 * pow(Re, 0.687))) : 0.44;      // F.C:371
+    double coeff;
+    if (alpha_f > 0.8) {
+        coeff = 0.75 * cd * alpha_f * alpha_p * rhoF * magUR * pow(alpha_f, -2.65);        // F.C:374
+    } else {
+        const double cf1 = 150 * ((alpha_p * alpha_p) / alpha_f) * ((nu * rhoF) / (dia * dia));
+        const double cf2 = 1.75 * alpha_p * rhoF * (1 / dia) * magUR;
+        coeff = cf1 + cf2;
+    }
+    const double pc = pv * coeff, ooap = 1 / (alpha_p);
+    double Fx = pc * urx * ooap, Fy = pc * ury * ooap, Fz = pc * urz * ooap;               // F.C:381
+    const double ax = pv * (-g[8] + g[5]), ay = pv * (-g[9] + g[6]), az = pv * (-g[10] + g[7]);   // F.C:426
+    Fx += ax; Fy += ay; Fz += az;
+    double am[3] = {0, 0, 0}, T[3] = {0.0, 0.0, 0.0};
+    if (EXTRA) {
+        if (fc.addedMass) {
+            addedMassOf(fc, pv, k, &g[11], vx, vy, vz, am);
+            Fx += am[0]; Fy += am[1]; Fz += am[2];
+        }
+        if (fc.torque) gaussTorqueOf(fc, dia, &g[14], rec, T);
+    }
+    if (lane == 0) {
+        F[0] = Fx; F[1] = Fy; F[2] = Fz;
+        F[3] = T[0]; F[4] = T[1]; F[5] = T[2];
+    }
+    const double oorho = 1 / rhoF;
+    for (int q = lane; q < it.ncand; q += 32) {
+        double d2;
+        const int c = it.cell(b, q, d2);
+        if (!(d2 < gc.maxDist)) continue;
+        const double wj = (exp(-d2 / gc.twoSigmaSq) * gc.interpRangeCu * gc.sigmaPi) / sw;
+        const double mcw = -coeff * wj;
+        atomicAdd(&uSourceDrag[c], mcw * oorho);                                           // F.C:385
+        const double ooCellVol = 1. / (V[c] * rhoF);
+        double sx = (mcw * uParticle[3 * (size_t)c]) / rhoF + (-ax * wj * ooCellVol);      // F.C:386, 433
+        double sy = (mcw * uParticle[3 * (size_t)c + 1]) / rhoF + (-ay * wj * ooCellVol);
+        double sz = (mcw * uParticle[3 * (size_t)c + 2]) / rhoF + (-az * wj * ooCellVol);
+        if (EXTRA && fc.addedMass) {
+            sx += (-am[0] * wj * ooCellVol);
+            sy += (-am[1] * wj * ooCellVol);
+            sz += (-am[2] * wj * ooCellVol);
+        }
+        atomicAdd(&uSource[3 * (size_t)c], sx);
+        atomicAdd(&uSource[3 * (size_t)c + 1], sy);
+        atomicAdd(&uSource[3 * (size_t)c + 2], sz);
+    }
+}
+
+__global__ void k_unpermute_counts(int n, const int* __restrict__ perm, const int* __restrict__ cnt, int* __restrict__ out)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) out[perm[t]] = cnt[t];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -499,38 +771,99 @@ int fyUnpermuteLists(fy_ctx* h, int n, int* d_cnt, int* d_ids, double* d_wts)
     return FY_OK;
 }
 
+
+namespace {
+RangeBox rangeBoxOf(const fy_ctx* h)
+{
+    return RangeBox{h->boxN[0], h->boxN[1], h->boxN[2], h->boxGeom[0], h->boxGeom[1], h->boxGeom[2], h->boxGeom[3],
+                    h->boxGeom[4], h->boxGeom[5], h->dAxis, std::sqrt(h->maxDist)};
+}
+ForceConst forceConstOf(const fy_ctx* h)
+{
+    return ForceConst{h->rhoF, h->nu, 1e-09 /* F.H:67 `small` */, h->rhoP, h->deltaT, h->addedMass ? 1 : 0, h->gaussTorque ? 1 : 0};
+}
+}  // namespace
+
+// Gaussian branch, pass 0: sort, locate + weights + per-cell accumulate (trail lists or full support)
+static int gaussLocate(fy_ctx* h, const double* d_pdata, int n, int* d_found)
+{
+    int rc;
+    const GaussConst gc{h->maxDist, 2 * std::pow(h->sigmaInterp, 2), h->interpRangeCu, h->sigmaPi};
+    if ((rc = fyReserve(h, h->dCnt, (size_t)n))) return rc;
+    if ((rc = fySortParticles(h, d_pdata, n))) return rc;
+    if (h->supportFull) {
+        if (!h->dAxis) { h->err = "full-support Gaussian mode needs a hex-box mesh whose centres are a tensor product (mesh.boxN)"; return FY_ERR_UNSUPPORTED; }
+        if ((rc = fyReserve(h, h->dAllWt, (size_t)n))) return rc;
+        k_range_accumulate<<<fyGrid(n, RANGE_WARPS), RANGE_WARPS * 32, 0, h->stream>>>(
+            rangeBoxOf(h), d_pdata, n, h->dPerm.p, gc, h->procSerial, h->dCnt.p, h->dAllWt.p, d_found, h->dPvol, h->dUpAcc, h->dStamp);
+        FY_CHECK_LAUNCH();
+        return FY_OK;
+    }
+    if ((rc = fyReserve(h, h->dIds, (size_t)n * FY_MAXLIST))) return rc;
+    if ((rc = fyReserve(h, h->dW, (size_t)n * FY_MAXLIST))) return rc;
+    if ((rc = kdFuncAttrs(h, (const void*)k_locate_gauss))) return rc;
+    k_locate_gauss<<<fyGrid(n, KD_BLOCK), KD_BLOCK, KD_SMEM, h->stream>>>(h->dTree, h->nTree, d_pdata, n, h->dPerm.p, gc, h->procSerial,
+                                                                          h->dIds.p, h->dCnt.p, h->dW.p, d_found, h->dPvol,
+                                                                          h->dUpAcc, h->dStamp);
+    FY_CHECK_LAUNCH();
+    return FY_OK;
+}
+
+// Gaussian branch, pass 2: forces + reaction scatter
+static int gaussForce(fy_ctx* h, const double* d_pdata, int n, double* d_force)
+{
+    const ForceConst fc = forceConstOf(h);
+    const bool extra = h->addedMass || h->gaussTorque;
+    double* const* f = h->dField;
+    if (h->supportFull) {
+        const GaussConst gc{h->maxDist, 2 * std::pow(h->sigmaInterp, 2), h->interpRangeCu, h->sigmaPi};
+        if (extra)
+            k_range_force<true><<<fyGrid(n, RANGE_WARPS), RANGE_WARPS * 32, 0, h->stream>>>(
+                rangeBoxOf(h), d_pdata, n, h->dPerm.p, h->dCnt.p, h->dAllWt.p, gc, fc, f[FY_F_U], f[FY_F_ALPHA], f[FY_F_UPARTICLE],
+                f[FY_F_GRADP], f[FY_F_DIVT], h->dV, f[FY_F_DDTU], f[FY_F_VGRAD], f[FY_F_USOURCEDRAG], f[FY_F_USOURCE], d_force);
+        else
+            k_range_force<false><<<fyGrid(n, RANGE_WARPS), RANGE_WARPS * 32, 0, h->stream>>>(
+                rangeBoxOf(h), d_pdata, n, h->dPerm.p, h->dCnt.p, h->dAllWt.p, gc, fc, f[FY_F_U], f[FY_F_ALPHA], f[FY_F_UPARTICLE],
+                f[FY_F_GRADP], f[FY_F_DIVT], h->dV, f[FY_F_DDTU], f[FY_F_VGRAD], f[FY_F_USOURCEDRAG], f[FY_F_USOURCE], d_force);
+    } else if (extra) {
+        k_force_gauss<true><<<fyGrid(n, 128), 128, 0, h->stream>>>(
+            d_pdata, n, h->dPerm.p, h->dIds.p, h->dCnt.p, h->dW.p, fc, f[FY_F_U], f[FY_F_ALPHA], f[FY_F_UPARTICLE], f[FY_F_GRADP],
+            f[FY_F_DIVT], h->dV, f[FY_F_DDTU], f[FY_F_VGRAD], f[FY_F_USOURCEDRAG], f[FY_F_USOURCE], d_force);
+    } else {
+        k_force_gauss<false><<<fyGrid(n, 128), 128, 0, h->stream>>>(
+            d_pdata, n, h->dPerm.p, h->dIds.p, h->dCnt.p, h->dW.p, fc, f[FY_F_U], f[FY_F_ALPHA], f[FY_F_UPARTICLE], f[FY_F_GRADP],
+            f[FY_F_DIVT], h->dV, f[FY_F_DDTU], f[FY_F_VGRAD], f[FY_F_USOURCEDRAG], f[FY_F_USOURCE], d_force);
+    }
+    FY_CHECK_LAUNCH();
+    return FY_OK;
+}
+
+int fyUnpermuteCounts(fy_ctx* h, int n, int* d_cnt)
+{
+    k_unpermute_counts<<<fyGrid(n, 256), 256, 0, h->stream>>>(n, h->dPerm.p, h->dCnt.p, d_cnt);
+    FY_CHECK_LAUNCH();
+    return FY_OK;
+}
+
 int fyCouplingProcDevice(fy_ctx* h, const double* d_pdata, int n, int* d_found, double* d_force)
 {
     if (!h->propsSet) { h->err = "fy_set_properties must be called first"; return FY_ERR_INVALID; }
     h->lastN = n;
     if (n <= 0) return FY_OK;
-    const ForceConst fc{h->rhoF, h->nu, 1e-09};                      // F.H:67 `small`
+    const ForceConst fc = forceConstOf(h);
     const bool prof = h->profiling;
     if (h->gaussian) {
         int rc;
-        if ((rc = fyReserve(h, h->dIds, (size_t)n * FY_MAXLIST))) return rc;
-        if ((rc = fyReserve(h, h->dCnt, (size_t)n))) return rc;
-        if ((rc = fyReserve(h, h->dW, (size_t)n * FY_MAXLIST))) return rc;
         h->procSerial++;
-        const GaussConst gc{h->maxDist, 2 * std::pow(h->sigmaInterp, 2), h->interpRangeCu, h->sigmaPi};
         if (prof) cudaEventRecord(h->ev[1], h->stream);
-        if ((rc = fySortParticles(h, d_pdata, n))) return rc;
-        if ((rc = kdFuncAttrs(h, (const void*)k_locate_gauss))) return rc;
-        k_locate_gauss<<<fyGrid(n, KD_BLOCK), KD_BLOCK, KD_SMEM, h->stream>>>(h->dTree, h->nTree, d_pdata, n, h->dPerm.p, gc, h->procSerial,
-                                                              h->dIds.p, h->dCnt.p, h->dW.p, d_found, h->dPvol,
-                                                              h->dUpAcc, h->dStamp);
-        FY_CHECK_LAUNCH();
+        if ((rc = gaussLocate(h, d_pdata, n, d_found))) return rc;
         if (prof) cudaEventRecord(h->ev[2], h->stream);
         k_void_fraction<<<fyGrid(h->nCells, 256), 256, 0, h->stream>>>(h->nCells, h->procSerial, h->dStamp, h->dPvol,
                                                                        h->dUpAcc, h->dV, h->dField[FY_F_ALPHA],
                                                                        h->dField[FY_F_UPARTICLE]);
         FY_CHECK_LAUNCH();
         if (prof) cudaEventRecord(h->ev[3], h->stream);
-        k_force_gauss<<<fyGrid(n, 128), 128, 0, h->stream>>>(
-            d_pdata, n, h->dPerm.p, h->dIds.p, h->dCnt.p, h->dW.p, fc, h->dField[FY_F_U], h->dField[FY_F_ALPHA],
-            h->dField[FY_F_UPARTICLE], h->dField[FY_F_GRADP], h->dField[FY_F_DIVT], h->dV,
-            h->dField[FY_F_USOURCEDRAG], h->dField[FY_F_USOURCE], d_force);
-        FY_CHECK_LAUNCH();
+        if ((rc = gaussForce(h, d_pdata, n, d_force))) return rc;
         if (prof) cudaEventRecord(h->ev[4], h->stream);
     } else {
         if (h->boxN[0] <= 0) { h->err = "point-force mode needs the hex-box findCell (mesh.boxN)"; return FY_ERR_UNSUPPORTED; }
@@ -556,22 +889,13 @@ int fyCouplingProcDevice(fy_ctx* h, const double* d_pdata, int n, int* d_found, 
 int fyCouplingPass(fy_ctx* h, int pass, const double* d_pdata, int n, int* d_found, double* d_force)
 {
     if (!h->propsSet) { h->err = "fy_set_properties must be called first"; return FY_ERR_INVALID; }
-    const ForceConst fc{h->rhoF, h->nu, 1e-09};
+    const ForceConst fc = forceConstOf(h);
     int rc;
     if (pass == 0) {
         h->lastN = n;
         h->procSerial++;                                   // every rank makes the same calls: same serial everywhere
         if (!h->gaussian || n <= 0) return FY_OK;
-        if ((rc = fyReserve(h, h->dIds, (size_t)n * FY_MAXLIST))) return rc;
-        if ((rc = fyReserve(h, h->dCnt, (size_t)n))) return rc;
-        if ((rc = fyReserve(h, h->dW, (size_t)n * FY_MAXLIST))) return rc;
-        const GaussConst gc{h->maxDist, 2 * std::pow(h->sigmaInterp, 2), h->interpRangeCu, h->sigmaPi};
-        if ((rc = fySortParticles(h, d_pdata, n))) return rc;
-        if ((rc = kdFuncAttrs(h, (const void*)k_locate_gauss))) return rc;
-        k_locate_gauss<<<fyGrid(n, KD_BLOCK), KD_BLOCK, KD_SMEM, h->stream>>>(h->dTree, h->nTree, d_pdata, n, h->dPerm.p, gc, h->procSerial,
-                                                              h->dIds.p, h->dCnt.p, h->dW.p, d_found, h->dPvol, h->dUpAcc,
-                                                              h->dStamp);
-        FY_CHECK_LAUNCH();
+        if ((rc = gaussLocate(h, d_pdata, n, d_found))) return rc;
     } else if (pass == 1) {
         if (!h->gaussian) return FY_OK;
         k_void_fraction<<<fyGrid(h->nCells, 256), 256, 0, h->stream>>>(h->nCells, h->procSerial, h->dStamp, h->dPvol, h->dUpAcc,
@@ -580,10 +904,7 @@ int fyCouplingPass(fy_ctx* h, int pass, const double* d_pdata, int n, int* d_fou
     } else {
         if (n <= 0) return FY_OK;
         if (h->gaussian) {
-            k_force_gauss<<<fyGrid(n, 128), 128, 0, h->stream>>>(
-                d_pdata, n, h->dPerm.p, h->dIds.p, h->dCnt.p, h->dW.p, fc, h->dField[FY_F_U], h->dField[FY_F_ALPHA],
-                h->dField[FY_F_UPARTICLE], h->dField[FY_F_GRADP], h->dField[FY_F_DIVT], h->dV, h->dField[FY_F_USOURCEDRAG],
-                h->dField[FY_F_USOURCE], d_force);
+            return gaussForce(h, d_pdata, n, d_force);
         } else {
             if (h->boxN[0] <= 0) { h->err = "point-force mode needs the hex-box findCell (mesh.boxN)"; return FY_ERR_UNSUPPORTED; }
             if ((rc = fyReserve(h, h->dCell, (size_t)n))) return rc;

@@ -171,6 +171,26 @@ int fy_create(const fy_mesh_desc* m, int device, fy_handle* out)
         if (cudaMalloc((void**)&h->dTree, tree.size() * sizeof(FyKdNode)) != cudaSuccess) { h->err = "cudaMalloc tree"; return fail(FY_ERR_ALLOC); }
         if (cudaMemcpy(h->dTree, tree.data(), tree.size() * sizeof(FyKdNode), cudaMemcpyHostToDevice) != cudaSuccess) { h->err = "tree upload"; return fail(FY_ERR_CUDA); }
     }
+    // hex box: the centre coordinates per axis, taken from mesh.C() itself and checked to BE a tensor product bit for bit
+    // (the full-support Gaussian mode evaluates distances from them; any other mesh leaves dAxis null)
+    if (h->boxN[0] > 0 && (long long)h->boxN[0] * h->boxN[1] * h->boxN[2] == m->nCells) {
+        const int nx = h->boxN[0], ny = h->boxN[1], nz = h->boxN[2];
+        std::vector<double> ax((size_t)nx + ny + nz);
+        for (int i = 0; i < nx; ++i) ax[i] = m->C[3 * (size_t)i];
+        for (int j = 0; j < ny; ++j) ax[nx + j] = m->C[3 * ((size_t)j * nx) + 1];
+        for (int k = 0; k < nz; ++k) ax[nx + ny + k] = m->C[3 * ((size_t)k * nx * ny) + 2];
+        bool ok = true;
+        for (int k = 0; k < nz && ok; ++k)
+            for (int j = 0; j < ny && ok; ++j)
+                for (int i = 0; i < nx; ++i) {
+                    const double* c = m->C + 3 * ((size_t)i + (size_t)nx * (j + (size_t)ny * k));
+                    if (c[0] != ax[i] || c[1] != ax[nx + j] || c[2] != ax[nx + ny + k]) { ok = false; break; }
+                }
+        if (ok) {
+            if (cudaMalloc((void**)&h->dAxis, ax.size() * sizeof(double)) != cudaSuccess) { h->err = "cudaMalloc axis"; return fail(FY_ERR_ALLOC); }
+            if (cudaMemcpy(h->dAxis, ax.data(), ax.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) { h->err = "axis upload"; return fail(FY_ERR_CUDA); }
+        }
+    }
     // initFields constants, host arithmetic exactly as FoamYade.C:69-72 and meshTree.C:155
     h->interpRange = 4 * std::pow(h->V0, 1.0 / 3.0);
     h->sigmaInterp = h->interpRange * 0.42460;
@@ -214,7 +234,7 @@ int fy_destroy(fy_handle h)
                     h->dWeights, h->dDeltaCoeffs, h->dBFaceCells, h->dBPatch, h->dBSf, h->dBMagSf, h->dBDeltaCoeffs,
                     h->dBStart, h->dBOrder, h->dTree, h->dPvol, h->dUpAcc, h->dStamp, h->dPdata.p, h->dFound.p,
                     h->dForce.p, h->dIds.p, h->dCnt.p, h->dW.p, h->dCell.p, h->dKey.p, h->dKey2.p, h->dIdx.p, h->dPerm.p,
-                    h->dSortTmp.p, h->dListCnt.p, h->dListIds.p, h->dListW.p};
+                    h->dSortTmp.p, h->dListCnt.p, h->dListIds.p, h->dListW.p, h->dAxis, h->dAllWt.p};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& f : h->dField) if (f) cudaFree(f);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
@@ -510,12 +530,36 @@ int fy_set_source_zero(fy_handle h)
     return FY_OK;
 }
 
+int fy_set_gaussian_options(fy_handle h, int support, int addedMass, int torque)
+{
+    FyDeviceGuard guard_(h);
+    if (!h || (support != FY_SUPPORT_TRAIL && support != FY_SUPPORT_FULL)) return FY_ERR_INVALID;
+    if (support == FY_SUPPORT_FULL && !h->dAxis) {
+        h->err = "fy_set_gaussian_options: the full-support mode needs a hex-box mesh (fy_mesh_desc.boxN) whose cell centres are a tensor product";
+        return FY_ERR_UNSUPPORTED;
+    }
+    h->supportFull = support == FY_SUPPORT_FULL;
+    h->addedMass = addedMass != 0;
+    h->gaussTorque = torque != 0;
+    return FY_OK;
+}
+
 int fy_get_last_lists(fy_handle h, int n, int* counts, int* ids, double* weights)
 {
     FyDeviceGuard guard_(h);
     if (!h || n < 0 || n > h->lastN) return FY_ERR_INVALID;
     if (n == 0) return FY_OK;
     if (!h->gaussian) { h->err = "fy_get_last_lists: Gaussian mode only"; return FY_ERR_INVALID; }
+    if (h->supportFull) {
+        // full-support mode: the cell sets are never materialised -- the counts are all there is
+        if (ids || weights) { h->err = "fy_get_last_lists: the full-support mode keeps no cell lists (counts only)"; return FY_ERR_UNSUPPORTED; }
+        int rc0;
+        if ((rc0 = fyReserve(h, h->dListCnt, (size_t)h->lastN))) return rc0;
+        if ((rc0 = fyUnpermuteCounts(h, h->lastN, h->dListCnt.p))) return rc0;
+        if (counts) FY_CUDA(cudaMemcpyAsync(counts, h->dListCnt.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        FY_CUDA(cudaStreamSynchronize(h->stream));
+        return FY_OK;
+    }
     // the lists live in sorted order, structure-of-arrays: back to wire order first (all lastN of them)
     const int m = h->lastN;
     int rc;

@@ -80,6 +80,10 @@ struct fy_ctx {
     bool propsSet = false;
     double interpRange = 0, sigmaInterp = 0, interpRangeCu = 0, sigmaPi = 0, maxDist = 0;
     double deltaT = 0;
+    // Gaussian-branch options (fy_set_gaussian_options): full-support cell sets instead of the k-d trail;
+    // addedMassForce (F.C:392-413) and the Gaussian torque (F.C:467-478), which the reference defines but never calls
+    bool supportFull = false, addedMass = false, gaussTorque = false;
+    double* dAxis = nullptr;      // [nx + ny + nz] cell-centre coordinates of the hex box (null: centres are no tensor product)
 
     // ---- coupling fields on the device
     double* dField[FY_F_COUNT] = {nullptr};
@@ -101,6 +105,7 @@ struct fy_ctx {
     FyBuf<int> dCnt;              // [n]
     FyBuf<double> dW;             // [12][n] normalised weights
     FyBuf<int> dCell;             // [n] point-force cell
+    FyBuf<double> dAllWt;         // [n] weight normaliser of the full-support mode (sorted order)
     // position sort of the current buffer (Gaussian mode): keys, identity, permutation (sorted slot -> wire index)
     FyBuf<unsigned int> dKey, dKey2;
     FyBuf<int> dIdx, dPerm;
@@ -181,6 +186,7 @@ int fyLaunchFindCell(fy_ctx* h, const double* d_xyz, int stride, int n, int* d_c
 int fyCouplingProcDevice(fy_ctx* h, const double* d_pdata, int n, int* d_found, double* d_force);
 int fySortParticles(fy_ctx* h, const double* d_pdata, int n);
 int fyUnpermuteLists(fy_ctx* h, int n, int* d_cnt, int* d_ids, double* d_wts);
+int fyUnpermuteCounts(fy_ctx* h, int n, int* d_cnt);
 int fyCouplingPass(fy_ctx* h, int pass, const double* d_pdata, int n, int* d_found, double* d_force);
 int fySourceZeroDevice(fy_ctx* h);
 int fyInitCouplingFields(fy_ctx* h);
