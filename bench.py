@@ -160,7 +160,8 @@ def config_of(args, world):
     replicas = args.partition == "replicas" and world > 1
     return {"workload": "%s: %s" % (args.workload, desc), "cells": N, "internal_faces": 3 * N - nx * ny - ny * nz - nx * nz,
             "particles_total": P * world if replicas else P,
-            "coupling": args.coupling, "fluid_solve": not args.coupling_only, "flow": flow, "gravity": list(gravity_of(args.workload)),
+            "coupling": args.coupling + (" (full support: every cell inside the search bound)" if getattr(args, "support", "trail") == "full" else ""),
+            "fluid_solve": not args.coupling_only, "flow": flow, "gravity": list(gravity_of(args.workload)),
             "dt": dt, "nu": nu,
             "solver": ("pimpleFoamYade (UcEqn.H/pEqn.H, nOuterCorrectors 1, laminar)" if pimple else "icoFoamYade"),
             "fvSolution": "PISO nCorrectors 2; p PCG/DIC 1e-06 relTol 0.05 (pFinal 0); U smoothSolver symGaussSeidel 1e-05",
@@ -220,6 +221,9 @@ def run_engine(args):
         P_total = P
     E = pkg.Engine(mp, device=local)
     E.set_properties(cases.RHOP, cases.RHOF, nu, gaussian)
+    full_support = gaussian and args.support == "full"
+    if full_support:
+        E.set_gaussian_options(support_full=True)
     fluid = not args.coupling_only
     if fluid and not E.fv_supported():
         raise SystemExit("bench.py: " + E.L.fy_last_error(E.h).decode())
@@ -403,7 +407,11 @@ def run_engine(args):
         Fi = 3 * N - nx * ny - ny * nz - nx * nz
         # kernel classes with their algorithmic bytes per launch (DESIGN.md "kernels and rooflines")
         cand = {}
-        if gaussian:
+        if full_support:
+            # (compulsory bytes as for the trail kernels; the ~370-cell gathers and REDs per particle are L2 work on top)
+            cand["k_range_accumulate"] = (phase[1], 84.0 * P + 32.0 * N)
+            cand["k_range_force"] = (phase[3], 48.0 * P + 136.0 * N)
+        elif gaussian:
             cand["k_locate_gauss"] = (phase[1], 84.0 * P + 32.0 * N)
             cand["k_force_gauss"] = (phase[3], 48.0 * P + 136.0 * N)
         else:
@@ -510,6 +518,8 @@ def cpu_baseline(args, state=None, steps=1, warmup=0, out=None):
     R = ref.RefFoamYade(mo, gaussian)
     t_tree = time.time() - t0
     R.set_properties(cases.RHOP, cases.RHOF, nu)
+    if gaussian and getattr(args, "support", "trail") == "full":
+        R.set_gaussian_options(True, False, False)
     fluid = not args.coupling_only
     O = None
     if fluid:
@@ -598,7 +608,7 @@ def cpu_all_cores(args, cores, state=None):
     procs = []
     for i in range(cores):
         cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", wl, "--coupling", args.coupling,
-               "--cpl-worker", "%d,%d,%d" % (i, cores, Ps)]
+               "--support", getattr(args, "support", "trail"), "--cpl-worker", "%d,%d,%d" % (i, cores, Ps)]
         procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, cwd=ROOT))
     t_fl, slabs = 0.0, min(cores, nz)
     if fluid and not pimple:
@@ -647,6 +657,8 @@ def cpl_worker(args):
     lo, hi = (i * Ps) // n, ((i + 1) * Ps) // n
     R = ref.RefFoamYade(mo, gaussian)
     R.set_properties(cases.RHOP, cases.RHOF, nu)
+    if gaussian and getattr(args, "support", "trail") == "full":
+        R.set_gaussian_options(True, False, False)
     R.field("U")[:] = U0
     t0 = time.time()
     R.step(dt, pd[lo:hi], pieces=True, truncate12=True, dense=True)
@@ -690,6 +702,9 @@ def main():
     ap.add_argument("--solver", default="ico", choices=["ico", "pimple"],
                     help="fluid step: icoFoamYade (default, the headline) or pimpleFoamYade (UcEqn.H/pEqn.H; Gaussian coupling)")
     ap.add_argument("--coupling-only", action="store_true")
+    ap.add_argument("--support", default="trail", choices=["trail", "full"],
+                    help="Gaussian cell sets: the reference's <= 12-cell k-d trail (default) or every cell inside the search bound "
+                         "(fy_set_gaussian_options FY_SUPPORT_FULL, ~370 cells per particle)")
     ap.add_argument("--partition", default="domain", choices=["domain", "particles", "replicas"],
                     help="N > 1: one domain, pressure solve z-slab decomposed + particle migration (strong scaling, default); "
                          "one domain with only the particle buffer sharded; or independent domain replicas (weak scaling)")
