@@ -475,6 +475,10 @@ def run_engine(args):
                                                      "(latency-bound: a few hundred KB per exchange at most)"}
         if not args.no_cpu_baseline and world == 1:
             state = dict(U=E.download("U"), p=E.download("p"), phi=E.download("phi")) if fluid else None
+            if fluid and flow == "closedbox":
+                # the fixedFluxPressure patches carry state from one time step to the next (the gradient constrainPressure
+                # set, which fvc::grad(p) of the next pre-coupling block reads): it is part of the flow state
+                state["bGradP"] = E.fv_get("bGradP")[int(mp["nInternalFaces"]):]
             ref_out = {}
             line["cpu_baseline"] = cpu_baseline(args, state=state, out=ref_out)
             if fluid and ref_out:
@@ -528,6 +532,8 @@ def cpu_baseline(args, state=None, steps=1, warmup=0, out=None):
         O.field("p")[:] = state["p"] if state else p0
         if state:
             O.field("phi")[:] = state["phi"]
+            if "bGradP" in state:
+                O.field("bGradP")[:] = state["bGradP"]
         else:
             O.create_phi()
     t_cpl = t_fl = 0.0

@@ -1487,6 +1487,7 @@ double* fvo_field(void* h, const char* name, long* n)
     else if (k == "diagU") v = &s->diagU; else if (k == "upperU") v = &s->upperU; else if (k == "lowerU") v = &s->lowerU;
     else if (k == "sourceU") v = &s->sourceU; else if (k == "diagP") v = &s->diagP; else if (k == "upperP") v = &s->upperP;
     else if (k == "sourceP") v = &s->sourceP; else if (k == "icU") v = &s->icU; else if (k == "bcU") v = &s->bcU;
+    else if (k == "bGradP") v = &s->m.bGradP;            // [nB] fixedFluxPressure gradient (state between time steps)
     if (!v) { if (n) *n = 0; return nullptr; }
     if (n) *n = (long)v->size();
     return v->data();

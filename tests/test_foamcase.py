@@ -1,0 +1,194 @@
+"""OpenFOAM case I/O of the standalone engine (yade-openfoam-coupling_b200/foamcase.py), on the CPU:
+the stock OpenFOAM-6 cavity tutorial's dictionaries and field files as they are on disk (tests/cases_foam/cavity, restated
+from tutorials/incompressible/icoFoam/cavity/cavity) + a polyMesh in blockMesh's conventions -> the case description ->
+the oracle reproduces the tutorial's public solver log from it; time directories round-trip."""
+import importlib.util
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+from oracle import meshgen, port
+from tests.test_fv_oracle import CAVITY_LOG, sig6
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _foamcase():
+    spec = importlib.util.spec_from_file_location("fy_foamcase", os.path.join(ROOT, "yade-openfoam-coupling_b200", "foamcase.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+fc = _foamcase()
+CAVITY_PATCHES = [("movingWall", ["ymax"]), ("fixedWalls", ["xmin", "xmax", "ymin"]), ("frontAndBack", ["zmin", "zmax"])]
+
+
+def cavity_case(tmp_path, n=(20, 20, 1)):
+    case = str(tmp_path / "cavity")
+    shutil.copytree(os.path.join(HERE, "cases_foam", "cavity"), case)
+    fc.write_box_poly_mesh(case, n, (0.1, 0.1, 0.01), patches=CAVITY_PATCHES,
+                           patch_types={"movingWall": "wall", "fixedWalls": "wall", "frontAndBack": "empty"})
+    return case
+
+
+def test_dictionary_syntax():
+    d = fc.parse_dict('''
+        FoamFile { version 2.0; format ascii; class dictionary; }   // header
+        /* block
+           comment */
+        nu              [0 2 -1 0 0 0 0] 0.01;
+        nuOld           nuOld [0 2 -1 0 0 0 0] 1e-06;
+        g               (0 0 -9.81);
+        solvers { p { solver PCG; tolerance 1e-06; relTol 0.05; } pFinal { $p; relTol 0; } "(U|k)" { solver smoothSolver; } }
+        on yes; name "quoted string"; list 3 (1 2 3);
+    ''')
+    assert fc.scalar_of(d["nu"], "nu") == 0.01 and fc.scalar_of(d["nuOld"], "nuOld") == 1e-6
+    assert fc.vector_of(d["g"], "g") == (0.0, 0.0, -9.81)
+    assert d["solvers"]["pFinal"] == {"solver": "PCG", "tolerance": 1e-06, "relTol": 0}
+    assert d["solvers"]["p"]["relTol"] == 0.05 and "(U|k)" in d["solvers"]
+    assert d["on"] == "yes" and d["name"] == "quoted string" and list(d["list"][1]) == [1, 2, 3]
+    with pytest.raises(fc.FoamCaseError):
+        fc.parse_dict("a { b 1; ")
+    with pytest.raises(fc.FoamCaseError):
+        fc.parse_dict("a { $missing; }")
+
+
+def test_cavity_case_is_read_as_the_tutorial_defines_it(tmp_path):
+    case = fc.load_case(cavity_case(tmp_path))
+    assert case["box"]["n"] == (20, 20, 1)
+    np.testing.assert_allclose(case["box"]["L"], (0.1, 0.1, 0.01), rtol=1e-15)
+    by = {p["name"]: p for p in case["patches"]}
+    assert by["movingWall"]["sides"] == ["ymax"] and by["movingWall"]["bcU"] == "fixedValue" and by["movingWall"]["valueU"] == (1.0, 0.0, 0.0)
+    assert sorted(by["fixedWalls"]["sides"]) == ["xmax", "xmin", "ymin"] and by["fixedWalls"]["bcU"] == "fixedValue"        # noSlip
+    assert by["fixedWalls"]["valueU"] == (0.0, 0.0, 0.0) and by["fixedWalls"]["bcP"] == "zeroGradient"
+    assert by["frontAndBack"]["bcU"] == by["frontAndBack"]["bcP"] == "empty"
+    assert case["nu"] == 0.01 and case["control"]["deltaT"] == 0.005 and case["control"]["endTime"] == 0.5
+    assert case["control"]["writeInterval"] == 20
+    assert case["piso"] == dict(nCorrectors=2, nNonOrthogonalCorrectors=0, momentumPredictor=1, pRefCell=0, pRefValue=0.0, pTol=1e-6,
+                                pRelTol=0.05, pFinalTol=1e-6, pFinalRelTol=0.0, UTol=1e-5, URelTol=0.0, maxIter=1000,
+                                preconditioner="DIC")
+    assert not np.any(case["U"]) and not np.any(case["p"]) and case["U"].shape == (400, 3)
+    # the mesh the description builds IS the synthetic generator's (same arrays, bit for bit)
+    m = fc.build_mesh(case, meshgen.hex_box_ldu, meshgen.set_bc, meshgen)
+    ref = meshgen.hex_box_ldu(20, 20, 1, 0.1, 0.1, 0.01, patches=CAVITY_PATCHES)
+    for k in ("owner", "neighbour", "Sf", "magSf", "weights", "deltaCoeffs", "V"):
+        assert np.array_equal(m[k], ref[k]), k
+    np.testing.assert_allclose(m["C"], ref["C"], rtol=0, atol=1e-17)
+
+
+@pytest.mark.skipif(not port.available(), reason="oracle/_build/liboracle.so not built")
+def test_cavity_case_from_disk_reproduces_the_tutorial_log(tmp_path):
+    """the public log.icoFoam digits (tests/test_fv_oracle.py) from the case DIRECTORY: reader -> mesh + controls -> oracle"""
+    case = fc.load_case(cavity_case(tmp_path))
+    m = fc.build_mesh(case, meshgen.hex_box_ldu, meshgen.set_bc, meshgen)
+    ctl = dict(case["piso"])
+    O = port.IcoOracle(m, nu=case["nu"], **ctl)
+    O.field("U")[:] = case["U"]
+    O.field("p")[:] = case["p"]
+    O.create_phi()
+    dt = case["control"]["deltaT"]
+    for ref in CAVITY_LOG:
+        O.pre(dt)
+        O.solve(dt)
+        st = O.stats()
+        assert (sig6(st["meanCoNum"]), sig6(st["CoNum"])) == ref["Co"]
+        for j, k in ((0, "Ux"), (1, "Uy")):
+            assert (sig6(st["U"][j]["initial"]), sig6(st["U"][j]["final"]), st["U"][j]["iters"]) == ref[k], k
+        for j, k in ((0, "p1"), (1, "p2")):
+            assert (sig6(st["p"][j]["initial"]), sig6(st["p"][j]["final"]), st["p"][j]["iters"]) == ref[k], k
+    # runTime.write(): the time directory reads back as written; at writePrecision 17 bit for bit
+    U, p = O.field("U").copy(), O.field("p").copy()
+    O.close()
+    case["control"]["writePrecision"] = 17
+    tname = fc.write_time(case, 3 * dt, U, p)
+    assert tname == "0.015"
+    back = fc.load_case(case["case_dir"], time=tname)
+    assert np.array_equal(back["U"], U) and np.array_equal(back["p"], p)
+    assert [(q["name"], q["bcU"], q["valueU"], q["bcP"]) for q in back["patches"]] == \
+           [(q["name"], q["bcU"], q["valueU"], q["bcP"]) for q in case["patches"]]
+    case["control"]["writePrecision"] = 6
+    fc.write_time(case, 4 * dt, U, p)
+    back6 = fc.load_case(case["case_dir"], time="0.02")
+    assert np.abs(back6["U"] - U).max() <= 5e-6 * np.abs(U).max()
+
+
+def test_3d_channel_case_with_nonuniform_fields_and_pimple_dictionaries(tmp_path):
+    """a 3-D box with inlet / outlet / walls, nonuniform internal fields, the pimpleFoamYade property names, a PIMPLE
+    dictionary with outer correctors and relaxationFactors, constant/g"""
+    case_dir = str(tmp_path / "chan")
+    n, L, org = (6, 5, 4), (2.0, 1.0, 0.5), (-1.0, 0.25, 3.0)
+    patches = [("inlet", ["xmin"]), ("outlet", ["xmax"]), ("walls", ["ymin", "ymax", "zmin", "zmax"])]
+    fc.write_box_poly_mesh(case_dir, n, L, org, patches, {"inlet": "patch", "outlet": "patch", "walls": "wall"})
+    N = 120
+    rng = np.random.default_rng(3)
+    U, p = rng.standard_normal((N, 3)), rng.standard_normal(N)
+    pl = [dict(name=a, sides=b) for a, b in patches]
+    fc.write_field(case_dir, "0", "Uc", U, (0, 1, -1, 0, 0, 0, 0), pl,
+                   {"inlet": ("fixedValue", np.array([0.3, 0, 0])), "outlet": ("zeroGradient", None), "walls": ("noSlip", None)}, prec=17)
+    fc.write_field(case_dir, "0", "p", p, (0, 2, -2, 0, 0, 0, 0), pl,
+                   {"inlet": ("zeroGradient", None), "outlet": ("fixedValue", 0.25), "walls": ("fixedFluxPressure", 0.0)}, prec=17)
+    os.makedirs(os.path.join(case_dir, "system"))
+    open(os.path.join(case_dir, "constant", "transportProperties"), "w").write(
+        "FoamFile{version 2.0;format ascii;class dictionary;object transportProperties;}\n"
+        "partDensity partDensity [1 -3 0 0 0 0 0] 2500;\nrhocValue rhocValue [1 -3 0 0 0 0 0] 1000;\nnuValue nuValue [0 2 -1 0 0 0 0] 1e-06;\n")
+    open(os.path.join(case_dir, "constant", "g"), "w").write(
+        "FoamFile{version 2.0;format ascii;class uniformDimensionedVectorField;object g;}\ndimensions [0 1 -2 0 0 0 0];\nvalue (0 0 -9.81);\n")
+    open(os.path.join(case_dir, "system", "controlDict"), "w").write(
+        "FoamFile{version 2.0;format ascii;class dictionary;object controlDict;}\napplication pimpleFoamYade;\nstartTime 0;\nendTime 1;\n"
+        "deltaT 1e-3;\nwriteControl timeStep;\nwriteInterval 100;\n")
+    open(os.path.join(case_dir, "system", "fvSolution"), "w").write(
+        "FoamFile{version 2.0;format ascii;class dictionary;object fvSolution;}\n"
+        "solvers { p { solver PCG; preconditioner diagonal; tolerance 1e-7; relTol 0.01; } pFinal { $p; relTol 0; }\n"
+        '          "(Uc|k)" { solver smoothSolver; smoother symGaussSeidel; tolerance 1e-6; relTol 0.1; } }\n'
+        "PIMPLE { nOuterCorrectors 3; nCorrectors 2; momentumPredictor no; nNonOrthogonalCorrectors 1; pRefCell 7; pRefValue 1.5; }\n"
+        'relaxationFactors { equations { "Uc.*" 0.7; UcFinal 1; } fields { p 0.3; pFinal 1; } }\n')
+    case = fc.load_case(case_dir, solver="pimpleFoamYade")
+    assert case["Uname"] == "Uc" and np.array_equal(case["U"], U) and np.array_equal(case["p"], p)
+    assert case["box"]["n"] == n and np.allclose(case["box"]["origin"], org) and np.allclose(case["box"]["L"], L)
+    by = {q["name"]: q for q in case["patches"]}
+    assert by["inlet"]["bcU"] == "fixedValue" and by["inlet"]["valueU"] == (0.3, 0.0, 0.0) and by["outlet"]["bcU"] == "zeroGradient"
+    assert by["outlet"]["bcP"] == "fixedValue" and by["outlet"]["valueP"] == 0.25 and by["walls"]["bcP"] == "fixedFluxPressure"
+    assert case["nu"] == 1e-6 and case["props"] == dict(nuValue=1e-6, rhocValue=1000.0, partDensity=2500.0) and case["g"] == (0.0, 0.0, -9.81)
+    assert case["piso"]["preconditioner"] == "diagonal" and case["piso"]["momentumPredictor"] == 0 and case["piso"]["pRefCell"] == 7
+    assert case["piso"]["nNonOrthogonalCorrectors"] == 1 and case["piso"]["URelTol"] == 0.1 and case["piso"]["pFinalRelTol"] == 0.0
+    assert case["pimple"] == dict(nOuterCorrectors=3, relaxU=0.7, relaxUFinal=1.0, relaxP=0.3, relaxPFinal=1.0)
+    m = fc.build_mesh(case, meshgen.hex_box_ldu, meshgen.set_bc, meshgen)
+    ref = meshgen.hex_box_ldu(*n, *L, origin=org, patches=patches)
+    assert np.array_equal(m["owner"], ref["owner"]) and np.allclose(m["C"], ref["C"], rtol=0, atol=1e-15)
+
+
+def test_unsupported_cases_are_refused_with_the_reason(tmp_path):
+    case_dir = cavity_case(tmp_path)
+    # a patch covering part of a side
+    pm = os.path.join(case_dir, "constant", "polyMesh", "boundary")
+    txt = open(pm).read()
+    open(pm, "w").write(txt.replace("nFaces          20;", "nFaces          10;", 1))
+    with pytest.raises(fc.FoamCaseError, match="whole sides|no patch|lie on no box side"):
+        fc.load_case(case_dir)
+    open(pm, "w").write(txt)
+    # binary files
+    pts = os.path.join(case_dir, "constant", "polyMesh", "points")
+    t2 = open(pts).read()
+    open(pts, "w").write(t2.replace("format      ascii;", "format      binary;", 1))
+    with pytest.raises(fc.FoamCaseError, match="ascii"):
+        fc.load_case(case_dir)
+    open(pts, "w").write(t2)
+    # a boundary condition the device path does not implement
+    u = os.path.join(case_dir, "0", "U")
+    t3 = open(u).read()
+    open(u, "w").write(t3.replace("type            noSlip;", "type            slip;"))
+    with pytest.raises(fc.FoamCaseError, match="slip"):
+        fc.load_case(case_dir)
+    open(u, "w").write(t3)
+    # a solver the engine does not have
+    fs = os.path.join(case_dir, "system", "fvSolution")
+    t4 = open(fs).read()
+    open(fs, "w").write(t4.replace("solver          PCG;", "solver          GAMG;"))
+    with pytest.raises(fc.FoamCaseError, match="GAMG"):
+        fc.load_case(case_dir)
+    open(fs, "w").write(t4)
+    fc.load_case(case_dir)

@@ -15,3 +15,4 @@ from .mesh import box_mesh, set_bc, BC_FIXED_VALUE, BC_ZERO_GRADIENT, BC_EMPTY, 
 from . import replicas  # noqa: F401,E402
 from . import sharded  # noqa: F401,E402
 from . import domain  # noqa: F401,E402
+from . import foamcase  # noqa: F401,E402

@@ -472,7 +472,7 @@ class Engine:
         nB = sum(int(p["faceCells"].shape[0]) for p in self.mesh["patches"])
         shape = dict(rAU=(self.N,), HbyA=(self.N, 3), gradP=(self.N, 3), diagU=(self.N,), sourceU=(self.N, 3),
                      phiHbyA=(nF + nB,), phi=(nF + nB,), upperP=(nF,), upperU=(nF,), lowerU=(nF,),
-                     phicForces=(nF + nB,), divDev=(self.N, 3))[name]
+                     phicForces=(nF + nB,), divDev=(self.N, 3), bGradP=(nF + nB,))[name]
         out = np.empty(shape)
         self._ck(self.L.fy_fv_get(self.h, name.encode(), _d(out)))
         return out

@@ -336,6 +336,14 @@ int fy_fv_get(fy_handle h, const char* name, double* dst)
         if ((rc = fvSlotsToFaces(h, s, (int)nF, s->phicForces, d))) return rc;
         return d2h(h, dst, d, nF);
     }
+    if (k == "bGradP") {             // snGrad(p) constrainPressure left on the fixedFluxPressure faces, [faces] (0 elsewhere)
+        const size_t nF = (size_t)s->nFi + s->nB;
+        if (!s->bGradP) { h->err = "fy_fv_get: the mesh has no fixedFluxPressure patch"; return FY_ERR_INVALID; }
+        double* d;
+        if ((rc = stage(h, s, nF, &d))) return rc;
+        if ((rc = fvSlotsToFaces(h, s, (int)nF, s->bGradP, d))) return rc;
+        return d2h(h, dst, d, nF);
+    }
     if (k == "phiHbyA" || k == "phi" || k == "upperP" || k == "upperU" || k == "lowerU") {
         const size_t nF = (k == "phiHbyA" || k == "phi") ? (size_t)s->nFi + s->nB : (size_t)s->nFi;
         double* d;
