@@ -300,14 +300,14 @@ int fy_ico_pre(fy_handle h, double dt);
  * the time step (Uc.oldTime() has just been stored from Uc).                                                    */
 int fy_pimple_pre(fy_handle h, double dt);
 /* pimpleFoamYade's fluid step after setParticleAction (pimpleFoamYade/pimpleFoamYade.C:82-104 with UcEqn.H, pEqn.H,
- * continuityErrs.H; one outer corrector, laminar): alphacf = interpolate(alphac), alphaPhic = alphacf*phic,
+ * continuityErrs.H; laminar; nOuterCorrectors / relaxation: fy_set_pimple_controls): alphacf = interpolate(alphac), alphaPhic = alphacf*phic,
  *   UcEqn = ddt(alphac,Uc) + div(alphaPhic,Uc) - Sp(ddt(alphac) + div(alphaPhic),Uc) + divDevRhoReff(Uc) == Sp(uSourceDrag,Uc)
  *   phicForces = flux(rAUc*uSource) + rAUcf*(g & Sf);  momentum predictor == reconstruct(phicForces/rAUcf - snGrad(p)*magSf)
  *   PISO: phiHbyA = flux(HbyA) + alphacf*rAUcf*ddtCorr + phicForces;  laplacian(alphacf*rAUcf, p) == ddt(alphac) + div(alphacf*phiHbyA)
  *         phic = phiHbyA - flux/alphacf;  Uc = HbyA + rAUc*reconstruct((phicForces - flux/alphacf)/rAUcf)
  * Reads the device fields the coupling pass left (FY_F_ALPHA, FY_F_USOURCE, FY_F_USOURCEDRAG), updates U, p, phi;
  * g = gravitational acceleration (NULL = 0).  fy_piso_controls / fy_get_ico_stats serve this solver too.  Patch types
- * as for icoFoam (no fixedFluxPressure, so walls + gravity are not a consistent case).                            */
+ * as for icoFoam plus fixedFluxPressure on p (constrainPressure, pEqn.H:21: closed boxes under gravity).           */
 int fy_pimple_solve(fy_handle h, double dt, const double g[3]);
 /* UEqn assembly with uSource, momentum predictor, PISO correctors (icoFoamYade.C:79-140).  Reads and
  * updates the device fields U (FY_F_U), p (FY_F_P), phi (FY_F_PHI); reads uSource (FY_F_USOURCE).    */
