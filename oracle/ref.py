@@ -217,6 +217,16 @@ class RefFoamYade:
         self.L.ref_download_fluid.argtypes = [C.c_void_p]
         self.L.ref_download_fluid(self.h)
 
+    def host_gaussian_options(self, support_full=False, added_mass=False, torque=False):
+        """host-class build only: FoamYadeB200::setGaussianOptions"""
+        self.L.ref_host_gaussian_options.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        self.L.ref_host_gaussian_options(self.h, int(support_full), int(added_mass), int(torque))
+
+    def host_pimple_controls(self, nOuterCorrectors=1, relaxU=0.0, relaxUFinal=0.0, relaxP=0.0, relaxPFinal=0.0):
+        """host-class build only: FoamYadeB200::setPimpleControls"""
+        self.L.ref_host_pimple_controls.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]
+        self.L.ref_host_pimple_controls(self.h, int(nOuterCorrectors), relaxU, relaxUFinal, relaxP, relaxPFinal)
+
     def set_batched_wire(self, on=True):
         """host-class build only: one message per direction and step (F1)"""
         self.L.ref_set_batched_wire.argtypes = [C.c_void_p, C.c_int]

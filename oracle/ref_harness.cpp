@@ -475,6 +475,16 @@ void ref_fluid_step(void* h, int solver, double dt, double yadeDT, const double*
 }
 
 void ref_download_fluid(void* h) { ((Ref*)h)->fy->downloadFluid(); }
+
+// the host class's setters for the options beyond the reference's loop (fycuda.h: fy_set_gaussian_options, fy_set_pimple_controls)
+void ref_host_gaussian_options(void* h, int full, int addedMass, int torque)
+{
+    ((Ref*)h)->fy->setGaussianOptions(full != 0, addedMass != 0, torque != 0);
+}
+void ref_host_pimple_controls(void* h, int nOuter, double relaxU, double relaxUFinal, double relaxP, double relaxPFinal)
+{
+    ((Ref*)h)->fy->setPimpleControls(nOuter, relaxU, relaxUFinal, relaxP, relaxPFinal);
+}
 #endif
 
 // the unmodified driver, F.C:605-632

@@ -129,6 +129,53 @@ def test_cpp_loop_drivers_run_the_fluid_step_on_the_device(pkg, solver, gaussian
     O.close()
 
 
+def test_host_class_options_beyond_the_reference_loop(pkg):
+    """FoamYadeB200::setGaussianOptions / setPimpleControls through the C++ class and the pimpleFoamYade loop body: full-support
+    Gaussian cell sets + addedMassForce + Gaussian torque on the wire, two outer PIMPLE correctors with relaxation -- three
+    time steps against (the unmodified reference's own functions fed with the full cell sets + the oracle's pimpleSolve)."""
+    from oracle import port
+    from tests import cases_fv
+    n = 16
+    mo, _ = cases_fv.cavity3d(None, (n, n, n), (1.0, 1.0, 1.0))
+    nu, dt = 1e-3, 2e-3
+    N = mo["nCells"]
+    U0 = 0.2 * cases.fields_for(mo["C"])["U"]
+    pd = cases.particles(300, 3, radius=0.1 / n, moving=True)
+    pd[:, 0:3] = 0.1 + 0.8 * pd[:, 0:3]
+    pim = dict(nOuterCorrectors=2, relaxU=0.8, relaxUFinal=1.0, relaxP=0.5, relaxPFinal=1.0)
+    O = port.IcoOracle(mo, nu=nu)
+    O.set_pimple_controls(**pim)
+    O.field("U")[:] = U0
+    O.create_phi()
+    R = ref.RefFoamYade(mo, True)
+    R.set_properties(cases.RHOP, cases.RHOF, nu)
+    R.set_gaussian_options(True, True, True)
+    H = ref.RefFoamYade(mo, True, host=True)
+    H.field("U")[:] = U0
+    H.set_fv_mesh(mo)
+    H.host_gaussian_options(True, True, True)          # before setScalarProperties: applied when the engine is created
+    H.host_pimple_controls(**pim)
+    H.set_properties(cases.RHOP, cases.RHOF, nu)
+    for step in range(3):
+        ddtU, gradP, divT, vGrad = O.pimple_pre(dt, R.field("alpha").reshape(N))
+        for k, v in (("U", O.field("U")), ("ddtU", ddtU), ("gradP", gradP), ("divT", divT), ("vGrad", vGrad)):
+            R.field(k)[:] = v.reshape(R.field(k).shape)
+        fo, Fo = R.step(dt, pd, pieces=True)
+        O.field("uSource")[:] = R.field("uSource")
+        O.pimple_solve(dt, R.field("alpha").reshape(N).copy(), R.field("uSourceDrag").reshape(N))
+        R.set_source_zero()
+        fe, Fe, lg = H.fluid_step("pimple", dt, pd)
+        H.download_fluid()
+        assert np.array_equal(fo, fe)
+        assert np.any(Fo[:, 3:6]) and cases.rel_l2(Fe, Fo) <= cases.TOL
+        assert len(lg["p_iters"]) == 4 and lg["p_iters"] == [q["iters"] for q in O.stats()["p"]]
+        assert cases.rel_l2(H.field("U"), O.field("U")) <= cases.TOL
+        assert cases.rel_l2(H.field("p"), O.field("p")) <= cases.TOL
+    H.close()
+    R.close()
+    O.close()
+
+
 @pytest.mark.parametrize("gaussian", [True, False])
 def test_batched_wire_mode(pkg, gaussian):
     """F1: with batchedWire the serial-Yade exchange is one message per direction and step -- Bcast n, Bcast records,
