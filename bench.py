@@ -496,6 +496,8 @@ def run_engine(args):
                     "force_rel_l2": cases.rel_l2(Fe, ref_out["force"]), "found_equal": bool(np.array_equal(fe, ref_out["found"])),
                     "p_iters_engine": [q["iters"] for q in st["p"]], "p_iters_cpu": ref_out["p_iters"],
                     "against": "oracle/_ref (unmodified FoamYade.C, canonical <=12 lists) + oracle/fv_oracle.cc, one step from the engine's state"}
+        if (world == 1 and wl == "C2" and gaussian and fluid and not pimple and not full_support and not args.no_extra):
+            line["extra_keys"] = extra_lines(args)
         print(json.dumps(line))
     torch.cuda.synchronize()
     S = None
@@ -503,6 +505,35 @@ def run_engine(args):
         dist.barrier()
         dist.destroy_process_group()         # before the engine (and the stream NCCL was ordered on) goes away
     E.close()
+
+
+def extra_lines(args):
+    """The other single-GPU configurations SURVEY.md 8(d) asks to see next to the headline, each measured by this same
+    script in a process of its own (same timing rules; CPU arm and full-size parity skipped) and condensed: C2 with the
+    point-force branch icoFoamYade hard-codes (icoFoamYade.C:53), and pimpleFoamYade on the closed box under gravity at
+    C2's size (C3s; BASELINE configs[2] itself, 256^3 / 10 M, takes minutes to set up: profiles/).  A failure of an extra
+    run is reported in its entry and never touches the headline line."""
+    out = {}
+    runs = {"C2_point_force": ["--coupling", "point"],
+            "C3s_pimpleFoamYade_closed_box": ["--workload", "C3s", "--solver", "pimple"]}
+    for name, extra in runs.items():
+        cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--steps", str(args.steps), "--warmup", str(args.warmup),
+               "--no-cpu-baseline", "--no-extra"] + extra
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+            ln = [x for x in r.stdout.splitlines() if x.startswith("{")]
+            if r.returncode != 0 or not ln:
+                out[name] = {"error": (r.stderr or r.stdout)[-300:]}
+                continue
+            d = json.loads(ln[-1])
+            out[name] = {"value": d["value"], "unit": d["unit"], "e2e": d["e2e"]["value"], "ms_per_step": d["ms_per_step"],
+                         "pcg_iterations_per_step": d["pcg_iterations_per_step"], "workload": d["config"]["workload"],
+                         "coupling": d["config"]["coupling"], "solver": d["config"]["solver"],
+                         "roofline_kernel": d["roofline"]["kernel"], "roofline_frac": d["roofline"]["frac"],
+                         "command": "python bench.py " + " ".join(cmd[2:])}
+        except Exception as e:                                   # noqa: BLE001
+            out[name] = {"error": repr(e)[-300:]}
+    return out
 
 
 def cpu_baseline(args, state=None, steps=1, warmup=0, out=None):
@@ -717,6 +748,7 @@ def main():
     ap.add_argument("--py", type=int, default=0,
                     help="--partition domain: y slabs of the rank grid (0: the library's choice, y first; 1: z slabs only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra single-GPU configurations reported under extra_keys")
     ap.add_argument("--e2e-blocking", action="store_true", help="e2e through the blocking fy_set_particle_action instead of the overlapped calls")
     ap.add_argument("--cpu-particles", type=int, default=200000)
     ap.add_argument("--cpu-one-core", action="store_true", help="CPU baseline on one core only (skip the all-core arm)")

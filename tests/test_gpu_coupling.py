@@ -202,15 +202,20 @@ def _ddtU(C):
     return np.stack([0.4 * np.sin(2.0 * C[:, 2]), -0.3 * np.cos(3.0 * C[:, 1]), 0.2 + 0.1 * C[:, 0]], 1)
 
 
-@pytest.mark.parametrize("n,P,seed,full,added_mass,torque", [(32, 1000, 42, True, False, False), (32, 1000, 42, False, True, True),
-                                                             (24, 3000, 9, True, True, True), (48, 6000, 7, True, False, True)])
-def test_full_support_and_dormant_forces_match_reference(pkg, n, P, seed, full, added_mass, torque):
+@pytest.mark.parametrize("n,P,seed,full,added_mass,torque,cap", [(32, 1000, 42, True, False, False, None), (32, 1000, 42, False, True, True, None),
+                                                                 (24, 3000, 9, True, True, True, None), (48, 6000, 7, True, False, True, None),
+                                                                 (24, 1500, 9, True, True, True, 300)])
+def test_full_support_and_dormant_forces_match_reference(pkg, n, P, seed, full, added_mass, torque, cap, monkeypatch):
     """the full-support Gaussian mode (every cell within the k-d search bound, one warp per particle with
     warp-shuffle reductions) and the forces the reference defines but never calls (addedMassForce F.C:392-413, Gaussian
     torque F.C:467-478) against the UNMODIFIED reference: its own calcInterpWeightGaussian / hydroDragForce /
     archimedesForce / addedMassForce / calcHydroTorque, fed with the full cell sets by the harness.  Cell counts
     bit-exact (the in-range test is evaluated in meshTree::distance's operation order), forces, torques and all four
-    per-cell fields within 1e-10; particles near and outside the walls included."""
+    per-cell fields within 1e-10; particles near and outside the walls included.  cap: the kernels keep a particle's hits
+    in shared memory up to a capacity and recompute beyond it -- FY_RANGE_CAP = 300 sends the interior particles down the
+    recomputing path and the wall particles down the compacted one."""
+    if cap is not None:
+        monkeypatch.setenv("FY_RANGE_CAP", str(cap))
     mo = meshgen.hex_box(n, n, n)
     mp = pkg.box_mesh(n, n, n, faces=False)
     flds = cases.fields_for(mo["C"])

@@ -16,10 +16,12 @@
 // and the x86-64 reference build has no FMA contraction.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 
 #include <mutex>
 #include <set>
 #include <utility>
+#include <type_traits>
 #include <cub/device/device_radix_sort.cuh>
 
 #include "fy_ctx.h"
@@ -54,10 +56,26 @@ __device__ __forceinline__ double dist2(double px, double py, double pz, const F
 // the root, so the root itself never qualifies, MT.C:156,192) and lies within maxDist is an
 // "improvement"; the reference's bounded container ends up holding the nearest (= latest) <= 12 of
 // them in ascending distance.  ring/ringD keep the last 12; nImp counts all of them.
-struct Trail {
+struct Trail {                                  // per-thread local memory (dynamically indexed)
     int id[FY_MAXLIST];
     double d2[FY_MAXLIST];
     int nImp;
+    __device__ __forceinline__ void put(int s, int c, double d) { id[s] = c; d2[s] = d; }
+    __device__ __forceinline__ int getId(int s) const { return id[s]; }
+    __device__ __forceinline__ double getD(int s) const { return d2[s]; }
+    __device__ __forceinline__ void setD(int s, double d) { d2[s] = d; }
+};
+// the same ring in SHARED memory, slot-major ([slot][thread]: conflict-free): 144 bytes per thread that no longer pass
+// through the per-thread local-memory window (which ncu shows being written back to DRAM once per thread).  Measured
+// slower than the local-memory ring (see gaussLocate); not the default.
+struct TrailS {
+    int* id;
+    double* d2;
+    int nImp;
+    __device__ __forceinline__ void put(int s, int c, double d) { id[s * blockDim.x] = c; d2[s * blockDim.x] = d; }
+    __device__ __forceinline__ int getId(int s) const { return id[s * blockDim.x]; }
+    __device__ __forceinline__ double getD(int s) const { return d2[s * blockDim.x]; }
+    __device__ __forceinline__ void setD(int s, double d) { d2[s * blockDim.x] = d; }
 };
 
 // The stack of pending "other" subtrees: 16 bytes per entry (the range [lo, hi) with the depth in the top 5 bits of hi,
@@ -70,8 +88,9 @@ constexpr int KD_STACK = 30;                  // >= tree depth (2^26 nodes: 27 l
 constexpr int KD_BLOCK = 128;
 constexpr int KD_SMEM = 0;
 
+template <class TR>
 __device__ __forceinline__ void kdDescend(const FyKdNode* __restrict__ tree, int nTree, double px, double py,
-                                          double pz, double maxDist, Trail& tr)
+                                          double pz, double maxDist, TR& tr)
 {
     tr.nImp = 0;
     if (nTree <= 0) return;
@@ -90,9 +109,7 @@ __device__ __forceinline__ void kdDescend(const FyKdNode* __restrict__ tree, int
             if (d < best) {                                         // MT.C:192 (and the re-tests at 217, 229)
                 best = d;
                 if (d < maxDist) {                                  // MT.C:195
-                    const int s = tr.nImp % FY_MAXLIST;
-                    tr.id[s] = nd.id;
-                    tr.d2[s] = d;
+                    tr.put(tr.nImp % FY_MAXLIST, nd.id, d);
                     tr.nImp++;
                 }
             }
@@ -140,7 +157,7 @@ __global__ void __launch_bounds__(128) k_locate(const FyKdNode* __restrict__ tre
     kdDescend(tree, nTree, px, py, pz, maxDist, tr);
     const int k = tr.nImp < FY_MAXLIST ? tr.nImp : FY_MAXLIST;
     for (int j = 0; j < FY_MAXLIST; ++j)
-        ids[(size_t)p * FY_MAXLIST + j] = j < k ? tr.id[(tr.nImp - 1 - j) % FY_MAXLIST] : -1;
+        ids[(size_t)p * FY_MAXLIST + j] = j < k ? tr.getId((tr.nImp - 1 - j) % FY_MAXLIST) : -1;
     cnt[p] = k;
 }
 
@@ -171,12 +188,15 @@ struct GaussConst {
     double sigmaPi;        // 1/pow(2 pi sigma^2, 1.5)                    (F.C:72)
 };
 
+template <bool SMEM_TRAIL>
 __global__ void __launch_bounds__(128)
 k_locate_gauss(const FyKdNode* __restrict__ tree, int nTree, const double* __restrict__ pdata, int n,
                const int* __restrict__ perm, GaussConst gc, int serial, int* __restrict__ ids, int* __restrict__ cnt,
                double* __restrict__ wts, int* __restrict__ found, double* __restrict__ pvolAcc,
                double* __restrict__ upAcc, int* __restrict__ stamp)
 {
+    __shared__ int sTrailId[SMEM_TRAIL ? FY_MAXLIST * KD_BLOCK : 1];
+    __shared__ double sTrailD[SMEM_TRAIL ? FY_MAXLIST * KD_BLOCK : 1];
     // thread t works on particle perm[t] (particles sorted by position so that a warp shares tree paths and cells);
     // cell lists / weights are kept in sorted order, structure-of-arrays: ids[j*n + t]
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -184,7 +204,8 @@ k_locate_gauss(const FyKdNode* __restrict__ tree, int nTree, const double* __res
     const int p = perm[t];
     const double* rec = pdata + (size_t)p * 10;
     const double px = rec[0], py = rec[1], pz = rec[2];
-    Trail tr;
+    typename std::conditional<SMEM_TRAIL, TrailS, Trail>::type tr;
+    if constexpr (SMEM_TRAIL) { tr.id = sTrailId + threadIdx.x; tr.d2 = sTrailD + threadIdx.x; }
     kdDescend(tree, nTree, px, py, pz, gc.maxDist, tr);
     const int k = tr.nImp < FY_MAXLIST ? tr.nImp : FY_MAXLIST;
     cnt[t] = k;
@@ -198,8 +219,8 @@ k_locate_gauss(const FyKdNode* __restrict__ tree, int nTree, const double* __res
     double allwt = 0.0;
     for (int j = 0; j < k; ++j) {
         const int s = (tr.nImp - 1 - j) % FY_MAXLIST;
-        const double wj = exp(-tr.d2[s] / gc.twoSigmaSq) * gc.interpRangeCu * gc.sigmaPi;
-        tr.d2[s] = wj;                                               // (the weight takes the distance's place: no second array)
+        const double wj = exp(-tr.getD(s) / gc.twoSigmaSq) * gc.interpRangeCu * gc.sigmaPi;
+        tr.setD(s, wj);                                              // (the weight takes the distance's place: no second array)
         allwt += wj;
     }
     const double vx = rec[3], vy = rec[4], vz = rec[5];
@@ -208,8 +229,8 @@ k_locate_gauss(const FyKdNode* __restrict__ tree, int nTree, const double* __res
     for (int j = 0; j < FY_MAXLIST; ++j) {
         if (j < k) {
             const int s = (tr.nImp - 1 - j) % FY_MAXLIST;
-            const double wj = tr.d2[s] / allwt;                      // F.C:313
-            const int c = tr.id[s];
+            const double wj = tr.getD(s) / allwt;                    // F.C:313
+            const int c = tr.getId(s);
             ids[(size_t)j * n + t] = c;
             wts[(size_t)j * n + t] = wj;
             // F.C:271-272 / 278-279: pVol*weight ; (linearVelocity*weight)*pVol
@@ -400,6 +421,7 @@ struct RangeBox {
     double x0, y0, z0, hx, hy, hz;
     const double* ax;      // centre coordinates: xs[nx] | ys[ny] | zs[nz]
     double R;              // sqrt(maxDist)
+    int cap;               // hits kept in shared memory per particle (<= RANGE_CAP; environment FY_RANGE_CAP, for tests)
 };
 
 __device__ __forceinline__ void rangeSpan(double p, double R, double x0, double h, int n, int& lo, int& cnt)
@@ -421,29 +443,79 @@ __device__ __forceinline__ double warpSum(double v)
 }
 
 struct RangeIter {
-    int lo[3], ni, nj, ncand;
+    int lo[3], ni, nj, nk;
     double px, py, pz;
     __device__ __forceinline__ void init(const RangeBox& b, double x, double y, double z)
     {
         px = x; py = y; pz = z;
-        int nk;
         rangeSpan(x, b.R, b.x0, b.hx, b.nx, lo[0], ni);
         rangeSpan(y, b.R, b.y0, b.hy, b.ny, lo[1], nj);
         rangeSpan(z, b.R, b.z0, b.hz, b.nz, lo[2], nk);
-        ncand = ni * nj * nk;
-    }
-    // candidate q -> cell index and squared distance (meshTree::distance's order, MT.C:54-64)
-    __device__ __forceinline__ int cell(const RangeBox& b, int q, double& d2) const
-    {
-        const int di = q % ni, r = q / ni, dj = r % nj, dk = r / nj;
-        const int i = lo[0] + di, j = lo[1] + dj, k = lo[2] + dk;
-        const double dx = __dsub_rn(b.ax[i], px), dy = __dsub_rn(b.ax[b.nx + j], py), dz = __dsub_rn(b.ax[b.nx + b.ny + k], pz);
-        d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-        return i + b.nx * (j + b.ny * k);
+        if (ni == 0 || nj == 0 || nk == 0) ni = nj = nk = 0;
     }
 };
 
+// One pass over the candidate cells of a particle, by the whole warp: lane l takes the candidate ROWS (j, k) l, l + 32, ...
+// (one integer division per row, not per candidate; the y and z terms of the distance once per row) and all lanes walk
+// i together.  f(hit, cell, d2) is called CONVERGENTLY for every step, so it may contain warp collectives; d2 is
+// ((dx^2 + dy^2) + dz^2) in meshTree::distance's order (MT.C:54-64).  A row whose y/z terms alone reach the bound is
+// skipped: rounding is monotone, so fl(fl(dx^2 + dy^2) + dz^2) >= fl(dy^2 + dz^2) for every dx.
+template <class F>
+__device__ __forceinline__ void rangeScan(const RangeBox& b, const RangeIter& it, double maxDist, F&& f)
+{
+    const int lane = threadIdx.x & 31;
+    const int nrows = it.nj * it.nk;
+    for (int base = 0; base < nrows; base += 32) {
+        const int r = base + lane;
+        const bool valid = r < nrows;
+        const int dk = valid ? r / it.nj : 0, dj = valid ? r - dk * it.nj : 0;
+        const int j = it.lo[1] + dj, k = it.lo[2] + dk;
+        const double dy = __dsub_rn(b.ax[b.nx + j], it.py), dz = __dsub_rn(b.ax[b.nx + b.ny + k], it.pz);
+        const double dysq = __dmul_rn(dy, dy), dzsq = __dmul_rn(dz, dz);
+        const bool rowOk = valid && __dadd_rn(dysq, dzsq) < maxDist;
+        if (!__any_sync(0xffffffffu, rowOk)) continue;
+        const int crow = b.nx * (j + b.ny * k);
+        for (int di = 0; di < it.ni; ++di) {
+            const int i = it.lo[0] + di;
+            const double dx = __dsub_rn(b.ax[i], it.px);
+            const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), dysq), dzsq);
+            f(rowOk && d2 < maxDist, crow + i, d2);
+        }
+    }
+}
+
 constexpr int RANGE_WARPS = 8;
+// The hits of a particle are compacted into shared memory (cell id + unnormalised weight: 12 bytes each) by the scan, so
+// that exp() is evaluated once per hit and pass, and the gather / scatter loops run over a dense list.  A uniform mesh
+// gives <= ~410 hits (range = 4 h); a particle with more (strongly anisotropic cells) takes the recomputing path.
+constexpr int RANGE_CAP = 448;
+
+struct RangeList {
+    int* id;
+    double* w;
+    int count;
+};
+
+// scan + compaction: fills L (up to RANGE_CAP entries), returns the lane-partial sum of the weights of ALL hits
+__device__ __forceinline__ double rangeCollect(const RangeBox& b, const RangeIter& it, const GaussConst& gc, RangeList& L)
+{
+    const int lane = threadIdx.x & 31;
+    double sw = 0.0;
+    int count = 0;
+    rangeScan(b, it, gc.maxDist, [&](bool hit, int c, double d2) {
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (hit) {
+            const double w = exp(-d2 / gc.twoSigmaSq) * gc.interpRangeCu * gc.sigmaPi;      // F.C:308
+            sw += w;
+            const int pos = count + __popc(m & ((1u << lane) - 1u));
+            if (pos < b.cap) { L.id[pos] = c; L.w[pos] = w; }
+        }
+        count += __popc(m);
+    });
+    L.count = count;
+    __syncwarp();
+    return sw;
+}
 
 // pass 1: count + normaliser + per-cell accumulate (locateAllParticles + calcInterpWeightGaussian + buildCellPartList)
 __global__ void __launch_bounds__(RANGE_WARPS * 32)
@@ -451,24 +523,18 @@ k_range_accumulate(RangeBox b, const double* __restrict__ pdata, int n, const in
                    int serial, int* __restrict__ cnt, double* __restrict__ allwtOut, int* __restrict__ found,
                    double* __restrict__ pvolAcc, double* __restrict__ upAcc, int* __restrict__ stamp)
 {
-    const int t = blockIdx.x * RANGE_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    __shared__ int sId[RANGE_WARPS][RANGE_CAP];
+    __shared__ double sW[RANGE_WARPS][RANGE_CAP];
+    const int wq = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * RANGE_WARPS + wq;
     if (t >= n) return;
     const int p = perm[t];
     const double* rec = pdata + (size_t)p * 10;
     RangeIter it;
     it.init(b, rec[0], rec[1], rec[2]);
-    double sw = 0.0;
-    int hits = 0;
-    for (int q = lane; q < it.ncand; q += 32) {
-        double d2;
-        it.cell(b, q, d2);
-        if (d2 < gc.maxDist) {
-            sw += exp(-d2 / gc.twoSigmaSq) * gc.interpRangeCu * gc.sigmaPi;      // F.C:308
-            ++hits;
-        }
-    }
-    sw = warpSum(sw);
-    hits = __reduce_add_sync(0xffffffffu, hits);
+    RangeList L{sId[wq], sW[wq], 0};
+    const double sw = warpSum(rangeCollect(b, it, gc, L));
+    const int hits = L.count;
     if (lane == 0) {
         cnt[t] = hits;
         allwtOut[t] = sw;
@@ -478,16 +544,20 @@ k_range_accumulate(RangeBox b, const double* __restrict__ pdata, int n, const in
     const double vx = rec[3], vy = rec[4], vz = rec[5];
     const double dia = 2 * rec[9];
     const double vol = M_PI * pow(dia, 3.0) / 6.0;
-    for (int q = lane; q < it.ncand; q += 32) {
-        double d2;
-        const int c = it.cell(b, q, d2);
-        if (!(d2 < gc.maxDist)) continue;
-        const double wj = (exp(-d2 / gc.twoSigmaSq) * gc.interpRangeCu * gc.sigmaPi) / sw;   // F.C:313
-        atomicAdd(&pvolAcc[c], vol * wj);
+    auto deposit = [&](int c, double w) {
+        const double wj = w / sw;                                                           // F.C:313
+        atomicAdd(&pvolAcc[c], vol * wj);                                                   // F.C:271-272 / 278-279
         atomicAdd(&upAcc[3 * (size_t)c], vx * wj * vol);
         atomicAdd(&upAcc[3 * (size_t)c + 1], vy * wj * vol);
         atomicAdd(&upAcc[3 * (size_t)c + 2], vz * wj * vol);
         stamp[c] = serial;
+    };
+    if (hits <= b.cap) {
+        for (int q = lane; q < hits; q += 32) deposit(L.id[q], L.w[q]);
+    } else {
+        rangeScan(b, it, gc.maxDist, [&](bool hit, int c, double d2) {
+            if (hit) deposit(c, exp(-d2 / gc.twoSigmaSq) * gc.interpRangeCu * gc.sigmaPi);
+        });
     }
 }
 
@@ -501,7 +571,10 @@ k_range_force(RangeBox b, const double* __restrict__ pdata, int n, const int* __
               const double* __restrict__ vGrad, double* __restrict__ uSourceDrag, double* __restrict__ uSource,
               double* __restrict__ force)
 {
-    const int t = blockIdx.x * RANGE_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    __shared__ int sId[RANGE_WARPS][RANGE_CAP];
+    __shared__ double sW[RANGE_WARPS][RANGE_CAP];
+    const int wq = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * RANGE_WARPS + wq;
     if (t >= n) return;
     const int p = perm[t];
     double* F = force + (size_t)p * 6;
@@ -518,15 +591,15 @@ k_range_force(RangeBox b, const double* __restrict__ pdata, int n, const int* __
     const double twoNu = 2.0 * nu;
     RangeIter it;
     it.init(b, rec[0], rec[1], rec[2]);
+    RangeList L{sId[wq], sW[wq], 0};
+    const bool dense = k <= b.cap;
+    if (dense) rangeCollect(b, it, gc, L);                 // the same hits and the same weights as pass 1, bit for bit
     // gathers: uf[3] alpha_f pv divt[3] pg[3] | ddtUf[3] wfluid[3]
     double g[EXTRA ? 17 : 11];
 #pragma unroll
     for (int m = 0; m < (EXTRA ? 17 : 11); ++m) g[m] = 0.0;
-    for (int q = lane; q < it.ncand; q += 32) {
-        double d2;
-        const int c = it.cell(b, q, d2);
-        if (!(d2 < gc.maxDist)) continue;
-        const double wj = (exp(-d2 / gc.twoSigmaSq) * gc.interpRangeCu * gc.sigmaPi) / sw;
+    auto gather = [&](int c, double w) {
+        const double wj = w / sw;
 #pragma unroll
         for (int m = 0; m < 3; ++m) {
             g[m] += U[3 * (size_t)c + m] * wj;                                            // F.C:360
@@ -545,6 +618,13 @@ k_range_force(RangeBox b, const double* __restrict__ pdata, int n, const int* __
                 g[16] += ((vg[3] - vg[1]) * wj);
             }
         }
+    };
+    if (dense) {
+        for (int q = lane; q < k; q += 32) gather(L.id[q], L.w[q]);
+    } else {
+        rangeScan(b, it, gc.maxDist, [&](bool hit, int c, double d2) {
+            if (hit) gather(c, exp(-d2 / gc.twoSigmaSq) * gc.interpRangeCu * gc.sigmaPi);
+        });
     }
 #pragma unroll
     for (int m = 0; m < (EXTRA ? 17 : 11); ++m) g[m] = warpSum(g[m]);
@@ -579,11 +659,8 @@ k_range_force(RangeBox b, const double* __restrict__ pdata, int n, const int* __
         F[3] = T[0]; F[4] = T[1]; F[5] = T[2];
     }
     const double oorho = 1 / rhoF;
-    for (int q = lane; q < it.ncand; q += 32) {
-        double d2;
-        const int c = it.cell(b, q, d2);
-        if (!(d2 < gc.maxDist)) continue;
-        const double wj = (exp(-d2 / gc.twoSigmaSq) * gc.interpRangeCu * gc.sigmaPi) / sw;
+    auto scatter = [&](int c, double w) {
+        const double wj = w / sw;
         const double mcw = -coeff * wj;
         atomicAdd(&uSourceDrag[c], mcw * oorho);                                           // F.C:385
         const double ooCellVol = 1. / (V[c] * rhoF);
@@ -598,6 +675,13 @@ k_range_force(RangeBox b, const double* __restrict__ pdata, int n, const int* __
         atomicAdd(&uSource[3 * (size_t)c], sx);
         atomicAdd(&uSource[3 * (size_t)c + 1], sy);
         atomicAdd(&uSource[3 * (size_t)c + 2], sz);
+    };
+    if (dense) {
+        for (int q = lane; q < k; q += 32) scatter(L.id[q], L.w[q]);
+    } else {
+        rangeScan(b, it, gc.maxDist, [&](bool hit, int c, double d2) {
+            if (hit) scatter(c, exp(-d2 / gc.twoSigmaSq) * gc.interpRangeCu * gc.sigmaPi);
+        });
     }
 }
 
@@ -775,8 +859,10 @@ int fyUnpermuteLists(fy_ctx* h, int n, int* d_cnt, int* d_ids, double* d_wts)
 namespace {
 RangeBox rangeBoxOf(const fy_ctx* h)
 {
+    int cap = RANGE_CAP;
+    if (const char* e = std::getenv("FY_RANGE_CAP")) cap = std::max(0, std::min(RANGE_CAP, std::atoi(e)));
     return RangeBox{h->boxN[0], h->boxN[1], h->boxN[2], h->boxGeom[0], h->boxGeom[1], h->boxGeom[2], h->boxGeom[3],
-                    h->boxGeom[4], h->boxGeom[5], h->dAxis, std::sqrt(h->maxDist)};
+                    h->boxGeom[4], h->boxGeom[5], h->dAxis, std::sqrt(h->maxDist), cap};
 }
 ForceConst forceConstOf(const fy_ctx* h)
 {
@@ -801,10 +887,18 @@ static int gaussLocate(fy_ctx* h, const double* d_pdata, int n, int* d_found)
     }
     if ((rc = fyReserve(h, h->dIds, (size_t)n * FY_MAXLIST))) return rc;
     if ((rc = fyReserve(h, h->dW, (size_t)n * FY_MAXLIST))) return rc;
-    if ((rc = kdFuncAttrs(h, (const void*)k_locate_gauss))) return rc;
-    k_locate_gauss<<<fyGrid(n, KD_BLOCK), KD_BLOCK, KD_SMEM, h->stream>>>(h->dTree, h->nTree, d_pdata, n, h->dPerm.p, gc, h->procSerial,
-                                                                          h->dIds.p, h->dCnt.p, h->dW.p, d_found, h->dPvol,
-                                                                          h->dUpAcc, h->dStamp);
+    if ((rc = kdFuncAttrs(h, nullptr))) return rc;
+    // the improvement trail in per-thread local memory (default) or in shared memory (FY_LOCATE_SMEM_TRAIL=1: measured SLOWER on
+    // B200, 1.35 against 1.27 ms at C2 and 12.9 against 12.3 ms at 256^3 / 10 M -- profiles/r2o_*; kept as an A/B knob)
+    static const bool smemTrail = [] { const char* e = std::getenv("FY_LOCATE_SMEM_TRAIL"); return e && std::atoi(e) != 0; }();
+    if (smemTrail)
+        k_locate_gauss<true><<<fyGrid(n, KD_BLOCK), KD_BLOCK, KD_SMEM, h->stream>>>(h->dTree, h->nTree, d_pdata, n, h->dPerm.p, gc, h->procSerial,
+                                                                                    h->dIds.p, h->dCnt.p, h->dW.p, d_found, h->dPvol,
+                                                                                    h->dUpAcc, h->dStamp);
+    else
+        k_locate_gauss<false><<<fyGrid(n, KD_BLOCK), KD_BLOCK, KD_SMEM, h->stream>>>(h->dTree, h->nTree, d_pdata, n, h->dPerm.p, gc, h->procSerial,
+                                                                                     h->dIds.p, h->dCnt.p, h->dW.p, d_found, h->dPvol,
+                                                                                     h->dUpAcc, h->dStamp);
     FY_CHECK_LAUNCH();
     return FY_OK;
 }
