@@ -495,6 +495,9 @@ def run_engine(args):
                     "U_rel_l2": cases.rel_l2(E.download("U"), ref_out["U"]), "p_rel_l2": cases.rel_l2(E.download("p"), ref_out["p"]),
                     "force_rel_l2": cases.rel_l2(Fe, ref_out["force"]), "found_equal": bool(np.array_equal(fe, ref_out["found"])),
                     "p_iters_engine": [q["iters"] for q in st["p"]], "p_iters_cpu": ref_out["p_iters"],
+                    # (scale of the comparison: in a closed box under gravity the fluid is almost at rest -- U is the small
+                    # difference HbyA - rAU grad p of terms of size |g| dt, and its relative error is amplified accordingly)
+                    "U_rms": float(np.sqrt(np.mean(ref_out["U"] ** 2))), "g_dt": float(np.linalg.norm(grav) * dt),
                     "against": "oracle/_ref (unmodified FoamYade.C, canonical <=12 lists) + oracle/fv_oracle.cc, one step from the engine's state"}
         if (world == 1 and wl == "C2" and gaussian and fluid and not pimple and not full_support and not args.no_extra):
             line["extra_keys"] = extra_lines(args)
