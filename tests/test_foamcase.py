@@ -192,3 +192,108 @@ def test_unsupported_cases_are_refused_with_the_reason(tmp_path):
         fc.load_case(case_dir)
     open(fs, "w").write(t4)
     fc.load_case(case_dir)
+
+
+# ---- the C++ twin (host/foamCase.H behind the standalone solver binary foamYadeB200) ------------------------------
+BIN = os.path.join(ROOT, "yade-openfoam-coupling_b200", "foamYadeB200")
+
+
+def _fnv(a):
+    h = 1469598103934665603
+    for b in np.ascontiguousarray(a).tobytes():
+        h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return "%016x" % h
+
+
+def _mesh_py():
+    spec = importlib.util.spec_from_file_location("fy_mesh", os.path.join(ROOT, "yade-openfoam-coupling_b200", "mesh.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def _dump(case_dir, *extra):
+    import json
+    import subprocess
+    r = subprocess.run([BIN, "-case", case_dir, "-dump"] + list(extra), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return json.loads(r.stdout)
+
+
+@pytest.mark.skipif(not os.path.exists(BIN), reason="foamYadeB200 not built")
+def test_cpp_case_reader_agrees_with_the_python_one(tmp_path):
+    """host/foamCase.H (C++, what the standalone solver binary uses) and foamcase.py read the same case to the same
+    description, and build the same fy_mesh_desc arrays bit for bit (FNV hashes of the raw bytes) -- for the stock cavity
+    tutorial and for a 3-D inlet / outlet / fixedFluxPressure case with nonuniform fields and the pimple dictionaries."""
+    mesh_py = _mesh_py()
+    code = {"fixedValue": 0, "zeroGradient": 1, "empty": 2, "fixedFluxPressure": 3}
+    cases = [(cavity_case(tmp_path), "icoFoamYade")]
+    # the 3-D case of the test above, written again
+    chan = str(tmp_path / "chan3")
+    n, L, org = (6, 5, 4), (2.0, 1.0, 0.5), (-1.0, 0.25, 3.0)
+    patches = [("inlet", ["xmin"]), ("outlet", ["xmax"]), ("walls", ["ymin", "ymax", "zmin", "zmax"])]
+    fc.write_box_poly_mesh(chan, n, L, org, patches, {"inlet": "patch", "outlet": "patch", "walls": "wall"})
+    rng = np.random.default_rng(3)
+    U, p = rng.standard_normal((120, 3)), rng.standard_normal(120)
+    pl = [dict(name=a, sides=b) for a, b in patches]
+    fc.write_field(chan, "0", "Uc", U, (0, 1, -1, 0, 0, 0, 0), pl,
+                   {"inlet": ("fixedValue", np.array([0.3, 0, 0])), "outlet": ("zeroGradient", None), "walls": ("noSlip", None)}, prec=17)
+    fc.write_field(chan, "0", "p", p, (0, 2, -2, 0, 0, 0, 0), pl,
+                   {"inlet": ("zeroGradient", None), "outlet": ("fixedValue", 0.25), "walls": ("fixedFluxPressure", 0.0)}, prec=17)
+    os.makedirs(os.path.join(chan, "system"))
+    open(os.path.join(chan, "constant", "transportProperties"), "w").write(
+        "FoamFile{version 2.0;format ascii;class dictionary;object transportProperties;}\n"
+        "partDensity partDensity [1 -3 0 0 0 0 0] 2400;\nrhocValue rhocValue [1 -3 0 0 0 0 0] 998;\nnuValue nuValue [0 2 -1 0 0 0 0] 1e-06;\n")
+    open(os.path.join(chan, "constant", "g"), "w").write(
+        "FoamFile{version 2.0;format ascii;class uniformDimensionedVectorField;object g;}\ndimensions [0 1 -2 0 0 0 0];\nvalue (0 0 -9.81);\n")
+    open(os.path.join(chan, "system", "controlDict"), "w").write(
+        "FoamFile{version 2.0;format ascii;class dictionary;object controlDict;}\napplication pimpleFoamYade;\nstartTime 0;\nendTime 1;\n"
+        "deltaT 1e-3;\nwriteControl timeStep;\nwriteInterval 100;\nwritePrecision 12;\n")
+    open(os.path.join(chan, "system", "fvSolution"), "w").write(
+        "FoamFile{version 2.0;format ascii;class dictionary;object fvSolution;}\n"
+        "solvers { p { solver PCG; preconditioner diagonal; tolerance 1e-7; relTol 0.01; } pFinal { $p; relTol 0; }\n"
+        '          "(Uc|k)" { solver smoothSolver; smoother symGaussSeidel; tolerance 1e-6; relTol 0.1; } }\n'
+        "PIMPLE { nOuterCorrectors 3; nCorrectors 2; momentumPredictor no; nNonOrthogonalCorrectors 1; pRefCell 7; pRefValue 1.5; }\n"
+        'relaxationFactors { equations { "Uc.*" 0.7; UcFinal 1; } fields { p 0.3; pFinal 1; } }\n')
+    cases.append((chan, "pimpleFoamYade"))
+    for case_dir, solver in cases:
+        py = fc.load_case(case_dir, solver=solver)
+        cc = _dump(case_dir, "-solver", solver)
+        assert tuple(cc["n"]) == py["box"]["n"] and cc["Uname"] == py["Uname"]
+        np.testing.assert_allclose(cc["origin"], py["box"]["origin"], rtol=0, atol=0)
+        np.testing.assert_allclose(cc["L"], py["box"]["L"], rtol=0, atol=0)
+        assert cc["nu"] == py["nu"] and tuple(cc["g"]) == tuple(py["g"])
+        assert cc["deltaT"] == py["control"]["deltaT"] and cc["endTime"] == py["control"]["endTime"]
+        assert cc["writeInterval"] == py["control"]["writeInterval"] and cc["writePrecision"] == py["control"]["writePrecision"]
+        pre = {"DIC": 0, "diagonal": 1, "none": 2}
+        for k, v in py["piso"].items():
+            assert cc["piso"][k] == (pre[v] if k == "preconditioner" else v), k
+        assert cc["pimple"] == py["pimple"]
+        assert len(cc["patches"]) == len(py["patches"])
+        for a, b in zip(cc["patches"], py["patches"]):
+            assert (a["name"], a["type"], a["sides"], a["start"], a["nFaces"]) == (b["name"], b["type"], b["sides"], b["start"], b["nFaces"])
+            assert (a["bcU"], a["bcP"]) == (code[b["bcU"]], code[b["bcP"]]) and tuple(a["valueU"]) == b["valueU"] and a["valueP"] == b["valueP"]
+        if solver == "pimpleFoamYade":
+            assert cc["rhoP"] == 2400.0 and cc["rhoF"] == 998.0
+        m = fc.build_mesh(py, mesh_py.box_mesh, mesh_py.set_bc, mesh_py)
+        hs = cc["hash"]
+        assert hs["U"] == _fnv(py["U"]) and hs["p"] == _fnv(py["p"])
+        for k in ("C", "V", "owner", "neighbour", "Sf", "magSf", "deltaCoeffs"):
+            assert hs[k] == _fnv(m[k]), k
+        for q, pt in enumerate(m["patches"]):
+            assert hs["faceCells%d" % q] == _fnv(pt["faceCells"]) and hs["bSf%d" % q] == _fnv(pt["Sf"])
+            assert hs["bDeltaCoeffs%d" % q] == _fnv(pt["deltaCoeffs"])
+    # the writer: the fields as read, written as a time directory by the C++ side, read back by the Python side
+    import subprocess
+    r = subprocess.run([BIN, "-case", chan, "-solver", "pimpleFoamYade", "-writeNow", "0.25"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    back = fc.load_case(chan, time="0.25", solver="pimpleFoamYade")
+    assert np.abs(back["U"] - U).max() <= 1e-11 * np.abs(U).max() and np.abs(back["p"] - p).max() <= 1e-11 * np.abs(p).max()
+    assert [(q["name"], q["bcU"], q["valueU"], q["bcP"], q["valueP"]) for q in back["patches"]] == \
+           [(q["name"], q["bcU"], q["valueU"], q["bcP"], q["valueP"]) for q in fc.load_case(chan, solver="pimpleFoamYade")["patches"]]
+    # refusals carry the reason
+    u = os.path.join(cases[0][0], "0", "U")
+    t3 = open(u).read()
+    open(u, "w").write(t3.replace("type            noSlip;", "type            slip;"))
+    r = subprocess.run([BIN, "-case", cases[0][0], "-dump"], capture_output=True, text=True)
+    assert r.returncode == 3 and "slip" in r.stderr
