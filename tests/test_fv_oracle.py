@@ -511,3 +511,42 @@ def test_pimple_UcEqn_matrix_with_boundary_cells():
                 - O.laplacian_gamma_vector(alpha * nu, W, gammaB=nu) - divDev - drag[:, None] * W)
     got = AW - rhs
     assert np.abs(got - want).max() <= 1e-10 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("solver", ["ico", "pimple"])
+def test_restatements_reproduce_plane_poiseuille_flow_at_second_order(solver):
+    """A pin that does not pass through OpenFOAM at all: the developed flow between two plates has the closed form
+    u(y) = 6 Um y (1 - y/H)/H, dp/dx = -12 nu Um / H^2.  Both restatements (icoFoamYade's PISO step; pimpleFoamYade's with
+    alphac = 1 and no particle sources, whose pressure-gradient form and face fluxes are assembled differently) march a
+    uniform inlet flow to the steady state on two grids: profile and pressure gradient converge to the analytic values
+    at second order (errors 1.4e-2 -> 3.7e-3 and 2 % -> 0.5 %)."""
+    nu, L, H = 0.1, 3.0, 1.0
+    errs = []
+    for nx, ny in ((30, 10), (60, 20)):
+        m = meshgen.hex_box_ldu(nx, ny, 1, L, H, 0.1, patches=[("inlet", ["xmin"]), ("outlet", ["xmax"]), ("walls", ["ymin", "ymax"]),
+                                                                 ("frontAndBack", ["zmin", "zmax"])])
+        meshgen.set_bc(m, "inlet", bcU=meshgen.BC_FIXED_VALUE, valueU=(1, 0, 0), bcP=meshgen.BC_ZERO_GRADIENT)
+        meshgen.set_bc(m, "outlet", bcU=meshgen.BC_ZERO_GRADIENT, bcP=meshgen.BC_FIXED_VALUE, valueP=0.0)
+        meshgen.set_bc(m, "frontAndBack", bcU=meshgen.BC_EMPTY, bcP=meshgen.BC_EMPTY)
+        O = port.IcoOracle(m, nu=nu)
+        O.field("U")[:] = [1.0, 0.0, 0.0]
+        O.create_phi()
+        h = L / nx
+        dt = 0.2 * h / 1.5
+        one, zero = np.ones(m["nCells"]), np.zeros(m["nCells"])
+        for it in range(int(3.0 / dt)):
+            if solver == "ico":
+                O.pre(dt)
+                O.solve(dt)
+            else:
+                O.pimple_solve(dt, one, zero)
+        U, p = O.field("U").reshape(ny, nx, 3), O.field("p").reshape(ny, nx)
+        y = (np.arange(ny) + 0.5) * H / ny
+        e_prof = np.abs(U[:, -2, 0] - 6 * y * (1 - y)).max()
+        dpdx = (p[:, -3].mean() - p[:, -8].mean()) / (5 * h)
+        errs.append((e_prof, abs(dpdx + 12 * nu) / (12 * nu)))
+        assert np.abs(U[:, -2, 1]).max() < 2e-3 and not np.any(U[:, :, 2])
+        O.close()
+    (e0, g0), (e1, g1) = errs
+    assert e0 < 2e-2 and e1 < 5e-3 and e1 < 0.35 * e0, errs
+    assert g0 < 3e-2 and g1 < 8e-3 and g1 < 0.4 * g0, errs
