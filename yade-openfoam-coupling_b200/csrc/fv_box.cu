@@ -1708,7 +1708,7 @@ void fvDestroy(fy_ctx* h)
     FvState* s = h->fv;
     if (!s) return;
     void* ptrs[] = {s->dSlotOfFace, s->phi, s->phi0, s->phiHbyA, s->U0, s->HbyA, s->rAU, s->gradP, s->diagU, s->loU, s->upU,
-                    s->srcU, s->dgU, s->bU, s->psiU, s->upP, s->dgP, s->bP, s->stage, s->phicForces, s->divDev, s->bGradP,
+                    s->srcU, s->dgU, s->bU, s->psiU, s->upP, s->dgP, s->bP, s->stage, s->phicForces, s->divDev, s->bGradP, s->pPrev,
                     s->red.partial, s->red.ticket, s->dSolve, s->dStep};
     for (void* p : ptrs) if (p) cudaFree(p);
     penDestroy(s);
