@@ -50,7 +50,39 @@ def one(name, n, P, seed, gaussian, moving, n_yade=1, unmodified=False):
     print(name, "found", int((out["found"] == 1).sum()), "/", P, "touched cells", touched.size)
 
 
+def ddtU_of(C):
+    return np.stack([0.4 * np.sin(2.0 * C[:, 2]), -0.3 * np.cos(3.0 * C[:, 1]), 0.2 + 0.1 * C[:, 0]], 1)
+
+
+def one_f3(name, n, P, seed, full, added_mass, torque):
+    """full-support cell sets fed to the reference's own weight / force functions, addedMassForce
+    (FoamYade.C:392-413) and the Gaussian torque (FoamYade.C:467-478) -- oracle/ref_harness.cpp ref_set_gaussian_options"""
+    mo = meshgen.hex_box(n, n, n)
+    flds = cases.fields_for(mo["C"])
+    flds["ddtU"] = ddtU_of(mo["C"])
+    pd = cases.particles(P, seed, radius=0.1 / n, moving=True)
+    pd[:, 0:3] = 0.05 + 0.9 * pd[:, 0:3]
+    R = ref.RefFoamYade(mo, True)
+    R.set_properties(cases.RHOP, cases.RHOF, cases.NU)
+    R.set_gaussian_options(full, added_mass, torque)
+    for k in ("U", "gradP", "divT", "vGrad", "ddtU"):
+        R.field(k)[:] = flds[k].reshape(R.field(k).shape)
+    found, force = R.step(1e-3, pd, yade_dt=5e-4, pieces=True, truncate12=True, dense=True)
+    cnt, _ = R.lists(P)
+    save = dict(n=n, P=P, seed=seed, full=int(full), added_mass=int(added_mass), torque=int(torque), found=found.astype(np.int8),
+                force=force.copy(), cnt=cnt.astype(np.int16), uSource=R.field("uSource").copy(), uSourceDrag=R.field("uSourceDrag").copy(),
+                alpha=R.field("alpha").copy(), uParticle=R.field("uParticle").copy())
+    R.close()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **save)
+    print(name, "found", int((found == 1).sum()), "/", P, "cells per particle", cnt.min(), "...", cnt.max())
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "f3":           # only the fixtures added in round 2 (the others stay byte-identical)
+        one_f3("n16_gauss_full_support", 16, 300, 21, True, False, False)
+        one_f3("n16_gauss_full_support_dormant", 16, 300, 21, True, True, True)
+        one_f3("n16_gauss_trail_dormant", 16, 300, 21, False, True, True)
+        sys.exit(0)
     one("c1_gauss_static", 32, 1000, 42, True, False, unmodified=True)
     one("c1_gauss_moving", 32, 1000, 42, True, True)
     one("c1_point_moving", 32, 1000, 42, False, True)

@@ -267,6 +267,31 @@ def test_full_support_and_dormant_forces_match_reference(pkg, n, P, seed, full, 
     E.close()
 
 
+@pytest.mark.parametrize("name", ["n16_gauss_full_support", "n16_gauss_full_support_dormant", "n16_gauss_trail_dormant"])
+def test_engine_matches_f3_fixture(pkg, name):
+    """the committed vectors of the full-support mode and of the dormant forces (tests/golden/gen_golden.py f3: the
+    reference's own functions) against the kernels: counts and found flags exact, forces / torques / fields 1e-10"""
+    from tests.golden.gen_golden import ddtU_of
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    n, P = int(g["n"]), int(g["P"])
+    mp = pkg.box_mesh(n, n, n, faces=False)
+    flds = cases.fields_for(mp["C"])
+    flds["ddtU"] = ddtU_of(mp["C"])
+    pd = cases.particles(P, int(g["seed"]), radius=0.1 / n, moving=True)
+    pd[:, 0:3] = 0.05 + 0.9 * pd[:, 0:3]
+    E = pkg.Engine(mp)
+    E.set_properties(cases.RHOP, cases.RHOF, cases.NU, True)
+    E.set_gaussian_options(bool(g["full"]), bool(g["added_mass"]), bool(g["torque"]))
+    for k in ("U", "gradP", "divT", "vGrad", "ddtU"):
+        E.upload(k, flds[k])
+    found, force = E.set_particle_action(1e-3, pd)
+    assert np.array_equal(found, g["found"]) and np.array_equal(E.last_counts(P), g["cnt"])
+    assert cases.rel_l2(force, g["force"]) <= TOL
+    for k in ("uSource", "uSourceDrag", "alpha", "uParticle"):
+        assert cases.rel_l2(E.download(k), g[k].reshape(E.download(k).shape)) <= TOL, k
+    E.close()
+
+
 def test_empty_and_all_outside(pkg):
     mp = pkg.box_mesh(8, 8, 8, faces=False)
     E = pkg.Engine(mp)

@@ -222,3 +222,31 @@ def test_full_support_lists_and_dormant_forces_of_the_harness():
     cf = out[True]["cnt"]
     assert cf.min() >= 340 and cf.max() <= 410 and abs(cf.mean() - 374.6) < 6                       # (a)
     assert np.all(out[False]["cnt"] <= 12)
+
+
+@pytest.mark.parametrize("name", ["n16_gauss_full_support", "n16_gauss_full_support_dormant", "n16_gauss_trail_dormant"])
+def test_f3_fixtures_are_reproduced_by_the_reference_harness(name):
+    """tests/golden/gen_golden.py f3: the committed full-support / dormant-force vectors are what the reference's own
+    functions give today, bit for bit (they travel to the GPU box, /root/reference does not)."""
+    import os
+    from oracle import meshgen, ref
+    from tests import cases
+    from tests.golden.gen_golden import ddtU_of
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    n, P = int(g["n"]), int(g["P"])
+    mo = meshgen.hex_box(n, n, n)
+    flds = cases.fields_for(mo["C"])
+    flds["ddtU"] = ddtU_of(mo["C"])
+    pd = cases.particles(P, int(g["seed"]), radius=0.1 / n, moving=True)
+    pd[:, 0:3] = 0.05 + 0.9 * pd[:, 0:3]
+    R = ref.RefFoamYade(mo, True)
+    R.set_properties(cases.RHOP, cases.RHOF, cases.NU)
+    R.set_gaussian_options(bool(g["full"]), bool(g["added_mass"]), bool(g["torque"]))
+    for k in ("U", "gradP", "divT", "vGrad", "ddtU"):
+        R.field(k)[:] = flds[k].reshape(R.field(k).shape)
+    found, force = R.step(1e-3, pd, yade_dt=5e-4, pieces=True, truncate12=True, dense=True)
+    cnt, _ = R.lists(P)
+    assert np.array_equal(found, g["found"]) and np.array_equal(cnt, g["cnt"]) and np.array_equal(force, g["force"])
+    for k in ("uSource", "uSourceDrag", "alpha", "uParticle"):
+        assert np.array_equal(R.field(k), g[k].reshape(R.field(k).shape)), k
+    R.close()
