@@ -298,6 +298,9 @@ struct Pen2Warp {              // per-warp constants of one sweep
     unsigned long long* tsec;  // PEN2_TIMING build: cycles per section of a step, summed over the sweep [5]
 };
 
+#ifndef PEN2_YPREFETCH
+#define PEN2_YPREFETCH 0
+#endif
 constexpr int P2_YRING = 64;                  // y ring depth (steps) per plane
 constexpr int P2_YG = 8;                      // steps per y group (one mbarrier phase)
 
@@ -340,6 +343,17 @@ __device__ __forceinline__ void pen2Block(const Op& op, const Pen2Warp& w, int t
 #pragma unroll
     for (int z = 0; z < Z; ++z) cp[z] = op.chain + (w.pos00 + (REV ? -32 : 32) * (t0 - z) + z * ((REV ? -32 : 32) + w.zoff));
     if (YIN && (t0 & (P2_YG - 1)) == 0) mbarWait(w.yFullS + ((t0 >> 3) & 7) * 8, (uint32_t)((t0 >> 6) & 1), fail);
+#if PEN2_YPREFETCH
+    // the block's R slots of the y ring belong to a group whose barrier has completed (groups are 8 steps, blocks R = 4 steps
+    // and aligned): read them all here, off the per-step critical path
+    double yvB[R][Z];
+    if (YIN) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int z = 0; z < Z; ++z) yvB[r][z] = ldSharedV(w.yInS + (uint32_t)((t0 + r) & (P2_YRING - 1)) * 8 + z * (P2_YRING * 8));
+    }
+#endif
 #ifdef PEN2_TIMING
     unsigned long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
 #endif
@@ -382,9 +396,14 @@ __device__ __forceinline__ void pen2Block(const Op& op, const Pen2Warp& w, int t
         // receiving a row and passing its own on.
         double yv[Z];
         if (YIN) {
+#if PEN2_YPREFETCH
+#pragma unroll
+            for (int z = 0; z < Z; ++z) yv[z] = yvB[r][z];
+#else
             const uint32_t ya = w.yInS + (uint32_t)(t & (P2_YRING - 1)) * 8;       // plane z's row t - z sits in slot t of its ring
 #pragma unroll
             for (int z = 0; z < Z; ++z) yv[z] = ldSharedV(ya + z * (P2_YRING * 8));
+#endif
         }
         double res[Z], side[Z], vyA[Z];
 #pragma unroll
