@@ -14,6 +14,7 @@ from tests.test_fv_oracle import CAVITY_LOG, sig6
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
+BIN_PATH = os.path.join(ROOT, "yade-openfoam-coupling_b200", "foamYadeB200")
 
 
 def _foamcase():
@@ -191,6 +192,22 @@ def test_unsupported_cases_are_refused_with_the_reason(tmp_path):
     with pytest.raises(fc.FoamCaseError, match="GAMG"):
         fc.load_case(case_dir)
     open(fs, "w").write(t4)
+    # a discretisation scheme the kernels do not implement
+    sch = os.path.join(case_dir, "system", "fvSchemes")
+    t5 = open(sch).read()
+    open(sch, "w").write(t5.replace("div(phi,U)      Gauss linear;", "div(phi,U)      Gauss upwind;"))
+    with pytest.raises(fc.FoamCaseError, match="upwind"):
+        fc.load_case(case_dir)
+    if os.path.exists(BIN_PATH):
+        import subprocess
+        r = subprocess.run([BIN_PATH, "-case", case_dir, "-dump"], capture_output=True, text=True)
+        assert r.returncode == 3 and "upwind" in r.stderr
+    open(sch, "w").write(t5.replace("default         Euler;", "default         backward;"))
+    with pytest.raises(fc.FoamCaseError, match="backward"):
+        fc.load_case(case_dir)
+    open(sch, "w").write(t5.replace("default         orthogonal;", "default         corrected;"))
+    fc.load_case(case_dir)                                # (the same scheme on an orthogonal box)
+    open(sch, "w").write(t5)
     fc.load_case(case_dir)
 
 

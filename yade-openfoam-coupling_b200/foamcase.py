@@ -33,7 +33,40 @@ class FoamCaseError(ValueError):
 # ---------------------------------------------------------------------------------------------------------------
 # dictionary syntax
 # ---------------------------------------------------------------------------------------------------------------
-_TOKEN = re.compile(r'"(?:[^"\\]|\\.)*"|[{}()\[\];]|[^\s{}()\[\];"]+')
+_PUNCT = "{}()[];"
+
+
+def _tokenize(t):
+    """words, numbers, strings and the punctuation { } ( ) [ ] ;  -- a WORD (it starts with a letter, `_`, `$` or `.`) keeps
+    balanced parentheses that follow it without white space, as OpenFOAM's keywords do: div(phi,U), grad(p)"""
+    toks, i, n = [], 0, len(t)
+    while i < n:
+        c = t[i]
+        if c.isspace():
+            i += 1
+        elif c == '"':
+            j = i + 1
+            while j < n and t[j] != '"':
+                j += 2 if t[j] == "\\" else 1
+            toks.append(t[i:j + 1])
+            i = j + 1
+        elif c in _PUNCT:
+            toks.append(c)
+            i += 1
+        else:
+            j, depth, wordy = i, 0, (c.isalpha() or c in "_$.")
+            while j < n:
+                ch = t[j]
+                if ch == "(" and wordy and j > i:
+                    depth += 1
+                elif ch == ")" and depth > 0:
+                    depth -= 1
+                elif depth == 0 and (ch.isspace() or ch in _PUNCT or ch == '"'):
+                    break
+                j += 1
+            toks.append(t[i:j])
+            i = j
+    return toks
 
 
 def _strip_comments(text):
@@ -126,7 +159,7 @@ def _parse_dict_tokens(toks, pos, parents=()):
 def parse_dict(text):
     """An OpenFOAM dictionary file (FoamFile header included) as nested dicts.  `key v1 v2 ...;` keeps a list of values,
     a dimensioned entry `nu [0 2 -1 0 0 0 0] 0.01;` becomes [('dimensions', (...)), 0.01]."""
-    toks = _TOKEN.findall(_strip_comments(text))
+    toks = _tokenize(_strip_comments(text))
     d, pos = _parse_dict_tokens(toks, 0)
     if pos != len(toks):
         raise FoamCaseError("unbalanced braces")
@@ -381,9 +414,49 @@ def _solver_entry(sol, name, path):
     return e
 
 
+def _words(entry):
+    vals = entry if isinstance(entry, list) and not isinstance(entry, FoamList) else [entry]
+    return [str(v) for v in vals]
+
+
+def check_schemes(case_dir):
+    """system/fvSchemes must ask for what the kernels implement (the stock cavity set): Euler ddt; Gauss linear gradients,
+    divergences and laplacians; linear interpolation; the surface-normal gradient and the laplacian's may be orthogonal,
+    uncorrected or corrected (the same thing on the orthogonal boxes this path supports).  A missing file is accepted
+    (the standalone engine has no other schemes to choose from); anything else is refused with the entry named."""
+    path = os.path.join(case_dir, "system", "fvSchemes")
+    if not os.path.exists(path):
+        return
+    d = read_dict(path)
+    ng = ("orthogonal", "uncorrected", "corrected")
+
+    def ok(section, key, words):
+        if section == "ddtSchemes":
+            return words == ["Euler"]
+        if section == "gradSchemes":
+            return words == ["Gauss", "linear"]
+        if section == "divSchemes":
+            return words == ["none"] or words == ["Gauss", "linear"]
+        if section == "laplacianSchemes":
+            return words[:2] == ["Gauss", "linear"] and len(words) == 3 and words[2] in ng
+        if section == "interpolationSchemes":
+            return words == ["linear"]
+        if section == "snGradSchemes":
+            return len(words) == 1 and words[0] in ng
+        return True
+    for section, entries in d.items():
+        if section == "FoamFile" or not isinstance(entries, dict):
+            continue
+        for key, val in entries.items():
+            w = _words(val)
+            if not ok(section, key, w):
+                raise FoamCaseError("%s: %s { %s %s; } is not implemented (Euler; Gauss linear; linear; orthogonal)" % (path, section, key, " ".join(w)))
+
+
 def load_case(case_dir, time="0", solver="icoFoamYade"):
     """Everything the engine needs from a case directory.  solver: 'icoFoamYade' (fields U, p; transportProperties nu; PISO
     dictionary) or 'pimpleFoamYade' (fields Uc | U, p; nuValue / rhocValue / partDensity; PIMPLE dictionary; constant/g)."""
+    check_schemes(case_dir)
     box = detect_hex_box(read_poly_mesh(case_dir))
     nx, ny, nz = box["n"]
     N = nx * ny * nz
