@@ -36,6 +36,47 @@ def cavity_case(tmp_path, n=(20, 20, 1)):
     return case
 
 
+def test_tutorial_directory_before_blockMesh_has_been_run(tmp_path):
+    """the stock cavity directory as OpenFOAM ships it -- system/blockMeshDict, no constant/polyMesh -- reads to the same
+    case as after `blockMesh` (here: after write_box_poly_mesh), up to the numbering of the boundary faces inside a patch"""
+    with_pm = fc.load_case(cavity_case(tmp_path))
+    bare = str(tmp_path / "bare")
+    shutil.copytree(os.path.join(HERE, "cases_foam", "cavity"), bare)
+    assert not os.path.exists(os.path.join(bare, "constant", "polyMesh"))
+    c = fc.load_case(bare)
+    assert c["box"]["n"] == with_pm["box"]["n"] == (20, 20, 1)
+    np.testing.assert_allclose(c["box"]["L"], with_pm["box"]["L"], rtol=1e-15)
+    np.testing.assert_allclose(c["box"]["origin"], with_pm["box"]["origin"], rtol=0, atol=1e-18)
+    key = lambda q: (q["name"], q["type"], sorted(q["sides"]), q["start"], q["nFaces"], q["bcU"], q["valueU"], q["bcP"], q["valueP"])   # noqa: E731
+    assert [key(q) for q in c["patches"]] == [key(q) for q in with_pm["patches"]]
+    assert c["piso"] == with_pm["piso"] and c["nu"] == with_pm["nu"]
+    m = fc.build_mesh(c, meshgen.hex_box_ldu, meshgen.set_bc, meshgen)
+    ref = meshgen.hex_box_ldu(20, 20, 1, 0.1, 0.1, 0.01, patches=CAVITY_PATCHES)
+    assert np.array_equal(m["owner"], ref["owner"]) and np.array_equal(m["V"], ref["V"])
+    # time directories can be written without a polyMesh on disk
+    tname = fc.write_time(c, 0.005, np.zeros((400, 3)), np.arange(400.0))
+    assert np.array_equal(fc.load_case(bare, time=tname)["p"], np.arange(400.0))
+    # refusals
+    bmd = os.path.join(bare, "system", "blockMeshDict")
+    txt = open(bmd).read()
+    open(bmd, "w").write(txt.replace("simpleGrading (1 1 1)", "simpleGrading (2 1 1)"))
+    with pytest.raises(fc.FoamCaseError, match="graded"):
+        fc.load_case(bare)
+    open(bmd, "w").write(txt.replace("            (4 5 6 7)\n", ""))
+    with pytest.raises(fc.FoamCaseError, match="without a patch"):
+        fc.load_case(bare)
+    open(bmd, "w").write(txt)
+    if os.path.exists(BIN_PATH):
+        import json
+        import subprocess
+        r = subprocess.run([BIN_PATH, "-case", bare, "-dump"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        cc = json.loads(r.stdout)
+        assert tuple(cc["n"]) == (20, 20, 1) and [q["sides"] for q in cc["patches"]] == [q["sides"] for q in c["patches"]]
+        assert [(q["start"], q["nFaces"]) for q in cc["patches"]] == [(q["start"], q["nFaces"]) for q in c["patches"]]
+        np.testing.assert_allclose(cc["L"], c["box"]["L"], rtol=1e-15)
+
+
 def test_dictionary_syntax():
     d = fc.parse_dict('''
         FoamFile { version 2.0; format ascii; class dictionary; }   // header
@@ -308,6 +349,34 @@ def test_cpp_case_reader_agrees_with_the_python_one(tmp_path):
     assert np.abs(back["U"] - U).max() <= 1e-11 * np.abs(U).max() and np.abs(back["p"] - p).max() <= 1e-11 * np.abs(p).max()
     assert [(q["name"], q["bcU"], q["valueU"], q["bcP"], q["valueP"]) for q in back["patches"]] == \
            [(q["name"], q["bcU"], q["valueU"], q["bcP"], q["valueP"]) for q in fc.load_case(chan, solver="pimpleFoamYade")["patches"]]
+    # the same case with only a blockMeshDict on disk: same description; the fixedFluxPressure patch values the C++ writer
+    # derives from the box equal the ones the Python writer derives
+    import shutil as _sh
+    _sh.rmtree(os.path.join(chan, "constant", "polyMesh"))
+    _sh.rmtree(os.path.join(chan, "0.25"))
+    open(os.path.join(chan, "system", "blockMeshDict"), "w").write(
+        "FoamFile{version 2.0;format ascii;class dictionary;object blockMeshDict;}\nconvertToMeters 0.5;\n"
+        "vertices ((-2 0.5 6) (2 0.5 6) (2 2.5 6) (-2 2.5 6) (-2 0.5 7) (2 0.5 7) (2 2.5 7) (-2 2.5 7));\n"
+        "blocks (hex (0 1 2 3 4 5 6 7) (6 5 4) simpleGrading (1 1 1));\nedges ();\n"
+        "boundary (inlet {type patch; faces ((0 4 7 3));} outlet {type patch; faces ((1 2 6 5));}\n"
+        "          walls {type wall; faces ((0 1 5 4) (3 7 6 2) (0 3 2 1) (4 5 6 7));});\n")
+    py2 = fc.load_case(chan, solver="pimpleFoamYade")
+    cc2 = _dump(chan, "-solver", "pimpleFoamYade")
+    assert py2["box"]["n"] == (6, 5, 4) and tuple(cc2["n"]) == (6, 5, 4)
+    np.testing.assert_allclose(py2["box"]["origin"], org, rtol=0, atol=1e-15)
+    np.testing.assert_allclose(cc2["origin"], org, rtol=0, atol=1e-15)
+    assert [q["sides"] for q in cc2["patches"]] == [q["sides"] for q in py2["patches"]] == [["xmin"], ["xmax"], ["ymin", "ymax", "zmin", "zmax"]]
+    assert [(q["start"], q["nFaces"]) for q in cc2["patches"]] == [(q["start"], q["nFaces"]) for q in py2["patches"]]
+    r = subprocess.run([BIN, "-case", chan, "-solver", "pimpleFoamYade", "-writeNow", "0.25"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    d_cpp = fc.read_dict(os.path.join(chan, "0.25", "p"))
+    os.rename(os.path.join(chan, "0.25"), os.path.join(chan, "0.25_cpp"))
+    py2["control"]["writePrecision"] = 12
+    fc.write_time(py2, 0.25, py2["U"], py2["p"])
+    d_py = fc.read_dict(os.path.join(chan, "0.25", "p"))
+    w_cpp = [float(x) for x in d_cpp["boundaryField"]["walls"]["value"][-1]]
+    w_py = [float(x) for x in d_py["boundaryField"]["walls"]["value"][-1]]
+    assert len(w_cpp) == 2 * 6 * 4 + 2 * 6 * 5 and w_cpp == w_py
     # refusals carry the reason
     u = os.path.join(cases[0][0], "0", "U")
     t3 = open(u).read()

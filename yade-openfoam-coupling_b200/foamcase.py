@@ -318,6 +318,80 @@ def detect_hex_box(pm, rtol=1e-9):
     return dict(n=(nx, ny, nz), origin=tuple(lo), L=tuple(L), patches=patches)
 
 
+def read_block_mesh_dict(case_dir):
+    """The box straight from system/blockMeshDict (what a tutorial directory holds BEFORE `blockMesh` has been run): one `hex`
+    block with axis-aligned edges (local x1, x2, x3 = global x, y, z, so that blockMesh's cell order is x fastest),
+    uniform grading, every block face listed in a boundary patch.  Returns what detect_hex_box returns; boundary faces are
+    numbered patch by patch after the internal faces, side by side, by increasing owner cell (this module's own order --
+    blockMesh's order inside a patch differs, which no patch type supported here can see)."""
+    path = os.path.join(case_dir, "system", "blockMeshDict")
+    if not os.path.exists(path):
+        path = os.path.join(case_dir, "constant", "polyMesh", "blockMeshDict")
+    if not os.path.exists(path):
+        raise FoamCaseError("%s: neither constant/polyMesh nor a blockMeshDict" % case_dir)
+    d = read_dict(path)
+    scale = float(d.get("convertToMeters", d.get("scale", 1.0)))
+    try:
+        verts = np.array([[float(x) for x in v] for v in d["vertices"]], dtype=np.float64) * scale
+        blocks = d["blocks"]
+    except (KeyError, TypeError, ValueError):
+        raise FoamCaseError("%s: vertices / blocks missing or malformed" % path)
+    if sum(1 for b in blocks if b == "hex") != 1 or len(blocks) < 3:
+        raise FoamCaseError("%s: exactly one hex block is supported" % path)
+    k = list(blocks).index("hex")
+    hexv, ncell = [int(x) for x in blocks[k + 1]], [int(x) for x in blocks[k + 2]]
+    grading = [g for g in blocks[k + 3:] if isinstance(g, FoamList)]
+    if len(hexv) != 8 or len(ncell) != 3:
+        raise FoamCaseError("%s: hex block needs 8 vertices and 3 cell counts" % path)
+    if grading and any(float(x) != 1.0 for x in grading[0]):
+        raise FoamCaseError("%s: graded blocks are not supported (uniform cells only)" % path)
+    v = verts[hexv]
+    lo, hi = v.min(0), v.max(0)
+    want = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], dtype=np.float64)
+    if np.abs(v - (lo + want * (hi - lo))).max() > 1e-12 * np.abs(hi - lo).max():
+        raise FoamCaseError("%s: the block is not an axis-aligned box with local axes x1 x2 x3 = x y z" % path)
+    nx, ny, nz = ncell
+    size = {"xmin": ny * nz, "xmax": ny * nz, "ymin": nx * nz, "ymax": nx * nz, "zmin": nx * ny, "zmax": nx * ny}
+    bnd = d.get("boundary")
+    if not isinstance(bnd, FoamList):
+        raise FoamCaseError("%s: no boundary list" % path)
+    patches, covered = [], {}
+    start = 3 * nx * ny * nz - nx * ny - ny * nz - nx * nz
+    it = iter(bnd)
+    for name in it:
+        pd = next(it, None)
+        if not isinstance(name, str) or not isinstance(pd, dict):
+            raise FoamCaseError("%s: boundary must alternate patch names and dictionaries" % path)
+        sides = []
+        for f in pd.get("faces", []):
+            fv = verts[[int(x) for x in f]]
+            side = None
+            for ax, nm in enumerate("xyz"):
+                if np.all(np.abs(fv[:, ax] - lo[ax]) <= 1e-12 * (hi[ax] - lo[ax])):
+                    side = nm + "min"
+                elif np.all(np.abs(fv[:, ax] - hi[ax]) <= 1e-12 * (hi[ax] - lo[ax])):
+                    side = nm + "max"
+            if side is None:
+                raise FoamCaseError("%s: patch %s: face %s is not a side of the block" % (path, name, list(f)))
+            if side in covered:
+                raise FoamCaseError("%s: side %s belongs to patches %s and %s" % (path, side, covered[side], name))
+            covered[side] = name
+            sides.append(side)
+        nf = sum(size[s_] for s_ in sides)
+        patches.append((name, str(pd.get("type", "patch")), sides, start, nf))
+        start += nf
+    if len(covered) != 6:
+        raise FoamCaseError("%s: block faces without a patch: %s (defaultFaces is not supported)" % (path, sorted(set(SIDES) - set(covered))))
+    return dict(n=(nx, ny, nz), origin=tuple(lo), L=tuple(hi - lo), patches=patches, from_block_mesh_dict=True)
+
+
+def read_box(case_dir):
+    """the hex box of a case: from constant/polyMesh when it exists, else from the blockMeshDict"""
+    if os.path.exists(os.path.join(case_dir, "constant", "polyMesh", "points")):
+        return detect_hex_box(read_poly_mesh(case_dir))
+    return read_block_mesh_dict(case_dir)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # fields
 # ---------------------------------------------------------------------------------------------------------------
@@ -457,7 +531,7 @@ def load_case(case_dir, time="0", solver="icoFoamYade"):
     """Everything the engine needs from a case directory.  solver: 'icoFoamYade' (fields U, p; transportProperties nu; PISO
     dictionary) or 'pimpleFoamYade' (fields Uc | U, p; nuValue / rhocValue / partDensity; PIMPLE dictionary; constant/g)."""
     check_schemes(case_dir)
-    box = detect_hex_box(read_poly_mesh(case_dir))
+    box = read_box(case_dir)
     nx, ny, nz = box["n"]
     N = nx * ny * nz
     pimple = solver == "pimpleFoamYade"
@@ -640,6 +714,13 @@ def write_field(case_dir, tname, obj, values, dims, patches, patch_entries, prec
 
 def boundary_owner_cells(case):
     """owner cell of every boundary face in the polyMesh's own face order, per patch (for zeroGradient patch values)"""
+    if case["box"].get("from_block_mesh_dict"):
+        # no polyMesh on disk: this module's own boundary order (side by side, by increasing owner cell; build_mesh's)
+        nx, ny, nz = case["box"]["n"]
+        c = np.arange(nx * ny * nz)
+        i, j, k = c % nx, (c // nx) % ny, c // (nx * ny)
+        on = dict(xmin=i == 0, xmax=i == nx - 1, ymin=j == 0, ymax=j == ny - 1, zmin=k == 0, zmax=k == nz - 1)
+        return {p["name"]: np.concatenate([c[on[s_]] for s_ in p["sides"]] or [c[:0]]) for p in case["patches"]}
     pm = read_poly_mesh(case["case_dir"])
     return {p["name"]: pm["owner"][p["start"]:p["start"] + p["nFaces"]] for p in case["patches"]}
 
